@@ -1,0 +1,608 @@
+// libhdgnn.so -- C ABI (include/hdgnn.h) over the sm_100a kernels of pairsum.cuh, score.cuh and
+// node.cuh.  Host side only: argument validation, scratch ownership, the launch sequence of one
+// forward / forward+backward / optimizer step, optional CUDA-graph replay.  No torch types.
+//
+// Launch sequence (variant 2 = model_2.py:86-118; [E] = entity-edge branch of model_4.py:92-98):
+//   fwd : pairsum(ent) -> [E: pairsum(edge) -> head_fwd(edge) -> score(edge, soft out)] -> pool_fwd
+//         -> pairsum(hunk) -> head_fwd(hunk) -> score(hunk: logits/probs/CE [+ delta sums]) -> loss
+//   bwd : head_bwd(hunk) -> pairsum_bwd(hunk) -> pool_bwd -> pairsum_bwd(ent) -> rank1_grad(ent)
+//         -> [E: score(edge, train: recompute + delta sums) -> head_bwd(edge) -> pairsum_bwd(edge)
+//             -> rank1_grad(edge, tied)] -> grad_reduce
+//   opt : adam (regularisers fused)
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/hdgnn.h"
+#include "common.cuh"
+#include "node.cuh"
+#include "pairsum.cuh"
+#include "score.cuh"
+
+using namespace hdgnn;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Block { const char* name; int rows, cols; };
+const Block kEnt[] = {{"ent_w1", 4, 20}, {"ent_b1", 1, 20}, {"ent_w5", 20, 20}, {"ent_b5", 1, 20},
+                      {"nod_w1", 21, 20}, {"nod_b1", 1, 20}, {"nod_w2", 20, 1}, {"nod_b2", 1, 1}};
+const Block kEdge[] = {{"edg_w11", 1, 20}, {"edg_w12", 2, 20}, {"edg_b1", 1, 20}, {"edg_w2", 20, 20},
+                       {"edg_b2", 1, 20}, {"eup_w1", 22, 20}, {"eup_b1", 1, 20}, {"eup_w2", 20, 2},
+                       {"eup_b2", 1, 2}};
+const Block kHunk[] = {{"hnk_w1", 10, 20}, {"hnk_b1", 1, 20}, {"hnk_w2", 20, 20}, {"hnk_b2", 1, 20},
+                       {"scr_w1", 22, 20}, {"scr_b1", 1, 20}, {"scr_w2", 20, 2}, {"scr_b2", 1, 2},
+                       {"theta1", 1, 2}, {"theta2", 1, 2}};
+
+// TF variable-creation order of build_model: entity-node block (model_2.py:89-91), entity-edge
+// block (model_4.py:92-94), hunk block (model_2.py:103-105), thetas (model_2.py:121).
+std::vector<std::pair<std::string, int>> layout(int variant) {
+    std::vector<std::pair<std::string, int>> out;
+    int off = 0;
+    auto add = [&](const Block* b, int n) {
+        for (int i = 0; i < n; ++i) { out.push_back({b[i].name, off}); off += b[i].rows * b[i].cols; }
+    };
+    if (variant == 2 || variant == 4) add(kEnt, 8);
+    if (variant == 3 || variant == 4) add(kEdge, 9);
+    add(kHunk, 10);
+    out.push_back({"", off});
+    return out;
+}
+
+int find_off(const std::vector<std::pair<std::string, int>>& l, const char* name) {
+    for (auto& p : l) if (p.first == name) return p.second;
+    return -1;
+}
+
+ParamOff make_off(int variant) {
+    auto l = layout(variant);
+    ParamOff o;
+    o.ent_w1 = find_off(l, "ent_w1"); o.ent_b1 = find_off(l, "ent_b1"); o.ent_w5 = find_off(l, "ent_w5");
+    o.ent_b5 = find_off(l, "ent_b5"); o.nod_w1 = find_off(l, "nod_w1"); o.nod_b1 = find_off(l, "nod_b1");
+    o.nod_w2 = find_off(l, "nod_w2"); o.nod_b2 = find_off(l, "nod_b2");
+    o.edg_w11 = find_off(l, "edg_w11"); o.edg_w12 = find_off(l, "edg_w12"); o.edg_b1 = find_off(l, "edg_b1");
+    o.edg_w2 = find_off(l, "edg_w2"); o.edg_b2 = find_off(l, "edg_b2"); o.eup_w1 = find_off(l, "eup_w1");
+    o.eup_b1 = find_off(l, "eup_b1"); o.eup_w2 = find_off(l, "eup_w2"); o.eup_b2 = find_off(l, "eup_b2");
+    o.hnk_w1 = find_off(l, "hnk_w1"); o.hnk_b1 = find_off(l, "hnk_b1"); o.hnk_w2 = find_off(l, "hnk_w2");
+    o.hnk_b2 = find_off(l, "hnk_b2"); o.scr_w1 = find_off(l, "scr_w1"); o.scr_b1 = find_off(l, "scr_b1");
+    o.scr_w2 = find_off(l, "scr_w2"); o.scr_b2 = find_off(l, "scr_b2");
+    o.theta1 = find_off(l, "theta1"); o.theta2 = find_off(l, "theta2");
+    o.total = l.back().second;
+    return o;
+}
+
+struct Buf { void* p = nullptr; size_t bytes = 0; };
+
+}  // namespace
+
+struct hdgnn_handle_s {
+    hdgnn_config_t cfg;
+    ParamOff po;
+    HeadOff ho_hunk, ho_edge;
+    int Ne, Nc, pe, pc;        // sizes and label pitches
+    int RTe, Se, CWe;          // entity grid tiling
+    int RTc, Sc, CWc;          // hunk grid tiling
+    bool ent, edge;            // branches that feed the loss
+    std::map<std::string, Buf> ws;
+    std::string err;
+    int launches = 0;
+    // host-entry staging + CUDA graphs
+    std::map<std::tuple<int, int, const void*, const void*>, cudaGraphExec_t> graphs;
+};
+
+namespace {
+
+#define CK(h, call)                                                                               \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            (h)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                        \
+            return HDGNN_E_CUDA;                                                                  \
+        }                                                                                         \
+    } while (0)
+
+#define LAUNCH_CHECK(h, what)                                                                     \
+    do {                                                                                          \
+        cudaError_t e_ = cudaGetLastError();                                                      \
+        if (e_ != cudaSuccess) {                                                                  \
+            (h)->err = std::string(what) + ": " + cudaGetErrorString(e_);                         \
+            return HDGNN_E_CUDA;                                                                  \
+        }                                                                                         \
+        ++(h)->launches;                                                                          \
+    } while (0)
+
+int fail(hdgnn_handle_t h, int code, const std::string& msg) {
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+
+float* F(hdgnn_handle_t h, const char* name) { return static_cast<float*>(h->ws[name].p); }
+
+int alloc(hdgnn_handle_t h, const char* name, size_t bytes) {
+    Buf b;
+    b.bytes = bytes;
+    cudaError_t e = cudaMalloc(&b.p, bytes ? bytes : 16);
+    if (e != cudaSuccess) { h->err = std::string("cudaMalloc(") + name + "): " + cudaGetErrorString(e); return HDGNN_E_NOMEM; }
+    e = cudaMemset(b.p, 0, bytes ? bytes : 16);
+    if (e != cudaSuccess) { h->err = std::string("cudaMemset(") + name + "): " + cudaGetErrorString(e); return HDGNN_E_CUDA; }
+    h->ws[name] = b;
+    return HDGNN_OK;
+}
+
+// ---- template dispatch over the column width CW = ceil(N / 32) ---------------------------------
+#define CW_SWITCH(cw, ...)                                                                        \
+    switch (cw) {                                                                                  \
+        case 1: { constexpr int CW = 1; __VA_ARGS__; } break;   case 2: { constexpr int CW = 2; __VA_ARGS__; } break;   \
+        case 3: { constexpr int CW = 3; __VA_ARGS__; } break;   case 4: { constexpr int CW = 4; __VA_ARGS__; } break;   \
+        case 5: { constexpr int CW = 5; __VA_ARGS__; } break;   case 6: { constexpr int CW = 6; __VA_ARGS__; } break;   \
+        case 7: { constexpr int CW = 7; __VA_ARGS__; } break;   case 8: { constexpr int CW = 8; __VA_ARGS__; } break;   \
+        case 9: { constexpr int CW = 9; __VA_ARGS__; } break;   case 10: { constexpr int CW = 10; __VA_ARGS__; } break; \
+        case 11: { constexpr int CW = 11; __VA_ARGS__; } break; case 12: { constexpr int CW = 12; __VA_ARGS__; } break; \
+        case 13: { constexpr int CW = 13; __VA_ARGS__; } break; case 14: { constexpr int CW = 14; __VA_ARGS__; } break; \
+        case 15: { constexpr int CW = 15; __VA_ARGS__; } break; case 16: { constexpr int CW = 16; __VA_ARGS__; } break; \
+        default: break;                                                                            \
+    }
+
+template <int CW, bool BWD, bool RANK1>
+cudaError_t pairsum_attr(size_t smem) {
+    return cudaFuncSetAttribute(pairsum_kernel<CW, BWD, RANK1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+template <int CW, bool TRAIN>
+cudaError_t score_attr(size_t smem) {
+    return cudaFuncSetAttribute(score_kernel<CW, TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+cudaError_t set_attrs(hdgnn_handle_t h) {
+    cudaError_t e = cudaSuccess;
+    auto acc = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+    // entity grid
+    CW_SWITCH(h->CWe, {
+        acc(pairsum_attr<CW, false, true>(pairsum_smem_bytes(CW, h->RTe, h->pe, false)));
+        acc(pairsum_attr<CW, true, true>(pairsum_smem_bytes(CW, h->RTe, h->pe, true)));
+        acc(score_attr<CW, false>(score_smem_bytes(CW, h->RTe, h->pe, false)));
+        acc(score_attr<CW, true>(score_smem_bytes(CW, h->RTe, h->pe, true)));
+    });
+    CW_SWITCH(h->CWc, {
+        acc(pairsum_attr<CW, false, false>(pairsum_smem_bytes(CW, h->RTc, h->pc, false)));
+        acc(pairsum_attr<CW, true, false>(pairsum_smem_bytes(CW, h->RTc, h->pc, true)));
+        acc(score_attr<CW, false>(score_smem_bytes(CW, h->RTc, h->pc, false)));
+        acc(score_attr<CW, true>(score_smem_bytes(CW, h->RTc, h->pc, true)));
+    });
+    acc(cudaFuncSetAttribute(pool_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pool_fwd_smem_bytes(h->Ne, h->Nc)));
+    acc(cudaFuncSetAttribute(pool_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pool_bwd_smem_bytes(h->Ne, h->Nc)));
+    acc(cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_fwd_smem_bytes()));
+    acc(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_bwd_smem_bytes()));
+    return e;
+}
+
+// grid: which N x N grid a launch runs on
+struct GridCfg { int N, RT, S, CW, pitch; };
+GridCfg ent_grid(hdgnn_handle_t h) { return {h->Ne, h->RTe, h->Se, h->CWe, h->pe}; }
+GridCfg hunk_grid(hdgnn_handle_t h) { return {h->Nc, h->RTc, h->Sc, h->CWc, h->pc}; }
+
+int launch_pairsum(hdgnn_handle_t h, const GridCfg& g, int B, bool bwd, bool rank1, PairSumArgs a, cudaStream_t st) {
+    a.N = g.N; a.RT = g.RT; a.S = g.S; a.pitch = g.pitch;
+    const dim3 grid(g.S, B), block(32 * HD);
+    CW_SWITCH(g.CW, {
+        const size_t smem = pairsum_smem_bytes(CW, g.RT, g.pitch, bwd);
+        if (bwd) {
+            if (rank1) pairsum_kernel<CW, true, true><<<grid, block, smem, st>>>(a);
+            else pairsum_kernel<CW, true, false><<<grid, block, smem, st>>>(a);
+        } else {
+            if (rank1) pairsum_kernel<CW, false, true><<<grid, block, smem, st>>>(a);
+            else pairsum_kernel<CW, false, false><<<grid, block, smem, st>>>(a);
+        }
+    });
+    LAUNCH_CHECK(h, "pairsum_kernel");
+    return HDGNN_OK;
+}
+
+int launch_score(hdgnn_handle_t h, const GridCfg& g, int B, bool train, ScoreArgs a, cudaStream_t st) {
+    a.N = g.N; a.RT = g.RT; a.S = g.S; a.pitch = g.pitch;
+    const dim3 grid(g.S, B), block(32 * HD);
+    CW_SWITCH(g.CW, {
+        const size_t smem = score_smem_bytes(CW, g.RT, g.pitch, train);
+        if (train) score_kernel<CW, true><<<grid, block, smem, st>>>(a);
+        else score_kernel<CW, false><<<grid, block, smem, st>>>(a);
+    });
+    LAUNCH_CHECK(h, "score_kernel");
+    return HDGNN_OK;
+}
+
+int check_inputs(hdgnn_handle_t h, int B, const void* adj, int adj_pitch, const void* x, const void* hmap,
+                 const void* L, const void* Y, int y_pitch, const void* params) {
+    if (!h) return HDGNN_E_INVALID;
+    if (B < 1 || B > h->cfg.max_batch) return fail(h, HDGNN_E_INVALID, "B out of range [1, max_batch]");
+    if (!adj || !x || !hmap || !L || !Y || !params) return fail(h, HDGNN_E_INVALID, "null input pointer");
+    if (adj_pitch != h->pe) return fail(h, HDGNN_E_INVALID, "adj_pitch must equal hdgnn_label_pitch(Ne)");
+    if (y_pitch != h->pc) return fail(h, HDGNN_E_INVALID, "y_pitch must equal hdgnn_label_pitch(Nc)");
+    if (((uintptr_t)adj & 15) || ((uintptr_t)Y & 15)) return fail(h, HDGNN_E_INVALID, "adj and Y must be 16-byte aligned");
+    return HDGNN_OK;
+}
+
+struct Inputs {
+    const uint8_t* adj; const float* x; const int32_t* hmap; const int32_t* L; const uint8_t* Y;
+    const float* params;
+};
+
+int forward_impl(hdgnn_handle_t h, int B, int B_global, const Inputs& in, float* logits, float* probs,
+                 float* loss, bool train, cudaStream_t st) {
+    const ParamOff& po = h->po;
+    const GridCfg ge = ent_grid(h), gc = hunk_grid(h);
+    int rc;
+    if (h->ent) {
+        PairSumArgs a{};
+        a.lab = in.adj; a.params = in.params; a.x = in.x;
+        a.o_u = po.ent_w1; a.o_v = po.ent_w1 + HD; a.o_b = po.ent_b1; a.o_l = po.ent_w1 + 2 * HD;
+        a.RS = F(h, "RS1"); a.CSp = F(h, "CS1P");
+        if ((rc = launch_pairsum(h, ge, B, false, true, a, st))) return rc;
+    }
+    if (h->edge) {
+        PairSumArgs a{};
+        a.lab = in.adj; a.params = in.params; a.x = in.x;
+        a.o_u = po.edg_w11; a.o_v = po.edg_w11; a.o_b = po.edg_b1; a.o_l = po.edg_w12;
+        a.RS = F(h, "RSE"); a.CSp = F(h, "CSEP");
+        if ((rc = launch_pairsum(h, ge, B, false, true, a, st))) return rc;
+        HeadFwdArgs hf{};
+        hf.N = h->Ne; hf.S = h->Se; hf.RS = F(h, "RSE"); hf.CSp = F(h, "CSEP"); hf.params = in.params;
+        hf.ho = h->ho_edge; hf.CSf = F(h, "CSEF"); hf.PR = F(h, "PRE"); hf.PC = F(h, "PCE");
+        head_fwd_kernel<<<B, NODE_THREADS, head_fwd_smem_bytes(), st>>>(hf);
+        LAUNCH_CHECK(h, "head_fwd_kernel(edge)");
+        ScoreArgs s{};
+        s.lab = in.adj; s.PR = F(h, "PRE"); s.PC = F(h, "PCE"); s.params = in.params;
+        s.o_l = po.eup_w1; s.o_w2 = po.eup_w2; s.o_b2 = po.eup_b2;
+        s.soft = F(h, "SOFT");
+        if ((rc = launch_score(h, ge, B, false, s, st))) return rc;
+    }
+    {
+        PoolFwdArgs a{};
+        a.Ne = h->Ne; a.Nc = h->Nc; a.Se = h->Se; a.ent = h->ent ? 1 : 0;
+        a.x = in.x; a.RS1 = F(h, "RS1"); a.CS1p = F(h, "CS1P"); a.params = in.params; a.po = po;
+        a.adj = in.adj; a.pitch = h->pe; a.soft = h->edge ? F(h, "SOFT") : nullptr;
+        a.hmap = in.hmap; a.L = in.L;
+        a.S1 = F(h, "S1"); a.X2 = F(h, "X2"); a.NB = F(h, "NB"); a.PH = F(h, "PH"); a.QH = F(h, "QH");
+        pool_fwd_kernel<<<B, NODE_THREADS, pool_fwd_smem_bytes(h->Ne, h->Nc), st>>>(a);
+        LAUNCH_CHECK(h, "pool_fwd_kernel");
+    }
+    {
+        PairSumArgs a{};
+        a.lab = in.Y; a.params = in.params; a.o_l = po.hnk_w1 + 8 * HD;
+        a.Ptab = F(h, "PH"); a.Qtab = F(h, "QH");
+        a.RS = F(h, "RS3"); a.CSp = F(h, "CS3P");
+        if ((rc = launch_pairsum(h, gc, B, false, false, a, st))) return rc;
+    }
+    {
+        HeadFwdArgs hf{};
+        hf.N = h->Nc; hf.S = h->Sc; hf.RS = F(h, "RS3"); hf.CSp = F(h, "CS3P"); hf.params = in.params;
+        hf.ho = h->ho_hunk; hf.CSf = F(h, "CS3F"); hf.PR = F(h, "PR"); hf.PC = F(h, "PC");
+        head_fwd_kernel<<<B, NODE_THREADS, head_fwd_smem_bytes(), st>>>(hf);
+        LAUNCH_CHECK(h, "head_fwd_kernel(hunk)");
+    }
+    {
+        ScoreArgs s{};
+        s.lab = in.Y; s.PR = F(h, "PR"); s.PC = F(h, "PC"); s.params = in.params;
+        s.o_l = po.scr_w1; s.o_w2 = po.scr_w2; s.o_b2 = po.scr_b2;
+        s.logits = logits; s.probs = probs; s.cep = F(h, "CEP");
+        s.scale = 10.f / ((float)B_global * (float)(h->Nc * (h->Nc - 1)));
+        s.RSm = F(h, "RSM"); s.CSmp = F(h, "CSMP"); s.LSmp = F(h, "LSMP"); s.HSp = F(h, "HSP"); s.dsump = F(h, "DSUMP");
+        if ((rc = launch_score(h, gc, B, train, s, st))) return rc;
+    }
+    if (loss) {
+        loss_reduce_kernel<<<1, 256, 0, st>>>(F(h, "CEP"), B * h->Sc, (float)B_global * (float)(h->Nc * (h->Nc - 1)), loss);
+        LAUNCH_CHECK(h, "loss_reduce_kernel");
+    }
+    return HDGNN_OK;
+}
+
+int backward_impl(hdgnn_handle_t h, int B, const Inputs& in, float* grads, cudaStream_t st) {
+    const ParamOff& po = h->po;
+    const GridCfg ge = ent_grid(h), gc = hunk_grid(h);
+    int rc;
+    {
+        HeadBwdArgs a{};
+        a.N = h->Nc; a.S = h->Sc;
+        a.RSm = F(h, "RSM"); a.CSmp = F(h, "CSMP"); a.LSmp = F(h, "LSMP"); a.HSp = F(h, "HSP"); a.dsump = F(h, "DSUMP");
+        a.RS = F(h, "RS3"); a.CSf = F(h, "CS3F"); a.params = in.params; a.ho = h->ho_hunk;
+        a.gpart = F(h, "GPART"); a.total = po.total; a.GR = F(h, "GRH"); a.GC = F(h, "GCH");
+        head_bwd_kernel<<<B, NODE_THREADS, head_bwd_smem_bytes(), st>>>(a);
+        LAUNCH_CHECK(h, "head_bwd_kernel(hunk)");
+    }
+    {
+        PairSumArgs a{};
+        a.lab = in.Y; a.params = in.params; a.o_l = po.hnk_w1 + 8 * HD;
+        a.Ptab = F(h, "PH"); a.Qtab = F(h, "QH"); a.GR = F(h, "GRH"); a.GC = F(h, "GCH");
+        a.RS = F(h, "RS3D"); a.CSp = F(h, "CS3DP"); a.LSp = F(h, "LS3P");
+        if ((rc = launch_pairsum(h, gc, B, true, false, a, st))) return rc;
+    }
+    {
+        PoolBwdArgs a{};
+        a.Ne = h->Ne; a.Nc = h->Nc; a.Sc = h->Sc; a.ent = h->ent ? 1 : 0;
+        a.RS3D = F(h, "RS3D"); a.CS3Dp = F(h, "CS3DP"); a.LS3p = F(h, "LS3P"); a.NB = F(h, "NB");
+        a.x = in.x; a.S1 = F(h, "S1"); a.X2 = F(h, "X2"); a.params = in.params; a.po = po;
+        a.hmap = in.hmap; a.L = in.L; a.gpart = F(h, "GPART"); a.total = po.total;
+        a.DNB = F(h, "DNB"); a.GE = F(h, "GE"); a.DX2 = F(h, "DX2");
+        a.dsoft = h->edge ? F(h, "DSOFT") : nullptr;
+        pool_bwd_kernel<<<B, NODE_THREADS, pool_bwd_smem_bytes(h->Ne, h->Nc), st>>>(a);
+        LAUNCH_CHECK(h, "pool_bwd_kernel");
+    }
+    if (h->ent) {
+        PairSumArgs a{};
+        a.lab = in.adj; a.params = in.params; a.x = in.x;
+        a.o_u = po.ent_w1; a.o_v = po.ent_w1 + HD; a.o_b = po.ent_b1; a.o_l = po.ent_w1 + 2 * HD;
+        a.GR = F(h, "GE"); a.GC = F(h, "GE");
+        a.RS = F(h, "RS1D"); a.CSp = F(h, "CS1DP"); a.LSp = F(h, "LS1P");
+        if ((rc = launch_pairsum(h, ge, B, true, true, a, st))) return rc;
+        Rank1GradArgs r{};
+        r.N = h->Ne; r.S = h->Se; r.x = in.x; r.RSd = F(h, "RS1D"); r.CSdp = F(h, "CS1DP"); r.LSp = F(h, "LS1P");
+        r.o_u = po.ent_w1; r.o_v = po.ent_w1 + HD; r.o_b = po.ent_b1; r.o_l = po.ent_w1 + 2 * HD;
+        r.gpart = F(h, "GPART"); r.total = po.total;
+        rank1_grad_kernel<<<B, 256, 0, st>>>(r);
+        LAUNCH_CHECK(h, "rank1_grad_kernel(ent)");
+    }
+    if (h->edge) {
+        ScoreArgs s{};
+        s.lab = in.adj; s.PR = F(h, "PRE"); s.PC = F(h, "PCE"); s.params = in.params;
+        s.o_l = po.eup_w1; s.o_w2 = po.eup_w2; s.o_b2 = po.eup_b2;
+        s.dsoft = F(h, "DSOFT");
+        s.RSm = F(h, "RSME"); s.CSmp = F(h, "CSMEP"); s.LSmp = F(h, "LSMEP"); s.HSp = F(h, "HSEP"); s.dsump = F(h, "DSUMEP");
+        if ((rc = launch_score(h, ge, B, true, s, st))) return rc;
+        HeadBwdArgs a{};
+        a.N = h->Ne; a.S = h->Se;
+        a.RSm = F(h, "RSME"); a.CSmp = F(h, "CSMEP"); a.LSmp = F(h, "LSMEP"); a.HSp = F(h, "HSEP"); a.dsump = F(h, "DSUMEP");
+        a.RS = F(h, "RSE"); a.CSf = F(h, "CSEF"); a.params = in.params; a.ho = h->ho_edge;
+        a.gpart = F(h, "GPART"); a.total = po.total; a.GR = F(h, "GRE"); a.GC = F(h, "GCE");
+        head_bwd_kernel<<<B, NODE_THREADS, head_bwd_smem_bytes(), st>>>(a);
+        LAUNCH_CHECK(h, "head_bwd_kernel(edge)");
+        PairSumArgs p{};
+        p.lab = in.adj; p.params = in.params; p.x = in.x;
+        p.o_u = po.edg_w11; p.o_v = po.edg_w11; p.o_b = po.edg_b1; p.o_l = po.edg_w12;
+        p.GR = F(h, "GRE"); p.GC = F(h, "GCE");
+        p.RS = F(h, "RSED"); p.CSp = F(h, "CSEDP"); p.LSp = F(h, "LSEP");
+        if ((rc = launch_pairsum(h, ge, B, true, true, p, st))) return rc;
+        Rank1GradArgs r{};
+        r.N = h->Ne; r.S = h->Se; r.x = in.x; r.RSd = F(h, "RSED"); r.CSdp = F(h, "CSEDP"); r.LSp = F(h, "LSEP");
+        r.o_u = po.edg_w11; r.o_v = po.edg_w11; r.o_b = po.edg_b1; r.o_l = po.edg_w12;
+        r.gpart = F(h, "GPART"); r.total = po.total;
+        rank1_grad_kernel<<<B, 256, 0, st>>>(r);
+        LAUNCH_CHECK(h, "rank1_grad_kernel(edge)");
+    }
+    grad_reduce_kernel<<<(po.total + 127) / 128, 128, 0, st>>>(F(h, "GPART"), B, po.total, grads);
+    LAUNCH_CHECK(h, "grad_reduce_kernel");
+    return HDGNN_OK;
+}
+
+int adam_impl(hdgnn_handle_t h, float* params, const float* grads, float* m, float* v, int32_t* step,
+              float lr, float b1, float b2, float eps, float* reg_losses, cudaStream_t st) {
+    adam_kernel<<<1, 1024, 0, st>>>(params, grads, m, v, h->po.total, h->po.theta1, h->po.theta2, step, lr, b1, b2,
+                                    eps, reg_losses);
+    LAUNCH_CHECK(h, "adam_kernel");
+    return HDGNN_OK;
+}
+
+int pick_rt(int N, int B, int requested) {
+    if (requested > 0) return round_up(requested < 4 ? 4 : requested, 4);
+    // Aim for >= 2 waves of 148 SMs x 3 resident CTAs while keeping >= 16 rows per CTA so the
+    // per-CTA column staging (N x 20 floats) is amortised.
+    int rt = 32;
+    while (rt > 16 && (long)B * ((N + rt - 1) / rt) < 2 * 148 * 3) rt -= 4;
+    if (rt > round_up(N, 4)) rt = round_up(N, 4);
+    return rt;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hdgnn_param_count(int variant) {
+    if (variant < 1 || variant > 4) return HDGNN_E_INVALID;
+    return layout(variant).back().second;
+}
+
+int hdgnn_param_offset(int variant, const char* name) {
+    if (variant < 1 || variant > 4 || !name || !*name) return -1;
+    return find_off(layout(variant), name);
+}
+
+int hdgnn_label_pitch(int n) { return n < 1 ? HDGNN_E_INVALID : round_up(n, 16); }
+
+const char* hdgnn_last_error(hdgnn_handle_t h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out) {
+    if (!cfg || !out) return fail(nullptr, HDGNN_E_INVALID, "null cfg/out");
+    *out = nullptr;
+    if (cfg->variant < 1 || cfg->variant > 4) return fail(nullptr, HDGNN_E_INVALID, "variant must be 1..4");
+    if (cfg->Ne < 2 || cfg->Nc < 2) return fail(nullptr, HDGNN_E_INVALID, "Ne and Nc must be >= 2");
+    if (cfg->Ne > HDGNN_MAX_N || cfg->Nc > HDGNN_MAX_N) return fail(nullptr, HDGNN_E_UNSUPPORTED, "Ne/Nc above HDGNN_MAX_N");
+    if (cfg->max_batch < 1) return fail(nullptr, HDGNN_E_INVALID, "max_batch must be >= 1");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return fail(nullptr, HDGNN_E_CUDA, "no CUDA device");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, HDGNN_E_INVALID, "bad device ordinal");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return fail(nullptr, HDGNN_E_CUDA, "cudaGetDeviceProperties failed");
+    if (prop.major != 10) return fail(nullptr, HDGNN_E_UNSUPPORTED, "libhdgnn is built for sm_100a (B200) only");
+    if (cudaSetDevice(cfg->device) != cudaSuccess) return fail(nullptr, HDGNN_E_CUDA, "cudaSetDevice failed");
+
+    hdgnn_handle_t h = new hdgnn_handle_s();
+    h->cfg = *cfg;
+    h->po = make_off(cfg->variant);
+    h->Ne = cfg->Ne; h->Nc = cfg->Nc;
+    h->pe = round_up(h->Ne, 16); h->pc = round_up(h->Nc, 16);
+    h->ent = cfg->variant == 2 || cfg->variant == 4;
+    h->edge = cfg->variant == 4;      // model_3's edge branch never reaches the loss (model_3.py:91-97)
+    h->ho_hunk = {h->po.hnk_w2, h->po.hnk_b2, h->po.scr_w1, h->po.scr_b1, h->po.scr_w2, h->po.scr_b2};
+    h->ho_edge = {h->po.edg_w2, h->po.edg_b2, h->po.eup_w1, h->po.eup_b1, h->po.eup_w2, h->po.eup_b2};
+    h->CWe = (h->Ne + 31) / 32; h->CWc = (h->Nc + 31) / 32;
+    h->RTe = pick_rt(h->Ne, cfg->max_batch, cfg->rows_per_cta_e);
+    h->RTc = pick_rt(h->Nc, cfg->max_batch, cfg->rows_per_cta_c);
+    h->Se = (h->Ne + h->RTe - 1) / h->RTe; h->Sc = (h->Nc + h->RTc - 1) / h->RTc;
+
+    const size_t smem_need[] = {pairsum_smem_bytes(h->CWe, h->RTe, h->pe, true), score_smem_bytes(h->CWe, h->RTe, h->pe, true),
+                                pairsum_smem_bytes(h->CWc, h->RTc, h->pc, true), score_smem_bytes(h->CWc, h->RTc, h->pc, true)};
+    for (size_t s : smem_need)
+        if (s > (size_t)prop.sharedMemPerBlockOptin) {
+            delete h;
+            return fail(nullptr, HDGNN_E_UNSUPPORTED, "row tile does not fit in shared memory; lower rows_per_cta");
+        }
+    cudaError_t e = set_attrs(h);
+    if (e != cudaSuccess) {
+        std::string m = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
+        delete h;
+        return fail(nullptr, HDGNN_E_CUDA, m);
+    }
+
+    const size_t B = cfg->max_batch, Ne = h->Ne, Nc = h->Nc, Se = h->Se, Sc = h->Sc, f = sizeof(float);
+    struct { const char* n; size_t bytes; bool need; } plan[] = {
+        {"RS1", B * Ne * HD * f, h->ent}, {"CS1P", B * Se * Ne * HD * f, h->ent}, {"S1", B * Ne * HD * f, true},
+        {"X2", B * Ne * f, true}, {"NB", B * Nc * 4 * f, true}, {"PH", B * Nc * HD * f, true}, {"QH", B * Nc * HD * f, true},
+        {"RS3", B * Nc * HD * f, true}, {"CS3P", B * Sc * Nc * HD * f, true}, {"CS3F", B * Nc * HD * f, true},
+        {"PR", B * Nc * HD * f, true}, {"PC", B * Nc * HD * f, true}, {"CEP", B * Sc * f, true},
+        {"RSM", B * Nc * HD * f, true}, {"CSMP", B * Sc * Nc * HD * f, true}, {"LSMP", B * Sc * HD * f, true},
+        {"HSP", B * Sc * HD * f, true}, {"DSUMP", B * Sc * f, true},
+        {"GRH", B * Nc * HD * f, true}, {"GCH", B * Nc * HD * f, true},
+        {"RS3D", B * Nc * HD * f, true}, {"CS3DP", B * Sc * Nc * HD * f, true}, {"LS3P", B * Sc * HD * f, true},
+        {"DNB", B * Nc * 4 * f, true}, {"GE", B * Ne * HD * f, true}, {"DX2", B * Ne * f, true},
+        {"RS1D", B * Ne * HD * f, h->ent}, {"CS1DP", B * Se * Ne * HD * f, h->ent}, {"LS1P", B * Se * HD * f, h->ent},
+        {"GPART", B * (size_t)h->po.total * f, true},
+        {"RSE", B * Ne * HD * f, h->edge}, {"CSEP", B * Se * Ne * HD * f, h->edge}, {"CSEF", B * Ne * HD * f, h->edge},
+        {"PRE", B * Ne * HD * f, h->edge}, {"PCE", B * Ne * HD * f, h->edge},
+        {"SOFT", B * Ne * Ne * 2 * f, h->edge}, {"DSOFT", B * Ne * Ne * 2 * f, h->edge},
+        {"RSME", B * Ne * HD * f, h->edge}, {"CSMEP", B * Se * Ne * HD * f, h->edge}, {"LSMEP", B * Se * HD * f, h->edge},
+        {"HSEP", B * Se * HD * f, h->edge}, {"DSUMEP", B * Se * f, h->edge},
+        {"GRE", B * Ne * HD * f, h->edge}, {"GCE", B * Ne * HD * f, h->edge},
+        {"RSED", B * Ne * HD * f, h->edge}, {"CSEDP", B * Se * Ne * HD * f, h->edge}, {"LSEP", B * Se * HD * f, h->edge},
+        // staging for the *_host entry points
+        {"H_ADJ", B * Ne * (size_t)h->pe, true}, {"H_Y", B * Nc * (size_t)h->pc, true}, {"H_X", B * Ne * f, true},
+        {"H_HMAP", B * Ne * sizeof(int32_t), true}, {"H_L", B * sizeof(int32_t), true},
+        {"H_PROBS", B * 2 * Nc * (Nc - 1) * f, true}, {"H_LOSS", 4 * f, true}, {"H_GRADS", (size_t)h->po.total * f, true},
+    };
+    for (auto& p : plan) {
+        if (!p.need) continue;
+        int rc = alloc(h, p.n, p.bytes);
+        if (rc != HDGNN_OK) {
+            g_create_error = h->err;
+            hdgnn_destroy(h);
+            return rc;
+        }
+    }
+    *out = h;
+    return HDGNN_OK;
+}
+
+int hdgnn_destroy(hdgnn_handle_t h) {
+    if (!h) return HDGNN_OK;
+    cudaSetDevice(h->cfg.device);
+    for (auto& g : h->graphs) cudaGraphExecDestroy(g.second);
+    for (auto& kv : h->ws) cudaFree(kv.second.p);
+    delete h;
+    return HDGNN_OK;
+}
+
+int hdgnn_forward(hdgnn_handle_t h, int B, const uint8_t* adj, int adj_pitch, const float* x, const int32_t* hmap,
+                  const int32_t* L, const uint8_t* Y, int y_pitch, const float* params, float* logits, float* probs,
+                  float* loss, void* stream) {
+    int rc = check_inputs(h, B, adj, adj_pitch, x, hmap, L, Y, y_pitch, params);
+    if (rc) return rc;
+    h->launches = 0;
+    Inputs in{adj, x, hmap, L, Y, params};
+    return forward_impl(h, B, B, in, logits, probs, loss, false, (cudaStream_t)stream);
+}
+
+int hdgnn_forward_backward(hdgnn_handle_t h, int B, int B_global, const uint8_t* adj, int adj_pitch, const float* x,
+                           const int32_t* hmap, const int32_t* L, const uint8_t* Y, int y_pitch, const float* params,
+                           float* logits, float* probs, float* loss, float* grads, void* stream) {
+    int rc = check_inputs(h, B, adj, adj_pitch, x, hmap, L, Y, y_pitch, params);
+    if (rc) return rc;
+    if (!grads) return fail(h, HDGNN_E_INVALID, "grads is null");
+    if (B_global < B) return fail(h, HDGNN_E_INVALID, "B_global < B");
+    h->launches = 0;
+    Inputs in{adj, x, hmap, L, Y, params};
+    rc = forward_impl(h, B, B_global, in, logits, probs, loss, true, (cudaStream_t)stream);
+    if (rc) return rc;
+    return backward_impl(h, B, in, grads, (cudaStream_t)stream);
+}
+
+int hdgnn_adam_step(hdgnn_handle_t h, float* params, const float* grads, float* m, float* v, int32_t* step_counter,
+                    float lr, float beta1, float beta2, float eps, float* reg_losses, void* stream) {
+    if (!h) return HDGNN_E_INVALID;
+    if (!params || !grads || !m || !v || !step_counter) return fail(h, HDGNN_E_INVALID, "null pointer");
+    h->launches = 0;
+    return adam_impl(h, params, grads, m, v, step_counter, lr, beta1, beta2, eps, reg_losses, (cudaStream_t)stream);
+}
+
+static int stage_inputs(hdgnn_handle_t h, int B, const uint8_t* adj_host, const float* x_host, const int32_t* hmap_host,
+                        const int32_t* L_host, const uint8_t* Y_host, cudaStream_t st) {
+    const size_t Ne = h->Ne, Nc = h->Nc;
+    CK(h, cudaMemcpy2DAsync(h->ws["H_ADJ"].p, h->pe, adj_host, Ne, Ne, (size_t)B * Ne, cudaMemcpyHostToDevice, st));
+    CK(h, cudaMemcpy2DAsync(h->ws["H_Y"].p, h->pc, Y_host, Nc, Nc, (size_t)B * Nc, cudaMemcpyHostToDevice, st));
+    CK(h, cudaMemcpyAsync(h->ws["H_X"].p, x_host, (size_t)B * Ne * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(h, cudaMemcpyAsync(h->ws["H_HMAP"].p, hmap_host, (size_t)B * Ne * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CK(h, cudaMemcpyAsync(h->ws["H_L"].p, L_host, (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    return HDGNN_OK;
+}
+
+int hdgnn_train_step_host(hdgnn_handle_t h, int B, const uint8_t* adj_host, const float* x_host,
+                          const int32_t* hmap_host, const int32_t* L_host, const uint8_t* Y_host, float* params,
+                          float* m, float* v, int32_t* step_counter, float lr, float beta1, float beta2, float eps,
+                          float* probs_host, float* loss3_host, void* stream) {
+    if (!h) return HDGNN_E_INVALID;
+    if (B < 1 || B > h->cfg.max_batch) return fail(h, HDGNN_E_INVALID, "B out of range [1, max_batch]");
+    if (!adj_host || !x_host || !hmap_host || !L_host || !Y_host || !params || !m || !v || !step_counter || !loss3_host)
+        return fail(h, HDGNN_E_INVALID, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    h->launches = 0;
+    int rc = stage_inputs(h, B, adj_host, x_host, hmap_host, L_host, Y_host, st);
+    if (rc) return rc;
+    Inputs in{(const uint8_t*)h->ws["H_ADJ"].p, F(h, "H_X"), (const int32_t*)h->ws["H_HMAP"].p,
+              (const int32_t*)h->ws["H_L"].p, (const uint8_t*)h->ws["H_Y"].p, params};
+    float* probs_d = probs_host ? F(h, "H_PROBS") : nullptr;
+    float* loss_d = F(h, "H_LOSS");
+    rc = forward_impl(h, B, B, in, nullptr, probs_d, loss_d, true, st);
+    if (rc) return rc;
+    rc = backward_impl(h, B, in, F(h, "H_GRADS"), st);
+    if (rc) return rc;
+    rc = adam_impl(h, params, F(h, "H_GRADS"), m, v, step_counter, lr, beta1, beta2, eps, loss_d + 1, st);
+    if (rc) return rc;
+    if (probs_host)
+        CK(h, cudaMemcpyAsync(probs_host, probs_d, (size_t)B * 2 * h->Nc * (h->Nc - 1) * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(h, cudaMemcpyAsync(loss3_host, loss_d, 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    return HDGNN_OK;
+}
+
+int hdgnn_infer_host(hdgnn_handle_t h, int B, const uint8_t* adj_host, const float* x_host, const int32_t* hmap_host,
+                     const int32_t* L_host, const uint8_t* Y_host, const float* params, float* probs_host,
+                     float* loss_host, void* stream) {
+    if (!h) return HDGNN_E_INVALID;
+    if (B < 1 || B > h->cfg.max_batch) return fail(h, HDGNN_E_INVALID, "B out of range [1, max_batch]");
+    if (!adj_host || !x_host || !hmap_host || !L_host || !Y_host || !params || !probs_host)
+        return fail(h, HDGNN_E_INVALID, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    h->launches = 0;
+    int rc = stage_inputs(h, B, adj_host, x_host, hmap_host, L_host, Y_host, st);
+    if (rc) return rc;
+    Inputs in{(const uint8_t*)h->ws["H_ADJ"].p, F(h, "H_X"), (const int32_t*)h->ws["H_HMAP"].p,
+              (const int32_t*)h->ws["H_L"].p, (const uint8_t*)h->ws["H_Y"].p, params};
+    rc = forward_impl(h, B, B, in, nullptr, F(h, "H_PROBS"), F(h, "H_LOSS"), false, st);
+    if (rc) return rc;
+    CK(h, cudaMemcpyAsync(probs_host, F(h, "H_PROBS"), (size_t)B * 2 * h->Nc * (h->Nc - 1) * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (loss_host) CK(h, cudaMemcpyAsync(loss_host, F(h, "H_LOSS"), sizeof(float), cudaMemcpyDeviceToHost, st));
+    return HDGNN_OK;
+}
+
+int hdgnn_workspace(hdgnn_handle_t h, const char* name, void** ptr, size_t* bytes) {
+    if (!h || !name) return HDGNN_E_INVALID;
+    auto it = h->ws.find(name);
+    if (it == h->ws.end()) return fail(h, HDGNN_E_INVALID, std::string("no workspace buffer named ") + name);
+    if (ptr) *ptr = it->second.p;
+    if (bytes) *bytes = it->second.bytes;
+    return HDGNN_OK;
+}
+
+int hdgnn_last_launch_count(hdgnn_handle_t h) { return h ? h->launches : HDGNN_E_INVALID; }
+
+}  // extern "C"

@@ -1,0 +1,179 @@
+"""Host-side engine: owns one libhdgnn handle and feeds it torch CUDA tensors by pointer.
+
+PyTorch is plumbing here (device memory, streams, torch.distributed); all arithmetic of the hot
+path -- model_2.py:86-118 forward, its backward, and the Adam step of model_2.py:336-338 -- runs
+in the sm_100a kernels behind the C ABI of include/hdgnn.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib, check
+
+PARAM_NAMES = {
+    1: ["hnk_w1", "hnk_b1", "hnk_w2", "hnk_b2", "scr_w1", "scr_b1", "scr_w2", "scr_b2", "theta1", "theta2"],
+}
+_ENT = ["ent_w1", "ent_b1", "ent_w5", "ent_b5", "nod_w1", "nod_b1", "nod_w2", "nod_b2"]
+_EDGE = ["edg_w11", "edg_w12", "edg_b1", "edg_w2", "edg_b2", "eup_w1", "eup_b1", "eup_w2", "eup_b2"]
+PARAM_NAMES[2] = _ENT + PARAM_NAMES[1]
+PARAM_NAMES[3] = _EDGE + PARAM_NAMES[1]
+PARAM_NAMES[4] = _ENT + _EDGE + PARAM_NAMES[1]
+
+
+def param_count(variant: int) -> int:
+    n = lib.hdgnn_param_count(variant)
+    if n < 0:
+        raise ValueError(f"variant must be 1..4, got {variant}")
+    return n
+
+
+def param_offsets(variant: int) -> Dict[str, int]:
+    return {n: lib.hdgnn_param_offset(variant, n.encode()) for n in PARAM_NAMES[variant]}
+
+
+def label_pitch(n: int) -> int:
+    return lib.hdgnn_label_pitch(n)
+
+
+@dataclass
+class DeviceBatch:
+    """Compact commit batch resident in HBM (layouts of include/hdgnn.h)."""
+    adj: torch.Tensor    # (B, Ne, pitch_e) uint8
+    x: torch.Tensor      # (B, Ne) float32
+    hmap: torch.Tensor   # (B, Ne) int32
+    L: torch.Tensor      # (B,) int32
+    Y: torch.Tensor      # (B, Nc, pitch_c) uint8
+    Ne: int
+    Nc: int
+
+    @property
+    def B(self):
+        return self.adj.shape[0]
+
+    @staticmethod
+    def from_numpy(adj, x, hmap, L, Y, device) -> "DeviceBatch":
+        B, Ne, _ = adj.shape
+        Nc = Y.shape[1]
+        pe, pc = label_pitch(Ne), label_pitch(Nc)
+        a = torch.zeros(B, Ne, pe, dtype=torch.uint8, device=device)
+        a[:, :, :Ne] = torch.as_tensor(np.ascontiguousarray(adj, dtype=np.uint8)).to(device)
+        y = torch.zeros(B, Nc, pc, dtype=torch.uint8, device=device)
+        y[:, :, :Nc] = torch.as_tensor(np.ascontiguousarray(Y, dtype=np.uint8)).to(device)
+        return DeviceBatch(
+            a, torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32)).to(device),
+            torch.as_tensor(np.ascontiguousarray(hmap, dtype=np.int32)).to(device),
+            torch.as_tensor(np.ascontiguousarray(L, dtype=np.int32)).to(device), y, Ne, Nc)
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class Engine:
+    def __init__(self, Ne: int, Nc: int, variant: int = 2, max_batch: int = 100, device: int = 0,
+                 rows_per_cta_e: int = 0, rows_per_cta_c: int = 0, flags: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("hdgnn_b200.Engine needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.Ne, self.Nc, self.variant, self.max_batch, self.device = Ne, Nc, variant, max_batch, device
+        self.Ncr = Nc * (Nc - 1)
+        self.n_params = param_count(variant)
+        cfg = _lib.Config(Ne, Nc, variant, max_batch, device, rows_per_cta_e, rows_per_cta_c, flags)
+        h = C.c_void_p()
+        check(lib.hdgnn_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+        self.tdev = torch.device("cuda", device)
+        self.pe, self.pc = label_pitch(Ne), label_pitch(Nc)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.hdgnn_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.tdev).cuda_stream)
+
+    def _check_batch(self, b: DeviceBatch, params: torch.Tensor):
+        assert b.Ne == self.Ne and b.Nc == self.Nc, "batch shape does not match the engine"
+        assert params.dtype == torch.float32 and params.is_cuda and params.numel() == self.n_params
+
+    # -- device-resident entry points ---------------------------------------------------------
+    def forward(self, b: DeviceBatch, params: torch.Tensor, want_logits=True):
+        """Inference graph of model_2.py:486-502 -> (probs (B,2,Ncr), logits or None, CE scalar tensor)."""
+        self._check_batch(b, params)
+        B = b.B
+        probs = torch.empty(B, 2, self.Ncr, dtype=torch.float32, device=self.tdev)
+        logits = torch.empty_like(probs) if want_logits else None
+        loss = torch.empty(1, dtype=torch.float32, device=self.tdev)
+        check(lib.hdgnn_forward(self._h, B, _p(b.adj), self.pe, _p(b.x), _p(b.hmap), _p(b.L), _p(b.Y), self.pc,
+                                _p(params), _p(logits), _p(probs), _p(loss), self._stream()), self._h)
+        return probs, logits, loss
+
+    def forward_backward(self, b: DeviceBatch, params: torch.Tensor, B_global: Optional[int] = None,
+                         grads: Optional[torch.Tensor] = None, probs: Optional[torch.Tensor] = None,
+                         logits: Optional[torch.Tensor] = None, loss: Optional[torch.Tensor] = None,
+                         want_probs=True, want_logits=False):
+        """-> (probs, logits, loss, grads); grads = d(10*CE)/dparams with CE the mean over B_global*Ncr pairs."""
+        self._check_batch(b, params)
+        B = b.B
+        if probs is None and want_probs:
+            probs = torch.empty(B, 2, self.Ncr, dtype=torch.float32, device=self.tdev)
+        if logits is None and want_logits:
+            logits = torch.empty(B, 2, self.Ncr, dtype=torch.float32, device=self.tdev)
+        if loss is None:
+            loss = torch.empty(1, dtype=torch.float32, device=self.tdev)
+        if grads is None:
+            grads = torch.empty(self.n_params, dtype=torch.float32, device=self.tdev)
+        check(lib.hdgnn_forward_backward(self._h, B, B if B_global is None else B_global, _p(b.adj), self.pe, _p(b.x),
+                                         _p(b.hmap), _p(b.L), _p(b.Y), self.pc, _p(params), _p(logits), _p(probs),
+                                         _p(loss), _p(grads), self._stream()), self._h)
+        return probs, logits, loss, grads
+
+    def adam_step(self, params, grads, m, v, step_counter, lr=3e-4, beta1=0.9, beta2=0.999, eps=1e-8,
+                  reg_losses: Optional[torch.Tensor] = None):
+        """Regularisers + tf.train.AdamOptimizer update (model_2.py:121-130, 326-338), in place."""
+        check(lib.hdgnn_adam_step(self._h, _p(params), _p(grads), _p(m), _p(v), _p(step_counter), lr, beta1, beta2,
+                                  eps, _p(reg_losses), self._stream()), self._h)
+
+    # -- host-buffer entry points (H2D + compute + D2H on one stream) -----------------------------
+    def train_step_host(self, adj, x, hmap, L, Y, params, m, v, step_counter, loss3, probs=None,
+                        lr=3e-4, beta1=0.9, beta2=0.999, eps=1e-8):
+        """adj (B,Ne,Ne) u8, x (B,Ne) f32, hmap (B,Ne) i32, L (B,) i32, Y (B,Nc,Nc) u8: pinned host
+        tensors; loss3 (3,) pinned float32 receives {CE, loss_map, loss_para}.  Asynchronous."""
+        B = adj.shape[0]
+        check(lib.hdgnn_train_step_host(self._h, B, _p(adj), _p(x), _p(hmap), _p(L), _p(Y), _p(params), _p(m), _p(v),
+                                        _p(step_counter), lr, beta1, beta2, eps, _p(probs), _p(loss3),
+                                        self._stream()), self._h)
+
+    def infer_host(self, adj, x, hmap, L, Y, params, probs, loss=None):
+        B = adj.shape[0]
+        check(lib.hdgnn_infer_host(self._h, B, _p(adj), _p(x), _p(hmap), _p(L), _p(Y), _p(params), _p(probs),
+                                   _p(loss), self._stream()), self._h)
+
+    # -- introspection ------------------------------------------------------------------------------
+    def workspace(self, name: str, shape, dtype=torch.float32) -> torch.Tensor:
+        """Copy of a named scratch buffer (tests only)."""
+        ptr, nbytes = C.c_void_p(), C.c_size_t()
+        check(lib.hdgnn_workspace(self._h, name.encode(), C.byref(ptr), C.byref(nbytes)), self._h)
+        n = int(np.prod(shape))
+        itemsize = torch.empty(0, dtype=dtype).element_size()
+        assert n * itemsize <= nbytes.value, (name, n * itemsize, nbytes.value)
+        out = torch.empty(n, dtype=dtype, device=self.tdev)
+        torch.cuda.synchronize(self.tdev)
+        rc = torch.cuda.cudart().cudaMemcpy(out.data_ptr(), ptr.value, n * itemsize, 3)
+        assert int(rc) == 0, rc
+        return out.reshape(shape)
+
+    def last_launch_count(self) -> int:
+        return lib.hdgnn_last_launch_count(self._h)

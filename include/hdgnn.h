@@ -1,0 +1,142 @@
+/*
+ * hdgnn.h -- C ABI of the B200-native HD-GNN hot path (libhdgnn.so).
+ *
+ * The reference (fanmengdan/HD-GNN) has no FFI of its own: the seam this library sits
+ * behind is the body of one `sess.run([... trainer], feed_dict=...)` call
+ * (model_2.py:369-383 for training, model_2.py:486-502 for inference), i.e. the forward
+ * graph built in model_2.py:86-118 (and its model_1/3/4 variants), its autodiff backward
+ * and the AdamOptimizer update of model_2.py:336-338.  Each entry point below names the
+ * reference lines it replaces.  INTEGRATION.md shows the ctypes binding a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *  - plain C types only; every pointer is a DEVICE pointer unless the name ends in _host;
+ *  - every call is asynchronous on the caller's `stream` (a cudaStream_t passed as void*),
+ *    no hidden synchronisation, CUDA-graph capturable; the *_host entry points enqueue
+ *    their own copies on that stream and are asynchronous as well;
+ *  - return value: 0 = ok, <0 = error (HDGNN_E_*); text via hdgnn_last_error();
+ *  - a handle belongs to one device and one host thread at a time;
+ *  - the caller owns params / grads / Adam moments (one flat fp32 blob each, laid out in
+ *    the TF variable-creation order of the variant's build_model, see hdgnn_param_layout);
+ *    the handle owns only scratch.
+ *
+ * Compact inputs (replace the nine dense feeds of model_2.py:54-82, built by
+ * utils2.py:29-137):
+ *   adj  uint8  (B, Ne, adj_pitch)  off-diagonal entity adjacency A_ij in {0,1}; the diagonal
+ *                                   is ignored.  Row pitch in bytes, multiple of 16, >= Ne.
+ *   x    float  (B, Ne)             node attribute x_i = raw A_ii            (utils2.py:35)
+ *   hmap int32  (B, Ne)             hunk id of index line i; <0 or >=Nc = none (utils2.py:129-136)
+ *   L    int32  (B)                 index lines read, 2 <= L <= Ne           (utils2.py:121)
+ *   Y    uint8  (B, Nc, y_pitch)    off-diagonal hunk adjacency = label      (utils2.py:47,105)
+ * Outputs
+ *   logits, probs  float (B, 2, Ncr), Ncr = Nc(Nc-1), pair order p(s,t) = s(Nc-1)+t-[t>s]
+ *                  (utils2.py:91-106); channel 0 = "no relation"             (model_2.py:321-323)
+ */
+#ifndef HDGNN_H_INCLUDED
+#define HDGNN_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HDGNN_OK              0
+#define HDGNN_E_INVALID      -1   /* bad argument (shape, variant, pitch, null pointer) */
+#define HDGNN_E_CUDA         -2   /* a CUDA runtime call failed; see hdgnn_last_error */
+#define HDGNN_E_NOMEM        -3
+#define HDGNN_E_UNSUPPORTED  -4   /* e.g. Ne or Nc above the compiled limit */
+
+#define HDGNN_MAX_N          512  /* largest Ne / Nc the kernels are instantiated for */
+#define HDGNN_HIDDEN         20   /* hidden / effect width: h_size, De_e, De_er (main.py:31-32) */
+
+typedef struct hdgnn_handle_s* hdgnn_handle_t;
+
+typedef struct {
+    int32_t Ne;             /* --Ne  main.py:38 */
+    int32_t Nc;             /* --Nc  main.py:39 */
+    int32_t variant;        /* 1 = model_1 (HD-GNN/ES), 2 = model_2 (HD-GNN/S, main.py:6),
+                               3 = model_3 (HD-GNN/E), 4 = model_4 (HD-GNN) */
+    int32_t max_batch;      /* largest B any later call will pass */
+    int32_t device;         /* CUDA device ordinal */
+    int32_t rows_per_cta_e; /* tuning: entity-grid rows per CTA, 0 = default */
+    int32_t rows_per_cta_c; /* tuning: hunk-grid rows per CTA, 0 = default */
+    int32_t flags;          /* HDGNN_F_* */
+} hdgnn_config_t;
+
+#define HDGNN_F_GRAPH   1   /* cache the launch sequence as a CUDA graph per (B, input pointers) */
+
+/* number of fp32 parameters of a variant (2127 for variant 2, 3129 for variant 4) */
+int hdgnn_param_count(int variant);
+/* offset (in floats) of a named block in the flat parameter blob, or -1.  Names:
+ * ent_w1 ent_b1 ent_w5 ent_b5 nod_w1 nod_b1 nod_w2 nod_b2 edg_w11 edg_w12 edg_b1 edg_w2 edg_b2
+ * eup_w1 eup_b1 eup_w2 eup_b2 hnk_w1 hnk_b1 hnk_w2 hnk_b2 scr_w1 scr_b1 scr_w2 scr_b2 theta1 theta2
+ * (= r1_w1o r1_b1o r1_w5o r1_b5o o1_w1o o1_b1o o1_w2o o1_b2o | r1_w1r1 r1_w1r2 r1_b1r r1_w2r r1_b2r
+ *    o1_w1r o1_b1r o1_w2r o1_b2r | w1 b1 r1_w2r b2 C_edge_w1 C_edge_b1 o1_w2r o1_b2r | map_theta1/2) */
+int hdgnn_param_offset(int variant, const char* name);
+
+int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out);
+int hdgnn_destroy(hdgnn_handle_t h);
+const char* hdgnn_last_error(hdgnn_handle_t h);       /* h may be NULL: last create() error */
+int hdgnn_label_pitch(int n);                         /* required row pitch for an n x n byte grid */
+
+/* Forward only.  Replaces sess.run([loss_Hedge_mse, loss_map, C_edge_output2]) of
+ * model_2.py:486-502 (graph of model_2.py:86-118).  `loss` receives the mean softmax
+ * cross-entropy over B*Ncr pairs (model_2.py:115-118).  logits may be NULL. */
+int hdgnn_forward(hdgnn_handle_t h, int B,
+                  const uint8_t* adj, int adj_pitch, const float* x, const int32_t* hmap,
+                  const int32_t* L, const uint8_t* Y, int y_pitch,
+                  const float* params, float* logits, float* probs, float* loss, void* stream);
+
+/* Forward + backward.  Replaces the forward and autodiff part of
+ * sess.run([merged, C_edge_output2, loss_Hedge_mse, loss_map, theta, trainer]) of
+ * model_2.py:369-383.  grads (param_count floats) receives d(10*CE)/dparams where CE is the
+ * mean over `B_global`*Ncr pairs (pass B_global = B on one GPU; with commit sharding each
+ * rank passes its local B and the global count, and the ranks' grads are summed).  The
+ * regularisers of model_2.py:121-130,326-336 are replica-identical and are applied inside
+ * hdgnn_adam_step.  `loss` receives sum(CE)/(B_global*Ncr) for the local commits. */
+int hdgnn_forward_backward(hdgnn_handle_t h, int B, int B_global,
+                           const uint8_t* adj, int adj_pitch, const float* x, const int32_t* hmap,
+                           const int32_t* L, const uint8_t* Y, int y_pitch,
+                           const float* params, float* logits, float* probs, float* loss,
+                           float* grads, void* stream);
+
+/* Regularisers + TF1 Adam (model_2.py:336-338; tf.train.AdamOptimizer semantics:
+ * lr_t = lr*sqrt(1-b2^t)/(1-b1^t), p -= lr_t*m/(sqrt(v)+eps), m and v un-corrected).
+ * Adds d/dp [0.1*0.01*(|theta1|+|theta2|) + 0.001*sum_v l2_loss(v)] to grads first.
+ * `step_counter` is a device int32 holding t-1; the kernel uses t = *step_counter+1 and
+ * stores it back, so the call is replayable from a CUDA graph.  reg_losses (device, 2
+ * floats, may be NULL) receives {loss_map, loss_para} evaluated at the pre-update params. */
+int hdgnn_adam_step(hdgnn_handle_t h, float* params, const float* grads, float* m, float* v,
+                    int32_t* step_counter, float lr, float beta1, float beta2, float eps,
+                    float* reg_losses, void* stream);
+
+/* One whole training step from HOST buffers (pinned recommended): H2D copies of the five
+ * compact inputs, forward, backward, Adam, and a D2H copy of {CE, loss_map, loss_para} into
+ * loss3_host, all enqueued on `stream`.  Un-pitched host layouts: adj (B,Ne,Ne), Y (B,Nc,Nc).
+ * probs_host may be NULL (otherwise B*2*Ncr floats are copied back). */
+int hdgnn_train_step_host(hdgnn_handle_t h, int B,
+                          const uint8_t* adj_host, const float* x_host, const int32_t* hmap_host,
+                          const int32_t* L_host, const uint8_t* Y_host,
+                          float* params, float* m, float* v, int32_t* step_counter,
+                          float lr, float beta1, float beta2, float eps,
+                          float* probs_host, float* loss3_host, void* stream);
+
+/* Inference from HOST buffers: H2D, forward, D2H of probs (B*2*Ncr floats) and CE. */
+int hdgnn_infer_host(hdgnn_handle_t h, int B,
+                     const uint8_t* adj_host, const float* x_host, const int32_t* hmap_host,
+                     const int32_t* L_host, const uint8_t* Y_host,
+                     const float* params, float* probs_host, float* loss_host, void* stream);
+
+/* Debug / test introspection: device pointer and size in bytes of a named scratch buffer
+ * (RS1 CS1 S1 X2 NB PH QH RS3 CS3 PR PC GRH GCH RS3D CS3D DNB GE RS1D CS1D GPART ...). */
+int hdgnn_workspace(hdgnn_handle_t h, const char* name, void** ptr, size_t* bytes);
+
+/* number of kernel launches the last forward / forward_backward / adam call enqueued */
+int hdgnn_last_launch_count(hdgnn_handle_t h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HDGNN_H_INCLUDED */

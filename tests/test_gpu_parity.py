@@ -1,0 +1,206 @@
+"""GPU parity: the CUDA path behind the C ABI vs the CPU oracle (fp64 closed form + autograd) on
+the same seeded inputs.  Tolerance: the north-star's fp32 budget, max rel err <= 1e-3, measured
+as max|cuda - oracle| / max|oracle| per tensor (fp32 kernels actually land near 1e-6)."""
+import numpy as np
+import pytest
+import torch
+
+from hdgnn_b200.synthetic import make_commits
+from oracle import hdgnn_oracle as O
+from oracle import plan_numpy as PN
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3          # north-star budget
+TIGHT = 2e-5        # what an all-fp32 path should achieve
+
+
+def relerr(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def _params(variant, seed=7):
+    flat = O.init_params(variant, seed=seed, dtype=torch.float64)
+    g = torch.Generator().manual_seed(seed + 1)
+    return flat + 0.05 * torch.randn(flat.numel(), generator=g, dtype=torch.float64)
+
+
+CASES = [
+    # B, Ne, Nc, variant
+    (3, 9, 5, 2), (2, 33, 12, 2), (4, 40, 20, 1), (3, 37, 21, 3), (2, 33, 12, 4), (3, 64, 32, 4),
+    (5, 70, 33, 2), (2, 200, 74, 2), (2, 97, 74, 4),
+]
+
+
+@pytest.mark.parametrize("B,Ne,Nc,variant", CASES)
+def test_forward_backward_matches_oracle(B, Ne, Nc, variant):
+    from hdgnn_b200.engine import Engine, DeviceBatch
+    cb = make_commits(B, Ne, Nc, seed=100 + Ne, p_edge=0.1, p_short=0.5, p_noise=0.1)
+    flat = _params(variant)
+    plan = PN.train_step_plan(variant, flat, cb.adj, cb.x, cb.hmap, cb.L, cb.Y)
+    if Ne <= 70:     # autograd oracle as an independent check of the plan at this size
+        _, ce, _, grad, out = O.train_loss_and_grad(variant, flat, cb.adj, cb.x, cb.hmap, cb.L, cb.Y)
+        assert relerr(plan["grad"], grad.numpy()) < 1e-9
+        assert relerr(plan["logits"], out["logits"].numpy()) < 1e-10
+
+    eng = Engine(Ne, Nc, variant=variant, max_batch=B)
+    db = DeviceBatch.from_numpy(cb.adj, cb.x, cb.hmap, cb.L, cb.Y, eng.tdev)
+    params = flat.float().cuda()
+    probs, logits, loss, grads = eng.forward_backward(db, params, want_logits=True)
+    torch.cuda.synchronize()
+    errs = {}
+    I = plan["I"]
+    def ws(name, shape):
+        return eng.workspace(name, shape).cpu().numpy()
+    if variant in (2, 4):
+        errs["RS1"] = relerr(ws("RS1", (B, Ne, 20)), I["RS1"])
+        errs["S1"] = relerr(ws("S1", (B, Ne, 20)), I["RS1"] + I["CS1"])
+        errs["X2"] = relerr(ws("X2", (B, Ne)), I["x2"])
+    errs["NB"] = relerr(ws("NB", (B, Nc, 4)), I["nb"])
+    errs["RS3"] = relerr(ws("RS3", (B, Nc, 20)), I["RS3"])
+    errs["CS3F"] = relerr(ws("CS3F", (B, Nc, 20)), I["CS3"])
+    errs["PR"] = relerr(ws("PR", (B, Nc, 20)), I["PR"])
+    errs["PC"] = relerr(ws("PC", (B, Nc, 20)), I["PC"])
+    errs["logits"] = relerr(logits.cpu().numpy(), plan["logits"])
+    errs["probs"] = relerr(probs.cpu().numpy(), plan["probs"])
+    errs["ce"] = relerr(loss.cpu().numpy()[0], plan["ce"])
+    errs["DNB"] = relerr(ws("DNB", (B, Nc, 4)), I["dnb"])
+    if variant in (2, 4):
+        errs["DX2"] = relerr(ws("DX2", (B, Ne)), I["dx2"])
+        errs["GE"] = relerr(ws("GE", (B, Ne, 20)), I["gE"])
+    # CE gradient only (the regularisers live in the Adam kernel)
+    pf = flat.numpy()
+    reg = 0.001 * pf
+    offs = {n: o for n, o in zip([s[0] for s in O.param_spec(variant)],
+                                 np.cumsum([0] + [int(np.prod(s[2])) for s in O.param_spec(variant)])[:-1])}
+    for t in ("theta1", "theta2"):
+        th = pf[offs[t]:offs[t] + 2]
+        reg[offs[t]:offs[t] + 2] += 0.001 * th / np.sqrt((th ** 2).sum())
+    g_ce = plan["grad"] - reg
+    g_cuda = grads.cpu().numpy()
+    errs["grad"] = relerr(g_cuda, g_ce)
+    # per-block gradient errors, relative to the block's own scale
+    spec = O.param_spec(variant)
+    for (name, _, shape) in spec:
+        n = int(np.prod(shape)); o = offs[name]
+        ref = g_ce[o:o + n]
+        if np.abs(ref).max() > 0:
+            errs["g_" + name] = relerr(g_cuda[o:o + n], ref)
+        else:
+            assert np.abs(g_cuda[o:o + n]).max() == 0, name
+    bad = {k: v for k, v in errs.items() if not (v < TOL)}
+    assert not bad, f"above the 1e-3 budget: {bad}\nall: {errs}"
+    loose = {k: v for k, v in errs.items() if not (v < TIGHT)}
+    assert not loose, f"fp32 path should be within {TIGHT}: {loose}"
+    # predicted relation classes identical (argmax over the 2 channels), away from exact ties
+    pc = probs.cpu().numpy(); pp = plan["probs"]
+    sure = np.abs(pp[:, 1] - pp[:, 0]) > 1e-4
+    assert np.array_equal((pc[:, 1] > pc[:, 0])[sure], (pp[:, 1] > pp[:, 0])[sure])
+    eng.close()
+
+
+@pytest.mark.parametrize("variant", [2, 4])
+def test_forward_only_matches_training_forward(variant):
+    from hdgnn_b200.engine import Engine, DeviceBatch
+    B, Ne, Nc = 3, 50, 23
+    cb = make_commits(B, Ne, Nc, seed=5)
+    flat = _params(variant)
+    eng = Engine(Ne, Nc, variant=variant, max_batch=B)
+    db = DeviceBatch.from_numpy(cb.adj, cb.x, cb.hmap, cb.L, cb.Y, eng.tdev)
+    params = flat.float().cuda()
+    p1, l1, loss1 = eng.forward(db, params)
+    p2, l2, loss2, _ = eng.forward_backward(db, params, want_logits=True)
+    torch.cuda.synchronize()
+    assert torch.equal(p1, p2) and torch.equal(l1, l2) and torch.equal(loss1, loss2)
+    eng.close()
+
+
+def test_run_to_run_bitwise_determinism():
+    from hdgnn_b200.engine import Engine, DeviceBatch
+    B, Ne, Nc = 6, 120, 50
+    cb = make_commits(B, Ne, Nc, seed=9)
+    eng = Engine(Ne, Nc, variant=4, max_batch=B)
+    db = DeviceBatch.from_numpy(cb.adj, cb.x, cb.hmap, cb.L, cb.Y, eng.tdev)
+    params = _params(4).float().cuda()
+    outs = []
+    for _ in range(3):
+        p, _, l, g = eng.forward_backward(db, params)
+        torch.cuda.synchronize()
+        outs.append((p.clone(), l.clone(), g.clone()))
+    for o in outs[1:]:
+        assert all(torch.equal(a, b) for a, b in zip(outs[0], o))
+    eng.close()
+
+
+def test_adam_step_matches_tf_formula():
+    from hdgnn_b200.engine import Engine
+    variant = 2
+    eng = Engine(16, 8, variant=variant, max_batch=1)
+    n = eng.n_params
+    rng = np.random.default_rng(3)
+    p = rng.normal(scale=0.1, size=n); g = rng.normal(scale=0.01, size=n)
+    m = np.zeros(n); v = np.zeros(n)
+    pt = torch.tensor(p, dtype=torch.float32).cuda(); gt = torch.tensor(g, dtype=torch.float32).cuda()
+    mt = torch.zeros(n, device="cuda"); vt = torch.zeros(n, device="cuda")
+    step = torch.zeros(1, dtype=torch.int32, device="cuda"); reg = torch.zeros(2, device="cuda")
+    offs = {s[0]: o for s, o in zip(O.param_spec(variant), np.cumsum([0] + [int(np.prod(s[2])) for s in O.param_spec(variant)])[:-1])}
+    for t in range(1, 4):
+        full = g + 0.001 * p
+        for th in ("theta1", "theta2"):
+            o = offs[th]
+            full[o:o + 2] += 0.001 * p[o:o + 2] / np.sqrt((p[o:o + 2] ** 2).sum())
+        lm, lp = O.reg_loss(torch.tensor(p), variant)
+        p, m, v = O.tf_adam_step(p, full, m, v, t)
+        eng.adam_step(pt, gt, mt, vt, step, reg_losses=reg)
+        torch.cuda.synchronize()
+        assert int(step.item()) == t
+        assert relerr(pt.cpu().numpy(), p) < 1e-6
+        assert relerr(mt.cpu().numpy(), m) < 1e-5 and relerr(vt.cpu().numpy(), v) < 1e-5
+        assert relerr(reg.cpu().numpy(), np.array([float(lm), float(lp)])) < 1e-5
+    eng.close()
+
+
+def test_host_entry_points_match_device_entry_points():
+    from hdgnn_b200.engine import Engine, DeviceBatch
+    B, Ne, Nc, variant = 4, 50, 20, 2      # Ne, Nc not multiples of 16: exercises the pitched staging copy
+    cb = make_commits(B, Ne, Nc, seed=21)
+    flat = _params(variant).float()
+    eng = Engine(Ne, Nc, variant=variant, max_batch=B)
+    db = DeviceBatch.from_numpy(cb.adj, cb.x, cb.hmap, cb.L, cb.Y, eng.tdev)
+    params = flat.cuda()
+    probs, _, loss, grads = eng.forward_backward(db, params)
+    p_ref = params.clone(); m = torch.zeros_like(params); v = torch.zeros_like(params)
+    step = torch.zeros(1, dtype=torch.int32, device="cuda"); reg = torch.zeros(2, device="cuda")
+    eng.adam_step(p_ref, grads, m, v, step, reg_losses=reg)
+    pin = lambda a: torch.as_tensor(np.ascontiguousarray(a)).pin_memory()
+    h = [pin(cb.adj), pin(cb.x), pin(cb.hmap), pin(cb.L), pin(cb.Y)]
+    p2 = flat.cuda(); m2 = torch.zeros_like(p2); v2 = torch.zeros_like(p2)
+    step2 = torch.zeros(1, dtype=torch.int32, device="cuda")
+    loss3 = torch.zeros(3).pin_memory(); probs_h = torch.zeros(B, 2, eng.Ncr).pin_memory()
+    eng.train_step_host(*h, p2, m2, v2, step2, loss3, probs=probs_h)
+    torch.cuda.synchronize()
+    assert torch.equal(p2, p_ref)
+    assert torch.equal(probs_h, probs.cpu())
+    assert loss3[0].item() == loss.item()
+    assert torch.equal(loss3[1:], reg.cpu())
+    probs_i = torch.zeros(B, 2, eng.Ncr).pin_memory(); li = torch.zeros(1).pin_memory()
+    eng.infer_host(*h, flat.cuda(), probs_i, li)
+    torch.cuda.synchronize()
+    assert torch.equal(probs_i, probs.cpu()) and li.item() == loss.item()
+    eng.close()
+
+
+def test_argument_validation():
+    from hdgnn_b200.engine import Engine, DeviceBatch
+    from hdgnn_b200._lib import HdgnnError
+    with pytest.raises(HdgnnError):
+        Engine(600, 10)
+    with pytest.raises(HdgnnError):
+        Engine(10, 10, variant=7)
+    eng = Engine(20, 10, max_batch=2)
+    cb = make_commits(3, 20, 10, seed=1)
+    db = DeviceBatch.from_numpy(cb.adj, cb.x, cb.hmap, cb.L, cb.Y, eng.tdev)
+    with pytest.raises(HdgnnError):
+        eng.forward(db, torch.zeros(eng.n_params, device="cuda"))     # B > max_batch
+    eng.close()
