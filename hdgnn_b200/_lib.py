@@ -43,6 +43,10 @@ def _load():
         "hdgnn_train_step_host": ([vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, f32, f32, f32, vp, vp, vp], i32),
         "hdgnn_infer_host": ([vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp], i32),
         "hdgnn_workspace": ([vp, C.c_char_p, C.POINTER(vp), C.POINTER(C.c_size_t)], i32),
+        "hdgnn_workspace_copy": ([vp, C.c_char_p, vp, C.c_size_t, vp], i32),
+        "hdgnn_profile": ([vp, i32], i32),
+        "hdgnn_profile_count": ([vp], i32),
+        "hdgnn_profile_get": ([vp, i32, C.c_char_p, i32, C.POINTER(f32)], i32),
         "hdgnn_last_launch_count": ([vp], i32),
     }
     for name, (argtypes, restype) in sig.items():

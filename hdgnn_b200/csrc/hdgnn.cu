@@ -92,6 +92,10 @@ struct hdgnn_handle_s {
     std::map<std::string, Buf> ws;
     std::string err;
     int launches = 0;
+    // opt-in per-launch timing (hdgnn_profile): events bracket every kernel launch
+    bool prof = false;
+    cudaEvent_t prof_start = nullptr;
+    std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> prof_ev;
     // host-entry staging + CUDA graphs
     std::map<std::tuple<int, int, const void*, const void*>, cudaGraphExec_t> graphs;
 };
@@ -107,7 +111,15 @@ namespace {
         }                                                                                         \
     } while (0)
 
-#define LAUNCH_CHECK(h, what)                                                                     \
+#define PROF_BEGIN(h, st)                                                                         \
+    do {                                                                                          \
+        if ((h)->prof) {                                                                          \
+            cudaEventCreate(&(h)->prof_start);                                                    \
+            cudaEventRecord((h)->prof_start, st);                                                 \
+        }                                                                                         \
+    } while (0)
+
+#define LAUNCH_CHECK(h, what, st)                                                                 \
     do {                                                                                          \
         cudaError_t e_ = cudaGetLastError();                                                      \
         if (e_ != cudaSuccess) {                                                                  \
@@ -115,6 +127,12 @@ namespace {
             return HDGNN_E_CUDA;                                                                  \
         }                                                                                         \
         ++(h)->launches;                                                                          \
+        if ((h)->prof) {                                                                          \
+            cudaEvent_t stop_;                                                                    \
+            cudaEventCreate(&stop_);                                                              \
+            cudaEventRecord(stop_, st);                                                           \
+            (h)->prof_ev.push_back({what, {(h)->prof_start, stop_}});                             \
+        }                                                                                         \
     } while (0)
 
 int fail(hdgnn_handle_t h, int code, const std::string& msg) {
@@ -186,9 +204,10 @@ struct GridCfg { int N, RT, S, CW, pitch; };
 GridCfg ent_grid(hdgnn_handle_t h) { return {h->Ne, h->RTe, h->Se, h->CWe, h->pe}; }
 GridCfg hunk_grid(hdgnn_handle_t h) { return {h->Nc, h->RTc, h->Sc, h->CWc, h->pc}; }
 
-int launch_pairsum(hdgnn_handle_t h, const GridCfg& g, int B, bool bwd, bool rank1, PairSumArgs a, cudaStream_t st) {
+int launch_pairsum(hdgnn_handle_t h, const char* what, const GridCfg& g, int B, bool bwd, bool rank1, PairSumArgs a, cudaStream_t st) {
     a.N = g.N; a.RT = g.RT; a.S = g.S; a.pitch = g.pitch;
     const dim3 grid(g.S, B), block(32 * HD);
+    PROF_BEGIN(h, st);
     CW_SWITCH(g.CW, {
         const size_t smem = pairsum_smem_bytes(CW, g.RT, g.pitch, bwd);
         if (bwd) {
@@ -199,19 +218,20 @@ int launch_pairsum(hdgnn_handle_t h, const GridCfg& g, int B, bool bwd, bool ran
             else pairsum_kernel<CW, false, false><<<grid, block, smem, st>>>(a);
         }
     });
-    LAUNCH_CHECK(h, "pairsum_kernel");
+    LAUNCH_CHECK(h, what, st);
     return HDGNN_OK;
 }
 
-int launch_score(hdgnn_handle_t h, const GridCfg& g, int B, bool train, ScoreArgs a, cudaStream_t st) {
+int launch_score(hdgnn_handle_t h, const char* what, const GridCfg& g, int B, bool train, ScoreArgs a, cudaStream_t st) {
     a.N = g.N; a.RT = g.RT; a.S = g.S; a.pitch = g.pitch;
     const dim3 grid(g.S, B), block(32 * HD);
+    PROF_BEGIN(h, st);
     CW_SWITCH(g.CW, {
         const size_t smem = score_smem_bytes(CW, g.RT, g.pitch, train);
         if (train) score_kernel<CW, true><<<grid, block, smem, st>>>(a);
         else score_kernel<CW, false><<<grid, block, smem, st>>>(a);
     });
-    LAUNCH_CHECK(h, "score_kernel");
+    LAUNCH_CHECK(h, what, st);
     return HDGNN_OK;
 }
 
@@ -241,24 +261,25 @@ int forward_impl(hdgnn_handle_t h, int B, int B_global, const Inputs& in, float*
         a.lab = in.adj; a.params = in.params; a.x = in.x;
         a.o_u = po.ent_w1; a.o_v = po.ent_w1 + HD; a.o_b = po.ent_b1; a.o_l = po.ent_w1 + 2 * HD;
         a.RS = F(h, "RS1"); a.CSp = F(h, "CS1P");
-        if ((rc = launch_pairsum(h, ge, B, false, true, a, st))) return rc;
+        if ((rc = launch_pairsum(h, "pairsum_fwd(ent)", ge, B, false, true, a, st))) return rc;
     }
     if (h->edge) {
         PairSumArgs a{};
         a.lab = in.adj; a.params = in.params; a.x = in.x;
         a.o_u = po.edg_w11; a.o_v = po.edg_w11; a.o_b = po.edg_b1; a.o_l = po.edg_w12;
         a.RS = F(h, "RSE"); a.CSp = F(h, "CSEP");
-        if ((rc = launch_pairsum(h, ge, B, false, true, a, st))) return rc;
+        if ((rc = launch_pairsum(h, "pairsum_fwd(edge)", ge, B, false, true, a, st))) return rc;
         HeadFwdArgs hf{};
         hf.N = h->Ne; hf.S = h->Se; hf.RS = F(h, "RSE"); hf.CSp = F(h, "CSEP"); hf.params = in.params;
         hf.ho = h->ho_edge; hf.CSf = F(h, "CSEF"); hf.PR = F(h, "PRE"); hf.PC = F(h, "PCE");
+        PROF_BEGIN(h, st);
         head_fwd_kernel<<<B, NODE_THREADS, head_fwd_smem_bytes(), st>>>(hf);
-        LAUNCH_CHECK(h, "head_fwd_kernel(edge)");
+        LAUNCH_CHECK(h, "head_fwd_kernel(edge)", st);
         ScoreArgs s{};
         s.lab = in.adj; s.PR = F(h, "PRE"); s.PC = F(h, "PCE"); s.params = in.params;
         s.o_l = po.eup_w1; s.o_w2 = po.eup_w2; s.o_b2 = po.eup_b2;
         s.soft = F(h, "SOFT");
-        if ((rc = launch_score(h, ge, B, false, s, st))) return rc;
+        if ((rc = launch_score(h, "score_fwd(edge)", ge, B, false, s, st))) return rc;
     }
     {
         PoolFwdArgs a{};
@@ -267,22 +288,24 @@ int forward_impl(hdgnn_handle_t h, int B, int B_global, const Inputs& in, float*
         a.adj = in.adj; a.pitch = h->pe; a.soft = h->edge ? F(h, "SOFT") : nullptr;
         a.hmap = in.hmap; a.L = in.L;
         a.S1 = F(h, "S1"); a.X2 = F(h, "X2"); a.NB = F(h, "NB"); a.PH = F(h, "PH"); a.QH = F(h, "QH");
+        PROF_BEGIN(h, st);
         pool_fwd_kernel<<<B, NODE_THREADS, pool_fwd_smem_bytes(h->Ne, h->Nc), st>>>(a);
-        LAUNCH_CHECK(h, "pool_fwd_kernel");
+        LAUNCH_CHECK(h, "pool_fwd_kernel", st);
     }
     {
         PairSumArgs a{};
         a.lab = in.Y; a.params = in.params; a.o_l = po.hnk_w1 + 8 * HD;
         a.Ptab = F(h, "PH"); a.Qtab = F(h, "QH");
         a.RS = F(h, "RS3"); a.CSp = F(h, "CS3P");
-        if ((rc = launch_pairsum(h, gc, B, false, false, a, st))) return rc;
+        if ((rc = launch_pairsum(h, "pairsum_fwd(hunk)", gc, B, false, false, a, st))) return rc;
     }
     {
         HeadFwdArgs hf{};
         hf.N = h->Nc; hf.S = h->Sc; hf.RS = F(h, "RS3"); hf.CSp = F(h, "CS3P"); hf.params = in.params;
         hf.ho = h->ho_hunk; hf.CSf = F(h, "CS3F"); hf.PR = F(h, "PR"); hf.PC = F(h, "PC");
+        PROF_BEGIN(h, st);
         head_fwd_kernel<<<B, NODE_THREADS, head_fwd_smem_bytes(), st>>>(hf);
-        LAUNCH_CHECK(h, "head_fwd_kernel(hunk)");
+        LAUNCH_CHECK(h, "head_fwd_kernel(hunk)", st);
     }
     {
         ScoreArgs s{};
@@ -291,11 +314,12 @@ int forward_impl(hdgnn_handle_t h, int B, int B_global, const Inputs& in, float*
         s.logits = logits; s.probs = probs; s.cep = F(h, "CEP");
         s.scale = 10.f / ((float)B_global * (float)(h->Nc * (h->Nc - 1)));
         s.RSm = F(h, "RSM"); s.CSmp = F(h, "CSMP"); s.LSmp = F(h, "LSMP"); s.HSp = F(h, "HSP"); s.dsump = F(h, "DSUMP");
-        if ((rc = launch_score(h, gc, B, train, s, st))) return rc;
+        if ((rc = launch_score(h, "score(hunk)", gc, B, train, s, st))) return rc;
     }
     if (loss) {
+        PROF_BEGIN(h, st);
         loss_reduce_kernel<<<1, 256, 0, st>>>(F(h, "CEP"), B * h->Sc, (float)B_global * (float)(h->Nc * (h->Nc - 1)), loss);
-        LAUNCH_CHECK(h, "loss_reduce_kernel");
+        LAUNCH_CHECK(h, "loss_reduce_kernel", st);
     }
     return HDGNN_OK;
 }
@@ -310,15 +334,16 @@ int backward_impl(hdgnn_handle_t h, int B, const Inputs& in, float* grads, cudaS
         a.RSm = F(h, "RSM"); a.CSmp = F(h, "CSMP"); a.LSmp = F(h, "LSMP"); a.HSp = F(h, "HSP"); a.dsump = F(h, "DSUMP");
         a.RS = F(h, "RS3"); a.CSf = F(h, "CS3F"); a.params = in.params; a.ho = h->ho_hunk;
         a.gpart = F(h, "GPART"); a.total = po.total; a.GR = F(h, "GRH"); a.GC = F(h, "GCH");
+        PROF_BEGIN(h, st);
         head_bwd_kernel<<<B, NODE_THREADS, head_bwd_smem_bytes(), st>>>(a);
-        LAUNCH_CHECK(h, "head_bwd_kernel(hunk)");
+        LAUNCH_CHECK(h, "head_bwd_kernel(hunk)", st);
     }
     {
         PairSumArgs a{};
         a.lab = in.Y; a.params = in.params; a.o_l = po.hnk_w1 + 8 * HD;
         a.Ptab = F(h, "PH"); a.Qtab = F(h, "QH"); a.GR = F(h, "GRH"); a.GC = F(h, "GCH");
         a.RS = F(h, "RS3D"); a.CSp = F(h, "CS3DP"); a.LSp = F(h, "LS3P");
-        if ((rc = launch_pairsum(h, gc, B, true, false, a, st))) return rc;
+        if ((rc = launch_pairsum(h, "pairsum_bwd(hunk)", gc, B, true, false, a, st))) return rc;
     }
     {
         PoolBwdArgs a{};
@@ -328,8 +353,9 @@ int backward_impl(hdgnn_handle_t h, int B, const Inputs& in, float* grads, cudaS
         a.hmap = in.hmap; a.L = in.L; a.gpart = F(h, "GPART"); a.total = po.total;
         a.DNB = F(h, "DNB"); a.GE = F(h, "GE"); a.DX2 = F(h, "DX2");
         a.dsoft = h->edge ? F(h, "DSOFT") : nullptr;
+        PROF_BEGIN(h, st);
         pool_bwd_kernel<<<B, NODE_THREADS, pool_bwd_smem_bytes(h->Ne, h->Nc), st>>>(a);
-        LAUNCH_CHECK(h, "pool_bwd_kernel");
+        LAUNCH_CHECK(h, "pool_bwd_kernel", st);
     }
     if (h->ent) {
         PairSumArgs a{};
@@ -337,13 +363,14 @@ int backward_impl(hdgnn_handle_t h, int B, const Inputs& in, float* grads, cudaS
         a.o_u = po.ent_w1; a.o_v = po.ent_w1 + HD; a.o_b = po.ent_b1; a.o_l = po.ent_w1 + 2 * HD;
         a.GR = F(h, "GE"); a.GC = F(h, "GE");
         a.RS = F(h, "RS1D"); a.CSp = F(h, "CS1DP"); a.LSp = F(h, "LS1P");
-        if ((rc = launch_pairsum(h, ge, B, true, true, a, st))) return rc;
+        if ((rc = launch_pairsum(h, "pairsum_bwd(ent)", ge, B, true, true, a, st))) return rc;
         Rank1GradArgs r{};
         r.N = h->Ne; r.S = h->Se; r.x = in.x; r.RSd = F(h, "RS1D"); r.CSdp = F(h, "CS1DP"); r.LSp = F(h, "LS1P");
         r.o_u = po.ent_w1; r.o_v = po.ent_w1 + HD; r.o_b = po.ent_b1; r.o_l = po.ent_w1 + 2 * HD;
         r.gpart = F(h, "GPART"); r.total = po.total;
+        PROF_BEGIN(h, st);
         rank1_grad_kernel<<<B, 256, 0, st>>>(r);
-        LAUNCH_CHECK(h, "rank1_grad_kernel(ent)");
+        LAUNCH_CHECK(h, "rank1_grad_kernel(ent)", st);
     }
     if (h->edge) {
         ScoreArgs s{};
@@ -351,37 +378,41 @@ int backward_impl(hdgnn_handle_t h, int B, const Inputs& in, float* grads, cudaS
         s.o_l = po.eup_w1; s.o_w2 = po.eup_w2; s.o_b2 = po.eup_b2;
         s.dsoft = F(h, "DSOFT");
         s.RSm = F(h, "RSME"); s.CSmp = F(h, "CSMEP"); s.LSmp = F(h, "LSMEP"); s.HSp = F(h, "HSEP"); s.dsump = F(h, "DSUMEP");
-        if ((rc = launch_score(h, ge, B, true, s, st))) return rc;
+        if ((rc = launch_score(h, "score_bwd(edge)", ge, B, true, s, st))) return rc;
         HeadBwdArgs a{};
         a.N = h->Ne; a.S = h->Se;
         a.RSm = F(h, "RSME"); a.CSmp = F(h, "CSMEP"); a.LSmp = F(h, "LSMEP"); a.HSp = F(h, "HSEP"); a.dsump = F(h, "DSUMEP");
         a.RS = F(h, "RSE"); a.CSf = F(h, "CSEF"); a.params = in.params; a.ho = h->ho_edge;
         a.gpart = F(h, "GPART"); a.total = po.total; a.GR = F(h, "GRE"); a.GC = F(h, "GCE");
+        PROF_BEGIN(h, st);
         head_bwd_kernel<<<B, NODE_THREADS, head_bwd_smem_bytes(), st>>>(a);
-        LAUNCH_CHECK(h, "head_bwd_kernel(edge)");
+        LAUNCH_CHECK(h, "head_bwd_kernel(edge)", st);
         PairSumArgs p{};
         p.lab = in.adj; p.params = in.params; p.x = in.x;
         p.o_u = po.edg_w11; p.o_v = po.edg_w11; p.o_b = po.edg_b1; p.o_l = po.edg_w12;
         p.GR = F(h, "GRE"); p.GC = F(h, "GCE");
         p.RS = F(h, "RSED"); p.CSp = F(h, "CSEDP"); p.LSp = F(h, "LSEP");
-        if ((rc = launch_pairsum(h, ge, B, true, true, p, st))) return rc;
+        if ((rc = launch_pairsum(h, "pairsum_bwd(edge)", ge, B, true, true, p, st))) return rc;
         Rank1GradArgs r{};
         r.N = h->Ne; r.S = h->Se; r.x = in.x; r.RSd = F(h, "RSED"); r.CSdp = F(h, "CSEDP"); r.LSp = F(h, "LSEP");
         r.o_u = po.edg_w11; r.o_v = po.edg_w11; r.o_b = po.edg_b1; r.o_l = po.edg_w12;
         r.gpart = F(h, "GPART"); r.total = po.total;
+        PROF_BEGIN(h, st);
         rank1_grad_kernel<<<B, 256, 0, st>>>(r);
-        LAUNCH_CHECK(h, "rank1_grad_kernel(edge)");
+        LAUNCH_CHECK(h, "rank1_grad_kernel(edge)", st);
     }
+    PROF_BEGIN(h, st);
     grad_reduce_kernel<<<(po.total + 127) / 128, 128, 0, st>>>(F(h, "GPART"), B, po.total, grads);
-    LAUNCH_CHECK(h, "grad_reduce_kernel");
+    LAUNCH_CHECK(h, "grad_reduce_kernel", st);
     return HDGNN_OK;
 }
 
 int adam_impl(hdgnn_handle_t h, float* params, const float* grads, float* m, float* v, int32_t* step,
               float lr, float b1, float b2, float eps, float* reg_losses, cudaStream_t st) {
+    PROF_BEGIN(h, st);
     adam_kernel<<<1, 1024, 0, st>>>(params, grads, m, v, h->po.total, h->po.theta1, h->po.theta2, step, lr, b1, b2,
                                     eps, reg_losses);
-    LAUNCH_CHECK(h, "adam_kernel");
+    LAUNCH_CHECK(h, "adam_kernel", st);
     return HDGNN_OK;
 }
 
@@ -600,6 +631,34 @@ int hdgnn_workspace(hdgnn_handle_t h, const char* name, void** ptr, size_t* byte
     if (it == h->ws.end()) return fail(h, HDGNN_E_INVALID, std::string("no workspace buffer named ") + name);
     if (ptr) *ptr = it->second.p;
     if (bytes) *bytes = it->second.bytes;
+    return HDGNN_OK;
+}
+
+int hdgnn_workspace_copy(hdgnn_handle_t h, const char* name, void* dst, size_t bytes, void* stream) {
+    if (!h || !name || !dst) return HDGNN_E_INVALID;
+    auto it = h->ws.find(name);
+    if (it == h->ws.end()) return fail(h, HDGNN_E_INVALID, std::string("no workspace buffer named ") + name);
+    if (bytes > it->second.bytes) return fail(h, HDGNN_E_INVALID, std::string("workspace buffer too small: ") + name);
+    CK(h, cudaMemcpyAsync(dst, it->second.p, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return HDGNN_OK;
+}
+
+int hdgnn_profile(hdgnn_handle_t h, int enable) {
+    if (!h) return HDGNN_E_INVALID;
+    for (auto& e : h->prof_ev) { cudaEventDestroy(e.second.first); cudaEventDestroy(e.second.second); }
+    h->prof_ev.clear();
+    h->prof = enable != 0;
+    return HDGNN_OK;
+}
+
+int hdgnn_profile_count(hdgnn_handle_t h) { return h ? (int)h->prof_ev.size() : HDGNN_E_INVALID; }
+
+int hdgnn_profile_get(hdgnn_handle_t h, int idx, char* name, int name_cap, float* ms) {
+    if (!h || idx < 0 || idx >= (int)h->prof_ev.size() || !ms) return HDGNN_E_INVALID;
+    auto& e = h->prof_ev[idx];
+    CK(h, cudaEventSynchronize(e.second.second));
+    CK(h, cudaEventElapsedTime(ms, e.second.first, e.second.second));
+    if (name && name_cap > 0) { strncpy(name, e.first.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
     return HDGNN_OK;
 }
 

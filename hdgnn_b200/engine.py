@@ -164,16 +164,25 @@ class Engine:
     # -- introspection ------------------------------------------------------------------------------
     def workspace(self, name: str, shape, dtype=torch.float32) -> torch.Tensor:
         """Copy of a named scratch buffer (tests only)."""
-        ptr, nbytes = C.c_void_p(), C.c_size_t()
-        check(lib.hdgnn_workspace(self._h, name.encode(), C.byref(ptr), C.byref(nbytes)), self._h)
         n = int(np.prod(shape))
-        itemsize = torch.empty(0, dtype=dtype).element_size()
-        assert n * itemsize <= nbytes.value, (name, n * itemsize, nbytes.value)
         out = torch.empty(n, dtype=dtype, device=self.tdev)
-        torch.cuda.synchronize(self.tdev)
-        rc = torch.cuda.cudart().cudaMemcpy(out.data_ptr(), ptr.value, n * itemsize, 3)
-        assert int(rc) == 0, rc
+        check(lib.hdgnn_workspace_copy(self._h, name.encode(), _p(out), n * out.element_size(), self._stream()),
+              self._h)
+        torch.cuda.current_stream(self.tdev).synchronize()
         return out.reshape(shape)
+
+    def profile(self, enable: bool):
+        check(lib.hdgnn_profile(self._h, 1 if enable else 0), self._h)
+
+    def profile_records(self):
+        """[(kernel label, milliseconds)] of every launch since profile(True)."""
+        out = []
+        buf = C.create_string_buffer(64)
+        ms = C.c_float()
+        for i in range(lib.hdgnn_profile_count(self._h)):
+            check(lib.hdgnn_profile_get(self._h, i, buf, 64, C.byref(ms)), self._h)
+            out.append((buf.value.decode(), ms.value))
+        return out
 
     def last_launch_count(self) -> int:
         return lib.hdgnn_last_launch_count(self._h)

@@ -1,0 +1,193 @@
+"""graph2graph -- host-side mirror of the reference's model class (model_2.py:15-544 and the
+model_1/3/4 ablations) over the B200 engine.
+
+Same constructor keywords, same train(args)/test(args)/save/load surface, same output files and
+log lines; the numeric work of every `sess.run` (model_2.py:369-383, 486-502) is one call into
+libhdgnn (include/hdgnn.h).  Commits are sharded across ranks when torch.distributed is
+initialised; the only collective is one all-reduce of the flat gradient per step.
+"""
+from __future__ import annotations
+
+import os
+import time
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .engine import Engine, DeviceBatch, param_count, param_offsets, PARAM_NAMES
+from .synthetic import CommitBatch
+
+H = 20
+
+_SHAPES = {
+    "ent_w1": (4, H), "ent_b1": (H,), "ent_w5": (H, H), "ent_b5": (H,), "nod_w1": (H + 1, H), "nod_b1": (H,),
+    "nod_w2": (H, 1), "nod_b2": (1,), "edg_w11": (1, H), "edg_w12": (2, H), "edg_b1": (H,), "edg_w2": (H, H),
+    "edg_b2": (H,), "eup_w1": (H + 2, H), "eup_b1": (H,), "eup_w2": (H, 2), "eup_b2": (2,),
+    "hnk_w1": (10, H), "hnk_b1": (H,), "hnk_w2": (H, H), "hnk_b2": (H,), "scr_w1": (H + 2, H), "scr_b1": (H,),
+    "scr_w2": (H, 2), "scr_b2": (2,), "theta1": (2,), "theta2": (2,),
+}
+# tf scope/name of every block (model_2.py:167-201, 257-264, 311-319, 329-330; model_4.py:219-229, 292-297)
+TF_NAMES = {
+    "ent_w1": "phi_E_O1/r1_w1o", "ent_b1": "phi_E_O1/r1_b1o", "ent_w5": "phi_E_O1/r1_w5o", "ent_b5": "phi_E_O1/r1_b5o",
+    "nod_w1": "phi_U_O1/o1_w1o", "nod_b1": "phi_U_O1/o1_b1o", "nod_w2": "phi_U_O1/o1_w2o", "nod_b2": "phi_U_O1/o1_b2o",
+    "edg_w11": "phi_E_R1/r1_w1r1", "edg_w12": "phi_E_R1/r1_w1r2", "edg_b1": "phi_E_R1/r1_b1r",
+    "edg_w2": "phi_E_R1/r1_w2r", "edg_b2": "phi_E_R1/r1_b2r", "eup_w1": "phi_U_R1/o1_w1r", "eup_b1": "phi_U_R1/o1_b1r",
+    "eup_w2": "phi_U_R1/o1_w2r", "eup_b2": "phi_U_R1/o1_b2r",
+    "hnk_w1": "mlp_hunk_B2/w1", "hnk_b1": "mlp_hunk_B2/b1", "hnk_w2": "mlp_hunk_B2/r1_w2r", "hnk_b2": "mlp_hunk_B2/b2",
+    "scr_w1": "phi_U_R1/C_edge_w1", "scr_b1": "phi_U_R1/C_edge_b1", "scr_w2": "phi_U_R1/o1_w2r", "scr_b2": "phi_U_R1/o1_b2r",
+    "theta1": "map_conv/map_theta1", "theta2": "map_conv/map_theta2",
+}
+
+
+def truncated_normal_init(variant: int, seed: Optional[int] = None) -> torch.Tensor:
+    """tf.truncated_normal(stddev=0.1) weights, tf.zeros biases (model_2.py:167-201); values beyond
+    two standard deviations are re-drawn.  The reference is unseeded; `seed` makes runs repeatable."""
+    g = torch.Generator()
+    if seed is None:
+        g.seed()
+    else:
+        g.manual_seed(seed)
+    parts = []
+    for name in PARAM_NAMES[variant]:
+        n = int(np.prod(_SHAPES[name]))
+        if "_b" in name:
+            parts.append(torch.zeros(n))
+            continue
+        v = torch.randn(n, generator=g)
+        bad = v.abs() > 2
+        while bad.any():
+            v[bad] = torch.randn(int(bad.sum()), generator=g)
+            bad = v.abs() > 2
+        parts.append(0.1 * v)
+    return torch.cat(parts)
+
+
+class HostBatch:
+    """Pinned host copy of a compact commit batch (the wire format into the hot path)."""
+
+    def __init__(self, cb: CommitBatch):
+        pin = torch.cuda.is_available()
+        mk = lambda a, dt: (torch.as_tensor(np.ascontiguousarray(a, dtype=dt)).pin_memory() if pin
+                            else torch.as_tensor(np.ascontiguousarray(a, dtype=dt)))
+        self.adj, self.x = mk(cb.adj, np.uint8), mk(cb.x, np.float32)
+        self.hmap, self.L, self.Y = mk(cb.hmap, np.int32), mk(cb.L, np.int32), mk(cb.Y, np.uint8)
+        self.B = self.adj.shape[0]
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in (self.adj, self.x, self.hmap, self.L, self.Y))
+
+    def tensors(self):
+        return self.adj, self.x, self.hmap, self.L, self.Y
+
+
+class graph2graph(object):
+    def __init__(self, sess=None, Ds=1, Ne=200, Nc=74, Ner=None, Ncr=None, Dr=2, De_e=20, De_er=20, Mini_batch=50,
+                 checkpoint_dir="./checkpoint40/", epoch=50, Ds_inter=1, Dr_inter=2, Step=2, Repo="glide",
+                 variant=2, device: Optional[int] = None, seed: Optional[int] = None, max_batch: Optional[int] = None):
+        # `sess` is accepted and ignored: there is no TF session (main.py:54-56).
+        Ner = Ne * (Ne - 1) if Ner is None else Ner
+        Ncr = Nc * (Nc - 1) if Ncr is None else Ncr
+        if Ner != Ne * (Ne - 1) or Ncr != Nc * (Nc - 1):
+            raise ValueError(f"Ner/Ncr must be Ne(Ne-1)/Nc(Nc-1) (utils2.py:69-83): got Ne={Ne} Ner={Ner} Nc={Nc} Ncr={Ncr}")
+        if (Ds, Ds_inter, Dr, Dr_inter, De_e, De_er) != (1, 1, 2, 2, 20, 20):
+            raise ValueError("the sm_100a kernels are specialised to the reference's dimensions "
+                             "Ds=Ds_inter=1, Dr=Dr_inter=2, De_e=De_er=20 (main.py:26-32; model_2.py:200-203 "
+                             "silently requires Ds==Ds_inter, Dr==Dr_inter)")
+        if variant not in (1, 2, 3, 4):
+            raise ValueError("variant must be 1 (model_1), 2 (model_2), 3 (model_3) or 4 (model_4)")
+        self.sess = sess
+        self.Ds, self.Ne, self.Nc, self.Ner, self.Ncr, self.Dr = Ds, Ne, Nc, Ner, Ncr, Dr
+        self.Ds_inter, self.Dr_inter, self.De_e, self.De_er = Ds_inter, Dr_inter, De_e, De_er
+        self.mini_batch_num = Mini_batch
+        self.epoch = epoch
+        self.checkpoint_dir = checkpoint_dir
+        self.Step, self.Repo = Step, Repo
+        self.variant = variant
+        self.seed = seed
+        self.world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
+        self.rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0")) if self.world > 1 else 0
+        self.device = device
+        self.max_batch = max_batch or Mini_batch
+        self.build_model()
+
+    # ------------------------------------------------------------------------------------------
+    def build_model(self):
+        torch.cuda.set_device(self.device)
+        self.engine = Engine(self.Ne, self.Nc, variant=self.variant, max_batch=self.max_batch, device=self.device)
+        self.n_params = param_count(self.variant)
+        self.offsets = param_offsets(self.variant)
+        dev = self.engine.tdev
+        self.params = torch.empty(self.n_params, dtype=torch.float32, device=dev)
+        self.m = torch.zeros_like(self.params)
+        self.v = torch.zeros_like(self.params)
+        self.grads = torch.zeros_like(self.params)
+        self.step_counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.reg = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.loss_d = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.loss3 = torch.zeros(3, dtype=torch.float32).pin_memory()
+        self.initialize()
+
+    def initialize(self, flat: Optional[torch.Tensor] = None):
+        """tf.global_variables_initializer (model_2.py:340-341): fresh weights, Adam slots zeroed."""
+        if flat is None:
+            flat = truncated_normal_init(self.variant, self.seed)
+            if self.world > 1:      # every rank must start from the same weights
+                t = flat.to(self.engine.tdev)
+                torch.distributed.broadcast(t, 0)
+                flat = t
+        assert flat.numel() == self.n_params
+        self.params.copy_(flat.to(torch.float32))
+        self.m.zero_(); self.v.zero_(); self.step_counter.zero_()
+
+    def named_params(self):
+        out = {}
+        flat = self.params.detach().cpu()
+        for name in PARAM_NAMES[self.variant]:
+            o = self.offsets[name]
+            out[name] = flat[o:o + int(np.prod(_SHAPES[name]))].reshape(_SHAPES[name]).clone()
+        return out
+
+    # ------------------------------------------------------------------------------------------
+    # one `sess.run([... trainer])` (model_2.py:369-383)
+    def train_step(self, hb: HostBatch, want_probs: bool = False, probs_out: Optional[torch.Tensor] = None):
+        """hb: this rank's shard of the global batch (pinned host tensors).  Returns the pinned
+        3-vector {CE (this rank's share of the global mean), loss_map, loss_para}; valid after a
+        stream synchronize."""
+        eng = self.engine
+        if self.world == 1:
+            eng.train_step_host(*hb.tensors(), self.params, self.m, self.v, self.step_counter, self.loss3,
+                                probs=probs_out if want_probs else None)
+            return self.loss3
+        db = self._stage(hb)
+        eng.forward_backward(db, self.params, B_global=hb.B * self.world, grads=self.grads, loss=self.loss_d,
+                             probs=self._probs_d if want_probs else None, want_probs=False)
+        torch.distributed.all_reduce(self.grads)        # the single collective of the step
+        eng.adam_step(self.params, self.grads, self.m, self.v, self.step_counter, reg_losses=self.reg)
+        self.loss3[0:1].copy_(self.loss_d, non_blocking=True)
+        self.loss3[1:3].copy_(self.reg, non_blocking=True)
+        if want_probs and probs_out is not None:
+            probs_out.copy_(self._probs_d[:hb.B], non_blocking=True)
+        return self.loss3
+
+    # one `sess.run([loss, loss_map, probs])` (model_2.py:486-502)
+    def infer(self, hb: HostBatch, probs_out: torch.Tensor, loss_out: Optional[torch.Tensor] = None):
+        self.engine.infer_host(*hb.tensors(), self.params, probs_out, loss_out)
+
+    def _stage(self, hb: HostBatch) -> DeviceBatch:
+        if not hasattr(self, "_db") or self._db.B != hb.B:
+            dev = self.engine.tdev
+            B, Ne, Nc, pe, pc = hb.B, self.Ne, self.Nc, self.engine.pe, self.engine.pc
+            self._db = DeviceBatch(torch.zeros(B, Ne, pe, dtype=torch.uint8, device=dev),
+                                   torch.zeros(B, Ne, dtype=torch.float32, device=dev),
+                                   torch.zeros(B, Ne, dtype=torch.int32, device=dev),
+                                   torch.zeros(B, dtype=torch.int32, device=dev),
+                                   torch.zeros(B, Nc, pc, dtype=torch.uint8, device=dev), Ne, Nc)
+            self._probs_d = torch.zeros(B, 2, self.Ncr, dtype=torch.float32, device=dev)
+        d = self._db
+        d.adj[:, :, :self.Ne].copy_(hb.adj, non_blocking=True)
+        d.Y[:, :, :self.Nc].copy_(hb.Y, non_blocking=True)
+        d.x.copy_(hb.x, non_blocking=True); d.hmap.copy_(hb.hmap, non_blocking=True); d.L.copy_(hb.L, non_blocking=True)
+        return d

@@ -132,6 +132,16 @@ int hdgnn_infer_host(hdgnn_handle_t h, int B,
 /* Debug / test introspection: device pointer and size in bytes of a named scratch buffer
  * (RS1 CS1 S1 X2 NB PH QH RS3 CS3 PR PC GRH GCH RS3D CS3D DNB GE RS1D CS1D GPART ...). */
 int hdgnn_workspace(hdgnn_handle_t h, const char* name, void** ptr, size_t* bytes);
+/* copy the first `bytes` bytes of a named scratch buffer to dst (device or host pointer) on `stream` */
+int hdgnn_workspace_copy(hdgnn_handle_t h, const char* name, void* dst, size_t bytes, void* stream);
+
+/* Opt-in per-launch timing for bench.py's roofline line: while enabled, every kernel launch is
+ * bracketed by CUDA events on the caller's stream (this perturbs the step; never enable it for
+ * a headline timing).  enable=0/1 also clears the recorded list.  hdgnn_profile_get returns the
+ * kernel's label and elapsed milliseconds of record `idx` (synchronises on its stop event). */
+int hdgnn_profile(hdgnn_handle_t h, int enable);
+int hdgnn_profile_count(hdgnn_handle_t h);
+int hdgnn_profile_get(hdgnn_handle_t h, int idx, char* name, int name_cap, float* ms);
 
 /* number of kernel launches the last forward / forward_backward / adam call enqueued */
 int hdgnn_last_launch_count(hdgnn_handle_t h);
