@@ -1,0 +1,134 @@
+// final: deterministic reduction of the per-commit / per-tile gradient partials into the flat
+// gradient, the mean cross-entropy (model_2.py:115-118) and -- on one GPU -- the regularisers
+// and TF1 Adam update (model_2.py:121-130, 326-338) in the same launch.
+#pragma once
+#include "common.cuh"
+
+namespace hdgnn {
+
+struct Rank1Map {            // where the four 20-vectors of an ent_bwd partial land in the flat gradient
+    const float* gp;         // (B,S,80) {db, dU, dV, LS} or null
+    int S, o_u, o_v, o_b, o_l;   // o_u == o_v: tied first-layer row (model_4.py:219-222)
+};
+
+struct FinalArgs {
+    int B, total;
+    const float* gpart;      // (B,total)
+    Rank1Map ent, edge;
+    const float* cep; int ncep; float loss_denom; float* loss;
+    float* grads;            // out: d(10 CE)/dparams for the local commits
+    // optional fused optimizer step
+    int apply_adam;
+    float* params; float* m; float* v; int* step; int o_t1, o_t2;
+    float lr, b1, b2, eps;
+    float* reg_losses;       // {loss_map, loss_para} at the pre-update parameters, or null
+    float* l2part;           // (gridDim.x) scratch
+    unsigned int* counter;   // zero-initialised; reset by the last CTA
+};
+
+constexpr int FIN_P = 128;   // parameters per CTA
+constexpr int FIN_SL = 8;    // commit slices per parameter
+
+__device__ __forceinline__ float rank1_extra(const Rank1Map& r, int B, int p, int slice, int nslice) {
+    if (!r.gp) return 0.f;
+    // which 20-vectors of the partial feed parameter p:  +db, +dU, +dV, +LS, -LS
+    int k = -1; float cb = 0.f, cu = 0.f, cv = 0.f, cl = 0.f;
+    if (p >= r.o_b && p < r.o_b + HD) { k = p - r.o_b; cb = 1.f; }
+    else if (p >= r.o_l && p < r.o_l + HD) { k = p - r.o_l; cb = 1.f; cl = -1.f; }
+    else if (p >= r.o_l + HD && p < r.o_l + 2 * HD) { k = p - r.o_l - HD; cl = 1.f; }
+    else if (p >= r.o_u && p < r.o_u + HD) { k = p - r.o_u; cu = 1.f; if (r.o_v == r.o_u) cv = 1.f; }
+    else if (r.o_v != r.o_u && p >= r.o_v && p < r.o_v + HD) { k = p - r.o_v; cv = 1.f; }
+    if (k < 0) return 0.f;
+    float acc = 0.f;
+    const int n = B * r.S;
+    for (int t = slice; t < n; t += nslice) {
+        const float* g = r.gp + (size_t)t * 4 * HD;
+        float e = 0.f;
+        if (cb != 0.f) e += g[k];
+        if (cu != 0.f) e += g[HD + k];
+        if (cv != 0.f) e += g[2 * HD + k];
+        if (cl != 0.f) e = fmaf(cl, g[3 * HD + k], e);
+        acc += e;
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(FIN_P * FIN_SL) reduce_adam_kernel(const FinalArgs a) {
+    __shared__ float part[FIN_SL][FIN_P];
+    __shared__ float scratch[32];
+    __shared__ float tn[2];
+    __shared__ int last;
+    const int tid = threadIdx.x, pl = tid % FIN_P, sl = tid / FIN_P;
+    const int p = blockIdx.x * FIN_P + pl;
+    float acc = 0.f;
+    if (p < a.total) {
+        int bb = sl;
+        for (; bb + 3 * FIN_SL < a.B; bb += 4 * FIN_SL) {
+            const float g0 = a.gpart[(size_t)bb * a.total + p], g1 = a.gpart[(size_t)(bb + FIN_SL) * a.total + p];
+            const float g2 = a.gpart[(size_t)(bb + 2 * FIN_SL) * a.total + p], g3 = a.gpart[(size_t)(bb + 3 * FIN_SL) * a.total + p];
+            acc += g0; acc += g1; acc += g2; acc += g3;
+        }
+        for (; bb < a.B; bb += FIN_SL) acc += a.gpart[(size_t)bb * a.total + p];
+        acc += rank1_extra(a.ent, a.B, p, sl, FIN_SL);
+        acc += rank1_extra(a.edge, a.B, p, sl, FIN_SL);
+    }
+    part[sl][pl] = acc;
+    if (blockIdx.x == 0 && a.loss) {          // mean CE: fixed-order block sum of the per-commit partials
+        float c = 0.f;
+        for (int i = tid; i < a.ncep; i += blockDim.x) c += a.cep[i];
+        const float t = block_sum(c, scratch);
+        if (tid == 0) *a.loss = t / a.loss_denom;
+    }
+    __syncthreads();
+    float g = 0.f;
+    if (sl == 0 && p < a.total) {
+#pragma unroll
+        for (int s = 0; s < FIN_SL; ++s) g += part[s][pl];
+        a.grads[p] = g;
+    }
+    if (!a.apply_adam) return;
+
+    // regularisers (evaluated at the pre-update parameters) + TF1 Adam
+    if (tid < 2) {
+        const int o = tid == 0 ? a.o_t1 : a.o_t2;
+        tn[tid] = sqrtf(a.params[o] * a.params[o] + a.params[o + 1] * a.params[o + 1]);
+    }
+    const float pv = (sl == 0 && p < a.total) ? a.params[p] : 0.f;
+    const float sq = block_sum(pv * pv, scratch);       // also orders tn[]
+    const int t = *a.step + 1;
+    if (sl == 0 && p < a.total) {
+        float gi = g + 0.001f * pv;
+        if (p >= a.o_t1 && p < a.o_t1 + 2) gi += 0.001f * pv / tn[0];
+        if (p >= a.o_t2 && p < a.o_t2 + 2) gi += 0.001f * pv / tn[1];
+        const float lr_t = a.lr * (float)(sqrt(1.0 - pow((double)a.b2, (double)t)) / (1.0 - pow((double)a.b1, (double)t)));
+        const float mi = a.b1 * a.m[p] + (1.f - a.b1) * gi;
+        const float vi = a.b2 * a.v[p] + (1.f - a.b2) * gi * gi;
+        a.m[p] = mi; a.v[p] = vi;
+        a.params[p] = pv - lr_t * mi / (sqrtf(vi) + a.eps);
+    }
+    // last CTA: step counter and the two regulariser values
+    if (tid == 0) {
+        a.l2part[blockIdx.x] = sq;
+        __threadfence();
+        const unsigned int done = atomicAdd(a.counter, 1u);
+        last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last && tid == 0) {
+        __threadfence();
+        float l2 = 0.f;
+        for (unsigned int i = 0; i < gridDim.x; ++i) l2 += a.l2part[i];
+        if (a.reg_losses) {
+            // theta norms at the pre-update values: this CTA may already have updated them, so they
+            // are recomputed from l2part-independent saved values by the CTA owning them (below)
+            a.reg_losses[1] = 0.001f * 0.5f * l2;
+        }
+        *a.step = t;
+        *a.counter = 0u;
+    }
+    // loss_map = 0.01 (|theta1| + |theta2|): written by the CTA that read the thetas before updating them
+    if (a.reg_losses && tid == 0 && a.o_t1 >= (int)(blockIdx.x * FIN_P) && a.o_t1 < (int)((blockIdx.x + 1) * FIN_P))
+        a.reg_losses[0] = 0.01f * (tn[0] + tn[1]);
+}
+
+}  // namespace hdgnn

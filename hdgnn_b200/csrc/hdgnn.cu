@@ -23,6 +23,10 @@
 #include "node.cuh"
 #include "pairsum.cuh"
 #include "score.cuh"
+#include "sweep.cuh"
+#include "ent.cuh"
+#include "mid.cuh"
+#include "final.cuh"
 
 using namespace hdgnn;
 
@@ -89,6 +93,9 @@ struct hdgnn_handle_s {
     int RTe, Se, CWe;          // entity grid tiling
     int RTc, Sc, CWc;          // hunk grid tiling
     bool ent, edge;            // branches that feed the loss
+    bool fused = false;        // ent_fwd -> mid -> ent_bwd -> reduce(+adam) path (variants 1-3)
+    bool debug = false;
+    int RTf = 0, Sf = 0;       // entity row tiling of the fused path
     std::map<std::string, Buf> ws;
     std::string err;
     int launches = 0;
@@ -416,6 +423,111 @@ int adam_impl(hdgnn_handle_t h, float* params, const float* grads, float* m, flo
     return HDGNN_OK;
 }
 
+
+// ================================================================================================
+// fused path: ent_fwd -> mid -> ent_bwd -> reduce (+ adam)
+// ================================================================================================
+constexpr int ENT_NW = 8;
+
+struct AdamArgs { float* params; float* m; float* v; int32_t* step; float lr, b1, b2, eps; float* reg; };
+
+EntArgs ent_args(hdgnn_handle_t h, const Inputs& in) {
+    EntArgs a{};
+    a.lab = in.adj; a.pitch = h->pe; a.N = h->Ne; a.RT = h->RTf; a.S = h->Sf;
+    a.params = in.params; a.x = in.x;
+    a.o_u = h->po.ent_w1; a.o_v = h->po.ent_w1 + HD; a.o_b = h->po.ent_b1; a.o_l = h->po.ent_w1 + 2 * HD;
+    return a;
+}
+
+int debug_scatter(hdgnn_handle_t h, int B, cudaStream_t st) {
+    const size_t Ne = h->Ne, Nc = h->Nc, T = Nc * HD, stride = mid_dbg_floats(h->Ne, h->Nc) * 4;
+    const char* src = (const char*)h->ws["DBG"].p;
+    struct { const char* name; size_t off, n; } parts[] = {
+        {"S1", 0, Ne * HD}, {"X2", Ne * HD, Ne}, {"NB", Ne * 21, Nc * 4}, {"RS3", Ne * 21 + Nc * 4, T},
+        {"CS3F", Ne * 21 + Nc * 4 + T, T}, {"PR", Ne * 21 + Nc * 4 + 2 * T, T}, {"PC", Ne * 21 + Nc * 4 + 3 * T, T},
+        {"DNB", Ne * 21 + Nc * 4 + 4 * T, Nc * 4}, {"DX2", Ne * 21 + Nc * 8 + 4 * T, Ne}};
+    for (auto& p : parts)
+        CK(h, cudaMemcpy2DAsync(h->ws[p.name].p, p.n * 4, src + p.off * 4, stride, p.n * 4, B, cudaMemcpyDeviceToDevice, st));
+    return HDGNN_OK;
+}
+
+int fused_forward(hdgnn_handle_t h, int B, int B_global, const Inputs& in, float* logits, float* probs, bool train,
+                  cudaStream_t st) {
+    if (h->ent) {
+        EntArgs a = ent_args(h, in);
+        a.RS = F(h, "RS1"); a.CSp = F(h, "CS1P");
+        PROF_BEGIN(h, st);
+        ent_fwd_kernel<ENT_NW><<<dim3(h->Sf, B), ENT_NW * 32, ent_smem_bytes(ENT_NW, h->Ne, h->RTf, h->pe, false), st>>>(a);
+        LAUNCH_CHECK(h, "ent_fwd", st);
+    }
+    MidArgs m{};
+    m.Ne = h->Ne; m.Nc = h->Nc; m.Se = h->Sf; m.ent = h->ent ? 1 : 0; m.train = train ? 1 : 0;
+    m.adj = in.adj; m.pe = h->pe; m.Y = in.Y; m.pc = h->pc; m.x = in.x; m.hmap = in.hmap; m.L = in.L;
+    m.params = in.params; m.po = h->po; m.RS1 = F(h, "RS1"); m.CS1p = F(h, "CS1P");
+    m.soft = nullptr; m.dsoft = nullptr; m.logits = logits; m.probs = probs; m.cep = F(h, "CEP");
+    m.scale = 10.f / ((float)B_global * (float)(h->Nc * (h->Nc - 1)));
+    m.GE = F(h, "GE"); m.gpart = F(h, "GPART"); m.total = h->po.total;
+    m.dbg = h->debug ? F(h, "DBG") : nullptr;
+    const size_t smem = mid_smem_bytes(h->Ne, h->Nc);
+    PROF_BEGIN(h, st);
+    if (train) {
+        if (logits) mid_kernel<true, true><<<B, MID_THREADS, smem, st>>>(m);
+        else mid_kernel<true, false><<<B, MID_THREADS, smem, st>>>(m);
+    } else {
+        if (logits) mid_kernel<false, true><<<B, MID_THREADS, smem, st>>>(m);
+        else mid_kernel<false, false><<<B, MID_THREADS, smem, st>>>(m);
+    }
+    LAUNCH_CHECK(h, train ? "mid(train)" : "mid(infer)", st);
+    if (h->debug) return debug_scatter(h, B, st);
+    return HDGNN_OK;
+}
+
+int fused_backward(hdgnn_handle_t h, int B, int B_global, const Inputs& in, float* loss, float* grads,
+                   const AdamArgs* adam, cudaStream_t st) {
+    if (h->ent) {
+        EntArgs a = ent_args(h, in);
+        a.GR = F(h, "GE"); a.GC = F(h, "GE"); a.gpart = F(h, "GPE");
+        PROF_BEGIN(h, st);
+        ent_bwd_kernel<ENT_NW><<<dim3(h->Sf, B), ENT_NW * 32, ent_smem_bytes(ENT_NW, h->Ne, h->RTf, h->pe, true), st>>>(a);
+        LAUNCH_CHECK(h, "ent_bwd", st);
+    }
+    FinalArgs f{};
+    f.B = B; f.total = h->po.total; f.gpart = F(h, "GPART");
+    if (h->ent) f.ent = {F(h, "GPE"), h->Sf, h->po.ent_w1, h->po.ent_w1 + HD, h->po.ent_b1, h->po.ent_w1 + 2 * HD};
+    f.cep = F(h, "CEP"); f.ncep = B; f.loss_denom = (float)B_global * (float)(h->Nc * (h->Nc - 1)); f.loss = loss;
+    f.grads = grads;
+    f.l2part = F(h, "FIN_L2"); f.counter = (unsigned int*)h->ws["FIN_CNT"].p;
+    if (adam) {
+        f.apply_adam = 1; f.params = adam->params; f.m = adam->m; f.v = adam->v; f.step = adam->step;
+        f.o_t1 = h->po.theta1; f.o_t2 = h->po.theta2; f.lr = adam->lr; f.b1 = adam->b1; f.b2 = adam->b2; f.eps = adam->eps;
+        f.reg_losses = adam->reg;
+    }
+    PROF_BEGIN(h, st);
+    reduce_adam_kernel<<<(h->po.total + FIN_P - 1) / FIN_P, FIN_P * FIN_SL, 0, st>>>(f);
+    LAUNCH_CHECK(h, adam ? "reduce_adam" : "grad_reduce", st);
+    return HDGNN_OK;
+}
+
+// rows per CTA of the fused entity sweeps: CTAs co-resident on an SM share its issue slots, so the
+// makespan is ~ ceil(B*S/148) * (rows per CTA + per-CTA overhead in row units).
+void pick_fused_tiling(int N, int B, int requested, int* RT, int* S) {
+    if (requested > 0) {
+        *RT = requested < ENT_NW ? ENT_NW : requested;
+        if (*RT > N) *RT = N;
+        *S = (N + *RT - 1) / *RT;
+        return;
+    }
+    double best = 1e30;
+    for (int s = 1; s <= 16; ++s) {
+        const int rt = (N + s - 1) / s;
+        if (rt < ENT_NW && s > 1) break;
+        const int ss = (N + rt - 1) / rt;
+        const double waves = (double)(((long)B * ss + 147) / 148);
+        const double cost = waves * (rt + 4.0);
+        if (cost < best - 1e-9) { best = cost; *RT = rt; *S = ss; }
+    }
+}
+
 int pick_rt(int N, int B, int requested) {
     if (requested > 0) return round_up(requested < 4 ? 4 : requested, 4);
     // Aim for >= 2 waves of 148 SMs x 3 resident CTAs while keeping >= 16 rows per CTA so the
@@ -480,26 +592,48 @@ int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out) {
             delete h;
             return fail(nullptr, HDGNN_E_UNSUPPORTED, "row tile does not fit in shared memory; lower rows_per_cta");
         }
+    h->debug = (cfg->flags & HDGNN_F_DEBUG) != 0;
+    pick_fused_tiling(h->Ne, cfg->max_batch, cfg->rows_per_cta_e, &h->RTf, &h->Sf);
+    h->fused = !h->edge && !(cfg->flags & HDGNN_F_LEGACY) &&
+               mid_smem_bytes(h->Ne, h->Nc) <= (size_t)prop.sharedMemPerBlockOptin &&
+               ent_smem_bytes(ENT_NW, h->Ne, h->RTf, h->pe, true) <= (size_t)prop.sharedMemPerBlockOptin;
     cudaError_t e = set_attrs(h);
+    if (e == cudaSuccess && h->fused) {
+        auto acc = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+        const int ms = (int)mid_smem_bytes(h->Ne, h->Nc);
+        acc(cudaFuncSetAttribute(mid_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
+        acc(cudaFuncSetAttribute(mid_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
+        acc(cudaFuncSetAttribute(mid_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
+        acc(cudaFuncSetAttribute(mid_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
+        acc(cudaFuncSetAttribute(ent_fwd_kernel<ENT_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)ent_smem_bytes(ENT_NW, h->Ne, h->RTf, h->pe, false)));
+        acc(cudaFuncSetAttribute(ent_bwd_kernel<ENT_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)ent_smem_bytes(ENT_NW, h->Ne, h->RTf, h->pe, true)));
+    }
     if (e != cudaSuccess) {
         std::string m = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
         delete h;
         return fail(nullptr, HDGNN_E_CUDA, m);
     }
 
-    const size_t B = cfg->max_batch, Ne = h->Ne, Nc = h->Nc, Se = h->Se, Sc = h->Sc, f = sizeof(float);
+    const size_t B = cfg->max_batch, Ne = h->Ne, Nc = h->Nc, Se = h->fused ? (size_t)h->Sf : (size_t)h->Se, Sc = h->Sc,
+                 f = sizeof(float);
+    const bool lg = !h->fused;     // buffers only the multi-kernel path needs (kept when debugging: dump targets)
+    const bool dbgbuf = lg || h->debug;
     struct { const char* n; size_t bytes; bool need; } plan[] = {
-        {"RS1", B * Ne * HD * f, h->ent}, {"CS1P", B * Se * Ne * HD * f, h->ent}, {"S1", B * Ne * HD * f, true},
-        {"X2", B * Ne * f, true}, {"NB", B * Nc * 4 * f, true}, {"PH", B * Nc * HD * f, true}, {"QH", B * Nc * HD * f, true},
-        {"RS3", B * Nc * HD * f, true}, {"CS3P", B * Sc * Nc * HD * f, true}, {"CS3F", B * Nc * HD * f, true},
-        {"PR", B * Nc * HD * f, true}, {"PC", B * Nc * HD * f, true}, {"CEP", B * Sc * f, true},
-        {"RSM", B * Nc * HD * f, true}, {"CSMP", B * Sc * Nc * HD * f, true}, {"LSMP", B * Sc * HD * f, true},
-        {"HSP", B * Sc * HD * f, true}, {"DSUMP", B * Sc * f, true},
-        {"GRH", B * Nc * HD * f, true}, {"GCH", B * Nc * HD * f, true},
-        {"RS3D", B * Nc * HD * f, true}, {"CS3DP", B * Sc * Nc * HD * f, true}, {"LS3P", B * Sc * HD * f, true},
-        {"DNB", B * Nc * 4 * f, true}, {"GE", B * Ne * HD * f, true}, {"DX2", B * Ne * f, true},
-        {"RS1D", B * Ne * HD * f, h->ent}, {"CS1DP", B * Se * Ne * HD * f, h->ent}, {"LS1P", B * Se * HD * f, h->ent},
+        {"RS1", B * Ne * HD * f, h->ent}, {"CS1P", B * Se * Ne * HD * f, h->ent}, {"S1", B * Ne * HD * f, dbgbuf},
+        {"X2", B * Ne * f, dbgbuf}, {"NB", B * Nc * 4 * f, dbgbuf}, {"PH", B * Nc * HD * f, lg}, {"QH", B * Nc * HD * f, lg},
+        {"RS3", B * Nc * HD * f, dbgbuf}, {"CS3P", B * Sc * Nc * HD * f, lg}, {"CS3F", B * Nc * HD * f, dbgbuf},
+        {"PR", B * Nc * HD * f, dbgbuf}, {"PC", B * Nc * HD * f, dbgbuf}, {"CEP", B * Sc * f, true},
+        {"RSM", B * Nc * HD * f, lg}, {"CSMP", B * Sc * Nc * HD * f, lg}, {"LSMP", B * Sc * HD * f, lg},
+        {"HSP", B * Sc * HD * f, lg}, {"DSUMP", B * Sc * f, lg},
+        {"GRH", B * Nc * HD * f, lg}, {"GCH", B * Nc * HD * f, lg},
+        {"RS3D", B * Nc * HD * f, lg}, {"CS3DP", B * Sc * Nc * HD * f, lg}, {"LS3P", B * Sc * HD * f, lg},
+        {"DNB", B * Nc * 4 * f, dbgbuf}, {"GE", B * Ne * HD * f, true}, {"DX2", B * Ne * f, dbgbuf},
+        {"RS1D", B * Ne * HD * f, h->ent && lg}, {"CS1DP", B * Se * Ne * HD * f, h->ent && lg}, {"LS1P", B * Se * HD * f, h->ent && lg},
         {"GPART", B * (size_t)h->po.total * f, true},
+        {"GPE", B * Se * 4 * HD * f, h->fused && h->ent}, {"FIN_L2", 64 * f, h->fused}, {"FIN_CNT", 16, h->fused},
+        {"DBG", B * mid_dbg_floats(h->Ne, h->Nc) * f, h->fused && h->debug},
         {"RSE", B * Ne * HD * f, h->edge}, {"CSEP", B * Se * Ne * HD * f, h->edge}, {"CSEF", B * Ne * HD * f, h->edge},
         {"PRE", B * Ne * HD * f, h->edge}, {"PCE", B * Ne * HD * f, h->edge},
         {"SOFT", B * Ne * Ne * 2 * f, h->edge}, {"DSOFT", B * Ne * Ne * 2 * f, h->edge},
@@ -534,6 +668,33 @@ int hdgnn_destroy(hdgnn_handle_t h) {
     return HDGNN_OK;
 }
 
+// forward [+ backward [+ adam]] on device-resident inputs; dispatches to the fused or the
+// multi-kernel path.
+static int run_step(hdgnn_handle_t h, int B, int B_global, const Inputs& in, float* logits, float* probs, float* loss,
+                    float* grads, const AdamArgs* adam, cudaStream_t st) {
+    const bool train = grads != nullptr;
+    int rc;
+    if (h->fused) {
+        rc = fused_forward(h, B, B_global, in, logits, probs, train, st);
+        if (rc) return rc;
+        if (!train) {
+            if (loss) {
+                PROF_BEGIN(h, st);
+                loss_reduce_kernel<<<1, 256, 0, st>>>(F(h, "CEP"), B, (float)B_global * (float)(h->Nc * (h->Nc - 1)), loss);
+                LAUNCH_CHECK(h, "loss_reduce_kernel", st);
+            }
+            return HDGNN_OK;
+        }
+        return fused_backward(h, B, B_global, in, loss, grads, adam, st);
+    }
+    rc = forward_impl(h, B, B_global, in, logits, probs, loss, train, st);
+    if (rc || !train) return rc;
+    rc = backward_impl(h, B, in, grads, st);
+    if (rc || !adam) return rc;
+    return adam_impl(h, adam->params, grads, adam->m, adam->v, adam->step, adam->lr, adam->b1, adam->b2, adam->eps,
+                     adam->reg, st);
+}
+
 int hdgnn_forward(hdgnn_handle_t h, int B, const uint8_t* adj, int adj_pitch, const float* x, const int32_t* hmap,
                   const int32_t* L, const uint8_t* Y, int y_pitch, const float* params, float* logits, float* probs,
                   float* loss, void* stream) {
@@ -541,7 +702,7 @@ int hdgnn_forward(hdgnn_handle_t h, int B, const uint8_t* adj, int adj_pitch, co
     if (rc) return rc;
     h->launches = 0;
     Inputs in{adj, x, hmap, L, Y, params};
-    return forward_impl(h, B, B, in, logits, probs, loss, false, (cudaStream_t)stream);
+    return run_step(h, B, B, in, logits, probs, loss, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 int hdgnn_forward_backward(hdgnn_handle_t h, int B, int B_global, const uint8_t* adj, int adj_pitch, const float* x,
@@ -553,9 +714,7 @@ int hdgnn_forward_backward(hdgnn_handle_t h, int B, int B_global, const uint8_t*
     if (B_global < B) return fail(h, HDGNN_E_INVALID, "B_global < B");
     h->launches = 0;
     Inputs in{adj, x, hmap, L, Y, params};
-    rc = forward_impl(h, B, B_global, in, logits, probs, loss, true, (cudaStream_t)stream);
-    if (rc) return rc;
-    return backward_impl(h, B, in, grads, (cudaStream_t)stream);
+    return run_step(h, B, B_global, in, logits, probs, loss, grads, nullptr, (cudaStream_t)stream);
 }
 
 int hdgnn_adam_step(hdgnn_handle_t h, float* params, const float* grads, float* m, float* v, int32_t* step_counter,
@@ -593,11 +752,8 @@ int hdgnn_train_step_host(hdgnn_handle_t h, int B, const uint8_t* adj_host, cons
               (const int32_t*)h->ws["H_L"].p, (const uint8_t*)h->ws["H_Y"].p, params};
     float* probs_d = probs_host ? F(h, "H_PROBS") : nullptr;
     float* loss_d = F(h, "H_LOSS");
-    rc = forward_impl(h, B, B, in, nullptr, probs_d, loss_d, true, st);
-    if (rc) return rc;
-    rc = backward_impl(h, B, in, F(h, "H_GRADS"), st);
-    if (rc) return rc;
-    rc = adam_impl(h, params, F(h, "H_GRADS"), m, v, step_counter, lr, beta1, beta2, eps, loss_d + 1, st);
+    AdamArgs ad{params, m, v, step_counter, lr, beta1, beta2, eps, loss_d + 1};
+    rc = run_step(h, B, B, in, nullptr, probs_d, loss_d, F(h, "H_GRADS"), &ad, st);
     if (rc) return rc;
     if (probs_host)
         CK(h, cudaMemcpyAsync(probs_host, probs_d, (size_t)B * 2 * h->Nc * (h->Nc - 1) * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -618,7 +774,7 @@ int hdgnn_infer_host(hdgnn_handle_t h, int B, const uint8_t* adj_host, const flo
     if (rc) return rc;
     Inputs in{(const uint8_t*)h->ws["H_ADJ"].p, F(h, "H_X"), (const int32_t*)h->ws["H_HMAP"].p,
               (const int32_t*)h->ws["H_L"].p, (const uint8_t*)h->ws["H_Y"].p, params};
-    rc = forward_impl(h, B, B, in, nullptr, F(h, "H_PROBS"), F(h, "H_LOSS"), false, st);
+    rc = run_step(h, B, B, in, nullptr, F(h, "H_PROBS"), F(h, "H_LOSS"), nullptr, nullptr, st);
     if (rc) return rc;
     CK(h, cudaMemcpyAsync(probs_host, F(h, "H_PROBS"), (size_t)B * 2 * h->Nc * (h->Nc - 1) * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (loss_host) CK(h, cudaMemcpyAsync(loss_host, F(h, "H_LOSS"), sizeof(float), cudaMemcpyDeviceToHost, st));

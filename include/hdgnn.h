@@ -65,7 +65,9 @@ typedef struct {
     int32_t flags;          /* HDGNN_F_* */
 } hdgnn_config_t;
 
-#define HDGNN_F_GRAPH   1   /* cache the launch sequence as a CUDA graph per (B, input pointers) */
+#define HDGNN_F_GRAPH   1   /* cache the launch sequence of the *_host entry points as a CUDA graph */
+#define HDGNN_F_DEBUG   2   /* keep named copies of intermediates for hdgnn_workspace (tests) */
+#define HDGNN_F_LEGACY  4   /* force the multi-kernel path (the only path for variant 4 / very large Nc) */
 
 /* number of fp32 parameters of a variant (2127 for variant 2, 3129 for variant 4) */
 int hdgnn_param_count(int variant);

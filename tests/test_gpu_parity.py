@@ -33,8 +33,12 @@ CASES = [
 ]
 
 
+F_DEBUG, F_LEGACY = 2, 4
+
+
+@pytest.mark.parametrize("path", ["default", "legacy"])
 @pytest.mark.parametrize("B,Ne,Nc,variant", CASES)
-def test_forward_backward_matches_oracle(B, Ne, Nc, variant):
+def test_forward_backward_matches_oracle(B, Ne, Nc, variant, path):
     from hdgnn_b200.engine import Engine, DeviceBatch
     cb = make_commits(B, Ne, Nc, seed=100 + Ne, p_edge=0.1, p_short=0.5, p_noise=0.1)
     flat = _params(variant)
@@ -44,7 +48,7 @@ def test_forward_backward_matches_oracle(B, Ne, Nc, variant):
         assert relerr(plan["grad"], grad.numpy()) < 1e-9
         assert relerr(plan["logits"], out["logits"].numpy()) < 1e-10
 
-    eng = Engine(Ne, Nc, variant=variant, max_batch=B)
+    eng = Engine(Ne, Nc, variant=variant, max_batch=B, flags=F_DEBUG | (F_LEGACY if path == "legacy" else 0))
     db = DeviceBatch.from_numpy(cb.adj, cb.x, cb.hmap, cb.L, cb.Y, eng.tdev)
     params = flat.float().cuda()
     probs, logits, loss, grads = eng.forward_backward(db, params, want_logits=True)
@@ -100,7 +104,7 @@ def test_forward_backward_matches_oracle(B, Ne, Nc, variant):
     eng.close()
 
 
-@pytest.mark.parametrize("variant", [2, 4])
+@pytest.mark.parametrize("variant", [1, 2, 4])
 def test_forward_only_matches_training_forward(variant):
     from hdgnn_b200.engine import Engine, DeviceBatch
     B, Ne, Nc = 3, 50, 23
@@ -116,13 +120,14 @@ def test_forward_only_matches_training_forward(variant):
     eng.close()
 
 
-def test_run_to_run_bitwise_determinism():
+@pytest.mark.parametrize("variant", [2, 4])
+def test_run_to_run_bitwise_determinism(variant):
     from hdgnn_b200.engine import Engine, DeviceBatch
     B, Ne, Nc = 6, 120, 50
     cb = make_commits(B, Ne, Nc, seed=9)
-    eng = Engine(Ne, Nc, variant=4, max_batch=B)
+    eng = Engine(Ne, Nc, variant=variant, max_batch=B)
     db = DeviceBatch.from_numpy(cb.adj, cb.x, cb.hmap, cb.L, cb.Y, eng.tdev)
-    params = _params(4).float().cuda()
+    params = _params(variant).float().cuda()
     outs = []
     for _ in range(3):
         p, _, l, g = eng.forward_backward(db, params)
@@ -180,14 +185,14 @@ def test_host_entry_points_match_device_entry_points():
     loss3 = torch.zeros(3).pin_memory(); probs_h = torch.zeros(B, 2, eng.Ncr).pin_memory()
     eng.train_step_host(*h, p2, m2, v2, step2, loss3, probs=probs_h)
     torch.cuda.synchronize()
-    assert torch.equal(p2, p_ref)
+    assert torch.allclose(p2, p_ref, rtol=1e-6, atol=1e-9)
     assert torch.equal(probs_h, probs.cpu())
-    assert loss3[0].item() == loss.item()
-    assert torch.equal(loss3[1:], reg.cpu())
+    assert abs(loss3[0].item() - loss.item()) <= 1e-6 * abs(loss.item())
+    assert torch.allclose(loss3[1:], reg.cpu(), rtol=1e-6)     # different (fixed) summation orders
     probs_i = torch.zeros(B, 2, eng.Ncr).pin_memory(); li = torch.zeros(1).pin_memory()
     eng.infer_host(*h, flat.cuda(), probs_i, li)
     torch.cuda.synchronize()
-    assert torch.equal(probs_i, probs.cpu()) and li.item() == loss.item()
+    assert torch.equal(probs_i, probs.cpu()) and abs(li.item() - loss.item()) <= 1e-6 * abs(loss.item())
     eng.close()
 
 
