@@ -191,3 +191,194 @@ class graph2graph(object):
         d.Y[:, :, :self.Nc].copy_(hb.Y, non_blocking=True)
         d.x.copy_(hb.x, non_blocking=True); d.hmap.copy_(hb.hmap, non_blocking=True); d.L.copy_(hb.L, non_blocking=True)
         return d
+
+    # ------------------------------------------------------------------------------------------
+    # data
+    def _load(self, root="."):
+        from .utils2 import read_compact, split_half
+        cb = read_compact(self.Repo, self.Step, self.Ne, self.Nc, root=root)
+        return split_half(cb)
+
+    def _batch(self, part: CommitBatch, maps: CommitBatch, j: int, quirk_q2: bool) -> CommitBatch:
+        """Batch j of `part`; with quirk Q2 (model_2.py:376-381, 495-500) the entity->hunk maps are always
+        those of the first Mini_batch commits of the whole data set."""
+        mb = self.mini_batch_num
+        lo = j * mb
+        src = maps.slice(0, mb) if quirk_q2 else part.slice(lo, lo + mb)
+        b = CommitBatch(part.adj[lo:lo + mb], part.x[lo:lo + mb], src.hmap, src.L, part.Y[lo:lo + mb])
+        if self.world > 1:                       # this rank's contiguous shard of the global batch
+            per = mb // self.world
+            b = b.slice(self.rank * per, (self.rank + 1) * per)
+        return b
+
+    def _model_dir(self):
+        return "%s" % (self.Repo + '/model_%d/' % self.variant + str(self.Step))
+
+    # ------------------------------------------------------------------------------------------
+    def train(self, args=None, data=None, root=".", quirk_q2=True, log=print):
+        """model_2.py:335-424.  `args` needs .Repo and .checkpoint_dir (main.py's namespace)."""
+        from .EvaluationFuncs import top_ACC
+        from .utils2 import edge_onehot
+        repo = getattr(args, "Repo", self.Repo)
+        ckpt = getattr(args, "checkpoint_dir", self.checkpoint_dir)
+        self.initialize()                                           # always from scratch (model_2.py:340-341)
+        train, _ = data if data is not None else self._load(root)
+        mb = self.mini_batch_num
+        if self.world > 1 and mb % self.world:
+            raise ValueError("Mini_batch must be divisible by the number of ranks")
+        nb = int(train.B / mb)                                      # remainder batch dropped (model_2.py:364)
+        labels = edge_onehot(train.Y[:nb * mb])
+        per = mb // self.world
+        probs_h = torch.zeros(per, 2, self.Ncr).pin_memory()
+        counter = 1
+        history = []
+        start_time1 = time.time()
+        for i in range(self.epoch):
+            tr_loss_Hedge = 0.0
+            tr_loss_map = 0.0
+            C_edge_t = []
+            for j in range(nb):
+                hb = HostBatch(self._batch(train, train, j, quirk_q2))
+                l3 = self.train_step(hb, want_probs=True, probs_out=probs_h)
+                torch.cuda.current_stream().synchronize()
+                ce = float(l3[0])
+                if self.world > 1:                                  # CE partials add up to the global mean
+                    t = torch.tensor([ce], device=self.engine.tdev)
+                    torch.distributed.all_reduce(t)
+                    ce = float(t.item())
+                tr_loss_Hedge += ce
+                tr_loss_map += float(l3[1])
+                C_edge_t.append(probs_h.numpy().copy())
+            pred = np.concatenate(C_edge_t, 0)
+            if self.world > 1:
+                lab = np.concatenate([labels[j * mb + self.rank * per: j * mb + (self.rank + 1) * per] for j in range(nb)], 0)
+                hit = torch.tensor([float(np.sum(np.argmax(pred, 1) == np.argmax(lab, 1))), float(lab.shape[0] * lab.shape[2])],
+                                   device=self.engine.tdev, dtype=torch.float64)
+                torch.distributed.all_reduce(hit)
+                acc_top = float(hit[0] / hit[1])
+            else:
+                acc_top = top_ACC(labels, pred)
+            theta = self.named_params()["theta2"].numpy().reshape([2])
+            resultString = "Epoch " + str(i + 1) + \
+                           " acc: " + str(acc_top)[0:6] + \
+                           " Hedge loss: " + str(tr_loss_Hedge / nb)[0:6] + \
+                           " map MSE: " + str(tr_loss_map / nb)[0:6] + \
+                           " theta: " + str(theta[0]) + ' ' + str(theta[1]) + '\n'
+            history.append(dict(epoch=i + 1, acc=acc_top, hedge_loss=tr_loss_Hedge / nb, map_loss=tr_loss_map / nb))
+            if self.rank == 0:
+                filepath = r'outputSelf/{}/model_{}/{}/result_{}.npy'.format(repo, self.variant, self.Step, self.Step)
+                filepath = os.path.join(root, filepath)
+                os.makedirs(os.path.dirname(filepath), exist_ok=True)
+                with open(filepath, "a", encoding='utf-8') as f:
+                    f.write(resultString)
+                log(resultString)
+            counter += 1
+            if self.rank == 0:
+                self.save(os.path.join(root, ckpt) if not os.path.isabs(ckpt) else ckpt, counter)
+        end_time1 = time.time()
+        if self.rank == 0:
+            log('test time:' + str(end_time1 - start_time1))       # sic (model_2.py:424)
+        return history
+
+    def test(self, args=None, data=None, root=".", quirk_q2=True, quirks=True, log=print):
+        """model_2.py:453-544: inference over the test half, writes C_edge_t{Ne}.npy / C_edge_y{Ne}.npy and
+        prints the metric lines."""
+        from .EvaluationFuncs import top_ACC, prec, recall, f1, AUC, process_edge
+        from .utils2 import edge_onehot
+        repo = getattr(args, "Repo", self.Repo)
+        train, test = data if data is not None else self._load(root)
+        self.initialize()
+        ckroot = self.checkpoint_dir if os.path.isabs(self.checkpoint_dir) else os.path.join(root, self.checkpoint_dir)
+        checkpoint_dir = os.path.join(ckroot, self.Repo)            # model_2.py:464 (path quirk Q8)
+        if self.load(checkpoint_dir) or self.load(ckroot, note=" [*] (found under the directory save() writes to)"):
+            log(" [*] Load SUCCESS")
+        else:
+            log(" [!] Load failed...")
+        mb = self.mini_batch_num
+        nb = int(test.B / mb)
+        probs_h = torch.zeros(mb, 2, self.Ncr).pin_memory()
+        loss_h = torch.zeros(1).pin_memory()
+        te_loss_Hedge = 0.0
+        C_edge_t = []
+        start_time = time.time()
+        end_time = start_time
+        for j in range(nb):
+            saved = (self.world, self.rank)
+            self.world, self.rank = 1, 0                            # inference is not sharded
+            hb = HostBatch(self._batch(test, train, j, quirk_q2))
+            self.world, self.rank = saved
+            self.infer(hb, probs_h, loss_h)
+            torch.cuda.current_stream().synchronize()
+            end_time = time.time()
+            te_loss_Hedge += float(loss_h[0])
+            C_edge_t.append(probs_h.numpy().copy())
+        n = nb * mb
+        C_edge_t1 = np.concatenate(C_edge_t, 0).reshape(n, self.Dr, self.Ncr) if nb else np.zeros((0, 2, self.Ncr), np.float32)
+        C_edge_test = edge_onehot(test.Y[:n])
+        out = {}
+        if self.rank == 0:
+            step_dir = os.path.join(root, 'outputSelf/' + repo + '/model_%d/' % self.variant + str(self.Step) + '/')
+            os.makedirs(step_dir, exist_ok=True)
+            np.save(step_dir + 'C_edge_t' + str(self.Ne) + '.npy', C_edge_t1)
+            np.save(step_dir + 'C_edge_y' + str(self.Ne) + '.npy', C_edge_test)
+            C_edge_t2 = process_edge(C_edge_t1)
+            out = dict(topol_acc=top_ACC(C_edge_test, C_edge_t2), prec=prec(C_edge_test, C_edge_t2, quirks),
+                       recall=recall(C_edge_test, C_edge_t2, quirks), f1=f1(C_edge_test, C_edge_t2, quirks),
+                       hedge_loss=te_loss_Hedge / max(nb, 1))
+            try:
+                out["auc"] = AUC(C_edge_test, C_edge_t2, quirks)
+            except ZeroDivisionError:
+                out["auc"] = float("nan")
+            log('topol_acc: ' + str(out["topol_acc"]))
+            log('prec: ' + str(out["prec"]))
+            log('recall: ' + str(out["recall"]))
+            log('F1-score: ' + str(out["f1"]))
+            log('AUC-score: ' + str(out["auc"]))
+            log('test time:' + str(end_time - start_time))
+        return out, C_edge_t1
+
+    # ------------------------------------------------------------------------------------------
+    # checkpoints: same directory layout and naming as tf.train.Saver (model_2.py:427-451), as .npz
+    def save(self, checkpoint_dir, step):
+        model_name = "g2g.model"
+        checkpoint_dir = os.path.join(checkpoint_dir, self._model_dir())
+        os.makedirs(checkpoint_dir, exist_ok=True)
+        named = {TF_NAMES[k].replace("/", "__"): v.numpy() for k, v in self.named_params().items()}
+        path = os.path.join(checkpoint_dir, f"{model_name}-{step}.npz")
+        np.savez(path, __flat__=self.params.detach().cpu().numpy(), __variant__=np.int32(self.variant),
+                 __adam_m__=self.m.cpu().numpy(), __adam_v__=self.v.cpu().numpy(),
+                 __adam_t__=self.step_counter.cpu().numpy(), **named)
+        index = os.path.join(checkpoint_dir, "checkpoint")
+        kept = []
+        if os.path.exists(index):
+            kept = [l.strip() for l in open(index) if l.strip()]
+        kept.append(os.path.basename(path))
+        for old in kept[:-5]:                                        # max_to_keep = 5 (tf.train.Saver default)
+            try:
+                os.remove(os.path.join(checkpoint_dir, old))
+            except OSError:
+                pass
+        with open(index, "w") as f:
+            f.write("\n".join(kept[-5:]) + "\n")
+        return path
+
+    def load(self, checkpoint_dir, note=None, restore_adam=False):
+        if note is None:
+            print(" [*] Reading checkpoint...")
+        checkpoint_dir = os.path.join(checkpoint_dir, self._model_dir())
+        index = os.path.join(checkpoint_dir, "checkpoint")
+        if not os.path.exists(index):
+            return False
+        names = [l.strip() for l in open(index) if l.strip()]
+        if not names:
+            return False
+        z = np.load(os.path.join(checkpoint_dir, names[-1]))
+        if int(z["__variant__"]) != self.variant or z["__flat__"].size != self.n_params:
+            return False
+        if note:
+            print(note)
+        self.params.copy_(torch.as_tensor(z["__flat__"]))
+        if restore_adam:                                             # the reference never does (Q12)
+            self.m.copy_(torch.as_tensor(z["__adam_m__"])); self.v.copy_(torch.as_tensor(z["__adam_v__"]))
+            self.step_counter.copy_(torch.as_tensor(z["__adam_t__"]))
+        return True
