@@ -160,6 +160,8 @@ int alloc(hdgnn_handle_t h, const char* name, size_t bytes) {
     return HDGNN_OK;
 }
 
+constexpr int ENT_NW = 8;      // warps per CTA of the fused entity sweeps
+
 // ---- template dispatch over the column width CW = ceil(N / 32) ---------------------------------
 #define CW_SWITCH(cw, ...)                                                                        \
     switch (cw) {                                                                                  \
@@ -183,26 +185,34 @@ cudaError_t score_attr(size_t smem) {
     return cudaFuncSetAttribute(score_kernel<CW, TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
-cudaError_t set_attrs(hdgnn_handle_t h) {
+// MaxDynamicSharedMemorySize is a per-function hard cap shared by every handle of the process, so it
+// is raised to the device's opt-in maximum once (occupancy follows the size actually launched).
+cudaError_t set_attrs(hdgnn_handle_t h, int optin) {
     cudaError_t e = cudaSuccess;
     auto acc = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
-    // entity grid
+    const cudaFuncAttribute A = cudaFuncAttributeMaxDynamicSharedMemorySize;
     CW_SWITCH(h->CWe, {
-        acc(pairsum_attr<CW, false, true>(pairsum_smem_bytes(CW, h->RTe, h->pe, false)));
-        acc(pairsum_attr<CW, true, true>(pairsum_smem_bytes(CW, h->RTe, h->pe, true)));
-        acc(score_attr<CW, false>(score_smem_bytes(CW, h->RTe, h->pe, false)));
-        acc(score_attr<CW, true>(score_smem_bytes(CW, h->RTe, h->pe, true)));
+        acc(cudaFuncSetAttribute(pairsum_kernel<CW, false, true>, A, optin));
+        acc(cudaFuncSetAttribute(pairsum_kernel<CW, true, true>, A, optin));
+        acc(cudaFuncSetAttribute(score_kernel<CW, false>, A, optin));
+        acc(cudaFuncSetAttribute(score_kernel<CW, true>, A, optin));
     });
     CW_SWITCH(h->CWc, {
-        acc(pairsum_attr<CW, false, false>(pairsum_smem_bytes(CW, h->RTc, h->pc, false)));
-        acc(pairsum_attr<CW, true, false>(pairsum_smem_bytes(CW, h->RTc, h->pc, true)));
-        acc(score_attr<CW, false>(score_smem_bytes(CW, h->RTc, h->pc, false)));
-        acc(score_attr<CW, true>(score_smem_bytes(CW, h->RTc, h->pc, true)));
+        acc(cudaFuncSetAttribute(pairsum_kernel<CW, false, false>, A, optin));
+        acc(cudaFuncSetAttribute(pairsum_kernel<CW, true, false>, A, optin));
+        acc(cudaFuncSetAttribute(score_kernel<CW, false>, A, optin));
+        acc(cudaFuncSetAttribute(score_kernel<CW, true>, A, optin));
     });
-    acc(cudaFuncSetAttribute(pool_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pool_fwd_smem_bytes(h->Ne, h->Nc)));
-    acc(cudaFuncSetAttribute(pool_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pool_bwd_smem_bytes(h->Ne, h->Nc)));
-    acc(cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_fwd_smem_bytes()));
-    acc(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_bwd_smem_bytes()));
+    acc(cudaFuncSetAttribute(pool_fwd_kernel, A, optin));
+    acc(cudaFuncSetAttribute(pool_bwd_kernel, A, optin));
+    acc(cudaFuncSetAttribute(head_fwd_kernel, A, optin));
+    acc(cudaFuncSetAttribute(head_bwd_kernel, A, optin));
+    acc(cudaFuncSetAttribute(mid_kernel<true, true>, A, optin));
+    acc(cudaFuncSetAttribute(mid_kernel<true, false>, A, optin));
+    acc(cudaFuncSetAttribute(mid_kernel<false, true>, A, optin));
+    acc(cudaFuncSetAttribute(mid_kernel<false, false>, A, optin));
+    acc(cudaFuncSetAttribute(ent_fwd_kernel<ENT_NW>, A, optin));
+    acc(cudaFuncSetAttribute(ent_bwd_kernel<ENT_NW>, A, optin));
     return e;
 }
 
@@ -448,7 +458,6 @@ __global__ void repitch_kernel(const uint8_t* __restrict__ src, uint8_t* __restr
 // ================================================================================================
 // fused path: ent_fwd -> mid -> ent_bwd -> reduce (+ adam)
 // ================================================================================================
-constexpr int ENT_NW = 8;
 
 struct AdamArgs { float* params; float* m; float* v; int32_t* step; float lr, b1, b2, eps; float* reg; };
 
@@ -618,19 +627,7 @@ int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out) {
     h->fused = !h->edge && !(cfg->flags & HDGNN_F_LEGACY) &&
                mid_smem_bytes(h->Ne, h->Nc) <= (size_t)prop.sharedMemPerBlockOptin &&
                ent_smem_bytes(ENT_NW, h->Ne, h->RTf, h->pe, true) <= (size_t)prop.sharedMemPerBlockOptin;
-    cudaError_t e = set_attrs(h);
-    if (e == cudaSuccess && h->fused) {
-        auto acc = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
-        const int ms = (int)mid_smem_bytes(h->Ne, h->Nc);
-        acc(cudaFuncSetAttribute(mid_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
-        acc(cudaFuncSetAttribute(mid_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
-        acc(cudaFuncSetAttribute(mid_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
-        acc(cudaFuncSetAttribute(mid_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
-        acc(cudaFuncSetAttribute(ent_fwd_kernel<ENT_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)ent_smem_bytes(ENT_NW, h->Ne, h->RTf, h->pe, false)));
-        acc(cudaFuncSetAttribute(ent_bwd_kernel<ENT_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)ent_smem_bytes(ENT_NW, h->Ne, h->RTf, h->pe, true)));
-    }
+    cudaError_t e = set_attrs(h, (int)prop.sharedMemPerBlockOptin);
     if (e != cudaSuccess) {
         std::string m = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
         delete h;
