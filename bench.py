@@ -171,9 +171,10 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
-        if args.steps > 20:
-            args.steps = 8
-        args.warmup = min(args.warmup, 2)
+        # K and W are honoured; the per-step sample shrinks if K steps would not finish in ~3 minutes
+        # (the oracle does ~100 commits/s on 16 cores at glide)
+        while args.ref_sample > 5 and (args.steps + args.warmup) * args.ref_sample / 80.0 > 180.0:
+            args.ref_sample = max(5, args.ref_sample // 2)
         return run_reference(args, wl)
 
     import torch
@@ -279,6 +280,9 @@ def main():
         "score_fwd(edge)": B * ner * 966, "score_bwd(edge)": B * ner * 3 * 966,
         "pairsum_fwd(hunk)": B * ncr * 1260, "pairsum_bwd(hunk)": B * ncr * 2520,
         "score(hunk)": B * ncr * 970 * 3,
+        # fused path: canonical (un-collapsed) FLOPs of the reference ops each kernel covers
+        "ent_fwd": B * ner * 1000, "ent_bwd": B * ner * 2000,
+        "mid(train)": B * 3 * (ncr * 2230 + ner * 8 + Ne * 880), "mid(infer)": B * (ncr * 2230 + ner * 8 + Ne * 880),
     }
     hbm_peak, bf16_peak, bf16_sus, src = measured_peaks()
     roof = {"kernel": top, "bound": "tensor", "unit": "TFLOP/s", "avg_us": top_us,
@@ -294,9 +298,10 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, cores, sec = cpu_oracle_rate(Ne, Nc, variant, args.ref_sample, 8, 1)
+        cpu_sample = min(B, 100)
+        rate, cores, sec = cpu_oracle_rate(Ne, Nc, variant, cpu_sample, 10, 1)
         cpu = {"value": rate, "unit": "commits/s", "cores": cores, "kind": "port",
-               "sample": f"{args.ref_sample} commits/step x 8 steps, closed-form PyTorch-CPU fp32 restatement "
+               "sample": f"{cpu_sample} commits/step x 10 steps, closed-form PyTorch-CPU fp32 restatement "
                          "(oracle/hdgnn_oracle.py) incl. autograd backward and TF-Adam"}
     if rank == 0:
         line = {
