@@ -7,8 +7,8 @@
 namespace hdgnn {
 
 struct Rank1Map {            // where the four 20-vectors of an ent_bwd partial land in the flat gradient
-    const float* gp;         // (B,S,80) {db, dU, dV, LS} or null
-    int S, o_u, o_v, o_b, o_l;   // o_u == o_v: tied first-layer row (model_4.py:219-222)
+    const float* gp;         // (n,80) {db, dU, dV, LS} per ent_bwd2 CTA, or null
+    int n, o_u, o_v, o_b, o_l;   // o_u == o_v: tied first-layer row (model_4.py:219-222)
 };
 
 struct FinalArgs {
@@ -40,7 +40,7 @@ __device__ __forceinline__ float rank1_extra(const Rank1Map& r, int B, int p, in
     else if (r.o_v != r.o_u && p >= r.o_v && p < r.o_v + HD) { k = p - r.o_v; cv = 1.f; }
     if (k < 0) return 0.f;
     float acc = 0.f;
-    const int n = B * r.S;
+    const int n = r.n;
     for (int t = slice; t < n; t += nslice) {
         const float* g = r.gp + (size_t)t * 4 * HD;
         float e = 0.f;
@@ -94,8 +94,8 @@ __global__ void __launch_bounds__(FIN_P * FIN_SL) reduce_adam_kernel(const Final
         tn[tid] = sqrtf(a.params[o] * a.params[o] + a.params[o + 1] * a.params[o + 1]);
     }
     const float pv = (sl == 0 && p < a.total) ? a.params[p] : 0.f;
+    const int t = *a.step + 1;                          // read before any CTA can publish the new count
     const float sq = block_sum(pv * pv, scratch);       // also orders tn[]
-    const int t = *a.step + 1;
     if (sl == 0 && p < a.total) {
         float gi = g + 0.001f * pv;
         if (p >= a.o_t1 && p < a.o_t1 + 2) gi += 0.001f * pv / tn[0];

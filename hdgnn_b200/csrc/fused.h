@@ -1,0 +1,31 @@
+// Launchers of the fused-path kernels; each kernel family is compiled in its own translation unit
+// (k_ent.cu, k_mid.cu) so the template instantiations build in parallel.
+#pragma once
+#include <cuda_runtime.h>
+#include "ent2.cuh"
+#include "mid2.cuh"
+
+namespace hdgnn {
+
+// kernel handle for cudaFuncSetAttribute / occupancy queries (nullptr if not instantiated)
+const void* ent2_fn_rt(int cwt, int nrg, bool bwd);
+const void* mid2_fn_rt(int cwt, bool train);
+void launch_ent2(int cwt, int nrg, bool bwd, int grid, size_t smem, cudaStream_t st, const Ent2Args& a);
+void launch_mid2(int cwt, bool train, int grid, size_t smem, cudaStream_t st, const Mid2Args& a);
+
+#define HDGNN_CWT_SWITCH(cwt, ...)                                                                  \
+    switch (cwt) {                                                                                  \
+        case 1: { constexpr int CWT = 1; __VA_ARGS__; } break; case 2: { constexpr int CWT = 2; __VA_ARGS__; } break; \
+        case 3: { constexpr int CWT = 3; __VA_ARGS__; } break; case 4: { constexpr int CWT = 4; __VA_ARGS__; } break; \
+        case 5: { constexpr int CWT = 5; __VA_ARGS__; } break; case 6: { constexpr int CWT = 6; __VA_ARGS__; } break; \
+        case 7: { constexpr int CWT = 7; __VA_ARGS__; } break; case 8: { constexpr int CWT = 8; __VA_ARGS__; } break; \
+        default: break;                                                                             \
+    }
+#define HDGNN_NRG_SWITCH(nrg, ...)                                                                  \
+    switch (nrg) {                                                                                  \
+        case 1: { constexpr int NRG = 1; __VA_ARGS__; } break; case 2: { constexpr int NRG = 2; __VA_ARGS__; } break; \
+        case 4: { constexpr int NRG = 4; __VA_ARGS__; } break;                                     \
+        default: break;                                                                             \
+    }
+
+}  // namespace hdgnn

@@ -11,6 +11,7 @@
 //   opt : adam (regularisers fused)
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -23,9 +24,8 @@
 #include "node.cuh"
 #include "pairsum.cuh"
 #include "score.cuh"
-#include "sweep.cuh"
-#include "ent.cuh"
-#include "mid.cuh"
+#include "pack.cuh"
+#include "fused.h"
 #include "final.cuh"
 
 using namespace hdgnn;
@@ -95,7 +95,12 @@ struct hdgnn_handle_s {
     bool ent, edge;            // branches that feed the loss
     bool fused = false;        // ent_fwd -> mid -> ent_bwd -> reduce(+adam) path (variants 1-3)
     bool debug = false;
-    int RTf = 0, Sf = 0;       // entity row tiling of the fused path
+    // fused path: label bitmaps + balanced row chunks of the entity grid (ent2.cuh)
+    int WPe = 0, WPc = 0;      // bitmap words per row
+    int nsm = 148;
+    int fwd_nrg = 2, bwd_nrg = 1, fwd_cwt = 0, bwd_cwt = 0;   // warp layout / column segments per pass
+    int fwd_occ = 1, bwd_occ = 1;                              // resident CTAs per SM
+    int Gf = 0, Gb = 0, Rf = 0, Rb = 0, SLf = 0;               // grids / rows per CTA / slots of the last launch
     std::map<std::string, Buf> ws;
     std::string err;
     int launches = 0;
@@ -160,7 +165,6 @@ int alloc(hdgnn_handle_t h, const char* name, size_t bytes) {
     return HDGNN_OK;
 }
 
-constexpr int ENT_NW = 8;      // warps per CTA of the fused entity sweeps
 
 // ---- template dispatch over the column width CW = ceil(N / 32) ---------------------------------
 #define CW_SWITCH(cw, ...)                                                                        \
@@ -207,12 +211,6 @@ cudaError_t set_attrs(hdgnn_handle_t h, int optin) {
     acc(cudaFuncSetAttribute(pool_bwd_kernel, A, optin));
     acc(cudaFuncSetAttribute(head_fwd_kernel, A, optin));
     acc(cudaFuncSetAttribute(head_bwd_kernel, A, optin));
-    acc(cudaFuncSetAttribute(mid_kernel<true, true>, A, optin));
-    acc(cudaFuncSetAttribute(mid_kernel<true, false>, A, optin));
-    acc(cudaFuncSetAttribute(mid_kernel<false, true>, A, optin));
-    acc(cudaFuncSetAttribute(mid_kernel<false, false>, A, optin));
-    acc(cudaFuncSetAttribute(ent_fwd_kernel<ENT_NW>, A, optin));
-    acc(cudaFuncSetAttribute(ent_bwd_kernel<ENT_NW>, A, optin));
     return e;
 }
 
@@ -456,21 +454,46 @@ __global__ void repitch_kernel(const uint8_t* __restrict__ src, uint8_t* __restr
 }
 
 // ================================================================================================
-// fused path: ent_fwd -> mid -> ent_bwd -> reduce (+ adam)
+// fused path: pack_bits -> ent_fwd2 -> mid2 -> ent_bwd2 -> reduce (+ adam)
 // ================================================================================================
 
 struct AdamArgs { float* params; float* m; float* v; int32_t* step; float lr, b1, b2, eps; float* reg; };
 
-EntArgs ent_args(hdgnn_handle_t h, const Inputs& in) {
-    EntArgs a{};
-    a.lab = in.adj; a.pitch = h->pe; a.N = h->Ne; a.RT = h->RTf; a.S = h->Sf;
+// column segments per pass of an entity sweep: the whole row when it fits 8 segments, else passes of 8
+int ent2_cwt(int N) { const int cw = (N + 31) / 32; return cw <= 8 ? cw : 8; }
+
+// Grid of an entity sweep for a batch of B commits: `occ` resident CTAs on each SM, one wave, the
+// B*N rows cut into equal chunks (at least 8 rows each).
+void ent2_grid(hdgnn_handle_t h, int B, int occ, int* G, int* R) {
+    const long long rows = (long long)B * h->Ne;
+    long long g = (long long)occ * h->nsm;
+    if (g > rows / 8) g = rows / 8 > 0 ? rows / 8 : 1;
+    *R = (int)((rows + g - 1) / g);
+    *G = (int)((rows + *R - 1) / *R);
+}
+
+// largest number of co-resident CTAs per SM (<= 4) whose row chunk fits next to each other
+int ent2_occupancy(hdgnn_handle_t h, int cwt, int nrg, bool bwd) {
+    const void* fn = ent2_fn_rt(cwt, nrg, bwd);
+    for (int occ = 4; occ > 1; --occ) {
+        int G, R, got = 0;
+        ent2_grid(h, h->cfg.max_batch, occ, &G, &R);
+        const size_t smem = ent2_smem_bytes(cwt, nrg, h->Ne, R, h->WPe, bwd);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&got, fn, KG * nrg * 32, smem) == cudaSuccess && got >= occ) return occ;
+    }
+    return 1;
+}
+
+Ent2Args ent2_args(hdgnn_handle_t h, int B, const Inputs& in) {
+    Ent2Args a{};
+    a.bits = (const uint32_t*)h->ws["EBITS"].p; a.WP = h->WPe; a.N = h->Ne; a.B = B;
     a.params = in.params; a.x = in.x;
     a.o_u = h->po.ent_w1; a.o_v = h->po.ent_w1 + HD; a.o_b = h->po.ent_b1; a.o_l = h->po.ent_w1 + 2 * HD;
     return a;
 }
 
 int debug_scatter(hdgnn_handle_t h, int B, cudaStream_t st) {
-    const size_t Ne = h->Ne, Nc = h->Nc, T = Nc * HD, stride = mid_dbg_floats(h->Ne, h->Nc) * 4;
+    const size_t Ne = h->Ne, Nc = h->Nc, T = Nc * HD, stride = mid2_dbg_floats(h->Ne, h->Nc) * 4;
     const char* src = (const char*)h->ws["DBG"].p;
     struct { const char* name; size_t off, n; } parts[] = {
         {"S1", 0, Ne * HD}, {"X2", Ne * HD, Ne}, {"NB", Ne * 21, Nc * 4}, {"RS3", Ne * 21 + Nc * 4, T},
@@ -483,30 +506,41 @@ int debug_scatter(hdgnn_handle_t h, int B, cudaStream_t st) {
 
 int fused_forward(hdgnn_handle_t h, int B, int B_global, const Inputs& in, float* logits, float* probs, bool train,
                   cudaStream_t st) {
-    if (h->ent) {
-        EntArgs a = ent_args(h, in);
-        a.RS = F(h, "RS1"); a.CSp = F(h, "CS1P");
+    {
+        PackArgs p{};
+        p.adj = in.adj; p.Ne = h->Ne; p.pe = h->pe; p.WPe = h->WPe; p.ebits = (uint32_t*)h->ws["EBITS"].p;
+        p.Y = in.Y; p.Nc = h->Nc; p.pc = h->pc; p.WPc = h->WPc; p.ybits = (uint32_t*)h->ws["YBITS"].p;
+        p.B = B;
+        const long long rows = (long long)B * (h->Ne + h->Nc);
         PROF_BEGIN(h, st);
-        ent_fwd_kernel<ENT_NW><<<dim3(h->Sf, B), ENT_NW * 32, ent_smem_bytes(ENT_NW, h->Ne, h->RTf, h->pe, false), st>>>(a);
+        pack_bits_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(p);
+        LAUNCH_CHECK(h, "pack_bits", st);
+    }
+    if (h->ent) {
+        Ent2Args a = ent2_args(h, B, in);
+        ent2_grid(h, B, h->fwd_occ, &h->Gf, &h->Rf);
+        h->SLf = ent2_max_slots(h->Ne, h->Rf);
+        a.R = h->Rf; a.SL = h->SLf; a.RS = F(h, "RS1"); a.CSp = F(h, "CS1P");
+        const size_t smem = ent2_smem_bytes(h->fwd_cwt, h->fwd_nrg, h->Ne, h->Rf, h->WPe, false);
+        PROF_BEGIN(h, st);
+        launch_ent2(h->fwd_cwt, h->fwd_nrg, false, h->Gf, smem, st, a);
         LAUNCH_CHECK(h, "ent_fwd", st);
     }
-    MidArgs m{};
-    m.Ne = h->Ne; m.Nc = h->Nc; m.Se = h->Sf; m.ent = h->ent ? 1 : 0; m.train = train ? 1 : 0;
-    m.adj = in.adj; m.pe = h->pe; m.Y = in.Y; m.pc = h->pc; m.x = in.x; m.hmap = in.hmap; m.L = in.L;
+    Mid2Args m{};
+    m.Ne = h->Ne; m.Nc = h->Nc; m.ent = h->ent ? 1 : 0; m.R = h->Rf; m.SL = h->SLf;
+    m.ebits = (const uint32_t*)h->ws["EBITS"].p; m.WPe = h->WPe;
+    m.ybits = (const uint32_t*)h->ws["YBITS"].p; m.WPc = h->WPc;
+    m.x = in.x; m.hmap = in.hmap; m.L = in.L;
     m.params = in.params; m.po = h->po; m.RS1 = F(h, "RS1"); m.CS1p = F(h, "CS1P");
-    m.soft = nullptr; m.dsoft = nullptr; m.logits = logits; m.probs = probs; m.cep = F(h, "CEP");
+    m.logits = logits; m.probs = probs; m.cep = F(h, "CEP");
     m.scale = 10.f / ((float)B_global * (float)(h->Nc * (h->Nc - 1)));
     m.GE = F(h, "GE"); m.gpart = F(h, "GPART"); m.total = h->po.total;
     m.dbg = h->debug ? F(h, "DBG") : nullptr;
-    const size_t smem = mid_smem_bytes(h->Ne, h->Nc);
+    m.clk = h->debug ? (long long*)h->ws["CLK"].p : nullptr;
+    const size_t smem = mid2_smem_bytes(h->Ne, h->Nc, train);
+    const int cwc = (h->Nc + 31) / 32;
     PROF_BEGIN(h, st);
-    if (train) {
-        if (logits) mid_kernel<true, true><<<B, MID_THREADS, smem, st>>>(m);
-        else mid_kernel<true, false><<<B, MID_THREADS, smem, st>>>(m);
-    } else {
-        if (logits) mid_kernel<false, true><<<B, MID_THREADS, smem, st>>>(m);
-        else mid_kernel<false, false><<<B, MID_THREADS, smem, st>>>(m);
-    }
+    launch_mid2(cwc, train, B, smem, st, m);
     LAUNCH_CHECK(h, train ? "mid(train)" : "mid(infer)", st);
     if (h->debug) return debug_scatter(h, B, st);
     return HDGNN_OK;
@@ -515,15 +549,17 @@ int fused_forward(hdgnn_handle_t h, int B, int B_global, const Inputs& in, float
 int fused_backward(hdgnn_handle_t h, int B, int B_global, const Inputs& in, float* loss, float* grads,
                    const AdamArgs* adam, cudaStream_t st) {
     if (h->ent) {
-        EntArgs a = ent_args(h, in);
-        a.GR = F(h, "GE"); a.GC = F(h, "GE"); a.gpart = F(h, "GPE");
+        Ent2Args a = ent2_args(h, B, in);
+        ent2_grid(h, B, h->bwd_occ, &h->Gb, &h->Rb);
+        a.R = h->Rb; a.SL = 0; a.GR = F(h, "GE"); a.GC = F(h, "GE"); a.gpart = F(h, "GPE");
+        const size_t smem = ent2_smem_bytes(h->bwd_cwt, h->bwd_nrg, h->Ne, h->Rb, h->WPe, true);
         PROF_BEGIN(h, st);
-        ent_bwd_kernel<ENT_NW><<<dim3(h->Sf, B), ENT_NW * 32, ent_smem_bytes(ENT_NW, h->Ne, h->RTf, h->pe, true), st>>>(a);
+        launch_ent2(h->bwd_cwt, h->bwd_nrg, true, h->Gb, smem, st, a);
         LAUNCH_CHECK(h, "ent_bwd", st);
     }
     FinalArgs f{};
     f.B = B; f.total = h->po.total; f.gpart = F(h, "GPART");
-    if (h->ent) f.ent = {F(h, "GPE"), h->Sf, h->po.ent_w1, h->po.ent_w1 + HD, h->po.ent_b1, h->po.ent_w1 + 2 * HD};
+    if (h->ent) f.ent = {F(h, "GPE"), h->Gb, h->po.ent_w1, h->po.ent_w1 + HD, h->po.ent_b1, h->po.ent_w1 + 2 * HD};
     f.cep = F(h, "CEP"); f.ncep = B; f.loss_denom = (float)B_global * (float)(h->Nc * (h->Nc - 1)); f.loss = loss;
     f.grads = grads;
     f.l2part = F(h, "FIN_L2"); f.counter = (unsigned int*)h->ws["FIN_CNT"].p;
@@ -538,24 +574,27 @@ int fused_backward(hdgnn_handle_t h, int B, int B_global, const Inputs& in, floa
     return HDGNN_OK;
 }
 
-// rows per CTA of the fused entity sweeps: CTAs co-resident on an SM share its issue slots, so the
-// makespan is ~ ceil(B*S/148) * (rows per CTA + per-CTA overhead in row units).
-void pick_fused_tiling(int N, int B, int requested, int* RT, int* S) {
-    if (requested > 0) {
-        *RT = requested < ENT_NW ? ENT_NW : requested;
-        if (*RT > N) *RT = N;
-        *S = (N + *RT - 1) / *RT;
-        return;
+// opt-in shared memory + occupancy of the fused kernels for this handle's shapes
+cudaError_t setup_fused(hdgnn_handle_t h, int optin) {
+    const cudaFuncAttribute A = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    cudaError_t e = cudaSuccess;
+    auto acc = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+    const int cwc = (h->Nc + 31) / 32;
+    acc(cudaFuncSetAttribute(mid2_fn_rt(cwc, true), A, optin));
+    acc(cudaFuncSetAttribute(mid2_fn_rt(cwc, false), A, optin));
+    if (h->ent) {
+        acc(cudaFuncSetAttribute(ent2_fn_rt(h->fwd_cwt, h->fwd_nrg, false), A, optin));
+        acc(cudaFuncSetAttribute(ent2_fn_rt(h->bwd_cwt, h->bwd_nrg, true), A, optin));
+        if (e != cudaSuccess) return e;
+        h->fwd_occ = ent2_occupancy(h, h->fwd_cwt, h->fwd_nrg, false);
+        h->bwd_occ = ent2_occupancy(h, h->bwd_cwt, h->bwd_nrg, true);
     }
-    double best = 1e30;
-    for (int s = 1; s <= 16; ++s) {
-        const int rt = (N + s - 1) / s;
-        if (rt < ENT_NW && s > 1) break;
-        const int ss = (N + rt - 1) / rt;
-        const double waves = (double)(((long)B * ss + 147) / 148);
-        const double cost = waves * (rt + 4.0);
-        if (cost < best - 1e-9) { best = cost; *RT = rt; *S = ss; }
-    }
+    return e;
+}
+
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
 }
 
 int pick_rt(int N, int B, int requested) {
@@ -623,23 +662,42 @@ int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out) {
             return fail(nullptr, HDGNN_E_UNSUPPORTED, "row tile does not fit in shared memory; lower rows_per_cta");
         }
     h->debug = (cfg->flags & HDGNN_F_DEBUG) != 0;
-    pick_fused_tiling(h->Ne, cfg->max_batch, cfg->rows_per_cta_e, &h->RTf, &h->Sf);
-    h->fused = !h->edge && !(cfg->flags & HDGNN_F_LEGACY) &&
-               mid_smem_bytes(h->Ne, h->Nc) <= (size_t)prop.sharedMemPerBlockOptin &&
-               ent_smem_bytes(ENT_NW, h->Ne, h->RTf, h->pe, true) <= (size_t)prop.sharedMemPerBlockOptin;
+    h->nsm = prop.multiProcessorCount;
+    h->WPe = bit_words(h->Ne); h->WPc = bit_words(h->Nc);
+    h->fwd_cwt = h->bwd_cwt = ent2_cwt(h->Ne);
+    {   // tuning overrides: a pass width below the row width must be a multiple of 4 (16-byte bitmap loads)
+        const int f = env_int("HDGNN_FWD_CWT", 0), bw = env_int("HDGNN_BWD_CWT", 0);
+        if ((f == 4 || f == 8) && f < h->fwd_cwt) h->fwd_cwt = f;
+        if ((bw == 4 || bw == 8) && bw < h->bwd_cwt) h->bwd_cwt = bw;
+    }
+    h->fwd_nrg = env_int("HDGNN_FWD_NRG", 2);
+    h->bwd_nrg = env_int("HDGNN_BWD_NRG", 1);
+    if (h->fwd_nrg != 1 && h->fwd_nrg != 2 && h->fwd_nrg != 4) h->fwd_nrg = 2;
+    if (h->bwd_nrg != 1 && h->bwd_nrg != 2 && h->bwd_nrg != 4) h->bwd_nrg = 1;
+    // the fused path needs the per-commit state of mid2 in one SM's shared memory and a hunk grid of <= 8 segments
+    h->fused = !h->edge && !(cfg->flags & HDGNN_F_LEGACY) && h->Nc <= 256 &&
+               mid2_smem_bytes(h->Ne, h->Nc, true) <= (size_t)prop.sharedMemPerBlockOptin;
     cudaError_t e = set_attrs(h, (int)prop.sharedMemPerBlockOptin);
+    if (e == cudaSuccess && h->fused) e = setup_fused(h, (int)prop.sharedMemPerBlockOptin);
     if (e != cudaSuccess) {
         std::string m = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
         delete h;
         return fail(nullptr, HDGNN_E_CUDA, m);
     }
+    int Gf_max = 0, Gb_max = 0, Rtmp = 0;
+    if (h->fused && h->ent) {
+        ent2_grid(h, cfg->max_batch, h->fwd_occ, &Gf_max, &Rtmp);
+        ent2_grid(h, cfg->max_batch, h->bwd_occ, &Gb_max, &Rtmp);
+        Gf_max = h->fwd_occ * h->nsm; Gb_max = h->bwd_occ * h->nsm;
+    }
 
-    const size_t B = cfg->max_batch, Ne = h->Ne, Nc = h->Nc, Se = h->fused ? (size_t)h->Sf : (size_t)h->Se, Sc = h->Sc,
-                 f = sizeof(float);
+    const size_t B = cfg->max_batch, Ne = h->Ne, Nc = h->Nc, Se = h->Se, Sc = h->Sc, f = sizeof(float);
+    // (B, SL, Ne, 20) column partials of ent_fwd2: B * SL <= grid + 2 B for every batch size <= max_batch
+    const size_t cs1p = h->fused ? ((size_t)Gf_max + 2 * B + 2) * Ne * HD * f : B * Se * Ne * HD * f;
     const bool lg = !h->fused;     // buffers only the multi-kernel path needs (kept when debugging: dump targets)
     const bool dbgbuf = lg || h->debug;
     struct { const char* n; size_t bytes; bool need; } plan[] = {
-        {"RS1", B * Ne * HD * f, h->ent}, {"CS1P", B * Se * Ne * HD * f, h->ent}, {"S1", B * Ne * HD * f, dbgbuf},
+        {"RS1", B * Ne * HD * f, h->ent}, {"CS1P", cs1p, h->ent}, {"S1", B * Ne * HD * f, dbgbuf},
         {"X2", B * Ne * f, dbgbuf}, {"NB", B * Nc * 4 * f, dbgbuf}, {"PH", B * Nc * HD * f, lg}, {"QH", B * Nc * HD * f, lg},
         {"RS3", B * Nc * HD * f, dbgbuf}, {"CS3P", B * Sc * Nc * HD * f, lg}, {"CS3F", B * Nc * HD * f, dbgbuf},
         {"PR", B * Nc * HD * f, dbgbuf}, {"PC", B * Nc * HD * f, dbgbuf}, {"CEP", B * Sc * f, true},
@@ -650,8 +708,10 @@ int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out) {
         {"DNB", B * Nc * 4 * f, dbgbuf}, {"GE", B * Ne * HD * f, true}, {"DX2", B * Ne * f, dbgbuf},
         {"RS1D", B * Ne * HD * f, h->ent && lg}, {"CS1DP", B * Se * Ne * HD * f, h->ent && lg}, {"LS1P", B * Se * HD * f, h->ent && lg},
         {"GPART", B * (size_t)h->po.total * f, true},
-        {"GPE", B * Se * 4 * HD * f, h->fused && h->ent}, {"FIN_L2", 64 * f, h->fused}, {"FIN_CNT", 16, h->fused},
-        {"DBG", B * mid_dbg_floats(h->Ne, h->Nc) * f, h->fused && h->debug},
+        {"GPE", ((size_t)Gb_max + 1) * 4 * HD * f, h->fused && h->ent}, {"FIN_L2", 64 * f, h->fused}, {"FIN_CNT", 16, h->fused},
+        {"EBITS", B * Ne * (size_t)h->WPe * 4, h->fused}, {"YBITS", B * Nc * (size_t)h->WPc * 4, h->fused},
+        {"DBG", B * mid2_dbg_floats(h->Ne, h->Nc) * f, h->fused && h->debug},
+        {"CLK", B * 16 * sizeof(long long), h->fused && h->debug},
         {"RSE", B * Ne * HD * f, h->edge}, {"CSEP", B * Se * Ne * HD * f, h->edge}, {"CSEF", B * Ne * HD * f, h->edge},
         {"PRE", B * Ne * HD * f, h->edge}, {"PCE", B * Ne * HD * f, h->edge},
         {"SOFT", B * Ne * Ne * 2 * f, h->edge}, {"DSOFT", B * Ne * Ne * 2 * f, h->edge},

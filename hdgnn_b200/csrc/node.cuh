@@ -12,20 +12,6 @@ namespace hdgnn {
 constexpr int NCH = 128;          // nodes per shared-memory chunk
 constexpr int NODE_THREADS = 512;
 
-__device__ __forceinline__ void copy_to_smem(float* dst, const float* src, int n) {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
-}
-
-// q = i*(n-1) + (j - [j>i])  ->  (i, j); q < 2^18 so the float reciprocal is exact after fix-up
-__device__ __forceinline__ void unflat_pair(int q, int nm1, float inv, int& i, int& j) {
-    int gi = (int)(((float)q + 0.5f) * inv);
-    int gr = q - gi * nm1;
-    if (gr < 0) { --gi; gr += nm1; }
-    else if (gr >= nm1) { ++gi; gr -= nm1; }
-    i = gi;
-    j = gr + (gr >= gi);
-}
-
 // ============================================================================================
 // forward: entity-state MLP + pooling + hunk-stage tables
 // ============================================================================================
