@@ -29,26 +29,31 @@ struct FinalArgs {
 constexpr int FIN_P = 128;   // parameters per CTA
 constexpr int FIN_SL = 8;    // commit slices per parameter
 
-__device__ __forceinline__ float rank1_extra(const Rank1Map& r, int B, int p, int slice, int nslice) {
+__device__ __forceinline__ float rank1_extra(const Rank1Map& r, int p, int slice, int nslice) {
     if (!r.gp) return 0.f;
-    // which 20-vectors of the partial feed parameter p:  +db, +dU, +dV, +LS, -LS
-    int k = -1; float cb = 0.f, cu = 0.f, cv = 0.f, cl = 0.f;
-    if (p >= r.o_b && p < r.o_b + HD) { k = p - r.o_b; cb = 1.f; }
-    else if (p >= r.o_l && p < r.o_l + HD) { k = p - r.o_l; cb = 1.f; cl = -1.f; }
-    else if (p >= r.o_l + HD && p < r.o_l + 2 * HD) { k = p - r.o_l - HD; cl = 1.f; }
-    else if (p >= r.o_u && p < r.o_u + HD) { k = p - r.o_u; cu = 1.f; if (r.o_v == r.o_u) cv = 1.f; }
-    else if (r.o_v != r.o_u && p >= r.o_v && p < r.o_v + HD) { k = p - r.o_v; cv = 1.f; }
-    if (k < 0) return 0.f;
+    // which of the four 20-vectors {db, dU, dV, LS} of a partial feed parameter p: c1 * g[i1] + c2 * g[i2]
+    int i1 = -1, i2 = -1; float c2 = 1.f;
+    if (p >= r.o_b && p < r.o_b + HD) { i1 = p - r.o_b; }                                                  // bias: db
+    else if (p >= r.o_l && p < r.o_l + HD) { i1 = p - r.o_l; i2 = 3 * HD + i1; c2 = -1.f; }                 // label-0 row: db - LS
+    else if (p >= r.o_l + HD && p < r.o_l + 2 * HD) { i1 = 3 * HD + (p - r.o_l - HD); }                     // label-1 row: LS
+    else if (p >= r.o_u && p < r.o_u + HD) { i1 = HD + (p - r.o_u); if (r.o_v == r.o_u) i2 = 2 * HD + (p - r.o_u); }
+    else if (r.o_v != r.o_u && p >= r.o_v && p < r.o_v + HD) { i1 = 2 * HD + (p - r.o_v); }
+    if (i1 < 0) return 0.f;
+    const bool two = i2 >= 0;
+    if (!two) i2 = i1;
     float acc = 0.f;
-    const int n = r.n;
-    for (int t = slice; t < n; t += nslice) {
+    const int n = r.n, step = nslice;
+    int t = slice;
+    for (; t + 3 * step < n; t += 4 * step) {        // four independent loads in flight; fixed summation order
         const float* g = r.gp + (size_t)t * 4 * HD;
-        float e = 0.f;
-        if (cb != 0.f) e += g[k];
-        if (cu != 0.f) e += g[HD + k];
-        if (cv != 0.f) e += g[2 * HD + k];
-        if (cl != 0.f) e = fmaf(cl, g[3 * HD + k], e);
-        acc += e;
+        const float a0 = g[i1], a1 = g[(size_t)step * 4 * HD + i1], a2 = g[(size_t)2 * step * 4 * HD + i1], a3 = g[(size_t)3 * step * 4 * HD + i1];
+        const float b0 = g[i2], b1 = g[(size_t)step * 4 * HD + i2], b2 = g[(size_t)2 * step * 4 * HD + i2], b3 = g[(size_t)3 * step * 4 * HD + i2];
+        acc += two ? fmaf(c2, b0, a0) : a0; acc += two ? fmaf(c2, b1, a1) : a1;
+        acc += two ? fmaf(c2, b2, a2) : a2; acc += two ? fmaf(c2, b3, a3) : a3;
+    }
+    for (; t < n; t += step) {
+        const float* g = r.gp + (size_t)t * 4 * HD;
+        acc += two ? fmaf(c2, g[i2], g[i1]) : g[i1];
     }
     return acc;
 }
@@ -56,7 +61,7 @@ __device__ __forceinline__ float rank1_extra(const Rank1Map& r, int B, int p, in
 __global__ void __launch_bounds__(FIN_P * FIN_SL) reduce_adam_kernel(const FinalArgs a) {
     __shared__ float part[FIN_SL][FIN_P];
     __shared__ float scratch[32];
-    __shared__ float tn[2];
+    __shared__ float tn[3];
     __shared__ int last;
     const int tid = threadIdx.x, pl = tid % FIN_P, sl = tid / FIN_P;
     const int p = blockIdx.x * FIN_P + pl;
@@ -69,8 +74,8 @@ __global__ void __launch_bounds__(FIN_P * FIN_SL) reduce_adam_kernel(const Final
             acc += g0; acc += g1; acc += g2; acc += g3;
         }
         for (; bb < a.B; bb += FIN_SL) acc += a.gpart[(size_t)bb * a.total + p];
-        acc += rank1_extra(a.ent, a.B, p, sl, FIN_SL);
-        acc += rank1_extra(a.edge, a.B, p, sl, FIN_SL);
+        acc += rank1_extra(a.ent, p, sl, FIN_SL);
+        acc += rank1_extra(a.edge, p, sl, FIN_SL);
     }
     part[sl][pl] = acc;
     if (blockIdx.x == 0 && a.loss) {          // mean CE: fixed-order block sum of the per-commit partials
@@ -95,12 +100,13 @@ __global__ void __launch_bounds__(FIN_P * FIN_SL) reduce_adam_kernel(const Final
     }
     const float pv = (sl == 0 && p < a.total) ? a.params[p] : 0.f;
     const int t = *a.step + 1;                          // read before any CTA can publish the new count
+    if (tid == 2) tn[2] = a.lr * (float)(sqrt(1.0 - pow((double)a.b2, (double)t)) / (1.0 - pow((double)a.b1, (double)t)));
     const float sq = block_sum(pv * pv, scratch);       // also orders tn[]
     if (sl == 0 && p < a.total) {
         float gi = g + 0.001f * pv;
         if (p >= a.o_t1 && p < a.o_t1 + 2) gi += 0.001f * pv / tn[0];
         if (p >= a.o_t2 && p < a.o_t2 + 2) gi += 0.001f * pv / tn[1];
-        const float lr_t = a.lr * (float)(sqrt(1.0 - pow((double)a.b2, (double)t)) / (1.0 - pow((double)a.b1, (double)t)));
+        const float lr_t = tn[2];
         const float mi = a.b1 * a.m[p] + (1.f - a.b1) * gi;
         const float vi = a.b2 * a.v[p] + (1.f - a.b2) * gi * gi;
         a.m[p] = mi; a.v[p] = vi;

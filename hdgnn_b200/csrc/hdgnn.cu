@@ -513,7 +513,8 @@ int fused_forward(hdgnn_handle_t h, int B, int B_global, const Inputs& in, float
         p.B = B;
         const long long rows = (long long)B * (h->Ne + h->Nc);
         PROF_BEGIN(h, st);
-        pack_bits_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(p);
+        if (h->pe <= 256 && h->pc <= 256) pack_bits_kernel<16><<<(unsigned)((rows + 15) / 16), 256, 0, st>>>(p);
+        else pack_bits_kernel<32><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(p);
         LAUNCH_CHECK(h, "pack_bits", st);
     }
     if (h->ent) {

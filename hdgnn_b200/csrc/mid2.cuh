@@ -23,7 +23,13 @@ namespace hdgnn {
 constexpr int M2_NRG = 4;
 constexpr int M2_NW = KG * M2_NRG;        // 20 warps
 constexpr int M2_T = M2_NW * 32;          // 640 threads
-constexpr int M2_CH = 128;                // entity nodes per chunk in the node-MLP phases
+constexpr int M2_CH = 128;                // entity nodes per chunk of the entity-state MLP backward
+constexpr int M2_NODE_F = 24 + 24 + 20 + 20 + 24;   // floats per node of that chunk: [S|nb5] [E|x|1] dz dE [relu(Z) du|du]
+// The entity block ent_w5 .. nod_b2 and the hunk block hnk_w1 .. scr_b2 are each contiguous in the
+// parameter blob (TF creation order, hdgnn.cu) with every array at a multiple of 4 floats from the
+// block start, so one copy per block keeps every matrix 16-byte aligned in shared memory.
+constexpr int M2_BLK1 = 400 + 20 + 420 + 20 + 20 + 1;              // 881
+constexpr int M2_BLK2 = 200 + 20 + 400 + 20 + 440 + 20 + 40 + 2;   // 1142
 
 struct Mid2Args {
     int Ne, Nc, ent, R, SL;                  // R, SL: row-chunk decomposition of ent_fwd2 (ent2.cuh)
@@ -46,7 +52,7 @@ __host__ __device__ inline size_t mid2_dbg_floats(int Ne, int Nc) { return (size
 
 struct Mid2Smem {
     // offsets in floats
-    int W5, b5, U1, c1, u2, c2, V1, d1, W2, b2, G1, g1b, G2, gb2, gam, Dh, Dg;
+    int blk1, blk2, gam, Dh, Dg, G1g;         // weight blocks (contiguous copies of the parameter blob), derived vectors
     int x, x2, hm, SP, TP, dl, dx2, nb, dnb, ebits, ybits, scratch, red, uni, total;
 };
 
@@ -54,9 +60,7 @@ __host__ __device__ inline Mid2Smem mid2_layout(int Ne, int Nc, bool train) {
     Mid2Smem m;
     int o = 0;
     auto take = [&](int n) { int r = o; o += (n + 7) & ~7; return r; };      // 32-byte granules
-    m.W5 = take(400); m.b5 = take(20); m.U1 = take(420); m.c1 = take(20); m.u2 = take(20); m.c2 = take(4);
-    m.V1 = take(200); m.d1 = take(20); m.W2 = take(400); m.b2 = take(20); m.G1 = take(440); m.g1b = take(20);
-    m.G2 = take(40); m.gb2 = take(4); m.gam = take(20); m.Dh = take(20); m.Dg = take(20);
+    m.blk1 = take(M2_BLK1); m.blk2 = take(M2_BLK2); m.gam = take(20); m.Dh = take(20); m.Dg = take(20); m.G1g = take(400);
     m.x = take(Ne); m.x2 = take(Ne); m.hm = take(Ne); m.SP = take(4 * Ne); m.TP = take(4 * Ne); m.dl = take(4 * Ne);
     m.dx2 = take(Ne); m.nb = take(4 * Nc); m.dnb = take(4 * Nc);
     m.ebits = take(Ne * bit_words(Ne)); m.ybits = take(Nc * bit_words(Nc));
@@ -65,7 +69,7 @@ __host__ __device__ inline Mid2Smem mid2_layout(int Ne, int Nc, bool train) {
     m.scratch = take(comb > pool ? comb : pool);
     m.red = take(64 + M2_NW * HD + 64);
     m.uni = o;
-    const int ent_phase = 5 * M2_CH * HD + M2_CH;
+    const int ent_phase = M2_CH * M2_NODE_F;
     const int hunk_phase = 12 * Nc * HD + (train ? Nc * cwc * 32 : 0);
     o += ent_phase > hunk_phase ? ent_phase : hunk_phase;
     m.total = o;
@@ -88,25 +92,118 @@ __device__ __forceinline__ float mid2_block_sum(float v, float* scratch) {
     return t;
 }
 
-// out[n][m] = bias_scale * bias[m] + sum_q in[n][q] * W[q][m]     (n < nn; 20 x 20, row-major W)
-__device__ __forceinline__ void m2_mm20(float* out, const float* in, const float* W, const float* bias, float bias_scale, int nn) {
-    for (int idx = threadIdx.x; idx < nn * HD; idx += M2_T) {
-        const int n = idx / HD, m = idx - n * HD;
-        float acc = bias ? bias_scale * bias[m] : 0.f;
+// y[m] += sum_q x[q] * W[q][m]        (W: 20 x 20 row-major in shared memory, 16-byte aligned; thread-private x, y)
+__device__ __forceinline__ void gemv20(float (&y)[HD], const float (&x)[HD], const float* W) {
 #pragma unroll
-        for (int q = 0; q < HD; ++q) acc = fmaf(in[n * HD + q], W[q * HD + m], acc);
-        out[idx] = acc;
+    for (int q = 0; q < HD; ++q) {
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const float4 w = *reinterpret_cast<const float4*>(W + q * HD + 4 * j);
+            y[4 * j] = fmaf(x[q], w.x, y[4 * j]); y[4 * j + 1] = fmaf(x[q], w.y, y[4 * j + 1]);
+            y[4 * j + 2] = fmaf(x[q], w.z, y[4 * j + 2]); y[4 * j + 3] = fmaf(x[q], w.w, y[4 * j + 3]);
+        }
     }
 }
-// out[n][q] = sum_m W[q][m] * in[n][m]      (multiply by W^T)
-__device__ __forceinline__ void m2_mm20t(float* out, const float* in, const float* W, int nn) {
-    for (int idx = threadIdx.x; idx < nn * HD; idx += M2_T) {
-        const int n = idx / HD, q = idx - n * HD;
+// y[q] = sum_m W[q][m] * x[m]          (multiply by W^T)
+__device__ __forceinline__ void gemv20t(float (&y)[HD], const float (&x)[HD], const float* W) {
+#pragma unroll
+    for (int q = 0; q < HD; ++q) {
         float acc = 0.f;
 #pragma unroll
-        for (int m = 0; m < HD; ++m) acc = fmaf(W[q * HD + m], in[n * HD + m], acc);
-        out[idx] = acc;
+        for (int j = 0; j < 5; ++j) {
+            const float4 w = *reinterpret_cast<const float4*>(W + q * HD + 4 * j);
+            acc = fmaf(w.x, x[4 * j], acc); acc = fmaf(w.y, x[4 * j + 1], acc);
+            acc = fmaf(w.z, x[4 * j + 2], acc); acc = fmaf(w.w, x[4 * j + 3], acc);
+        }
+        y[q] = acc;
     }
+}
+__device__ __forceinline__ void load20s(float (&v)[HD], const float* src) {      // 16-byte aligned source
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const float4 t = reinterpret_cast<const float4*>(src)[j];
+        v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+    }
+}
+__device__ __forceinline__ void store20s(float* dst, const float (&v)[HD]) {
+#pragma unroll
+    for (int j = 0; j < 5; ++j) reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+// acc[4 i + j] += sum_{n = n0, n0 + 16, ... < nn} A[n][a0 + i] * B[n][b0 + j]     (4 x 4 register tile of A^T B)
+__device__ __forceinline__ void tile_acc(float (&acc)[16], const float* A, int lda, const float* B, int ldb, int a0, int b0,
+                                         int n0, int nn) {
+    for (int n = n0; n < nn; n += 16) {
+        const float4 av = *reinterpret_cast<const float4*>(A + (size_t)n * lda + a0);
+        const float4 bv = *reinterpret_cast<const float4*>(B + (size_t)n * ldb + b0);
+        const float ar[4] = {av.x, av.y, av.z, av.w}, br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[4 * i + j] = fmaf(ar[i], br[j], acc[4 * i + j]);
+    }
+}
+// Transpose-reduce 16 per-lane values over the 16 lanes of a half warp (xor 8, 4, 2, 1): returns the
+// total of value (lane & 15).  Fixed exchange order.
+__device__ __forceinline__ float reduce16(const float (&v)[16], int lane) {
+    const unsigned hm16 = (lane & 16) ? 0xffff0000u : 0x0000ffffu;     // the two half warps may be in different branches
+    float a[8], b4[4], c[2];
+    const bool h8 = lane & 8, h4 = lane & 4, h2 = lane & 2, h1 = lane & 1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float keep = h8 ? v[i + 8] : v[i], send = h8 ? v[i] : v[i + 8];
+        a[i] = keep + __shfl_xor_sync(hm16, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float keep = h4 ? a[i + 4] : a[i], send = h4 ? a[i] : a[i + 4];
+        b4[i] = keep + __shfl_xor_sync(hm16, send, 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float keep = h2 ? b4[i + 2] : b4[i], send = h2 ? b4[i] : b4[i + 2];
+        c[i] = keep + __shfl_xor_sync(hm16, send, 2);
+    }
+    const float keep = h1 ? c[1] : c[0], send = h1 ? c[0] : c[1];
+    return keep + __shfl_xor_sync(hm16, send, 1);
+}
+// sum over the 16 lanes of a half warp, every lane gets the total
+__device__ __forceinline__ float half_sum(float v) {
+    const unsigned hm16 = (threadIdx.x & 16) ? 0xffff0000u : 0x0000ffffu;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(hm16, v, o);
+    return v;
+}
+// dst[0..n] = exclusive prefix sums of src[0], src[stride], ... (dst[n] = total); executed by ONE warp, fixed order
+__device__ __forceinline__ void warp_excl_scan(float* dst, const float* src, int stride, int n, int lane) {
+    const int per = (n + 31) >> 5, lo = min(lane * per, n), hi = min(lo + per, n);
+    float sum = 0.f;
+    for (int i = lo; i < hi; ++i) sum += src[(size_t)i * stride];
+    float incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    float run = incl - sum;
+    for (int i = lo; i < hi; ++i) { dst[i] = run; run += src[(size_t)i * stride]; }
+    if (lane == 31) dst[n] = incl;
+}
+// number of set bits of a bitmap row in columns [ja, jb)
+__device__ __forceinline__ int range_popc(const uint32_t* row, int ja, int jb) {
+    if (jb <= ja) return 0;
+    const int wa = ja >> 5, wb = (jb - 1) >> 5;
+    int c = 0;
+    for (int w = wa; w <= wb; ++w) {
+        uint32_t v = row[w];
+        if (w == wa) v &= 0xffffffffu << (ja & 31);
+        if (w == wb) { const int e = jb - (wb << 5); if (e < 32) v &= (1u << e) - 1u; }
+        c += __popc(v);
+    }
+    return c;
+}
+// sum_{p' < p} v[p' + (p' >= g)]  from the exclusive prefix PV of v  (off-diagonal enumeration of row g)
+__device__ __forceinline__ float offdiag_prefix(const float* PV, const float* v, int vstride, int g, int p) {
+    return p > g ? PV[p + 1] - v[(size_t)g * vstride] : PV[p];
 }
 // element k of row n of a [n][KG][2][4] table (half 0)
 __device__ __forceinline__ int p01_idx(int n, int k) { return n * PROW + (k >> 2) * 8 + (k & 3); }
@@ -121,10 +218,12 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
     const int kg = warp % KG, rg = warp / KG, k0 = kg * 4;
     const int WPe = a.WPe, WPc = a.WPc;
     const Mid2Smem L_ = mid2_layout(Ne, Nc, TRAIN);
-    float* W5 = sm + L_.W5; float* b5 = sm + L_.b5; float* U1 = sm + L_.U1; float* c1 = sm + L_.c1;
-    float* u2 = sm + L_.u2; float* c2 = sm + L_.c2; float* V1 = sm + L_.V1; float* d1 = sm + L_.d1;
-    float* W2 = sm + L_.W2; float* b2 = sm + L_.b2; float* G1 = sm + L_.G1; float* g1b = sm + L_.g1b;
-    float* G2 = sm + L_.G2; float* gb2 = sm + L_.gb2; float* gam = sm + L_.gam; float* Dh = sm + L_.Dh; float* Dg = sm + L_.Dg;
+    float* blk1 = sm + L_.blk1; float* blk2 = sm + L_.blk2;
+    float* W5 = blk1; float* b5 = blk1 + 400; float* U1 = blk1 + 420; float* c1 = blk1 + 840;
+    float* u2 = blk1 + 860; float* c2 = blk1 + 880;
+    float* V1 = blk2; float* d1 = blk2 + 200; float* W2 = blk2 + 220; float* b2 = blk2 + 620;
+    float* G1 = blk2 + 640; float* g1b = blk2 + 1080; float* G2 = blk2 + 1100; float* gb2 = blk2 + 1140;
+    float* gam = sm + L_.gam; float* Dh = sm + L_.Dh; float* Dg = sm + L_.Dg; float* G1g = sm + L_.G1g;
     float* xs = sm + L_.x; float* x2 = sm + L_.x2; int* hm = reinterpret_cast<int*>(sm + L_.hm);
     float* SP = sm + L_.SP; float* TP = sm + L_.TP; float* dl = sm + L_.dl; float* dx2 = sm + L_.dx2;
     float* nb = sm + L_.nb; float* dnb = sm + L_.dnb;
@@ -150,19 +249,23 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         bulk_g2s(ebits, a.ebits + (size_t)b * Ne * WPe, be, bar);
         bulk_g2s(ybits, a.ybits + (size_t)b * Nc * WPc, bc, bar);
     }
-    if (a.ent) {
-        copy_to_smem(W5, par + po.ent_w5, 400); copy_to_smem(b5, par + po.ent_b5, 20);
-        copy_to_smem(U1, par + po.nod_w1, 420); copy_to_smem(c1, par + po.nod_b1, 20);
-        copy_to_smem(u2, par + po.nod_w2, 20);  copy_to_smem(c2, par + po.nod_b2, 1);
-    }
-    copy_to_smem(V1, par + po.hnk_w1, 200); copy_to_smem(d1, par + po.hnk_b1, 20);
-    copy_to_smem(W2, par + po.hnk_w2, 400); copy_to_smem(b2, par + po.hnk_b2, 20);
-    copy_to_smem(G1, par + po.scr_w1, 440); copy_to_smem(g1b, par + po.scr_b1, 20);
-    copy_to_smem(G2, par + po.scr_w2, 40);  copy_to_smem(gb2, par + po.scr_b2, 2);
-    if (tid < HD) {
-        gam[tid] = par[po.scr_w2 + 2 * tid + 1] - par[po.scr_w2 + 2 * tid];
-        Dh[tid] = par[po.hnk_w1 + 9 * HD + tid] - par[po.hnk_w1 + 8 * HD + tid];
-        Dg[tid] = par[po.scr_w1 + HD + tid] - par[po.scr_w1 + tid];
+    {   // both weight blocks with all global loads in flight before the first store
+        const float* p1 = par + (a.ent ? po.ent_w5 : po.hnk_w1);
+        const float* p2 = par + po.hnk_w1;
+        const int n1 = a.ent ? M2_BLK1 : 0;
+        constexpr int NLD = (M2_BLK1 + M2_BLK2 + M2_T - 1) / M2_T;
+        float v[NLD];
+#pragma unroll
+        for (int u = 0; u < NLD; ++u) {
+            const int idx = tid + u * M2_T;
+            v[u] = idx < n1 ? p1[idx] : (idx < n1 + M2_BLK2 ? p2[idx - n1] : 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < NLD; ++u) {
+            const int idx = tid + u * M2_T;
+            if (idx < n1) blk1[idx] = v[u];
+            else if (idx < n1 + M2_BLK2) blk2[idx - n1] = v[u];
+        }
     }
     const int Lb = a.L[b];
     for (int i = tid; i < Ne; i += M2_T) {
@@ -173,41 +276,44 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         if (!a.ent) x2[i] = xv;
     }
     __syncthreads();
+    if (tid < HD) {
+        gam[tid] = G2[2 * tid + 1] - G2[2 * tid];
+        Dh[tid] = V1[9 * HD + tid] - V1[8 * HD + tid];
+        Dg[tid] = G1[HD + tid] - G1[tid];
+    }
+    if (TRAIN) for (int e = tid; e < 400; e += M2_T) G1g[e] = G1[2 * HD + e] * (G2[2 * (e % HD) + 1] - G2[2 * (e % HD)]);
+    __syncthreads();
     M2_PHASE(1);
 
-    // ---------------- B/C. entity-state MLP forward, chunks of M2_CH nodes -------------------------
+    // ---------------- B/C. entity-state MLP forward: one thread per entity, weights broadcast from smem ------
     const int nsl = a.ent ? ent2_slots(b, Ne, a.R) : 0;
-    if (a.ent) {
-        float* sS = uni; float* sE = sS + M2_CH * HD; float* sZ = sE + M2_CH * HD;
-        const float nb5 = 2.f * (float)(Ne - 1);
-        for (int c0 = 0; c0 < Ne; c0 += M2_CH) {
-            const int nn = min(M2_CH, Ne - c0);
-            for (int idx = tid; idx < nn * HD; idx += M2_T) {
-                const size_t g = ((size_t)b * Ne + c0) * HD + idx;
-                float v = a.RS1[g];
-                for (int s = 0; s < nsl; ++s) v += a.CS1p[((size_t)b * a.SL + s) * Ne * HD + (size_t)c0 * HD + idx];
-                sS[idx] = v;
-                if (dbg) dbg[(size_t)c0 * HD + idx] = v;
-            }
-            __syncthreads();
-            m2_mm20(sE, sS, W5, b5, nb5, nn);
-            __syncthreads();
-            for (int idx = tid; idx < nn * HD; idx += M2_T) {
-                const int n = idx / HD, k = idx - n * HD;
-                float acc = fmaf(xs[c0 + n], U1[k], c1[k]);
+    const float nb5 = 2.f * (float)(Ne - 1);
+    // S_n = RS1_n + sum_slots CS1p_n  (all loads of a node in flight at once)
+    auto load_S = [&](float (&S)[HD], int node) {
+        load20s(S, a.RS1 + ((size_t)b * Ne + node) * HD);
+        for (int sl = 0; sl < nsl; ++sl) {
+            float t[HD];
+            load20s(t, a.CS1p + (((size_t)b * a.SL + sl) * Ne + node) * HD);
 #pragma unroll
-                for (int m = 0; m < HD; ++m) acc = fmaf(sE[n * HD + m], U1[(1 + m) * HD + k], acc);
-                sZ[idx] = fmaxf(acc, 0.f);
-            }
-            __syncthreads();
-            for (int n = tid; n < nn; n += M2_T) {
-                float acc = c2[0];
-#pragma unroll
-                for (int k = 0; k < HD; ++k) acc = fmaf(sZ[n * HD + k], u2[k], acc);
-                x2[c0 + n] = fmaxf(acc, 0.f);
-            }
-            __syncthreads();
+            for (int k = 0; k < HD; ++k) S[k] += t[k];
         }
+    };
+    if (a.ent) {
+        for (int node = tid; node < Ne; node += M2_T) {
+            float S[HD], E[HD], Z[HD];
+            load_S(S, node);
+            if (dbg) for (int k = 0; k < HD; ++k) dbg[(size_t)node * HD + k] = S[k];
+            const float xv = xs[node];
+#pragma unroll
+            for (int k = 0; k < HD; ++k) { E[k] = nb5 * b5[k]; Z[k] = fmaf(xv, U1[k], c1[k]); }
+            gemv20(E, S, W5);
+            gemv20(Z, E, U1 + HD);
+            float acc = c2[0];
+#pragma unroll
+            for (int k = 0; k < HD; ++k) acc = fmaf(fmaxf(Z[k], 0.f), u2[k], acc);
+            x2[node] = fmaxf(acc, 0.f);
+        }
+        __syncthreads();
     }
     if (dbg) for (int i = tid; i < Ne; i += M2_T) dbg[(size_t)Ne * HD + i] = x2[i];
     mbar_wait(bar, 0);
@@ -240,45 +346,73 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             TP[4 * i] = X - xi; TP[4 * i + 1] = fn * xi; TP[4 * i + 2] = fn - TP[4 * i + 3];
         }
     } else {
-        const float inv = 1.f / (float)nm1;
+        // general path: SP[li] = sum of the m = L-1 consecutive entries B2[li m .. li m + m) (closed form from
+        // prefix sums and bit-range popcounts); TP[lj] = sum_li B2[li m + lj - (lj > li)] gathered with
+        // incrementally updated grid coordinates.
+        const int n = nm1, m = Lb - 1;
+        float* PX = dl;                                 // exclusive prefix of x2 (dl is free until the backward)
+        if (warp == 0) warp_excl_scan(PX, x2, 1, Ne, lane);
         int nchunk = M2_T / Lb;
         nchunk = nchunk < 1 ? 1 : (nchunk > 4 ? 4 : nchunk);
-        float* partR = scratch;                    // [nchunk][Lb][4]
-        float* partC = scratch + 4 * 4 * Ne;
+        float* partC = scratch;                         // [nchunk][Lb][4]
         for (int t = tid; t < nchunk * Lb; t += M2_T) {
             const int c = t / Lb, me = t - c * Lb;
             const int lo = (int)(((long long)c * Lb) / nchunk), hi = (int)(((long long)(c + 1) * Lb) / nchunk);
-            float r0 = 0.f, r1 = 0.f, r3 = 0.f, q0 = 0.f, q1 = 0.f, q3 = 0.f;
-            int cntr = 0, cntc = 0;
-            for (int o = lo; o < hi; ++o) {
-                if (o == me) continue;
-                int gi, gj;
-                unflat_pair(me * (Lb - 1) + o - (o > me), nm1, inv, gi, gj);          // row pass: li = me, lj = o
-                r0 += x2[gi]; r1 += x2[gj]; r3 += (float)((ebits[gi * WPe + (gj >> 5)] >> (gj & 31)) & 1u); ++cntr;
-                unflat_pair(o * (Lb - 1) + me - (me > o), nm1, inv, gi, gj);          // column pass: li = o, lj = me
-                q0 += x2[gi]; q1 += x2[gj]; q3 += (float)((ebits[gi * WPe + (gj >> 5)] >> (gj & 31)) & 1u); ++cntc;
+            float q0 = 0.f, q1 = 0.f;
+            int q3 = 0, cnt = 0;
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {      // li < lj (flat column lj - 1), then li > lj (flat column lj)
+                const int l0 = part == 0 ? lo : max(lo, me + 1), l1 = part == 0 ? min(hi, me) : hi;
+                if (l0 >= l1) continue;
+                const int q = l0 * m + me - (part == 0 ? 1 : 0);
+                int gi = q / n, pp = q - gi * n;
+                for (int li = l0; li < l1; ++li) {
+                    const int gj = pp + (pp >= gi);
+                    q0 += x2[gi]; q1 += x2[gj];
+                    q3 += (ebits[gi * WPe + (gj >> 5)] >> (gj & 31)) & 1u;
+                    ++cnt;
+                    pp += m;
+                    if (pp >= n) { pp -= n; ++gi; }
+                }
             }
-            float* pr = partR + ((size_t)c * Lb + me) * 4;
             float* pc = partC + ((size_t)c * Lb + me) * 4;
-            pr[0] = r0; pr[1] = r1; pr[2] = (float)cntr - r3; pr[3] = r3;
-            pc[0] = q0; pc[1] = q1; pc[2] = (float)cntc - q3; pc[3] = q3;
+            pc[0] = q0; pc[1] = q1; pc[2] = (float)(cnt - q3); pc[3] = (float)q3;
         }
         __syncthreads();
+        for (int li = tid; li < Lb; li += M2_T) {
+            const int qs = li * m;
+            int g = qs / n, p0 = qs - g * n, rem = m, c3 = 0;
+            float a0 = 0.f, a1 = 0.f;
+            while (rem > 0) {
+                const int c = min(rem, n - p0), pb = p0 + c;
+                a0 = fmaf((float)c, x2[g], a0);
+                a1 += offdiag_prefix(PX, x2, 1, g, pb) - offdiag_prefix(PX, x2, 1, g, p0);
+                c3 += range_popc(ebits + g * WPe, p0 + (p0 >= g), pb - 1 + (pb - 1 >= g) + 1);
+                rem -= c; ++g; p0 = 0;
+            }
+            SP[4 * li] = a0; SP[4 * li + 1] = a1; SP[4 * li + 2] = (float)(m - c3); SP[4 * li + 3] = (float)c3;
+        }
         for (int idx = tid; idx < 4 * Lb; idx += M2_T) {
-            float s = 0.f, t = 0.f;
-            for (int c = 0; c < nchunk; ++c) { s += partR[(size_t)c * Lb * 4 + idx]; t += partC[(size_t)c * Lb * 4 + idx]; }
-            SP[idx] = s; TP[idx] = t;
+            float t = 0.f;
+            for (int c = 0; c < nchunk; ++c) t += partC[(size_t)c * Lb * 4 + idx];
+            TP[idx] = t;
         }
     }
     __syncthreads();
-    // segmented reduce by hunk id in ascending entity-line order
-    for (int idx = tid; idx < Nc * 4; idx += M2_T) {
-        const int c = idx >> 2, chn = idx & 3;
+    // segmented reduce by hunk id in ascending entity-line order; two threads per (hunk, channel), halves in order
+    for (int base = 0; base < Nc * 8; base += M2_T) {
+        const int idx2 = base + tid, idx = idx2 >> 1, half = idx2 & 1;
+        const int c = idx >> 2, chn = idx & 3, mid_i = Lb >> 1;
         float acc = 0.f;
-        for (int i = 0; i < Lb; ++i)
-            if (hm[i] == c) acc += SP[4 * i + chn] + TP[4 * i + chn];
-        nb[idx] = acc;
-        if (dbg) dbg[(size_t)Ne * 21 + idx] = acc;
+        if (idx2 < Nc * 8)
+            for (int i = half ? mid_i : 0; i < (half ? Lb : mid_i); ++i)
+                if (hm[i] == c) acc += SP[4 * i + chn] + TP[4 * i + chn];
+        const float other = __shfl_xor_sync(0xffffffffu, acc, 1);
+        if (idx2 < Nc * 8 && half == 0) {
+            const float v = acc + other;
+            nb[idx] = v;
+            if (dbg) dbg[(size_t)Ne * 21 + idx] = v;
+        }
     }
     __syncthreads();
     M2_PHASE(3);
@@ -341,20 +475,24 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
     M2_PHASE(4);
 
     // ---------------- F. linear second layer on the sums + head tables (model_2.py:263-275, 311-315) --
-    m2_mm20(rr, RS3, W2, b2, (float)(Nc - 1), Nc);
-    m2_mm20(cc, CS3, W2, b2, (float)(Nc - 1), Nc);
-    __syncthreads();
-    for (int idx = tid; idx < T; idx += M2_T) {
-        const int n = idx / HD, k = idx - n * HD;
-        float p = g1b[k] + G1[k], q = 0.f;
+    // one thread per (hunk, side): r_n = (Nc-1) b2 + RS3_n W2 and PR_n = g1b + G1[0] + r_n G1e, or the c / PC side
+    for (int t = tid; t < 2 * Nc; t += M2_T) {
+        const bool cside = t >= Nc;
+        const int n = cside ? t - Nc : t;
+        float in[HD], r[HD], pq[HD];
+        load20s(in, (cside ? CS3 : RS3) + n * HD);
 #pragma unroll
-        for (int m = 0; m < HD; ++m) {
-            p = fmaf(rr[n * HD + m], G1[(2 + m) * HD + k], p);
-            q = fmaf(cc[n * HD + m], G1[(2 + m) * HD + k], q);
+        for (int k = 0; k < HD; ++k) { r[k] = (float)(Nc - 1) * b2[k]; pq[k] = cside ? 0.f : g1b[k] + G1[k]; }
+        gemv20(r, in, W2);
+        gemv20(pq, r, G1 + 2 * HD);
+        store20s((cside ? cc : rr) + n * HD, r);
+        if (cside) {
+            store20s(PC + n * HD, pq);
+        } else {
+#pragma unroll
+            for (int k = 0; k < HD; ++k) { const int pi = p01_idx(n, k); PR01[pi] = pq[k]; PR01[pi + 4] = pq[k] + Dg[k]; }
         }
-        const int pi = p01_idx(n, k);
-        PR01[pi] = p; PR01[pi + 4] = p + Dg[k]; PC[idx] = q;
-        if (dbg) { dbg[(size_t)Ne * 21 + Nc * 4 + 2 * T + idx] = p; dbg[(size_t)Ne * 21 + Nc * 4 + 3 * T + idx] = q; }
+        if (dbg) for (int k = 0; k < HD; ++k) dbg[(size_t)Ne * 21 + Nc * 4 + (cside ? 3 : 2) * T + n * HD + k] = pq[k];
     }
     __syncthreads();
     M2_PHASE(5);
@@ -482,77 +620,93 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
     M2_PHASE(7);
 
     // ---------------- H. head backward (node level) ------------------------------------------------------
+    // RS4 = gam * RSm and CS4 = gam * CSm are never formed: gam is applied to the outputs / folded into G1g.
+    float* dr = PR01; float* dc = PC;          // written in round 2, after their last readers of round 1
     {
-        // HS[k] = sum_pairs relu(pre)[k] * delta  via  relu(pre) = m * (PR0_i + l Dg + PC_j)
-        if (tid < HD) {
-            const int k = tid;
-            float acc = 0.f;
-            for (int n = 0; n < Nc; ++n) {
-                acc = fmaf(PR01[p01_idx(n, k)], RSm[n * HD + k], acc);
-                acc = fmaf(PC[n * HD + k], CSm[n * HD + k], acc);
+        const int slice = tid & 15, grp = tid >> 4;
+        // round 1: scr_w1 rows 2.. (25 tiles), HS -> scr_w2, column sums of RSm -> scr_b1 and the label rows
+        if (grp < 25) {
+            float acc[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+            const int a0 = 4 * (grp / 5), b0 = 4 * (grp % 5);
+            tile_acc(acc, rr, HD, RSm, HD, a0, b0, slice, Nc);
+            tile_acc(acc, cc, HD, CSm, HD, a0, b0, slice, Nc);
+            const float v = reduce16(acc, lane);
+            const int m = a0 + (slice >> 2), k = b0 + (slice & 3);
+            gp[po.scr_w1 + 2 * HD + m * HD + k] = v * gam[k];            // dG1e[m][k]
+        } else if (grp < 30) {
+            // HS[k] = sum_pairs relu(pre)[k] * delta  via  relu(pre) = m * (PR0_i + l Dg + PC_j); 4 channels per group
+            const int kb = 4 * (grp - 25);
+            float hs[4] = {0.f, 0.f, 0.f, 0.f}, cs[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int n = slice; n < Nc; n += 16) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float rs = RSm[n * HD + kb + j];
+                    hs[j] = fmaf(PR01[p01_idx(n, kb + j)], rs, hs[j]);
+                    hs[j] = fmaf(PC[n * HD + kb + j], CSm[n * HD + kb + j], hs[j]);
+                    cs[j] += rs;
+                }
             }
-            acc = fmaf(Dg[k], misc[k], acc);
-            gp[po.scr_w2 + 2 * k + 1] = acc;
-            gp[po.scr_w2 + 2 * k] = -acc;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { hs[j] = half_sum(hs[j]); cs[j] = half_sum(cs[j]); }
+            if (slice < 4) {
+                const int k = kb + slice;
+                const float h = fmaf(Dg[k], misc[k], slice == 0 ? hs[0] : slice == 1 ? hs[1] : slice == 2 ? hs[2] : hs[3]);
+                const float c = (slice == 0 ? cs[0] : slice == 1 ? cs[1] : slice == 2 ? cs[2] : cs[3]) * gam[k];
+                const float ls4 = misc[k] * gam[k];
+                gp[po.scr_w2 + 2 * k + 1] = h; gp[po.scr_w2 + 2 * k] = -h;
+                gp[po.scr_b1 + k] = c; gp[po.scr_w1 + HD + k] = ls4; gp[po.scr_w1 + k] = c - ls4;
+            }
+        }
+        if (tid == 0) { gp[po.scr_b2 + 1] = misc[40]; gp[po.scr_b2] = -misc[40]; }
+        __syncthreads();
+        // round 2: dr = RS4 G1e^T = RSm G1g^T, dc = CSm G1g^T (one thread per (hunk, side))
+        for (int t = tid; t < 2 * Nc; t += M2_T) {
+            const bool cside = t >= Nc;
+            const int n = cside ? t - Nc : t;
+            float in[HD], out[HD];
+            load20s(in, (cside ? CSm : RSm) + n * HD);
+            gemv20t(out, in, G1g);
+            store20s((cside ? dc : dr) + n * HD, out);
         }
         __syncthreads();
-        for (int idx = tid; idx < T; idx += M2_T) {       // RS4 = gam * RSm, CS4 = gam * CSm (in place)
-            const int k = idx % HD;
-            RSm[idx] *= gam[k]; CSm[idx] *= gam[k];
-        }
-        if (tid < HD) misc[tid] *= gam[tid];                     // LS4
-        __syncthreads();
-    }
-    float* RS4 = RSm; float* CS4 = CSm;
-    // scr_w1 rows 2.. : dG1e[m][k] = sum_n r[n][m] RS4[n][k] + c[n][m] CS4[n][k];  400 outputs
-    for (int e = tid; e < 400 + HD; e += M2_T) {
-        if (e < 400) {
-            const int m = e / HD, k = e - m * HD;
-            float acc = 0.f;
-            for (int n = 0; n < Nc; ++n) {
-                acc = fmaf(rr[n * HD + m], RS4[n * HD + k], acc);
-                acc = fmaf(cc[n * HD + m], CS4[n * HD + k], acc);
-            }
-            gp[po.scr_w1 + 2 * HD + e] = acc;
-        } else {                          // scr_b1 and the two label rows
-            const int k = e - 400;
-            float acc = 0.f;
-            for (int n = 0; n < Nc; ++n) acc += RS4[n * HD + k];
-            gp[po.scr_b1 + k] = acc;
-            gp[po.scr_w1 + HD + k] = misc[k];
-            gp[po.scr_w1 + k] = acc - misc[k];
-        }
-    }
-    if (tid == 0) { gp[po.scr_b2 + 1] = misc[40]; gp[po.scr_b2] = -misc[40]; }
-    __syncthreads();
-    // dr = RS4 G1e^T -> PR01 buffer (first T) ; dc = CS4 G1e^T -> PC buffer
-    float* dr = PR01; float* dc = PC;
-    m2_mm20t(dr, RS4, G1 + 2 * HD, Nc);
-    m2_mm20t(dc, CS4, G1 + 2 * HD, Nc);
-    __syncthreads();
-    // hnk_w2[q][m] = sum_n RS3[n][q] dr[n][m] + CS3[n][q] dc[n][m] ; hnk_b2[m] = (Nc-1) sum_n (dr+dc)[n][m]
-    for (int e = tid; e < 400 + HD; e += M2_T) {
-        if (e < 400) {
-            const int q = e / HD, m = e - q * HD;
-            float acc = 0.f;
-            for (int n = 0; n < Nc; ++n) {
-                acc = fmaf(RS3[n * HD + q], dr[n * HD + m], acc);
-                acc = fmaf(CS3[n * HD + q], dc[n * HD + m], acc);
-            }
-            gp[po.hnk_w2 + e] = acc;
+        // round 3: hnk_w2 / hnk_b2 gradients (25 tiles + 5 groups of column sums) and GR = dr W2^T, GC = dc W2^T
+        float* GR = PR01 + T; float* GC = rr;
+        if (grp < 25) {
+            float acc[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+            const int a0 = 4 * (grp / 5), b0 = 4 * (grp % 5);
+            tile_acc(acc, RS3, HD, dr, HD, a0, b0, slice, Nc);
+            tile_acc(acc, CS3, HD, dc, HD, a0, b0, slice, Nc);
+            const float v = reduce16(acc, lane);
+            gp[po.hnk_w2 + (a0 + (slice >> 2)) * HD + b0 + (slice & 3)] = v;
+        } else if (grp < 30) {
+            const int kb = 4 * (grp - 25);
+            float cs[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int n = slice; n < Nc; n += 16)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) cs[j] += dr[n * HD + kb + j] + dc[n * HD + kb + j];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cs[j] = half_sum(cs[j]);
+            if (slice < 4)
+                gp[po.hnk_b2 + kb + slice] = (float)(Nc - 1) * (slice == 0 ? cs[0] : slice == 1 ? cs[1] : slice == 2 ? cs[2] : cs[3]);
         } else {
-            const int m = e - 400;
-            float acc = 0.f;
-            for (int n = 0; n < Nc; ++n) acc += dr[n * HD + m] + dc[n * HD + m];
-            gp[po.hnk_b2 + m] = (float)(Nc - 1) * acc;
+            // threads 480..639: GR / GC rows (rr is dead: its last readers ran in round 1)
+            for (int t = tid - 480; t < 2 * Nc; t += M2_T - 480) {
+                const bool cside = t >= Nc;
+                const int n = cside ? t - Nc : t;
+                float in[HD], out[HD];
+                load20s(in, (cside ? dc : dr) + n * HD);
+                gemv20t(out, in, W2);
+                store20s((cside ? GC : GR) + n * HD, out);
+            }
         }
+        __syncthreads();
     }
     float* GR = PR01 + T; float* GC = rr;
-    __syncthreads();                 // rr (r) fully consumed above before it is overwritten by GC
-    m2_mm20t(GR, dr, W2, Nc);
-    m2_mm20t(GC, dc, W2, Nc);
     float* RS3d = RSm; float* CS3d = CSm;
-    __syncthreads();
     M2_PHASE(8);
 
     // ---------------- I. hunk pair layer backward sweep ------------------------------------------------------
@@ -639,38 +793,50 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             dx2[i] = (fmaf(fn, a0, D0 - a0)) + (fmaf(fn, a1, D1 - a1));
         }
     } else {
-        const int lm1 = Lb - 1, qmax = Lb * lm1;
-        const float invl = 1.f / (float)lm1;
+        // general path (mirror of the forward): the row part of dx2[gi] runs over the consecutive flat indices
+        // [gi n, gi n + n) below qmax = L (L-1) -> closed form from prefix sums of dl; the column part is gathered
+        // with incrementally updated local coordinates.
+        const int n = nm1, m = Lb - 1, qmax = Lb * m, d = n - m;
+        float* PD = SP;                                 // exclusive prefix of dl[.][0] over the L index lines
+        if (warp == 0) warp_excl_scan(PD, dl, 4, Lb, lane);
         int nchunk = M2_T / Ne;
         nchunk = nchunk < 1 ? 1 : (nchunk > 4 ? 4 : nchunk);
-        float* partR = scratch;                    // [nchunk][Ne]
-        float* partC = scratch + 4 * Ne;
+        float* partC = scratch;                         // [nchunk][Ne]
         for (int t = tid; t < nchunk * Ne; t += M2_T) {
             const int c = t / Ne, me = t - c * Ne;
             const int lo = (int)(((long long)c * Ne) / nchunk), hi = (int)(((long long)(c + 1) * Ne) / nchunk);
-            float accr = 0.f, accc = 0.f;
-            for (int o = lo; o < hi; ++o) {
-                if (o == me) continue;
-                int q = me * nm1 + o - (o > me);                 // row pass: gi = me, gj = o
-                if (q < qmax) {
-                    int li, lj;
-                    unflat_pair(q, lm1, invl, li, lj);
-                    accr += dl[4 * li] + dl[4 * lj];
-                }
-                q = o * nm1 + me - (me > o);                     // column pass: gi = o, gj = me
-                if (q < qmax) {
-                    int li, lj;
-                    unflat_pair(q, lm1, invl, li, lj);
-                    accc += dl[4 * li + 1] + dl[4 * lj + 1];
+            float acc = 0.f;
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {      // gi < gj (flat column gj - 1), then gi > gj (flat column gj)
+                const int g0 = part == 0 ? lo : max(lo, me + 1), g1 = part == 0 ? min(hi, me) : hi;
+                if (g0 >= g1) continue;
+                int q = g0 * n + me - (part == 0 ? 1 : 0);
+                int li = q / m, sloc = q - li * m;
+                for (int gi = g0; gi < g1 && q < qmax; ++gi) {
+                    const int lj = sloc + (sloc >= li);
+                    acc += dl[4 * li + 1] + dl[4 * lj + 1];
+                    q += n; sloc += d; ++li;
+                    while (sloc >= m) { sloc -= m; ++li; }
                 }
             }
-            partR[(size_t)c * Ne + me] = accr; partC[(size_t)c * Ne + me] = accc;
+            partC[(size_t)c * Ne + me] = acc;
         }
         __syncthreads();
-        for (int n = tid; n < Ne; n += M2_T) {
-            float s = 0.f, t = 0.f;
-            for (int c = 0; c < nchunk; ++c) { s += partR[(size_t)c * Ne + n]; t += partC[(size_t)c * Ne + n]; }
-            dx2[n] = s + t;
+        for (int gi = tid; gi < Ne; gi += M2_T) {
+            const int qa = gi * n, qb = min(qa + n, qmax);
+            float acc = 0.f;
+            if (qa < qmax) {
+                int li = qa / m, sloc = qa - li * m, rem = qb - qa;
+                while (rem > 0) {
+                    const int c = min(rem, m - sloc), sb = sloc + c;
+                    acc = fmaf((float)c, dl[4 * li], acc);
+                    acc += offdiag_prefix(PD, dl, 4, li, sb) - offdiag_prefix(PD, dl, 4, li, sloc);
+                    rem -= c; ++li; sloc = 0;
+                }
+            }
+            float t = 0.f;
+            for (int c = 0; c < nchunk; ++c) t += partC[(size_t)c * Ne + gi];
+            dx2[gi] = acc + t;
         }
     }
     __syncthreads();
@@ -679,94 +845,75 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
 
     // ---------------- L. entity-state MLP backward (model_2.py:190-205) and W5/b5 (model_2.py:172-175) ------------
     {
-        float* sS = uni; float* sE = sS + M2_CH * HD; float* sZp = sE + M2_CH * HD; float* sDz = sZp + M2_CH * HD;
-        float* sDE = sDz + M2_CH * HD; float* sdu = sDE + M2_CH * HD;
-        const float nb5 = 2.f * (float)(Ne - 1);
-        constexpr int NREP = (881 + M2_T - 1) / M2_T;
-        float accw[NREP];
-#pragma unroll
-        for (int rep = 0; rep < NREP; ++rep) accw[rep] = 0.f;
+        // per-node rows of a chunk: Sa [S | nb5 0 0 0], Ea [E | x 1 0 0], dz, dE, ZD [relu(Z) du | du 0 0 0]
+        float* Sa = uni; float* Ea = Sa + M2_CH * 24; float* dzs = Ea + M2_CH * 24; float* dEs = dzs + M2_CH * HD;
+        float* ZD = dEs + M2_CH * HD;
+        const int slice = tid & 15, grp = tid >> 4;
+        float accA = 0.f, accB = 0.f, accC = 0.f;      // one reduced output per thread and round, summed over the chunks
         for (int c0 = 0; c0 < Ne; c0 += M2_CH) {
             const int nn = min(M2_CH, Ne - c0);
-            for (int idx = tid; idx < nn * HD; idx += M2_T) {
-                const size_t g = ((size_t)b * Ne + c0) * HD + idx;
-                float v = a.RS1[g];
-                for (int s = 0; s < nsl; ++s) v += a.CS1p[((size_t)b * a.SL + s) * Ne * HD + (size_t)c0 * HD + idx];
-                sS[idx] = v;
-            }
-            __syncthreads();
-            m2_mm20(sE, sS, W5, b5, nb5, nn);
-            __syncthreads();
-            for (int idx = tid; idx < nn * HD; idx += M2_T) {
-                const int n = idx / HD, k = idx - n * HD;
-                float acc = fmaf(xs[c0 + n], U1[k], c1[k]);
+            // step 1: one thread per entity: recompute the forward, back-propagate, write GE
+            for (int n = tid; n < nn; n += M2_T) {
+                const int node = c0 + n;
+                float S[HD], E[HD], Z[HD];
+                load_S(S, node);
+                const float xv = xs[node];
 #pragma unroll
-                for (int m = 0; m < HD; ++m) acc = fmaf(sE[n * HD + m], U1[(1 + m) * HD + k], acc);
-                sZp[idx] = acc;
-            }
-            for (int n = tid; n < nn; n += M2_T) sdu[n] = x2[c0 + n] > 0.f ? dx2[c0 + n] : 0.f;
-            __syncthreads();
-            for (int idx = tid; idx < nn * HD; idx += M2_T) {
-                const int n = idx / HD, k = idx - n * HD;
-                sDz[idx] = sZp[idx] > 0.f ? sdu[n] * u2[k] : 0.f;
-            }
-            __syncthreads();
-            for (int idx = tid; idx < nn * HD; idx += M2_T) {
-                const int n = idx / HD, m = idx - n * HD;
-                float acc = 0.f;
+                for (int k = 0; k < HD; ++k) { E[k] = nb5 * b5[k]; Z[k] = fmaf(xv, U1[k], c1[k]); }
+                gemv20(E, S, W5);
+                store20s(Sa + n * 24, S);
+                *reinterpret_cast<float4*>(Sa + n * 24 + HD) = make_float4(nb5, 0.f, 0.f, 0.f);
+                gemv20(Z, E, U1 + HD);
+                store20s(Ea + n * 24, E);
+                *reinterpret_cast<float4*>(Ea + n * 24 + HD) = make_float4(xv, 1.f, 0.f, 0.f);
+                const float du = x2[node] > 0.f ? dx2[node] : 0.f;
+                float dz[HD], zd[HD];
 #pragma unroll
-                for (int k = 0; k < HD; ++k) acc = fmaf(U1[(1 + m) * HD + k], sDz[n * HD + k], acc);
-                sDE[idx] = acc;
+                for (int k = 0; k < HD; ++k) { dz[k] = Z[k] > 0.f ? du * u2[k] : 0.f; zd[k] = fmaxf(Z[k], 0.f) * du; }
+                store20s(dzs + n * HD, dz);
+                store20s(ZD + n * 24, zd);
+                *reinterpret_cast<float4*>(ZD + n * 24 + HD) = make_float4(du, 0.f, 0.f, 0.f);
+                float dE[HD], ge[HD];
+                gemv20t(dE, dz, U1 + HD);
+                store20s(dEs + n * HD, dE);
+                gemv20t(ge, dE, W5);
+                store20s(a.GE + ((size_t)b * Ne + node) * HD, ge);
             }
             __syncthreads();
+            // step 2: weight gradients = A^T B over the chunk's nodes, 4 x 4 register tiles, 16 node slices per tile
+            if (grp < 30) {
+                const int a0 = 4 * (grp / 5), b0 = 4 * (grp % 5);
+                float acc[16];
 #pragma unroll
-            for (int rep = 0; rep < NREP; ++rep) {
-                const int e = tid + rep * M2_T;
-                float acc = 0.f;
-                if (e < 400) {                       // dU1[1+m][k]
-                    const int m = e / HD, k = e - m * HD;
-                    for (int n = 0; n < nn; ++n) acc = fmaf(sE[n * HD + m], sDz[n * HD + k], acc);
-                } else if (e < 420) {                // dU1[0][k]
-                    const int k = e - 400;
-                    for (int n = 0; n < nn; ++n) acc = fmaf(xs[c0 + n], sDz[n * HD + k], acc);
-                } else if (e < 440) {                // dc1[k]
-                    const int k = e - 420;
-                    for (int n = 0; n < nn; ++n) acc += sDz[n * HD + k];
-                } else if (e < 460) {                // du2[k]
-                    const int k = e - 440;
-                    for (int n = 0; n < nn; ++n) acc = fmaf(sdu[n], fmaxf(sZp[n * HD + k], 0.f), acc);
-                } else if (e == 460) {               // dc2
-                    for (int n = 0; n < nn; ++n) acc += sdu[n];
-                } else if (e < 861) {                // dW5[q][m]
-                    const int q = (e - 461) / HD, m = (e - 461) - q * HD;
-                    for (int n = 0; n < nn; ++n) acc = fmaf(sS[n * HD + q], sDE[n * HD + m], acc);
-                } else if (e < 881) {                // db5[m]
-                    const int m = e - 861;
-                    for (int n = 0; n < nn; ++n) acc += sDE[n * HD + m];
-                    acc *= nb5;
+                for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+                tile_acc(acc, Ea, 24, dzs, HD, a0, b0, slice, nn);       // rows 0..19 dU1[1+m], 20 dU1[0], 21 dc1
+                accA += reduce16(acc, lane);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+                tile_acc(acc, Sa, 24, dEs, HD, a0, b0, slice, nn);       // rows 0..19 dW5, 20 db5 (column nb5)
+                accB += reduce16(acc, lane);
+            } else if (grp < 36) {
+                const int kb = 4 * (grp - 30);                             // column sums of ZD: du2[0..19], dc2
+                float cs[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int n = slice; n < nn; n += 16) {
+                    const float4 v = *reinterpret_cast<const float4*>(ZD + n * 24 + kb);
+                    cs[0] += v.x; cs[1] += v.y; cs[2] += v.z; cs[3] += v.w;
                 }
-                accw[rep] += acc;
-            }
-            for (int idx = tid; idx < nn * HD; idx += M2_T) {      // GE = dEbar W5^T
-                const int n = idx / HD, q = idx - n * HD;
-                float acc = 0.f;
 #pragma unroll
-                for (int m = 0; m < HD; ++m) acc = fmaf(W5[q * HD + m], sDE[n * HD + m], acc);
-                a.GE[((size_t)b * Ne + c0) * HD + idx] = acc;
+                for (int j = 0; j < 4; ++j) cs[j] = half_sum(cs[j]);
+                accC += slice == 0 ? cs[0] : slice == 1 ? cs[1] : slice == 2 ? cs[2] : cs[3];
             }
             __syncthreads();
         }
-#pragma unroll
-        for (int rep = 0; rep < NREP; ++rep) {
-            const int e = tid + rep * M2_T;
-            const float v = accw[rep];
-            if (e < 400) gp[po.nod_w1 + HD + e] = v;
-            else if (e < 420) gp[po.nod_w1 + (e - 400)] = v;
-            else if (e < 440) gp[po.nod_b1 + (e - 420)] = v;
-            else if (e < 460) gp[po.nod_w2 + (e - 440)] = v;
-            else if (e == 460) gp[po.nod_b2] = v;
-            else if (e < 861) gp[po.ent_w5 + (e - 461)] = v;
-            else if (e < 881) gp[po.ent_b5 + (e - 861)] = v;
+        if (grp < 30) {
+            const int r = 4 * (grp / 5) + (slice >> 2), k = 4 * (grp % 5) + (slice & 3);
+            if (r < HD) { gp[po.nod_w1 + HD + r * HD + k] = accA; gp[po.ent_w5 + r * HD + k] = accB; }
+            else if (r == HD) { gp[po.nod_w1 + k] = accA; gp[po.ent_b5 + k] = accB; }
+            else if (r == HD + 1) gp[po.nod_b1 + k] = accA;
+        } else if (grp < 36 && slice < 4) {
+            const int k = 4 * (grp - 30) + slice;
+            if (k < HD) gp[po.nod_w2 + k] = accC;
+            else if (k == HD) gp[po.nod_b2] = accC;
         }
     }
     M2_PHASE(11);

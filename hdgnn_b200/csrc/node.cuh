@@ -627,7 +627,15 @@ __global__ void grad_reduce_kernel(const float* gpart, int B, int total, float* 
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= total) return;
     float acc = 0.f;
-    for (int b = 0; b < B; ++b) acc += gpart[(size_t)b * total + p];
+    int b = 0;
+    for (; b + 7 < B; b += 8) {          // eight loads in flight, fixed summation order
+        float g[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) g[u] = gpart[(size_t)(b + u) * total + p];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += g[u];
+    }
+    for (; b < B; ++b) acc += gpart[(size_t)b * total + p];
     grads[p] = acc;
 }
 
@@ -637,13 +645,14 @@ __global__ void __launch_bounds__(1024) adam_kernel(float* p, const float* g, fl
                                                     int o_t1, int o_t2, int* step, float lr, float b1,
                                                     float b2, float eps, float* reg_losses) {
     __shared__ float scratch[32];
-    __shared__ float tn[2];
+    __shared__ float tn[3];
     const int tid = threadIdx.x;
     const int t = *step + 1;
     if (tid < 2) {
         const int o = tid == 0 ? o_t1 : o_t2;
         tn[tid] = sqrtf(p[o] * p[o] + p[o + 1] * p[o + 1]);
     }
+    if (tid == 32) tn[2] = lr * (float)(sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t)));
     float sq = 0.f;
     for (int i = tid; i < n; i += blockDim.x) sq = fmaf(p[i], p[i], sq);
     const float l2 = block_sum(sq, scratch);
@@ -652,7 +661,7 @@ __global__ void __launch_bounds__(1024) adam_kernel(float* p, const float* g, fl
         reg_losses[0] = 0.01f * (tn[0] + tn[1]);
         reg_losses[1] = 0.001f * 0.5f * l2;
     }
-    const float lr_t = lr * (float)(sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t)));
+    const float lr_t = tn[2];
     for (int i = tid; i < n; i += blockDim.x) {
         float gi = g[i] + 0.001f * p[i];
         if (i >= o_t1 && i < o_t1 + 2) gi += 0.001f * p[i] / tn[0];
