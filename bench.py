@@ -210,12 +210,16 @@ def main():
     probs = torch.empty(B, 2, eng.Ncr, dtype=torch.float32, device=dev)
     loss = torch.zeros(1, dtype=torch.float32, device=dev)
 
+    loss3 = torch.zeros(3, dtype=torch.float32, device=dev)
+
     def device_step(k):
         db = dev_pool[k % pool_n]
+        if world == 1:      # one fused call: forward, backward, gradient reduction + regularisers + Adam
+            eng.train_step(db, model.params, model.m, model.v, model.step_counter, loss3, probs=probs)
+            return eng.last_launch_count()
         eng.forward_backward(db, model.params, B_global=Bg, grads=model.grads, probs=probs, loss=loss)
         n = eng.last_launch_count()
-        if world > 1:
-            dist.all_reduce(model.grads)
+        dist.all_reduce(model.grads)
         eng.adam_step(model.params, model.grads, model.m, model.v, model.step_counter, reg_losses=model.reg)
         return n + eng.last_launch_count()
 
@@ -285,12 +289,32 @@ def main():
         "mid(train)": B * 3 * (ncr * 2230 + ner * 8 + Ne * 880), "mid(infer)": B * (ncr * 2230 + ner * 8 + Ne * 880),
     }
     hbm_peak, bf16_peak, bf16_sus, src = measured_peaks()
+    # The contract's two bounds are quoted for the dominant kernel against the measured peaks; neither
+    # binds this path (K = 20 contractions collapse algebraically): the bound that does is
+    # the SM issue rate, reported under "issue" from the kernel's executed warp instructions (ncu
+    # smsp__inst_executed.sum of the same launch shape, profiles/inst_counts.json) over the live time.
     roof = {"kernel": top, "bound": "tensor", "unit": "TFLOP/s", "avg_us": top_us,
             "achieved": alg.get(top, 0) / (top_us * 1e-6) / 1e12, "peak": bf16_peak,
-            "peak_source": f"MEASURED_PEAKS.json bf16 burst ({src}); the arithmetic is fp32 on the FMA/ALU pipes, "
-                           "see DESIGN.md: the algebraic collapse removes the per-pair GEMM",
+            "peak_source": f"MEASURED_PEAKS.json bf16 burst ({src}); achieved = canonical (un-collapsed) FLOPs of "
+                           "SURVEY 8(d) / live kernel time; the executed arithmetic is fp32 on the FMA/ALU pipes",
             "traffic": None, "kernels": kernels}
     roof["frac"] = roof["achieved"] / roof["peak"]
+    try:
+        ic = json.load(open(os.path.join(ROOT, "profiles", "inst_counts.json")))
+        key = f"{args.workload}_B{B}_v{variant}"
+        sm_clk = (clocks or {}).get("sm_mhz") or 1965.0
+        issue = {}
+        for name, rec in ic.get(key, {}).items():
+            if name in kernels:
+                slots = kernels[name]["avg_us"] * 1e-6 * sm_clk * 1e6 * 148 * 4
+                issue[name] = {"warp_insts": rec["inst"], "issue_frac": rec["inst"] / slots,
+                               "dram_bytes": rec.get("dram_bytes")}
+        roof["issue"] = {"unit": "fraction of 148 SM x 4 issue slots x SM clock", "sm_mhz": sm_clk, "kernels": issue,
+                         "source": ic.get("_source")}
+        if top in issue:
+            roof["traffic"] = issue[top]["dram_bytes"]
+    except Exception:
+        pass
     step_flops = 3 * flops_fwd_per_commit(Ne, Nc, variant)
     roof["step"] = {"algorithmic_tflops": value * step_flops / 1e12,
                     "algorithmic_hbm_gbs": value * bytes_per_commit_train(Ne, Nc) / 1e9,

@@ -51,8 +51,9 @@ __host__ __device__ inline size_t ent2_smem_bytes(int CWT, int NRG, int N, int R
     return off + 16;
 }
 
+// launch bounds: 20 resident warps per SM (4 / 2 / 1 CTAs for NRG = 1 / 2 / 4)
 template <int CWT, int NRG>
-__global__ void __launch_bounds__(KG * NRG * 32) ent_fwd2_kernel(const Ent2Args a) {
+__global__ void __launch_bounds__(KG * NRG * 32, 4 / NRG) ent_fwd2_kernel(const Ent2Args a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int N = a.N, WP = a.WP, RC = a.R < N ? a.R : N;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, kg = warp % KG, rg = warp / KG;
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(KG * NRG * 32) ent_fwd2_kernel(const Ent2Args 
 }
 
 template <int CWT, int NRG>
-__global__ void __launch_bounds__(KG * NRG * 32) ent_bwd2_kernel(const Ent2Args a) {
+__global__ void __launch_bounds__(KG * NRG * 32, NRG == 1 ? 3 : 1) ent_bwd2_kernel(const Ent2Args a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int N = a.N, WP = a.WP, RC = a.R < N ? a.R : N;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, kg = warp % KG, rg = warp / KG;

@@ -26,6 +26,13 @@ struct FinalArgs {
     unsigned int* counter;   // zero-initialised; reset by the last CTA
 };
 
+// lr_t = lr sqrt(1 - b2^t) / (1 - b1^t) (tf.train.AdamOptimizer), with 1 - b^t = -expm1(t log b) so that the
+// small differences keep full float precision (fp64 pow costs ~10 us on this part's fp64 pipe)
+__device__ __forceinline__ float adam_lr_t(float lr, float b1, float b2, int t) {
+    const float omb2 = -expm1f((float)t * logf(b2)), omb1 = -expm1f((float)t * logf(b1));
+    return lr * sqrtf(omb2) / omb1;
+}
+
 constexpr int FIN_P = 128;   // parameters per CTA
 constexpr int FIN_SL = 8;    // commit slices per parameter
 
@@ -100,7 +107,7 @@ __global__ void __launch_bounds__(FIN_P * FIN_SL) reduce_adam_kernel(const Final
     }
     const float pv = (sl == 0 && p < a.total) ? a.params[p] : 0.f;
     const int t = *a.step + 1;                          // read before any CTA can publish the new count
-    if (tid == 2) tn[2] = a.lr * (float)(sqrt(1.0 - pow((double)a.b2, (double)t)) / (1.0 - pow((double)a.b1, (double)t)));
+    if (tid == 2) tn[2] = adam_lr_t(a.lr, a.b1, a.b2, t);
     const float sq = block_sum(pv * pv, scratch);       // also orders tn[]
     if (sl == 0 && p < a.total) {
         float gi = g + 0.001f * pv;

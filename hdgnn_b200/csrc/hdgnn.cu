@@ -671,10 +671,10 @@ int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out) {
         if ((f == 4 || f == 8) && f < h->fwd_cwt) h->fwd_cwt = f;
         if ((bw == 4 || bw == 8) && bw < h->bwd_cwt) h->bwd_cwt = bw;
     }
-    h->fwd_nrg = env_int("HDGNN_FWD_NRG", 2);
-    h->bwd_nrg = env_int("HDGNN_BWD_NRG", 1);
-    if (h->fwd_nrg != 1 && h->fwd_nrg != 2 && h->fwd_nrg != 4) h->fwd_nrg = 2;
-    if (h->bwd_nrg != 1 && h->bwd_nrg != 2 && h->bwd_nrg != 4) h->bwd_nrg = 1;
+    h->fwd_nrg = env_int("HDGNN_FWD_NRG", 1);
+    h->bwd_nrg = env_int("HDGNN_BWD_NRG", 2);
+    if (h->fwd_nrg != 1 && h->fwd_nrg != 2 && h->fwd_nrg != 4) h->fwd_nrg = 1;
+    if (h->bwd_nrg != 1 && h->bwd_nrg != 2 && h->bwd_nrg != 4) h->bwd_nrg = 2;
     // the fused path needs the per-commit state of mid2 in one SM's shared memory and a hunk grid of <= 8 segments
     h->fused = !h->edge && !(cfg->flags & HDGNN_F_LEGACY) && h->Nc <= 256 &&
                mid2_smem_bytes(h->Ne, h->Nc, true) <= (size_t)prop.sharedMemPerBlockOptin;
@@ -803,6 +803,19 @@ int hdgnn_adam_step(hdgnn_handle_t h, float* params, const float* grads, float* 
     if (!params || !grads || !m || !v || !step_counter) return fail(h, HDGNN_E_INVALID, "null pointer");
     h->launches = 0;
     return adam_impl(h, params, grads, m, v, step_counter, lr, beta1, beta2, eps, reg_losses, (cudaStream_t)stream);
+}
+
+int hdgnn_train_step(hdgnn_handle_t h, int B, const uint8_t* adj, int adj_pitch, const float* x, const int32_t* hmap,
+                     const int32_t* L, const uint8_t* Y, int y_pitch, float* params, float* m, float* v,
+                     int32_t* step_counter, float lr, float beta1, float beta2, float eps, float* logits, float* probs,
+                     float* loss3, void* stream) {
+    int rc = check_inputs(h, B, adj, adj_pitch, x, hmap, L, Y, y_pitch, params);
+    if (rc) return rc;
+    if (!m || !v || !step_counter || !loss3) return fail(h, HDGNN_E_INVALID, "null pointer");
+    h->launches = 0;
+    Inputs in{adj, x, hmap, L, Y, params};
+    AdamArgs ad{params, m, v, step_counter, lr, beta1, beta2, eps, loss3 + 1};
+    return run_step(h, B, B, in, logits, probs, loss3, F(h, "H_GRADS"), &ad, (cudaStream_t)stream);
 }
 
 static int stage_inputs(hdgnn_handle_t h, int B, const uint8_t* adj_host, const float* x_host, const int32_t* hmap_host,

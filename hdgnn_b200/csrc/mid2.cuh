@@ -23,8 +23,8 @@ namespace hdgnn {
 constexpr int M2_NRG = 4;
 constexpr int M2_NW = KG * M2_NRG;        // 20 warps
 constexpr int M2_T = M2_NW * 32;          // 640 threads
-constexpr int M2_CH = 128;                // entity nodes per chunk of the entity-state MLP backward
-constexpr int M2_NODE_F = 24 + 24 + 20 + 20 + 24;   // floats per node of that chunk: [S|nb5] [E|x|1] dz dE [relu(Z) du|du]
+constexpr int M2_CH = 256;                // entity nodes per chunk of the entity-state MLP backward
+constexpr int M2_NODE_F = 24 + 20 + 24;   // floats per node of that chunk: [S|x|1|0|0] dz [relu(Z) du|du|0|0|0]
 // The entity block ent_w5 .. nod_b2 and the hunk block hnk_w1 .. scr_b2 are each contiguous in the
 // parameter blob (TF creation order, hdgnn.cu) with every array at a multiple of 4 floats from the
 // block start, so one copy per block keeps every matrix 16-byte aligned in shared memory.
@@ -52,7 +52,7 @@ __host__ __device__ inline size_t mid2_dbg_floats(int Ne, int Nc) { return (size
 
 struct Mid2Smem {
     // offsets in floats
-    int blk1, blk2, gam, Dh, Dg, G1g;         // weight blocks (contiguous copies of the parameter blob), derived vectors
+    int blk1, blk2, gam, Dh, Dg, G1g, W5U, c1p;   // weight blocks (contiguous copies of the parameter blob), derived tables
     int x, x2, hm, SP, TP, dl, dx2, nb, dnb, ebits, ybits, scratch, red, uni, total;
 };
 
@@ -61,6 +61,7 @@ __host__ __device__ inline Mid2Smem mid2_layout(int Ne, int Nc, bool train) {
     int o = 0;
     auto take = [&](int n) { int r = o; o += (n + 7) & ~7; return r; };      // 32-byte granules
     m.blk1 = take(M2_BLK1); m.blk2 = take(M2_BLK2); m.gam = take(20); m.Dh = take(20); m.Dg = take(20); m.G1g = take(400);
+    m.W5U = take(400); m.c1p = take(20);
     m.x = take(Ne); m.x2 = take(Ne); m.hm = take(Ne); m.SP = take(4 * Ne); m.TP = take(4 * Ne); m.dl = take(4 * Ne);
     m.dx2 = take(Ne); m.nb = take(4 * Nc); m.dnb = take(4 * Nc);
     m.ebits = take(Ne * bit_words(Ne)); m.ybits = take(Nc * bit_words(Nc));
@@ -224,6 +225,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
     float* V1 = blk2; float* d1 = blk2 + 200; float* W2 = blk2 + 220; float* b2 = blk2 + 620;
     float* G1 = blk2 + 640; float* g1b = blk2 + 1080; float* G2 = blk2 + 1100; float* gb2 = blk2 + 1140;
     float* gam = sm + L_.gam; float* Dh = sm + L_.Dh; float* Dg = sm + L_.Dg; float* G1g = sm + L_.G1g;
+    float* W5U = sm + L_.W5U; float* c1p = sm + L_.c1p;
     float* xs = sm + L_.x; float* x2 = sm + L_.x2; int* hm = reinterpret_cast<int*>(sm + L_.hm);
     float* SP = sm + L_.SP; float* TP = sm + L_.TP; float* dl = sm + L_.dl; float* dx2 = sm + L_.dx2;
     float* nb = sm + L_.nb; float* dnb = sm + L_.dnb;
@@ -282,12 +284,30 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         Dg[tid] = G1[HD + tid] - G1[tid];
     }
     if (TRAIN) for (int e = tid; e < 400; e += M2_T) G1g[e] = G1[2 * HD + e] * (G2[2 * (e % HD) + 1] - G2[2 * (e % HD)]);
+    const float nb5 = 2.f * (float)(Ne - 1);
+    if (a.ent) {
+        // the entity effect layer (x W5 + (Ne-1) 2 b5, model_2.py:172-175 after aggregation) and the first layer of
+        // the entity-state MLP compose into one 20 x 20 map: Z = c1' + x U1[0] + S W5U
+        for (int e = tid; e < 420; e += M2_T) {
+            float acc = 0.f;
+            if (e < 400) {
+                const int q = e / HD, k = e - q * HD;
+#pragma unroll
+                for (int m = 0; m < HD; ++m) acc = fmaf(W5[q * HD + m], U1[(1 + m) * HD + k], acc);
+                W5U[e] = acc;
+            } else {
+                const int k = e - 400;
+#pragma unroll
+                for (int m = 0; m < HD; ++m) acc = fmaf(b5[m], U1[(1 + m) * HD + k], acc);
+                c1p[k] = fmaf(nb5, acc, c1[k]);
+            }
+        }
+    }
     __syncthreads();
     M2_PHASE(1);
 
-    // ---------------- B/C. entity-state MLP forward: one thread per entity, weights broadcast from smem ------
+    // ---------------- B/C. entity-state MLP forward: two threads per entity (10 hidden units each) ----------
     const int nsl = a.ent ? ent2_slots(b, Ne, a.R) : 0;
-    const float nb5 = 2.f * (float)(Ne - 1);
     // S_n = RS1_n + sum_slots CS1p_n  (all loads of a node in flight at once)
     auto load_S = [&](float (&S)[HD], int node) {
         load20s(S, a.RS1 + ((size_t)b * Ne + node) * HD);
@@ -298,20 +318,34 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             for (int k = 0; k < HD; ++k) S[k] += t[k];
         }
     };
+    // Zh[j] = pre-activation of hidden unit 10 h + j of the entity-state MLP for effect sums S and attribute xv
+    auto hidden_half = [&](float (&Zh)[10], const float (&S)[HD], float xv, int h) {
+#pragma unroll
+        for (int j = 0; j < 10; ++j) Zh[j] = fmaf(xv, U1[10 * h + j], c1p[10 * h + j]);
+#pragma unroll
+        for (int q = 0; q < HD; ++q) {
+#pragma unroll
+            for (int j2 = 0; j2 < 5; ++j2) {
+                const float2 w = *reinterpret_cast<const float2*>(W5U + q * HD + 10 * h + 2 * j2);
+                Zh[2 * j2] = fmaf(S[q], w.x, Zh[2 * j2]); Zh[2 * j2 + 1] = fmaf(S[q], w.y, Zh[2 * j2 + 1]);
+            }
+        }
+    };
     if (a.ent) {
-        for (int node = tid; node < Ne; node += M2_T) {
-            float S[HD], E[HD], Z[HD];
-            load_S(S, node);
-            if (dbg) for (int k = 0; k < HD; ++k) dbg[(size_t)node * HD + k] = S[k];
-            const float xv = xs[node];
+        for (int base = 0; base < 2 * Ne; base += M2_T) {
+            const int t = base + tid, node = t >> 1, h = t & 1;
+            const bool valid = node < Ne;
+            float acc = 0.f;
+            if (valid) {
+                float S[HD], Zh[10];
+                load_S(S, node);
+                if (dbg && h == 0) for (int k = 0; k < HD; ++k) dbg[(size_t)node * HD + k] = S[k];
+                hidden_half(Zh, S, xs[node], h);
 #pragma unroll
-            for (int k = 0; k < HD; ++k) { E[k] = nb5 * b5[k]; Z[k] = fmaf(xv, U1[k], c1[k]); }
-            gemv20(E, S, W5);
-            gemv20(Z, E, U1 + HD);
-            float acc = c2[0];
-#pragma unroll
-            for (int k = 0; k < HD; ++k) acc = fmaf(fmaxf(Z[k], 0.f), u2[k], acc);
-            x2[node] = fmaxf(acc, 0.f);
+                for (int j = 0; j < 10; ++j) acc = fmaf(fmaxf(Zh[j], 0.f), u2[10 * h + j], acc);
+            }
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            if (valid && h == 0) x2[node] = fmaxf(acc + c2[0], 0.f);
         }
         __syncthreads();
     }
@@ -544,7 +578,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
                         a.logits[((size_t)b * 2 + 1) * npair + q] = l0 + d;
                     }
                     const float z = lab ? -d : d;
-                    ce_acc += fmaxf(z, 0.f) + log1pf(e);
+                    ce_acc += fmaxf(z, 0.f) + __logf(1.f + e);     // e in (0, 1]: absolute error ~1e-7
                 }
                 if (TRAIN) {
                     const float dv = valid ? a.scale * (p1 - (lab ? 1.f : 0.f)) : 0.f;
@@ -576,13 +610,13 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             Q[sg][0] = q.x; Q[sg][1] = q.y; col[sg][0] = 0ull; col[sg][1] = 0ull;
         }
         const uint32_t lmask = 1u << lane;
-        for (int r = rg; r < Nc; r += M2_NRG) {
+        auto delta_row = [&](int r, u64& rp0, u64& rp1) {
             uint32_t w[CWT];
             load_words<CWT>(w, ybits + (size_t)r * WPc);
             const float* prow0 = PR01 + (size_t)r * PROW + kg * 8;
             const float* prow1 = prow0 + 4;
             const float* drow = dlt + (size_t)r * DW + lane;
-            u64 rp0 = 0ull, rp1 = 0ull;
+            rp0 = 0ull; rp1 = 0ull;
 #pragma unroll
             for (int sg = 0; sg < CWT; ++sg) {
                 const bool bit = (w[sg] & lmask) != 0u;
@@ -596,7 +630,19 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
                 const u64 l2 = pk2(lf, lf);
                 lsm[0] = fma2(l2, v0, lsm[0]); lsm[1] = fma2(l2, v1, lsm[1]);
             }
-            const float tot = reduce4(rp0, rp1, lane);
+        };
+        int r = rg;
+        for (; r + M2_NRG < Nc; r += 2 * M2_NRG) {
+            u64 a0, a1, c0, c1;
+            delta_row(r, a0, a1);
+            delta_row(r + M2_NRG, c0, c1);
+            const float tot = reduce8(a0, a1, c0, c1, lane);
+            if ((lane & 3) == 0) RSm[((lane & 16) ? r + M2_NRG : r) * HD + k0 + reduce8_channel(lane)] = tot;
+        }
+        if (r < Nc) {
+            u64 a0, a1;
+            delta_row(r, a0, a1);
+            const float tot = reduce4(a0, a1, lane);
             if ((lane & 7) == 0) RSm[r * HD + k0 + ch] = tot;
         }
         combine_cols<CWT>(col, scratch, rg, M2_NRG, kg, lane);
@@ -845,53 +891,75 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
 
     // ---------------- L. entity-state MLP backward (model_2.py:190-205) and W5/b5 (model_2.py:172-175) ------------
     {
-        // per-node rows of a chunk: Sa [S | nb5 0 0 0], Ea [E | x 1 0 0], dz, dE, ZD [relu(Z) du | du 0 0 0]
-        float* Sa = uni; float* Ea = Sa + M2_CH * 24; float* dzs = Ea + M2_CH * 24; float* dEs = dzs + M2_CH * HD;
-        float* ZD = dEs + M2_CH * HD;
+        // per-node rows of a chunk: Sa [S | x 1 0 0], dz, ZD [relu(Z) du | du 0 0 0]
+        float* Sa = uni; float* dzs = Sa + M2_CH * 24; float* ZD = dzs + M2_CH * HD;
+        float* Mx = scratch;                           // [22][20]: M = S^T dz, then sum_n x dz, sum_n dz
         const int slice = tid & 15, grp = tid >> 4;
-        float accA = 0.f, accB = 0.f, accC = 0.f;      // one reduced output per thread and round, summed over the chunks
+        float accA = 0.f, accC = 0.f;                  // one reduced output per thread, summed over the chunks
         for (int c0 = 0; c0 < Ne; c0 += M2_CH) {
             const int nn = min(M2_CH, Ne - c0);
-            // step 1: one thread per entity: recompute the forward, back-propagate, write GE
-            for (int n = tid; n < nn; n += M2_T) {
-                const int node = c0 + n;
-                float S[HD], E[HD], Z[HD];
-                load_S(S, node);
-                const float xv = xs[node];
+            // step 1: two threads per entity: recompute the hidden layer, back-propagate, write GE
+            for (int base = 0; base < 2 * nn; base += M2_T) {
+                const int t = base + tid, n = t >> 1, h = t & 1, node = c0 + n;
+                const bool valid = n < nn;
+                float dzh[10];
 #pragma unroll
-                for (int k = 0; k < HD; ++k) { E[k] = nb5 * b5[k]; Z[k] = fmaf(xv, U1[k], c1[k]); }
-                gemv20(E, S, W5);
-                store20s(Sa + n * 24, S);
-                *reinterpret_cast<float4*>(Sa + n * 24 + HD) = make_float4(nb5, 0.f, 0.f, 0.f);
-                gemv20(Z, E, U1 + HD);
-                store20s(Ea + n * 24, E);
-                *reinterpret_cast<float4*>(Ea + n * 24 + HD) = make_float4(xv, 1.f, 0.f, 0.f);
-                const float du = x2[node] > 0.f ? dx2[node] : 0.f;
-                float dz[HD], zd[HD];
+                for (int j = 0; j < 10; ++j) dzh[j] = 0.f;
+                if (valid) {
+                    float S[HD], Zh[10];
+                    load_S(S, node);
+                    const float xv = xs[node];
+                    hidden_half(Zh, S, xv, h);
+                    const float du = x2[node] > 0.f ? dx2[node] : 0.f;
 #pragma unroll
-                for (int k = 0; k < HD; ++k) { dz[k] = Z[k] > 0.f ? du * u2[k] : 0.f; zd[k] = fmaxf(Z[k], 0.f) * du; }
-                store20s(dzs + n * HD, dz);
-                store20s(ZD + n * 24, zd);
-                *reinterpret_cast<float4*>(ZD + n * 24 + HD) = make_float4(du, 0.f, 0.f, 0.f);
-                float dE[HD], ge[HD];
-                gemv20t(dE, dz, U1 + HD);
-                store20s(dEs + n * HD, dE);
-                gemv20t(ge, dE, W5);
-                store20s(a.GE + ((size_t)b * Ne + node) * HD, ge);
+                    for (int j2 = 0; j2 < 5; ++j2) {
+                        const int k = 10 * h + 2 * j2;
+                        dzh[2 * j2] = Zh[2 * j2] > 0.f ? du * u2[k] : 0.f;
+                        dzh[2 * j2 + 1] = Zh[2 * j2 + 1] > 0.f ? du * u2[k + 1] : 0.f;
+                        *reinterpret_cast<float2*>(dzs + n * HD + k) = make_float2(dzh[2 * j2], dzh[2 * j2 + 1]);
+                        *reinterpret_cast<float2*>(ZD + n * 24 + k) =
+                            make_float2(fmaxf(Zh[2 * j2], 0.f) * du, fmaxf(Zh[2 * j2 + 1], 0.f) * du);
+                    }
+                    if (h == 0) {
+                        store20s(Sa + n * 24, S);
+                        *reinterpret_cast<float4*>(Sa + n * 24 + HD) = make_float4(xv, 1.f, 0.f, 0.f);
+                        *reinterpret_cast<float4*>(ZD + n * 24 + HD) = make_float4(du, 0.f, 0.f, 0.f);
+                    }
+                }
+                float dz[HD];
+#pragma unroll
+                for (int j = 0; j < 10; ++j) {
+                    const float o = __shfl_xor_sync(0xffffffffu, dzh[j], 1);
+                    dz[j] = h ? o : dzh[j]; dz[10 + j] = h ? dzh[j] : o;
+                }
+                if (valid) {                           // GE_n[q] = sum_k W5U[q][k] dz[k], q = 10 h .. 10 h + 9
+                    float* ge = a.GE + ((size_t)b * Ne + node) * HD + 10 * h;
+#pragma unroll
+                    for (int j2 = 0; j2 < 5; ++j2) {
+                        float g0 = 0.f, g1 = 0.f;
+                        const float* w0 = W5U + (10 * h + 2 * j2) * HD;
+#pragma unroll
+                        for (int k4 = 0; k4 < 5; ++k4) {
+                            const float4 u = *reinterpret_cast<const float4*>(w0 + 4 * k4);
+                            const float4 v = *reinterpret_cast<const float4*>(w0 + HD + 4 * k4);
+                            g0 = fmaf(u.x, dz[4 * k4], g0); g0 = fmaf(u.y, dz[4 * k4 + 1], g0);
+                            g0 = fmaf(u.z, dz[4 * k4 + 2], g0); g0 = fmaf(u.w, dz[4 * k4 + 3], g0);
+                            g1 = fmaf(v.x, dz[4 * k4], g1); g1 = fmaf(v.y, dz[4 * k4 + 1], g1);
+                            g1 = fmaf(v.z, dz[4 * k4 + 2], g1); g1 = fmaf(v.w, dz[4 * k4 + 3], g1);
+                        }
+                        *reinterpret_cast<float2*>(ge + 2 * j2) = make_float2(g0, g1);
+                    }
+                }
             }
             __syncthreads();
-            // step 2: weight gradients = A^T B over the chunk's nodes, 4 x 4 register tiles, 16 node slices per tile
+            // step 2: [S | x | 1]^T dz over the chunk's nodes, 4 x 4 register tiles, 16 node slices per tile
             if (grp < 30) {
                 const int a0 = 4 * (grp / 5), b0 = 4 * (grp % 5);
                 float acc[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-                tile_acc(acc, Ea, 24, dzs, HD, a0, b0, slice, nn);       // rows 0..19 dU1[1+m], 20 dU1[0], 21 dc1
+                tile_acc(acc, Sa, 24, dzs, HD, a0, b0, slice, nn);
                 accA += reduce16(acc, lane);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-                tile_acc(acc, Sa, 24, dEs, HD, a0, b0, slice, nn);       // rows 0..19 dW5, 20 db5 (column nb5)
-                accB += reduce16(acc, lane);
             } else if (grp < 36) {
                 const int kb = 4 * (grp - 30);                             // column sums of ZD: du2[0..19], dc2
                 float cs[4] = {0.f, 0.f, 0.f, 0.f};
@@ -907,13 +975,37 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         }
         if (grp < 30) {
             const int r = 4 * (grp / 5) + (slice >> 2), k = 4 * (grp % 5) + (slice & 3);
-            if (r < HD) { gp[po.nod_w1 + HD + r * HD + k] = accA; gp[po.ent_w5 + r * HD + k] = accB; }
-            else if (r == HD) { gp[po.nod_w1 + k] = accA; gp[po.ent_b5 + k] = accB; }
-            else if (r == HD + 1) gp[po.nod_b1 + k] = accA;
+            if (r < HD + 2) Mx[r * HD + k] = accA;
         } else if (grp < 36 && slice < 4) {
             const int k = 4 * (grp - 30) + slice;
             if (k < HD) gp[po.nod_w2 + k] = accC;
             else if (k == HD) gp[po.nod_b2] = accC;
+        }
+        __syncthreads();
+        // dU1e = W5^T M + nb5 b5 (x) dc1 ; dW5 = M U1e^T ; db5 = nb5 U1e dc1 ; dU1[0] = sum x dz ; dc1 = sum dz
+        const float* dc1v = Mx + (HD + 1) * HD;
+        for (int e = tid; e < 860; e += M2_T) {
+            float acc = 0.f;
+            if (e < 400) {
+                const int m = e / HD, k = e - m * HD;
+#pragma unroll
+                for (int q = 0; q < HD; ++q) acc = fmaf(W5[q * HD + m], Mx[q * HD + k], acc);
+                gp[po.nod_w1 + HD + e] = fmaf(nb5 * b5[m], dc1v[k], acc);
+            } else if (e < 800) {
+                const int q = (e - 400) / HD, m = (e - 400) - q * HD;
+#pragma unroll
+                for (int k = 0; k < HD; ++k) acc = fmaf(Mx[q * HD + k], U1[(1 + m) * HD + k], acc);
+                gp[po.ent_w5 + (e - 400)] = acc;
+            } else if (e < 820) {
+                const int m = e - 800;
+#pragma unroll
+                for (int k = 0; k < HD; ++k) acc = fmaf(U1[(1 + m) * HD + k], dc1v[k], acc);
+                gp[po.ent_b5 + m] = nb5 * acc;
+            } else if (e < 840) {
+                gp[po.nod_w1 + (e - 820)] = Mx[HD * HD + (e - 820)];
+            } else {
+                gp[po.nod_b1 + (e - 840)] = dc1v[e - 840];
+            }
         }
     }
     M2_PHASE(11);

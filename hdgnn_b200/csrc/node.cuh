@@ -652,7 +652,10 @@ __global__ void __launch_bounds__(1024) adam_kernel(float* p, const float* g, fl
         const int o = tid == 0 ? o_t1 : o_t2;
         tn[tid] = sqrtf(p[o] * p[o] + p[o + 1] * p[o + 1]);
     }
-    if (tid == 32) tn[2] = lr * (float)(sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t)));
+    if (tid == 32) {       // 1 - b^t = -expm1(t log b): full float precision without the fp64 pipe
+        const float omb2 = -expm1f((float)t * logf(b2)), omb1 = -expm1f((float)t * logf(b1));
+        tn[2] = lr * sqrtf(omb2) / omb1;
+    }
     float sq = 0.f;
     for (int i = tid; i < n; i += blockDim.x) sq = fmaf(p[i], p[i], sq);
     const float l2 = block_sum(sq, scratch);

@@ -97,34 +97,77 @@ __device__ __forceinline__ void load_words(uint32_t (&w)[CW], const uint32_t* ro
     for (int s = 0; s < CW; ++s) w[s] = t[s];
 }
 
+// Sum 8 per-lane values (4 channels of two rows: a = row r, c = row r2) over the 32 lanes.  Afterwards the
+// lanes with (lane & 3) == 0 hold the total of row ((lane >> 4) & 1), channel reduce8_channel(lane).
+__device__ __forceinline__ float reduce8(u64 a01, u64 a23, u64 c01, u64 c23, int lane) {
+    float a0, a1, a2, a3, c0, c1, c2, c3;
+    upk2(a01, a0, a1); upk2(a23, a2, a3); upk2(c01, c0, c1); upk2(c23, c2, c3);
+    const bool h16 = lane & 16;
+    float k0 = h16 ? c0 : a0, k1 = h16 ? c1 : a1, k2 = h16 ? c2 : a2, k3 = h16 ? c3 : a3;
+    const float s0 = h16 ? a0 : c0, s1 = h16 ? a1 : c1, s2 = h16 ? a2 : c2, s3 = h16 ? a3 : c3;
+    k0 += __shfl_xor_sync(0xffffffffu, s0, 16); k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+    k2 += __shfl_xor_sync(0xffffffffu, s2, 16); k3 += __shfl_xor_sync(0xffffffffu, s3, 16);
+    const bool h8 = lane & 8;
+    float m0 = h8 ? k2 : k0, m1 = h8 ? k3 : k1;
+    const float t0 = h8 ? k0 : k2, t1 = h8 ? k1 : k3;
+    m0 += __shfl_xor_sync(0xffffffffu, t0, 8); m1 += __shfl_xor_sync(0xffffffffu, t1, 8);
+    const bool h4 = lane & 4;
+    float k = h4 ? m1 : m0;
+    const float t = h4 ? m0 : m1;
+    k += __shfl_xor_sync(0xffffffffu, t, 4);
+    k += __shfl_xor_sync(0xffffffffu, k, 2);
+    k += __shfl_xor_sync(0xffffffffu, k, 1);
+    return k;
+}
+__device__ __forceinline__ int reduce8_channel(int lane) { return 2 * ((lane >> 3) & 1) + ((lane >> 2) & 1); }
+
 // ---- forward pair sum ------------------------------------------------------------------------
 //   P01   smem [rows][KG][2][4], 32-byte aligned       bits  smem [rows][WP], this pass's words first
 //   Q     this lane's column values per segment (packed), NEG_BIG in both halves for columns >= N
 //   col   column accumulators (in/out)                  rowacc smem [rows][20]
 // ACCUM: add to rowacc instead of storing (later column passes of a wide grid).
+// One row of one warp: per-lane partial row sums rp0/rp1 (channels 0,1 / 2,3), column sums updated.
+template <int CW>
+__device__ __forceinline__ void sweep2_fwd_row(const float* P01, const uint32_t* bits, int WP, int r, int kg, uint32_t lmask,
+                                               const u64 (&Q)[CW][2], u64 (&col)[CW][2], u64& rp0, u64& rp1) {
+    uint32_t w[CW];
+    load_words<CW>(w, bits + (size_t)r * WP);
+    const float* prow0 = P01 + (size_t)r * PROW + kg * 8;
+    const float* prow1 = prow0 + 4;
+    rp0 = 0ull; rp1 = 0ull;
+#pragma unroll
+    for (int sg = 0; sg < CW; ++sg) {
+        const ulonglong2 p = *reinterpret_cast<const ulonglong2*>((w[sg] & lmask) ? prow1 : prow0);
+        const u64 h0 = relu2(add2(p.x, Q[sg][0])), h1 = relu2(add2(p.y, Q[sg][1]));
+        col[sg][0] = add2(col[sg][0], h0); col[sg][1] = add2(col[sg][1], h1);
+        rp0 = add2(rp0, h0); rp1 = add2(rp1, h1);
+    }
+}
+
+template <bool ACCUM>
+__device__ __forceinline__ void row_store(float* rowacc, int r, int k, float tot) {
+    float* dst = rowacc + (size_t)r * HD + k;
+    if (ACCUM) *dst += tot; else *dst = tot;
+}
+
+// rows are taken two at a time so that one 8-value transpose-reduce serves both
 template <int CW, bool ACCUM>
 __device__ __forceinline__ void sweep2_fwd(const float* P01, const uint32_t* bits, int WP, int nrows, int rg, int nrg,
                                            int kg, const u64 (&Q)[CW][2], u64 (&col)[CW][2], float* rowacc, int lane) {
-    const int ch = reduce4_channel(lane);
     const uint32_t lmask = 1u << lane;
-    for (int r = rg; r < nrows; r += nrg) {
-        uint32_t w[CW];
-        load_words<CW>(w, bits + (size_t)r * WP);
-        const float* prow0 = P01 + (size_t)r * PROW + kg * 8;
-        const float* prow1 = prow0 + 4;
-        u64 rp0 = 0ull, rp1 = 0ull;
-#pragma unroll
-        for (int sg = 0; sg < CW; ++sg) {
-            const ulonglong2 p = *reinterpret_cast<const ulonglong2*>((w[sg] & lmask) ? prow1 : prow0);
-            const u64 h0 = relu2(add2(p.x, Q[sg][0])), h1 = relu2(add2(p.y, Q[sg][1]));
-            col[sg][0] = add2(col[sg][0], h0); col[sg][1] = add2(col[sg][1], h1);
-            rp0 = add2(rp0, h0); rp1 = add2(rp1, h1);
-        }
-        const float tot = reduce4(rp0, rp1, lane);
-        if ((lane & 7) == 0) {
-            float* dst = rowacc + (size_t)r * HD + kg * 4 + ch;
-            if (ACCUM) *dst += tot; else *dst = tot;
-        }
+    int r = rg;
+    for (; r + nrg < nrows; r += 2 * nrg) {
+        u64 a0, a1, c0, c1;
+        sweep2_fwd_row<CW>(P01, bits, WP, r, kg, lmask, Q, col, a0, a1);
+        sweep2_fwd_row<CW>(P01, bits, WP, r + nrg, kg, lmask, Q, col, c0, c1);
+        const float tot = reduce8(a0, a1, c0, c1, lane);
+        if ((lane & 3) == 0) row_store<ACCUM>(rowacc, (lane & 16) ? r + nrg : r, kg * 4 + reduce8_channel(lane), tot);
+    }
+    if (r < nrows) {
+        u64 a0, a1;
+        sweep2_fwd_row<CW>(P01, bits, WP, r, kg, lmask, Q, col, a0, a1);
+        const float tot = reduce4(a0, a1, lane);
+        if ((lane & 7) == 0) row_store<ACCUM>(rowacc, r, kg * 4 + reduce4_channel(lane), tot);
     }
 }
 
@@ -132,36 +175,48 @@ __device__ __forceinline__ void sweep2_fwd(const float* P01, const uint32_t* bit
 //   v_ij[k] = [pre_ij[k] > 0] * (GR_i[k] + GC_j[k])
 //   rowacc = sum_j v ; col += sum_i v ; lacc += sum_{l_ij = 1} v
 //   GRt   smem [rows][20]
+template <int CW>
+__device__ __forceinline__ void sweep2_bwd_row(const float* P01, const float* GRt, const uint32_t* bits, int WP, int r, int kg,
+                                               uint32_t lmask, const u64 (&Q)[CW][2], const u64 (&GC)[CW][2],
+                                               u64 (&col)[CW][2], u64 (&lacc)[2], u64& rp0, u64& rp1) {
+    uint32_t w[CW];
+    load_words<CW>(w, bits + (size_t)r * WP);
+    const float* prow0 = P01 + (size_t)r * PROW + kg * 8;
+    const float* prow1 = prow0 + 4;
+    const ulonglong2 g = *reinterpret_cast<const ulonglong2*>(GRt + (size_t)r * HD + kg * 4);
+    rp0 = 0ull; rp1 = 0ull;
+#pragma unroll
+    for (int sg = 0; sg < CW; ++sg) {
+        const bool bit = (w[sg] & lmask) != 0u;
+        const ulonglong2 p = *reinterpret_cast<const ulonglong2*>(bit ? prow1 : prow0);
+        const u64 v0 = gate2(add2(p.x, Q[sg][0]), add2(g.x, GC[sg][0]));
+        const u64 v1 = gate2(add2(p.y, Q[sg][1]), add2(g.y, GC[sg][1]));
+        col[sg][0] = add2(col[sg][0], v0); col[sg][1] = add2(col[sg][1], v1);
+        rp0 = add2(rp0, v0); rp1 = add2(rp1, v1);
+        const float lf = bit ? 1.f : 0.f;
+        const u64 l2 = pk2(lf, lf);
+        lacc[0] = fma2(l2, v0, lacc[0]); lacc[1] = fma2(l2, v1, lacc[1]);
+    }
+}
+
 template <int CW, bool ACCUM>
 __device__ __forceinline__ void sweep2_bwd(const float* P01, const float* GRt, const uint32_t* bits, int WP, int nrows,
                                            int rg, int nrg, int kg, const u64 (&Q)[CW][2], const u64 (&GC)[CW][2],
                                            u64 (&col)[CW][2], u64 (&lacc)[2], float* rowacc, int lane) {
-    const int ch = reduce4_channel(lane);
     const uint32_t lmask = 1u << lane;
-    for (int r = rg; r < nrows; r += nrg) {
-        uint32_t w[CW];
-        load_words<CW>(w, bits + (size_t)r * WP);
-        const float* prow0 = P01 + (size_t)r * PROW + kg * 8;
-        const float* prow1 = prow0 + 4;
-        const ulonglong2 g = *reinterpret_cast<const ulonglong2*>(GRt + (size_t)r * HD + kg * 4);
-        u64 rp0 = 0ull, rp1 = 0ull;
-#pragma unroll
-        for (int sg = 0; sg < CW; ++sg) {
-            const bool bit = (w[sg] & lmask) != 0u;
-            const ulonglong2 p = *reinterpret_cast<const ulonglong2*>(bit ? prow1 : prow0);
-            const u64 v0 = gate2(add2(p.x, Q[sg][0]), add2(g.x, GC[sg][0]));
-            const u64 v1 = gate2(add2(p.y, Q[sg][1]), add2(g.y, GC[sg][1]));
-            col[sg][0] = add2(col[sg][0], v0); col[sg][1] = add2(col[sg][1], v1);
-            rp0 = add2(rp0, v0); rp1 = add2(rp1, v1);
-            const float lf = bit ? 1.f : 0.f;
-            const u64 l2 = pk2(lf, lf);
-            lacc[0] = fma2(l2, v0, lacc[0]); lacc[1] = fma2(l2, v1, lacc[1]);
-        }
-        const float tot = reduce4(rp0, rp1, lane);
-        if ((lane & 7) == 0) {
-            float* dst = rowacc + (size_t)r * HD + kg * 4 + ch;
-            if (ACCUM) *dst += tot; else *dst = tot;
-        }
+    int r = rg;
+    for (; r + nrg < nrows; r += 2 * nrg) {
+        u64 a0, a1, c0, c1;
+        sweep2_bwd_row<CW>(P01, GRt, bits, WP, r, kg, lmask, Q, GC, col, lacc, a0, a1);
+        sweep2_bwd_row<CW>(P01, GRt, bits, WP, r + nrg, kg, lmask, Q, GC, col, lacc, c0, c1);
+        const float tot = reduce8(a0, a1, c0, c1, lane);
+        if ((lane & 3) == 0) row_store<ACCUM>(rowacc, (lane & 16) ? r + nrg : r, kg * 4 + reduce8_channel(lane), tot);
+    }
+    if (r < nrows) {
+        u64 a0, a1;
+        sweep2_bwd_row<CW>(P01, GRt, bits, WP, r, kg, lmask, Q, GC, col, lacc, a0, a1);
+        const float tot = reduce4(a0, a1, lane);
+        if ((lane & 7) == 0) row_store<ACCUM>(rowacc, r, kg * 4 + reduce4_channel(lane), tot);
     }
 }
 

@@ -146,6 +146,15 @@ class Engine:
         check(lib.hdgnn_adam_step(self._h, _p(params), _p(grads), _p(m), _p(v), _p(step_counter), lr, beta1, beta2,
                                   eps, _p(reg_losses), self._stream()), self._h)
 
+    def train_step(self, b: DeviceBatch, params, m, v, step_counter, loss3, probs=None, logits=None,
+                   lr=3e-4, beta1=0.9, beta2=0.999, eps=1e-8):
+        """One fused training step on one GPU (forward, backward, regularisers, TF1 Adam): the body of
+        sess.run([..., trainer]) of model_2.py:369-383.  loss3 (3,) receives {CE, loss_map, loss_para}."""
+        self._check_batch(b, params)
+        check(lib.hdgnn_train_step(self._h, b.B, _p(b.adj), self.pe, _p(b.x), _p(b.hmap), _p(b.L), _p(b.Y), self.pc,
+                                   _p(params), _p(m), _p(v), _p(step_counter), lr, beta1, beta2, eps,
+                                   _p(logits), _p(probs), _p(loss3), self._stream()), self._h)
+
     # -- host-buffer entry points (H2D + compute + D2H on one stream) -----------------------------
     def train_step_host(self, adj, x, hmap, L, Y, params, m, v, step_counter, loss3, probs=None,
                         lr=3e-4, beta1=0.9, beta2=0.999, eps=1e-8):

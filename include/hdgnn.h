@@ -114,6 +114,19 @@ int hdgnn_adam_step(hdgnn_handle_t h, float* params, const float* grads, float* 
                     int32_t* step_counter, float lr, float beta1, float beta2, float eps,
                     float* reg_losses, void* stream);
 
+/* One whole training step on device-resident inputs: forward, backward, regularisers and TF1 Adam
+ * (= hdgnn_forward_backward with B_global = B followed by hdgnn_adam_step, with the gradient
+ * reduction and the optimizer fused into one launch).  Replaces one
+ * sess.run([merged, C_edge_output2, loss_Hedge_mse, loss_map, theta, trainer]) of model_2.py:369-383
+ * on ONE GPU (with commit sharding use hdgnn_forward_backward + all-reduce + hdgnn_adam_step).
+ * loss3 (device, 3 floats) receives {CE, loss_map, loss_para}; probs / logits may be NULL. */
+int hdgnn_train_step(hdgnn_handle_t h, int B,
+                     const uint8_t* adj, int adj_pitch, const float* x, const int32_t* hmap,
+                     const int32_t* L, const uint8_t* Y, int y_pitch,
+                     float* params, float* m, float* v, int32_t* step_counter,
+                     float lr, float beta1, float beta2, float eps,
+                     float* logits, float* probs, float* loss3, void* stream);
+
 /* One whole training step from HOST buffers (pinned recommended): H2D copies of the five
  * compact inputs, forward, backward, Adam, and a D2H copy of {CE, loss_map, loss_para} into
  * loss3_host, all enqueued on `stream`.  Un-pitched host layouts: adj (B,Ne,Ne), Y (B,Nc,Nc).

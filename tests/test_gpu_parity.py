@@ -209,3 +209,34 @@ def test_argument_validation():
     with pytest.raises(HdgnnError):
         eng.forward(db, torch.zeros(eng.n_params, device="cuda"))     # B > max_batch
     eng.close()
+
+
+@pytest.mark.parametrize("variant", [1, 2, 4])
+def test_fused_train_step_matches_separate_calls(variant):
+    """hdgnn_train_step (one call) == hdgnn_forward_backward + hdgnn_adam_step, and both follow the oracle's
+    TF-Adam trajectory for three steps."""
+    from hdgnn_b200.engine import Engine, DeviceBatch
+    B, Ne, Nc = 5, 45, 19
+    cb = make_commits(B, Ne, Nc, seed=33, p_short=0.5)
+    flat = _params(variant)
+    eng = Engine(Ne, Nc, variant=variant, max_batch=B)
+    db = DeviceBatch.from_numpy(cb.adj, cb.x, cb.hmap, cb.L, cb.Y, eng.tdev)
+    pa = flat.float().cuda(); ma = torch.zeros_like(pa); va = torch.zeros_like(pa)
+    pb = flat.float().cuda(); mb = torch.zeros_like(pb); vb = torch.zeros_like(pb)
+    sa = torch.zeros(1, dtype=torch.int32, device="cuda"); sb = torch.zeros(1, dtype=torch.int32, device="cuda")
+    loss3 = torch.zeros(3, device="cuda"); reg = torch.zeros(2, device="cuda")
+    p_ref = flat.clone(); m_ref = torch.zeros_like(flat); v_ref = torch.zeros_like(flat)
+    for t in range(1, 4):
+        eng.train_step(db, pa, ma, va, sa, loss3)
+        _, _, loss, g = eng.forward_backward(db, pb)
+        eng.adam_step(pb, g, mb, vb, sb, reg_losses=reg)
+        _, ce, _, grad, _ = O.train_loss_and_grad(variant, p_ref, cb.adj, cb.x, cb.hmap, cb.L, cb.Y)
+        p_ref, m_ref, v_ref = O.tf_adam_step(p_ref, grad, m_ref, v_ref, t)
+        torch.cuda.synchronize()
+        assert int(sa.item()) == t and int(sb.item()) == t
+        assert torch.allclose(pa, pb, rtol=1e-6, atol=1e-9)
+        assert abs(loss3[0].item() - loss.item()) <= 1e-6 * abs(loss.item())
+        assert torch.allclose(loss3[1:], reg, rtol=1e-6)
+        assert relerr(pa.cpu().numpy(), p_ref.numpy()) < TIGHT
+        assert abs(loss3[0].item() - float(ce)) < TIGHT * float(ce)
+    eng.close()
