@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         float* partC = scratch;                         // [nchunk][Lb][4]
         for (int t = tid; t < nchunk * Lb; t += M2_T) {
             const int c = t / Lb, me = t - c * Lb;
-            const int lo = (int)(((long long)c * Lb) / nchunk), hi = (int)(((long long)(c + 1) * Lb) / nchunk);
+            const int lo = (c * Lb) / nchunk, hi = ((c + 1) * Lb) / nchunk;
             float q0 = 0.f, q1 = 0.f;
             int q3 = 0, cnt = 0;
 #pragma unroll
@@ -400,19 +400,24 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
                 if (l0 >= l1) continue;
                 const int q = l0 * m + me - (part == 0 ? 1 : 0);
                 int gi = q / n, pp = q - gi * n;
-                for (int li = l0; li < l1; ++li) {
+                const int trips = l1 - l0;
+                cnt += trips;
+#pragma unroll 4
+                for (int it = 0; it < trips; ++it) {    // counted and branch-free: m < n, at most one row wrap per step
                     const int gj = pp + (pp >= gi);
                     q0 += x2[gi]; q1 += x2[gj];
                     q3 += (ebits[gi * WPe + (gj >> 5)] >> (gj & 31)) & 1u;
-                    ++cnt;
                     pp += m;
-                    if (pp >= n) { pp -= n; ++gi; }
+                    const int w = pp >= n;
+                    pp -= w ? n : 0;
+                    gi += w;
                 }
             }
             float* pc = partC + ((size_t)c * Lb + me) * 4;
             pc[0] = q0; pc[1] = q1; pc[2] = (float)(cnt - q3); pc[3] = (float)q3;
         }
         __syncthreads();
+        M2_PHASE(14);
         for (int li = tid; li < Lb; li += M2_T) {
             const int qs = li * m;
             int g = qs / n, p0 = qs - g * n, rem = m, c3 = 0;
@@ -828,6 +833,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         dl[idx] = (i < Lb && hm[i] >= 0) ? dnb[4 * hm[i] + chn] : 0.f;
     }
     __syncthreads();
+    M2_PHASE(12);
     if (ident) {
         float p0 = 0.f, p1 = 0.f;
         for (int i = tid; i < Ne; i += M2_T) { p0 += dl[4 * i]; p1 += dl[4 * i + 1]; }
@@ -848,26 +854,44 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         int nchunk = M2_T / Ne;
         nchunk = nchunk < 1 ? 1 : (nchunk > 4 ? 4 : nchunk);
         float* partC = scratch;                         // [nchunk][Ne]
+        float* dl1 = TP;                                // channel 1 of dl, planar (TP is dead after the forward)
+        for (int i = tid; i < Ne; i += M2_T) dl1[i] = dl[4 * i + 1];
+        __syncthreads();
         for (int t = tid; t < nchunk * Ne; t += M2_T) {
             const int c = t / Ne, me = t - c * Ne;
-            const int lo = (int)(((long long)c * Ne) / nchunk), hi = (int)(((long long)(c + 1) * Ne) / nchunk);
+            const int lo = (c * Ne) / nchunk, hi = ((c + 1) * Ne) / nchunk;
             float acc = 0.f;
 #pragma unroll
             for (int part = 0; part < 2; ++part) {      // gi < gj (flat column gj - 1), then gi > gj (flat column gj)
                 const int g0 = part == 0 ? lo : max(lo, me + 1), g1 = part == 0 ? min(hi, me) : hi;
                 if (g0 >= g1) continue;
-                int q = g0 * n + me - (part == 0 ? 1 : 0);
+                const int q = g0 * n + me - (part == 0 ? 1 : 0);
+                if (q >= qmax) continue;
                 int li = q / m, sloc = q - li * m;
-                for (int gi = g0; gi < g1 && q < qmax; ++gi) {
-                    const int lj = sloc + (sloc >= li);
-                    acc += dl[4 * li + 1] + dl[4 * lj + 1];
-                    q += n; sloc += d; ++li;
-                    while (sloc >= m) { sloc -= m; ++li; }
+                const int trips = min(g1 - g0, (qmax - 1 - q) / n + 1);      // rows with flat index below qmax
+                if (d < m) {                            // counted and branch-free: at most one local-row wrap per step
+#pragma unroll 4
+                    for (int it = 0; it < trips; ++it) {
+                        const int lj = sloc + (sloc >= li);
+                        acc += dl1[li] + dl1[lj];
+                        sloc += d;
+                        const int w = sloc >= m;
+                        sloc -= w ? m : 0;
+                        li += 1 + w;
+                    }
+                } else {
+                    for (int it = 0; it < trips; ++it) {
+                        const int lj = sloc + (sloc >= li);
+                        acc += dl1[li] + dl1[lj];
+                        sloc += d; ++li;
+                        while (sloc >= m) { sloc -= m; ++li; }
+                    }
                 }
             }
             partC[(size_t)c * Ne + me] = acc;
         }
         __syncthreads();
+        M2_PHASE(13);
         for (int gi = tid; gi < Ne; gi += M2_T) {
             const int qa = gi * n, qb = min(qa + n, qmax);
             float acc = 0.f;

@@ -21,5 +21,11 @@ ident = cb.L == Ne
 print(f"commits {B}, L==Ne for {int(ident.sum())}")
 for i, n in enumerate(names):
     print(f"{n:20s} mean {d[:, i].mean():9.0f}  max {d[:, i].max():9.0f}   ident {d[ident, i].mean():9.0f}  general {d[~ident, i].mean() if (~ident).any() else 0:9.0f}")
+g = ~ident
+if g.any():
+    print("general commits: J (9->12) %.0f | K gather (12->13) %.0f | K rest (13->10) %.0f | D: scan+TP gather (2->14) %.0f, rest (14->3) %.0f" % (
+        (clk[g, 12] - clk[g, 9]).mean(), (clk[g, 13] - clk[g, 12]).mean(), (clk[g, 10] - clk[g, 13]).mean(),
+        (clk[g, 14] - clk[g, 2]).mean(), (clk[g, 3] - clk[g, 14]).mean()))
+print("ident commits: J (9->12) %.0f | K (12->10) %.0f" % ((clk[ident, 12] - clk[ident, 9]).mean(), (clk[ident, 10] - clk[ident, 12]).mean()))
 tot = clk[:, 11] - clk[:, 0]
 print(f"total mean {tot.mean():.0f} max {tot.max():.0f} cycles")
