@@ -108,8 +108,12 @@ struct hdgnn_handle_s {
     bool prof = false;
     cudaEvent_t prof_start = nullptr;
     std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> prof_ev;
-    // host-entry staging + CUDA graphs
-    std::map<std::tuple<int, int, const void*, const void*>, cudaGraphExec_t> graphs;
+    // host-entry staging: two slots filled on a private copy stream so the H2D copies of call k+1 overlap
+    // the kernels of call k (both calls only enqueue work; ordering is by events)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    bool done_valid[2] = {false, false};
+    int slot = 0, cur = 0;
 };
 
 namespace {
@@ -721,9 +725,12 @@ int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out) {
         {"GRE", B * Ne * HD * f, h->edge}, {"GCE", B * Ne * HD * f, h->edge},
         {"RSED", B * Ne * HD * f, h->edge}, {"CSEDP", B * Se * Ne * HD * f, h->edge}, {"LSEP", B * Se * HD * f, h->edge},
         // staging for the *_host entry points
-        {"H_ADJ", B * Ne * (size_t)h->pe, true}, {"H_Y", B * Nc * (size_t)h->pc, true}, {"H_X", B * Ne * f, true},
-        {"H_ADJ_RAW", B * Ne * Ne, h->pe != h->Ne}, {"H_Y_RAW", B * Nc * Nc, h->pc != h->Nc},
-        {"H_HMAP", B * Ne * sizeof(int32_t), true}, {"H_L", B * sizeof(int32_t), true},
+        {"H_ADJ0", B * Ne * (size_t)h->pe, true}, {"H_Y0", B * Nc * (size_t)h->pc, true}, {"H_X0", B * Ne * f, true},
+        {"H_ADJ_RAW0", B * Ne * Ne, h->pe != h->Ne}, {"H_Y_RAW0", B * Nc * Nc, h->pc != h->Nc},
+        {"H_HMAP0", B * Ne * sizeof(int32_t), true}, {"H_L0", B * sizeof(int32_t), true},
+        {"H_ADJ1", B * Ne * (size_t)h->pe, true}, {"H_Y1", B * Nc * (size_t)h->pc, true}, {"H_X1", B * Ne * f, true},
+        {"H_ADJ_RAW1", B * Ne * Ne, h->pe != h->Ne}, {"H_Y_RAW1", B * Nc * Nc, h->pc != h->Nc},
+        {"H_HMAP1", B * Ne * sizeof(int32_t), true}, {"H_L1", B * sizeof(int32_t), true},
         {"H_PROBS", B * 2 * Nc * (Nc - 1) * f, true}, {"H_LOSS", 4 * f, true}, {"H_GRADS", (size_t)h->po.total * f, true},
     };
     for (auto& p : plan) {
@@ -735,6 +742,15 @@ int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out) {
             return rc;
         }
     }
+    bool ok = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; ++i)
+        ok = cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+        g_create_error = "cudaStreamCreate / cudaEventCreate failed";
+        hdgnn_destroy(h);
+        return HDGNN_E_CUDA;
+    }
     *out = h;
     return HDGNN_OK;
 }
@@ -742,7 +758,8 @@ int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out) {
 int hdgnn_destroy(hdgnn_handle_t h) {
     if (!h) return HDGNN_OK;
     cudaSetDevice(h->cfg.device);
-    for (auto& g : h->graphs) cudaGraphExecDestroy(g.second);
+    if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    for (int i = 0; i < 2; ++i) { if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]); if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]); }
     for (auto& kv : h->ws) cudaFree(kv.second.p);
     delete h;
     return HDGNN_OK;
@@ -818,9 +835,22 @@ int hdgnn_train_step(hdgnn_handle_t h, int B, const uint8_t* adj, int adj_pitch,
     return run_step(h, B, B, in, logits, probs, loss3, F(h, "H_GRADS"), &ad, (cudaStream_t)stream);
 }
 
+// Host buffers -> staging slot `h->cur` (un-pitched rows are re-pitched on the device).  Outside stream capture the
+// copies run on the handle's copy stream: slot s is reused only after the kernels that read it (two calls ago)
+// have finished, and the caller's stream waits for the copies, so consecutive calls overlap copy and compute.
+static std::string slot_name(const char* base, int slot) { return std::string(base) + (slot ? "1" : "0"); }
+
 static int stage_inputs(hdgnn_handle_t h, int B, const uint8_t* adj_host, const float* x_host, const int32_t* hmap_host,
                         const int32_t* L_host, const uint8_t* Y_host, cudaStream_t st) {
     const size_t Ne = h->Ne, Nc = h->Nc;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    const bool side = cap == cudaStreamCaptureStatusNone;
+    const int slot = h->slot;
+    h->cur = slot;
+    h->slot ^= 1;
+    cudaStream_t cs = side ? h->copy_stream : st;
+    if (side && h->done_valid[slot]) CK(h, cudaStreamWaitEvent(cs, h->ev_done[slot], 0));
     const uint8_t* srcs[2] = {adj_host, Y_host};
     const char* raw[2] = {"H_ADJ_RAW", "H_Y_RAW"};
     const char* dstn[2] = {"H_ADJ", "H_Y"};
@@ -828,21 +858,45 @@ static int stage_inputs(hdgnn_handle_t h, int B, const uint8_t* adj_host, const 
     const int pitch[2] = {h->pe, h->pc};
     for (int t = 0; t < 2; ++t) {
         const size_t rows = (size_t)B * n[t];
+        void* dst = h->ws[slot_name(dstn[t], slot)].p;
         if (pitch[t] == (int)n[t]) {
-            CK(h, cudaMemcpyAsync(h->ws[dstn[t]].p, srcs[t], rows * n[t], cudaMemcpyHostToDevice, st));
+            CK(h, cudaMemcpyAsync(dst, srcs[t], rows * n[t], cudaMemcpyHostToDevice, cs));
         } else {
-            CK(h, cudaMemcpyAsync(h->ws[raw[t]].p, srcs[t], rows * n[t], cudaMemcpyHostToDevice, st));
+            void* rawp = h->ws[slot_name(raw[t], slot)].p;
+            CK(h, cudaMemcpyAsync(rawp, srcs[t], rows * n[t], cudaMemcpyHostToDevice, cs));
             const size_t work = rows * (size_t)pitch[t] / 4;
             int blocks = (int)((work + 255) / 256);
             if (blocks > 148 * 8) blocks = 148 * 8;
-            PROF_BEGIN(h, st);
-            repitch_kernel<<<blocks, 256, 0, st>>>((const uint8_t*)h->ws[raw[t]].p, (uint8_t*)h->ws[dstn[t]].p, rows, (int)n[t], pitch[t]);
-            LAUNCH_CHECK(h, "repitch_kernel", st);
+            PROF_BEGIN(h, cs);
+            repitch_kernel<<<blocks, 256, 0, cs>>>((const uint8_t*)rawp, (uint8_t*)dst, rows, (int)n[t], pitch[t]);
+            LAUNCH_CHECK(h, "repitch_kernel", cs);
         }
     }
-    CK(h, cudaMemcpyAsync(h->ws["H_X"].p, x_host, (size_t)B * Ne * sizeof(float), cudaMemcpyHostToDevice, st));
-    CK(h, cudaMemcpyAsync(h->ws["H_HMAP"].p, hmap_host, (size_t)B * Ne * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    CK(h, cudaMemcpyAsync(h->ws["H_L"].p, L_host, (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CK(h, cudaMemcpyAsync(h->ws[slot_name("H_X", slot)].p, x_host, (size_t)B * Ne * sizeof(float), cudaMemcpyHostToDevice, cs));
+    CK(h, cudaMemcpyAsync(h->ws[slot_name("H_HMAP", slot)].p, hmap_host, (size_t)B * Ne * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
+    CK(h, cudaMemcpyAsync(h->ws[slot_name("H_L", slot)].p, L_host, (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
+    if (side) {
+        CK(h, cudaEventRecord(h->ev_copy[slot], cs));
+        CK(h, cudaStreamWaitEvent(st, h->ev_copy[slot], 0));
+    }
+    return HDGNN_OK;
+}
+
+// device-side views of the staging slot filled by the last stage_inputs call
+static Inputs staged_inputs(hdgnn_handle_t h, const float* params) {
+    const int s = h->cur;
+    return Inputs{(const uint8_t*)h->ws[slot_name("H_ADJ", s)].p, (const float*)h->ws[slot_name("H_X", s)].p,
+                  (const int32_t*)h->ws[slot_name("H_HMAP", s)].p, (const int32_t*)h->ws[slot_name("H_L", s)].p,
+                  (const uint8_t*)h->ws[slot_name("H_Y", s)].p, params};
+}
+
+// the kernels reading slot h->cur have been enqueued on `st`: the slot may be refilled once they are done
+static int release_slot(hdgnn_handle_t h, cudaStream_t st) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    if (cap != cudaStreamCaptureStatusNone) return HDGNN_OK;
+    CK(h, cudaEventRecord(h->ev_done[h->cur], st));
+    h->done_valid[h->cur] = true;
     return HDGNN_OK;
 }
 
@@ -858,17 +912,35 @@ int hdgnn_train_step_host(hdgnn_handle_t h, int B, const uint8_t* adj_host, cons
     h->launches = 0;
     int rc = stage_inputs(h, B, adj_host, x_host, hmap_host, L_host, Y_host, st);
     if (rc) return rc;
-    Inputs in{(const uint8_t*)h->ws["H_ADJ"].p, F(h, "H_X"), (const int32_t*)h->ws["H_HMAP"].p,
-              (const int32_t*)h->ws["H_L"].p, (const uint8_t*)h->ws["H_Y"].p, params};
+    Inputs in = staged_inputs(h, params);
     float* probs_d = probs_host ? F(h, "H_PROBS") : nullptr;
     float* loss_d = F(h, "H_LOSS");
     AdamArgs ad{params, m, v, step_counter, lr, beta1, beta2, eps, loss_d + 1};
     rc = run_step(h, B, B, in, nullptr, probs_d, loss_d, F(h, "H_GRADS"), &ad, st);
     if (rc) return rc;
+    if ((rc = release_slot(h, st))) return rc;
     if (probs_host)
         CK(h, cudaMemcpyAsync(probs_host, probs_d, (size_t)B * 2 * h->Nc * (h->Nc - 1) * sizeof(float), cudaMemcpyDeviceToHost, st));
     CK(h, cudaMemcpyAsync(loss3_host, loss_d, 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
     return HDGNN_OK;
+}
+
+int hdgnn_forward_backward_host(hdgnn_handle_t h, int B, int B_global, const uint8_t* adj_host, const float* x_host,
+                                const int32_t* hmap_host, const int32_t* L_host, const uint8_t* Y_host, const float* params,
+                                float* probs, float* loss, float* grads, void* stream) {
+    if (!h) return HDGNN_E_INVALID;
+    if (B < 1 || B > h->cfg.max_batch) return fail(h, HDGNN_E_INVALID, "B out of range [1, max_batch]");
+    if (!adj_host || !x_host || !hmap_host || !L_host || !Y_host || !params || !grads)
+        return fail(h, HDGNN_E_INVALID, "null pointer");
+    if (B_global < B) return fail(h, HDGNN_E_INVALID, "B_global < B");
+    cudaStream_t st = (cudaStream_t)stream;
+    h->launches = 0;
+    int rc = stage_inputs(h, B, adj_host, x_host, hmap_host, L_host, Y_host, st);
+    if (rc) return rc;
+    Inputs in = staged_inputs(h, params);
+    rc = run_step(h, B, B_global, in, nullptr, probs, loss, grads, nullptr, st);
+    if (rc) return rc;
+    return release_slot(h, st);
 }
 
 int hdgnn_infer_host(hdgnn_handle_t h, int B, const uint8_t* adj_host, const float* x_host, const int32_t* hmap_host,
@@ -882,10 +954,10 @@ int hdgnn_infer_host(hdgnn_handle_t h, int B, const uint8_t* adj_host, const flo
     h->launches = 0;
     int rc = stage_inputs(h, B, adj_host, x_host, hmap_host, L_host, Y_host, st);
     if (rc) return rc;
-    Inputs in{(const uint8_t*)h->ws["H_ADJ"].p, F(h, "H_X"), (const int32_t*)h->ws["H_HMAP"].p,
-              (const int32_t*)h->ws["H_L"].p, (const uint8_t*)h->ws["H_Y"].p, params};
+    Inputs in = staged_inputs(h, params);
     rc = run_step(h, B, B, in, nullptr, F(h, "H_PROBS"), F(h, "H_LOSS"), nullptr, nullptr, st);
     if (rc) return rc;
+    if ((rc = release_slot(h, st))) return rc;
     CK(h, cudaMemcpyAsync(probs_host, F(h, "H_PROBS"), (size_t)B * 2 * h->Nc * (h->Nc - 1) * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (loss_host) CK(h, cudaMemcpyAsync(loss_host, F(h, "H_LOSS"), sizeof(float), cudaMemcpyDeviceToHost, st));
     return HDGNN_OK;

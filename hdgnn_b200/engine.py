@@ -165,6 +165,12 @@ class Engine:
                                         _p(step_counter), lr, beta1, beta2, eps, _p(probs), _p(loss3),
                                         self._stream()), self._h)
 
+    def forward_backward_host(self, adj, x, hmap, L, Y, params, grads, B_global, loss=None, probs=None):
+        """Commit-sharded training from pinned host tensors: H2D + forward + backward; grads / loss / probs on device."""
+        B = adj.shape[0]
+        check(lib.hdgnn_forward_backward_host(self._h, B, B_global, _p(adj), _p(x), _p(hmap), _p(L), _p(Y), _p(params),
+                                              _p(probs), _p(loss), _p(grads), self._stream()), self._h)
+
     def infer_host(self, adj, x, hmap, L, Y, params, probs, loss=None):
         B = adj.shape[0]
         check(lib.hdgnn_infer_host(self._h, B, _p(adj), _p(x), _p(hmap), _p(L), _p(Y), _p(params), _p(probs),

@@ -161,9 +161,10 @@ class graph2graph(object):
             eng.train_step_host(*hb.tensors(), self.params, self.m, self.v, self.step_counter, self.loss3,
                                 probs=probs_out if want_probs else None)
             return self.loss3
-        db = self._stage(hb)
-        eng.forward_backward(db, self.params, B_global=hb.B * self.world, grads=self.grads, loss=self.loss_d,
-                             probs=self._probs_d if want_probs else None, want_probs=False)
+        if want_probs and (not hasattr(self, "_probs_d") or self._probs_d.shape[0] < hb.B):
+            self._probs_d = torch.zeros(hb.B, 2, self.Ncr, dtype=torch.float32, device=eng.tdev)
+        eng.forward_backward_host(*hb.tensors(), self.params, self.grads, hb.B * self.world, loss=self.loss_d,
+                                  probs=self._probs_d if want_probs else None)
         torch.distributed.all_reduce(self.grads)        # the single collective of the step
         eng.adam_step(self.params, self.grads, self.m, self.v, self.step_counter, reg_losses=self.reg)
         self.loss3[0:1].copy_(self.loss_d, non_blocking=True)
@@ -175,22 +176,6 @@ class graph2graph(object):
     # one `sess.run([loss, loss_map, probs])` (model_2.py:486-502)
     def infer(self, hb: HostBatch, probs_out: torch.Tensor, loss_out: Optional[torch.Tensor] = None):
         self.engine.infer_host(*hb.tensors(), self.params, probs_out, loss_out)
-
-    def _stage(self, hb: HostBatch) -> DeviceBatch:
-        if not hasattr(self, "_db") or self._db.B != hb.B:
-            dev = self.engine.tdev
-            B, Ne, Nc, pe, pc = hb.B, self.Ne, self.Nc, self.engine.pe, self.engine.pc
-            self._db = DeviceBatch(torch.zeros(B, Ne, pe, dtype=torch.uint8, device=dev),
-                                   torch.zeros(B, Ne, dtype=torch.float32, device=dev),
-                                   torch.zeros(B, Ne, dtype=torch.int32, device=dev),
-                                   torch.zeros(B, dtype=torch.int32, device=dev),
-                                   torch.zeros(B, Nc, pc, dtype=torch.uint8, device=dev), Ne, Nc)
-            self._probs_d = torch.zeros(B, 2, self.Ncr, dtype=torch.float32, device=dev)
-        d = self._db
-        d.adj[:, :, :self.Ne].copy_(hb.adj, non_blocking=True)
-        d.Y[:, :, :self.Nc].copy_(hb.Y, non_blocking=True)
-        d.x.copy_(hb.x, non_blocking=True); d.hmap.copy_(hb.hmap, non_blocking=True); d.L.copy_(hb.L, non_blocking=True)
-        return d
 
     # ------------------------------------------------------------------------------------------
     # data

@@ -129,7 +129,9 @@ int hdgnn_train_step(hdgnn_handle_t h, int B,
 
 /* One whole training step from HOST buffers (pinned recommended): H2D copies of the five
  * compact inputs, forward, backward, Adam, and a D2H copy of {CE, loss_map, loss_para} into
- * loss3_host, all enqueued on `stream`.  Un-pitched host layouts: adj (B,Ne,Ne), Y (B,Nc,Nc).
+ * loss3_host.  The kernels and the D2H copy are enqueued on `stream`; the H2D copies go through two staging
+ * slots on a copy stream owned by the handle (ordered against `stream` by events), so the copies of one call
+ * overlap the kernels of the previous one.  Host buffers must stay unchanged until `stream` has passed the call.  Un-pitched host layouts: adj (B,Ne,Ne), Y (B,Nc,Nc).
  * probs_host may be NULL (otherwise B*2*Ncr floats are copied back). */
 int hdgnn_train_step_host(hdgnn_handle_t h, int B,
                           const uint8_t* adj_host, const float* x_host, const int32_t* hmap_host,
@@ -137,6 +139,14 @@ int hdgnn_train_step_host(hdgnn_handle_t h, int B,
                           float* params, float* m, float* v, int32_t* step_counter,
                           float lr, float beta1, float beta2, float eps,
                           float* probs_host, float* loss3_host, void* stream);
+
+/* Forward + backward from HOST buffers (the commit-sharded form of hdgnn_train_step_host): H2D copies of this
+ * rank's commits, then as hdgnn_forward_backward.  probs / loss / grads are DEVICE pointers (grads is the buffer
+ * the caller all-reduces before hdgnn_adam_step); probs and loss may be NULL. */
+int hdgnn_forward_backward_host(hdgnn_handle_t h, int B, int B_global,
+                                const uint8_t* adj_host, const float* x_host, const int32_t* hmap_host,
+                                const int32_t* L_host, const uint8_t* Y_host,
+                                const float* params, float* probs, float* loss, float* grads, void* stream);
 
 /* Inference from HOST buffers: H2D, forward, D2H of probs (B*2*Ncr floats) and CE. */
 int hdgnn_infer_host(hdgnn_handle_t h, int B,

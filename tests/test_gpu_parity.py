@@ -189,6 +189,12 @@ def test_host_entry_points_match_device_entry_points():
     assert torch.equal(probs_h, probs.cpu())
     assert abs(loss3[0].item() - loss.item()) <= 1e-6 * abs(loss.item())
     assert torch.allclose(loss3[1:], reg.cpu(), rtol=1e-6)     # different (fixed) summation orders
+    # commit-sharded host entry: same gradient as the device entry, back-to-back calls alternate staging slots
+    for _ in range(3):
+        g2 = torch.zeros_like(grads); l2 = torch.zeros(1, device="cuda"); pr2 = torch.zeros_like(probs)
+        eng.forward_backward_host(*h, flat.cuda(), g2, B, loss=l2, probs=pr2)
+        torch.cuda.synchronize()
+        assert torch.equal(g2, grads) and torch.equal(pr2, probs) and torch.equal(l2, loss)
     probs_i = torch.zeros(B, 2, eng.Ncr).pin_memory(); li = torch.zeros(1).pin_memory()
     eng.infer_host(*h, flat.cuda(), probs_i, li)
     torch.cuda.synchronize()
