@@ -186,6 +186,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from hdgnn_b200.engine import DeviceBatch
     from hdgnn_b200.model import graph2graph, HostBatch
@@ -338,7 +340,8 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "commits/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": host_pool[0].nbytes(), "d2h_bytes_per_step": 12,
-                    "api": "hdgnn_b200.model.graph2graph.train_step (pinned host buffers -> hdgnn_train_step_host)"},
+                    "api": "hdgnn_b200.model.graph2graph.train_step: pinned host buffers -> hdgnn_train_step_host (1 GPU) / "
+                           "hdgnn_forward_backward_host + all-reduce + hdgnn_adam_step (N GPUs); H2D of step k+1 overlaps the kernels of step k"},
             "gpu_launches": launches,
             "roofline": roof,
             "cpu_baseline": cpu,

@@ -201,3 +201,53 @@ class Engine:
 
     def last_launch_count(self) -> int:
         return lib.hdgnn_last_launch_count(self._h)
+
+
+# -- legacy operator of model.py (normalize_adj + propagation, Chebyshev map_conv) -------------------------------
+P_SELF_LOOP, P_RELU, P_NO_TRANSPOSE = 1, 2, 4
+
+
+def _pitched(adj: torch.Tensor) -> torch.Tensor:
+    """(B,N,N) uint8 cuda -> (B,N,pitch) with the row pitch the kernels need."""
+    B, N, M = adj.shape
+    pitch = label_pitch(N)
+    if M == pitch:
+        return adj.contiguous()
+    out = torch.zeros(B, N, pitch, dtype=torch.uint8, device=adj.device)
+    out[:, :, :N] = adj[:, :, :N]
+    return out
+
+
+def normalize_propagate(adj: torch.Tensor, H: torch.Tensor, W: Optional[torch.Tensor] = None,
+                        bias: Optional[torch.Tensor] = None, eps: float = 1e-3, flags: int = 0):
+    """act(A_hat (H W) + b) with the reference's normalize_adj (model.py:360-367).  adj (B,N,N|pitch) uint8 cuda,
+    H (B,N,d_in) float32 cuda.  Returns (out (B,N,d_out), dinv (B,N))."""
+    if not (adj.is_cuda and H.is_cuda):
+        raise RuntimeError("normalize_propagate needs CUDA tensors; there is no CPU fallback")
+    a = _pitched(adj)
+    B, N, pitch = a.shape
+    H = H.contiguous().float()
+    d_in = H.shape[2]
+    d_out = d_in if W is None else W.shape[1]
+    out = torch.empty(B, N, d_out, dtype=torch.float32, device=a.device)
+    dinv = torch.empty(B, N, dtype=torch.float32, device=a.device)
+    st = C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream)
+    check(lib.hdgnn_normalize_propagate(B, N, _p(a), pitch, _p(H), d_in, _p(None if W is None else W.contiguous().float()),
+                                        _p(None if bias is None else bias.contiguous().float()), d_out, eps, flags,
+                                        _p(out), _p(dinv), st))
+    return out, dinv
+
+
+def map_conv(adj: torch.Tensor, x: torch.Tensor, theta: torch.Tensor, lam_max: float = 1.5, eps: float = 1e-3,
+             flags: int = 0):
+    """map_conv of model.py:394-403 (k = 2, Ds = 1).  Returns (loss scalar tensor, per-commit (B,))."""
+    if not (adj.is_cuda and x.is_cuda):
+        raise RuntimeError("map_conv needs CUDA tensors; there is no CPU fallback")
+    a = _pitched(adj)
+    B, N, pitch = a.shape
+    per = torch.empty(B, dtype=torch.float32, device=a.device)
+    loss = torch.empty(1, dtype=torch.float32, device=a.device)
+    st = C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream)
+    check(lib.hdgnn_map_conv(B, N, _p(a), pitch, _p(x.contiguous().float()), _p(theta.reshape(-1).contiguous().float()),
+                             lam_max, eps, flags, _p(per), _p(loss), st))
+    return loss, per

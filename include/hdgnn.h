@@ -154,6 +154,27 @@ int hdgnn_infer_host(hdgnn_handle_t h, int B,
                      const int32_t* L_host, const uint8_t* Y_host,
                      const float* params, float* probs_host, float* loss_host, void* stream);
 
+/* ---- legacy operator of model.py (not used by the live model_1..4) ------------------------------
+ * out (B,N,d_out) = act( A_hat (H W) + bias ),  A_hat = D^-1/2 A^T D^-1/2,  D = rowsum(A) + eps: the
+ * normalize_adj of model.py:360-367 (eps = 1e-3, no self loop, transposed) fused with one propagation.
+ * H (B,N,d_in); W (d_in,d_out) row-major or NULL (then d_in == d_out); bias (d_out) or NULL; d_in, d_out <= 32;
+ * dinv_out (B,N) optionally receives D^-1/2.  flags select the variants.  Stateless (no handle); the
+ * per-commit state (N * pitch bytes of adjacency + two bitmaps + N * d_out floats) must fit one SM's shared
+ * memory (N ~ 380 at d_out = 20), else HDGNN_E_UNSUPPORTED. */
+#define HDGNN_P_SELF_LOOP     1   /* normalise and propagate A + I (the textbook GCN form) */
+#define HDGNN_P_RELU          2
+#define HDGNN_P_NO_TRANSPOSE  4   /* A_hat = D^-1/2 A D^-1/2 */
+int hdgnn_normalize_propagate(int B, int N, const uint8_t* adj, int adj_pitch, const float* H, int d_in,
+                              const float* W, const float* bias, int d_out, float eps, int flags,
+                              float* out, float* dinv_out, void* stream);
+
+/* map_conv of model.py:394-403 with k = 2 and Ds = 1 (chebyshev_polynomials, model.py:335-391):
+ * per_commit[b] = (x_b^T (t0 I + t1 ((2/lam_max)(I - A_hat) - I)) x_b)^2,  t = softmax(theta),  and
+ * *loss = mean_b per_commit[b] (loss may be NULL).  theta: device, 2 floats (raw).  The reference uses
+ * lam_max = 1.5, eps = 1e-3, flags = 0. */
+int hdgnn_map_conv(int B, int N, const uint8_t* adj, int adj_pitch, const float* x, const float* theta,
+                   float lam_max, float eps, int flags, float* per_commit, float* loss, void* stream);
+
 /* Debug / test introspection: device pointer and size in bytes of a named scratch buffer
  * (RS1 CS1 S1 X2 NB PH QH RS3 CS3 PR PC GRH GCH RS3D CS3D DNB GE RS1D CS1D GPART ...). */
 int hdgnn_workspace(hdgnn_handle_t h, const char* name, void** ptr, size_t* bytes);

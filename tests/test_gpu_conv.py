@@ -1,0 +1,91 @@
+"""GPU parity of the legacy operator (model.py:335-403): normalize_adj fused with propagation and the Chebyshev
+map_conv regulariser, against the oracle (literal S.T / matrix_diag transcription and its closed form)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import hdgnn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _adj(B, N, p, seed):
+    rng = np.random.default_rng(seed)
+    a = (rng.random((B, N, N)) < p).astype(np.uint8)
+    a[:, np.arange(N), np.arange(N)] = 0
+    return a
+
+
+def _ref_propagate(adj, H, W, bias, eps, self_loop, relu, transpose):
+    A = adj.astype(np.float64)
+    N = A.shape[1]
+    if self_loop:
+        A = A + np.eye(N)
+    d = (A.sum(2) + eps) ** -0.5
+    M = np.transpose(A, (0, 2, 1)) if transpose else A
+    Ahat = d[:, :, None] * M * d[:, None, :]
+    Z = H.astype(np.float64) if W is None else H.astype(np.float64) @ W.astype(np.float64)
+    out = Ahat @ Z + (0 if bias is None else bias.astype(np.float64))
+    return (np.maximum(out, 0) if relu else out), d
+
+
+@pytest.mark.parametrize("B,N,d_in,d_out,p", [(3, 9, 4, 4, 0.3), (4, 50, 7, 20, 0.1), (2, 200, 20, 20, 0.05), (2, 250, 1, 1, 0.05),
+                                              (1, 300, 20, 32, 0.02)])
+@pytest.mark.parametrize("flags", [0, 1, 2 | 4, 1 | 2])
+def test_normalize_propagate(B, N, d_in, d_out, p, flags):
+    from hdgnn_b200.engine import normalize_propagate
+    rng = np.random.default_rng(N + flags)
+    adj = _adj(B, N, p, N)
+    H = rng.normal(size=(B, N, d_in)).astype(np.float32)
+    W = None if d_in == d_out and flags == 0 else rng.normal(scale=0.3, size=(d_in, d_out)).astype(np.float32)
+    bias = rng.normal(size=d_out).astype(np.float32) if flags & 2 else None
+    out, dinv = normalize_propagate(torch.tensor(adj).cuda(), torch.tensor(H).cuda(), None if W is None else torch.tensor(W).cuda(),
+                                    None if bias is None else torch.tensor(bias).cuda(), eps=1e-3, flags=flags)
+    torch.cuda.synchronize()
+    ref, d = _ref_propagate(adj, H, W, bias, 1e-3, bool(flags & 1), bool(flags & 2), not (flags & 4))
+    assert np.abs(dinv.cpu().numpy() - d).max() / d.max() < 1e-6
+    assert np.abs(out.cpu().numpy() - ref).max() / max(np.abs(ref).max(), 1e-30) < 1e-5      # fp32 sums vs fp64
+
+
+@pytest.mark.parametrize("B,N,p", [(3, 6, 0.4), (5, 40, 0.15), (4, 200, 0.05), (2, 333, 0.03)])
+def test_map_conv_matches_oracle(B, N, p):
+    from hdgnn_b200.engine import map_conv
+    rng = np.random.default_rng(N)
+    adj = _adj(B, N, p, N + 1)
+    x = rng.integers(0, 10, size=(B, N)).astype(np.float32) / 3.0
+    theta = torch.tensor([0.13, -0.21], dtype=torch.float64)
+    ref = float(O.map_conv_closed(theta, torch.tensor(adj), torch.tensor(x, dtype=torch.float64)))
+    if N <= 40:     # the literal transcription (S, T, matrix_diag, transposes) agrees with the closed form
+        No = N
+        Ra = torch.zeros(B, 2, No * (No - 1), dtype=torch.float64)
+        q = 0
+        for i in range(No):
+            for j in range(No):
+                if i != j:
+                    Ra[:, 1, q] = torch.tensor(adj[:, i, j], dtype=torch.float64); q += 1
+        Ra[:, 0] = 1 - Ra[:, 1]
+        lit = float(O.map_conv_dense(theta, Ra, torch.tensor(x, dtype=torch.float64).reshape(B, 1, No)))
+        assert abs(lit - ref) <= 1e-9 * abs(ref)
+    loss, per = map_conv(torch.tensor(adj).cuda(), torch.tensor(x).cuda(), theta.float().cuda())
+    torch.cuda.synchronize()
+    assert abs(loss.item() - ref) <= 1e-4 * abs(ref), (loss.item(), ref)
+    # textbook variant: A + I, un-transposed
+    ref2 = float(O.map_conv_closed(theta, torch.tensor(np.transpose(adj, (0, 2, 1)).copy()), torch.tensor(x, dtype=torch.float64), self_loop=True))
+    loss2, _ = map_conv(torch.tensor(adj).cuda(), torch.tensor(x).cuda(), theta.float().cuda(), flags=1 | 4)
+    torch.cuda.synchronize()
+    # with the self loop the degrees of A^T + I differ from those of A + I, so only compare on symmetric graphs
+    sym = np.maximum(adj, np.transpose(adj, (0, 2, 1)))
+    ref3 = float(O.map_conv_closed(theta, torch.tensor(sym), torch.tensor(x, dtype=torch.float64), self_loop=True))
+    loss3, _ = map_conv(torch.tensor(sym).cuda(), torch.tensor(x).cuda(), theta.float().cuda(), flags=1 | 4)
+    torch.cuda.synchronize()
+    assert abs(loss3.item() - ref3) <= 1e-4 * abs(ref3)
+    del ref2, loss2
+
+
+def test_tile_too_large_is_reported():
+    from hdgnn_b200.engine import normalize_propagate
+    from hdgnn_b200._lib import HdgnnError, E_UNSUPPORTED
+    adj = torch.zeros(1, 500, 512, dtype=torch.uint8, device="cuda")
+    with pytest.raises(HdgnnError) as e:
+        normalize_propagate(adj, torch.zeros(1, 500, 20, device="cuda"))
+    assert e.value.code == E_UNSUPPORTED
