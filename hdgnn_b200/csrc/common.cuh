@@ -68,6 +68,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (spin > (1u << 26)) __trap();
 }
 
+// ---- programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialization attribute
+// may start while its predecessor drains; it must not touch the predecessor's outputs before pdl_wait().
+// Both are no-ops for a normally launched kernel.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- reductions ------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

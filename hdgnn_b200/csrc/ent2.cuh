@@ -74,6 +74,8 @@ __global__ void __launch_bounds__(KG * NRG * 32, 4 / NRG) ent_fwd2_kernel(const 
         wts[3 * HD + tid] = par[a.o_l + HD + tid] - par[a.o_l + tid];
     }
     __syncthreads();
+    pdl_wait();                     // the label bitmap comes from pack_bits
+    pdl_launch_dependents();
     const int k0 = kg * 4;
     const float V0 = wts[HD + k0], V1 = wts[HD + k0 + 1], V2 = wts[HD + k0 + 2], V3 = wts[HD + k0 + 3];
     const int cw = (N + 31) >> 5, npass = (cw + CWT - 1) / CWT;
@@ -170,6 +172,8 @@ __global__ void __launch_bounds__(KG * NRG * 32, NRG == 1 ? 3 : 1) ent_bwd2_kern
     }
     if (tid < 4 * HD) acc80[tid] = 0.f;
     __syncthreads();
+    pdl_wait();                     // GE comes from mid2
+    pdl_launch_dependents();
     const int k0 = kg * 4;
     const float V0 = wts[HD + k0], V1 = wts[HD + k0 + 1], V2 = wts[HD + k0 + 2], V3 = wts[HD + k0 + 3];
     const int cw = (N + 31) >> 5, npass = (cw + CWT - 1) / CWT;

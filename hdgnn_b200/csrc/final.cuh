@@ -72,13 +72,25 @@ __global__ void __launch_bounds__(FIN_P * FIN_SL) reduce_adam_kernel(const Final
     __shared__ int last;
     const int tid = threadIdx.x, pl = tid % FIN_P, sl = tid / FIN_P;
     const int p = blockIdx.x * FIN_P + pl;
+    // optimizer state first: these loads overlap the reduction below (the kernel is a chain of global latencies)
+    const bool own = a.apply_adam && sl == 0 && p < a.total;
+    const float pv = own ? a.params[p] : 0.f, m_old = own ? a.m[p] : 0.f, v_old = own ? a.v[p] : 0.f;
+    const int t = a.apply_adam ? *a.step + 1 : 0;       // read before any CTA can publish the new count
+    float th[4] = {0.f, 0.f, 0.f, 0.f};
+    if (a.apply_adam && tid < 2) {
+        const int o = tid == 0 ? a.o_t1 : a.o_t2;
+        th[0] = a.params[o]; th[1] = a.params[o + 1];
+    }
+    pdl_wait();                     // gradient partials come from mid2 / ent_bwd2
     float acc = 0.f;
     if (p < a.total) {
         int bb = sl;
-        for (; bb + 3 * FIN_SL < a.B; bb += 4 * FIN_SL) {
-            const float g0 = a.gpart[(size_t)bb * a.total + p], g1 = a.gpart[(size_t)(bb + FIN_SL) * a.total + p];
-            const float g2 = a.gpart[(size_t)(bb + 2 * FIN_SL) * a.total + p], g3 = a.gpart[(size_t)(bb + 3 * FIN_SL) * a.total + p];
-            acc += g0; acc += g1; acc += g2; acc += g3;
+        for (; bb + 7 * FIN_SL < a.B; bb += 8 * FIN_SL) {       // eight loads in flight, fixed summation order
+            float g[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) g[u] = a.gpart[(size_t)(bb + u * FIN_SL) * a.total + p];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc += g[u];
         }
         for (; bb < a.B; bb += FIN_SL) acc += a.gpart[(size_t)bb * a.total + p];
         acc += rank1_extra(a.ent, p, sl, FIN_SL);
@@ -101,12 +113,7 @@ __global__ void __launch_bounds__(FIN_P * FIN_SL) reduce_adam_kernel(const Final
     if (!a.apply_adam) return;
 
     // regularisers (evaluated at the pre-update parameters) + TF1 Adam
-    if (tid < 2) {
-        const int o = tid == 0 ? a.o_t1 : a.o_t2;
-        tn[tid] = sqrtf(a.params[o] * a.params[o] + a.params[o + 1] * a.params[o + 1]);
-    }
-    const float pv = (sl == 0 && p < a.total) ? a.params[p] : 0.f;
-    const int t = *a.step + 1;                          // read before any CTA can publish the new count
+    if (tid < 2) tn[tid] = sqrtf(th[0] * th[0] + th[1] * th[1]);
     if (tid == 2) tn[2] = adam_lr_t(a.lr, a.b1, a.b2, t);
     const float sq = block_sum(pv * pv, scratch);       // also orders tn[]
     if (sl == 0 && p < a.total) {
@@ -114,8 +121,8 @@ __global__ void __launch_bounds__(FIN_P * FIN_SL) reduce_adam_kernel(const Final
         if (p >= a.o_t1 && p < a.o_t1 + 2) gi += 0.001f * pv / tn[0];
         if (p >= a.o_t2 && p < a.o_t2 + 2) gi += 0.001f * pv / tn[1];
         const float lr_t = tn[2];
-        const float mi = a.b1 * a.m[p] + (1.f - a.b1) * gi;
-        const float vi = a.b2 * a.v[p] + (1.f - a.b2) * gi * gi;
+        const float mi = a.b1 * m_old + (1.f - a.b1) * gi;
+        const float vi = a.b2 * v_old + (1.f - a.b2) * gi * gi;
         a.m[p] = mi; a.v[p] = vi;
         a.params[p] = pv - lr_t * mi / (sqrtf(vi) + a.eps);
     }

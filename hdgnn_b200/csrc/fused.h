@@ -10,8 +10,21 @@ namespace hdgnn {
 // kernel handle for cudaFuncSetAttribute / occupancy queries (nullptr if not instantiated)
 const void* ent2_fn_rt(int cwt, int nrg, bool bwd);
 const void* mid2_fn_rt(int cwt, bool train);
-void launch_ent2(int cwt, int nrg, bool bwd, int grid, size_t smem, cudaStream_t st, const Ent2Args& a);
-void launch_mid2(int cwt, bool train, int grid, size_t smem, cudaStream_t st, const Mid2Args& a);
+// pdl: launch with programmatic stream serialization (the kernel calls pdl_wait() before it reads its
+// predecessor's outputs, so its prologue overlaps the predecessor's tail)
+void launch_ent2(int cwt, int nrg, bool bwd, int grid, size_t smem, cudaStream_t st, const Ent2Args& a, bool pdl);
+void launch_mid2(int cwt, bool train, int grid, size_t smem, cudaStream_t st, const Mid2Args& a, bool pdl);
+
+template <typename Kern, typename Args>
+inline cudaError_t launch_ex(Kern kern, int grid, int block, size_t smem, cudaStream_t st, bool pdl, const Args& a) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, a);
+}
 
 #define HDGNN_CWT_SWITCH(cwt, ...)                                                                  \
     switch (cwt) {                                                                                  \

@@ -100,6 +100,7 @@ struct hdgnn_handle_s {
     int nsm = 148;
     int fwd_nrg = 2, bwd_nrg = 1, fwd_cwt = 0, bwd_cwt = 0;   // warp layout / column segments per pass
     int fwd_occ = 1, bwd_occ = 1;                              // resident CTAs per SM
+    bool pdl = true;                                           // programmatic dependent launch between the fused kernels
     int Gf = 0, Gb = 0, Rf = 0, Rb = 0, SLf = 0;               // grids / rows per CTA / slots of the last launch
     std::map<std::string, Buf> ws;
     std::string err;
@@ -528,7 +529,7 @@ int fused_forward(hdgnn_handle_t h, int B, int B_global, const Inputs& in, float
         a.R = h->Rf; a.SL = h->SLf; a.RS = F(h, "RS1"); a.CSp = F(h, "CS1P");
         const size_t smem = ent2_smem_bytes(h->fwd_cwt, h->fwd_nrg, h->Ne, h->Rf, h->WPe, false);
         PROF_BEGIN(h, st);
-        launch_ent2(h->fwd_cwt, h->fwd_nrg, false, h->Gf, smem, st, a);
+        launch_ent2(h->fwd_cwt, h->fwd_nrg, false, h->Gf, smem, st, a, h->pdl);
         LAUNCH_CHECK(h, "ent_fwd", st);
     }
     Mid2Args m{};
@@ -545,7 +546,7 @@ int fused_forward(hdgnn_handle_t h, int B, int B_global, const Inputs& in, float
     const size_t smem = mid2_smem_bytes(h->Ne, h->Nc, train);
     const int cwc = (h->Nc + 31) / 32;
     PROF_BEGIN(h, st);
-    launch_mid2(cwc, train, B, smem, st, m);
+    launch_mid2(cwc, train, B, smem, st, m, h->pdl && h->ent);
     LAUNCH_CHECK(h, train ? "mid(train)" : "mid(infer)", st);
     if (h->debug) return debug_scatter(h, B, st);
     return HDGNN_OK;
@@ -559,7 +560,7 @@ int fused_backward(hdgnn_handle_t h, int B, int B_global, const Inputs& in, floa
         a.R = h->Rb; a.SL = 0; a.GR = F(h, "GE"); a.GC = F(h, "GE"); a.gpart = F(h, "GPE");
         const size_t smem = ent2_smem_bytes(h->bwd_cwt, h->bwd_nrg, h->Ne, h->Rb, h->WPe, true);
         PROF_BEGIN(h, st);
-        launch_ent2(h->bwd_cwt, h->bwd_nrg, true, h->Gb, smem, st, a);
+        launch_ent2(h->bwd_cwt, h->bwd_nrg, true, h->Gb, smem, st, a, h->pdl);
         LAUNCH_CHECK(h, "ent_bwd", st);
     }
     FinalArgs f{};
@@ -574,7 +575,7 @@ int fused_backward(hdgnn_handle_t h, int B, int B_global, const Inputs& in, floa
         f.reg_losses = adam->reg;
     }
     PROF_BEGIN(h, st);
-    reduce_adam_kernel<<<(h->po.total + FIN_P - 1) / FIN_P, FIN_P * FIN_SL, 0, st>>>(f);
+    launch_ex(reduce_adam_kernel, (h->po.total + FIN_P - 1) / FIN_P, FIN_P * FIN_SL, 0, st, h->pdl, f);
     LAUNCH_CHECK(h, adam ? "reduce_adam" : "grad_reduce", st);
     return HDGNN_OK;
 }
@@ -675,6 +676,7 @@ int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out) {
         if ((f == 4 || f == 8) && f < h->fwd_cwt) h->fwd_cwt = f;
         if ((bw == 4 || bw == 8) && bw < h->bwd_cwt) h->bwd_cwt = bw;
     }
+    h->pdl = env_int("HDGNN_PDL", 1) != 0 && !h->debug;
     h->fwd_nrg = env_int("HDGNN_FWD_NRG", 1);
     h->bwd_nrg = env_int("HDGNN_BWD_NRG", 2);
     if (h->fwd_nrg != 1 && h->fwd_nrg != 2 && h->fwd_nrg != 4) h->fwd_nrg = 1;

@@ -14,9 +14,9 @@ const void* ent2_fn_rt(int cwt, int nrg, bool bwd) {
     return fn;
 }
 
-void launch_ent2(int cwt, int nrg, bool bwd, int grid, size_t smem, cudaStream_t st, const Ent2Args& a) {
-    if (bwd) { HDGNN_CWT_SWITCH(cwt, HDGNN_NRG_SWITCH(nrg, (ent_bwd2_kernel<CWT, NRG><<<grid, KG * NRG * 32, smem, st>>>(a)))); }
-    else { HDGNN_CWT_SWITCH(cwt, HDGNN_NRG_SWITCH(nrg, (ent_fwd2_kernel<CWT, NRG><<<grid, KG * NRG * 32, smem, st>>>(a)))); }
+void launch_ent2(int cwt, int nrg, bool bwd, int grid, size_t smem, cudaStream_t st, const Ent2Args& a, bool pdl) {
+    if (bwd) { HDGNN_CWT_SWITCH(cwt, HDGNN_NRG_SWITCH(nrg, launch_ex(ent_bwd2_kernel<CWT, NRG>, grid, KG * NRG * 32, smem, st, pdl, a))); }
+    else { HDGNN_CWT_SWITCH(cwt, HDGNN_NRG_SWITCH(nrg, launch_ex(ent_fwd2_kernel<CWT, NRG>, grid, KG * NRG * 32, smem, st, pdl, a))); }
 }
 
 }  // namespace hdgnn

@@ -62,7 +62,7 @@ __host__ __device__ inline Mid2Smem mid2_layout(int Ne, int Nc, bool train) {
     auto take = [&](int n) { int r = o; o += (n + 7) & ~7; return r; };      // 32-byte granules
     m.blk1 = take(M2_BLK1); m.blk2 = take(M2_BLK2); m.gam = take(20); m.Dh = take(20); m.Dg = take(20); m.G1g = take(400);
     m.W5U = take(400); m.c1p = take(20);
-    m.x = take(Ne); m.x2 = take(Ne); m.hm = take(Ne); m.SP = take(4 * Ne); m.TP = take(4 * Ne); m.dl = take(4 * Ne);
+    m.x = take(Ne); m.x2 = take(Ne); m.hm = take(Ne);
     m.dx2 = take(Ne); m.nb = take(4 * Nc); m.dnb = take(4 * Nc);
     m.ebits = take(Ne * bit_words(Ne)); m.ybits = take(Nc * bit_words(Nc));
     const int cwc = (Nc + 31) / 32;
@@ -70,8 +70,12 @@ __host__ __device__ inline Mid2Smem mid2_layout(int Ne, int Nc, bool train) {
     m.scratch = take(comb > pool ? comb : pool);
     m.red = take(64 + M2_NW * HD + 64);
     m.uni = o;
+    // union region: [hunk tables 12 Nc 20][dlt (training) | SP TP dl (pooling: dead while dlt is live)]; the
+    // entity-state backward (after the pooling backward) reuses it from the start
     const int ent_phase = M2_CH * M2_NODE_F;
-    const int hunk_phase = 12 * Nc * HD + (train ? Nc * cwc * 32 : 0);
+    const int dlt = train ? Nc * cwc * 32 : 0, pool3 = 3 * ((4 * Ne + 7) & ~7);
+    const int hunk_phase = ((12 * Nc * HD + 7) & ~7) + (dlt > pool3 ? dlt : pool3);
+    m.SP = m.uni + ((12 * Nc * HD + 7) & ~7); m.TP = m.SP + ((4 * Ne + 7) & ~7); m.dl = m.TP + ((4 * Ne + 7) & ~7);
     o += ent_phase > hunk_phase ? ent_phase : hunk_phase;
     m.total = o;
     return m;
@@ -304,6 +308,8 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         }
     }
     __syncthreads();
+    pdl_wait();                     // RS1 / CS1p come from ent_fwd2 (everything above reads inputs, weights, bitmaps)
+    pdl_launch_dependents();
     M2_PHASE(1);
 
     // ---------------- B/C. entity-state MLP forward: two threads per entity (10 hidden units each) ----------
@@ -468,7 +474,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
     float* PC = uni + 9 * T;        // later dc
     float* RSm = uni + 10 * T;      // later RS3d
     float* CSm = uni + 11 * T;      // later CS3d
-    float* dlt = uni + 12 * T;      // [Nc][CWT*32] dL/dlogit-difference per pair (training)
+    float* dlt = uni + ((12 * T + 7) & ~7);     // [Nc][CWT*32] dL/dlogit-difference per pair (training); aliases SP/TP/dl
     constexpr int DW = CWT * 32;
     for (int idx = tid; idx < T; idx += M2_T) {
         const int c = idx / HD, k = idx - c * HD;
