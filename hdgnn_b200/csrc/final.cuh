@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(FIN_P * FIN_SL) reduce_adam_kernel(const Final
     __shared__ int last;
     const int tid = threadIdx.x, pl = tid % FIN_P, sl = tid / FIN_P;
     const int p = blockIdx.x * FIN_P + pl;
+    pdl_launch_dependents();        // the next step's pack_bits may run beside this kernel (see pack.cuh)
     // optimizer state first: these loads overlap the reduction below (the kernel is a chain of global latencies)
     const bool own = a.apply_adam && sl == 0 && p < a.total;
     const float pv = own ? a.params[p] : 0.f, m_old = own ? a.m[p] : 0.f, v_old = own ? a.v[p] : 0.f;

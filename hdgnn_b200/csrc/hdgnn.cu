@@ -101,6 +101,7 @@ struct hdgnn_handle_s {
     int fwd_nrg = 2, bwd_nrg = 1, fwd_cwt = 0, bwd_cwt = 0;   // warp layout / column segments per pass
     int fwd_occ = 1, bwd_occ = 1;                              // resident CTAs per SM
     bool pdl = true;                                           // programmatic dependent launch between the fused kernels
+    int bslot = 0;                                             // bitmap buffer of the current step (two alternate)
     int Gf = 0, Gb = 0, Rf = 0, Rb = 0, SLf = 0;               // grids / rows per CTA / slots of the last launch
     std::map<std::string, Buf> ws;
     std::string err;
@@ -491,7 +492,7 @@ int ent2_occupancy(hdgnn_handle_t h, int cwt, int nrg, bool bwd) {
 
 Ent2Args ent2_args(hdgnn_handle_t h, int B, const Inputs& in) {
     Ent2Args a{};
-    a.bits = (const uint32_t*)h->ws["EBITS"].p; a.WP = h->WPe; a.N = h->Ne; a.B = B;
+    a.bits = (const uint32_t*)h->ws[h->bslot ? "EBITS1" : "EBITS0"].p; a.WP = h->WPe; a.N = h->Ne; a.B = B;
     a.params = in.params; a.x = in.x;
     a.o_u = h->po.ent_w1; a.o_v = h->po.ent_w1 + HD; a.o_b = h->po.ent_b1; a.o_l = h->po.ent_w1 + 2 * HD;
     return a;
@@ -512,14 +513,15 @@ int debug_scatter(hdgnn_handle_t h, int B, cudaStream_t st) {
 int fused_forward(hdgnn_handle_t h, int B, int B_global, const Inputs& in, float* logits, float* probs, bool train,
                   cudaStream_t st) {
     {
+        h->bslot ^= 1;
         PackArgs p{};
-        p.adj = in.adj; p.Ne = h->Ne; p.pe = h->pe; p.WPe = h->WPe; p.ebits = (uint32_t*)h->ws["EBITS"].p;
-        p.Y = in.Y; p.Nc = h->Nc; p.pc = h->pc; p.WPc = h->WPc; p.ybits = (uint32_t*)h->ws["YBITS"].p;
+        p.adj = in.adj; p.Ne = h->Ne; p.pe = h->pe; p.WPe = h->WPe; p.ebits = (uint32_t*)h->ws[h->bslot ? "EBITS1" : "EBITS0"].p;
+        p.Y = in.Y; p.Nc = h->Nc; p.pc = h->pc; p.WPc = h->WPc; p.ybits = (uint32_t*)h->ws[h->bslot ? "YBITS1" : "YBITS0"].p;
         p.B = B;
         const long long rows = (long long)B * (h->Ne + h->Nc);
         PROF_BEGIN(h, st);
-        if (h->pe <= 256 && h->pc <= 256) pack_bits_kernel<16><<<(unsigned)((rows + 15) / 16), 256, 0, st>>>(p);
-        else pack_bits_kernel<32><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(p);
+        if (h->pe <= 256 && h->pc <= 256) launch_ex(pack_bits_kernel<16>, (int)((rows + 15) / 16), 256, 0, st, h->pdl, p);
+        else launch_ex(pack_bits_kernel<32>, (int)((rows + 7) / 8), 256, 0, st, h->pdl, p);
         LAUNCH_CHECK(h, "pack_bits", st);
     }
     if (h->ent) {
@@ -534,8 +536,8 @@ int fused_forward(hdgnn_handle_t h, int B, int B_global, const Inputs& in, float
     }
     Mid2Args m{};
     m.Ne = h->Ne; m.Nc = h->Nc; m.ent = h->ent ? 1 : 0; m.R = h->Rf; m.SL = h->SLf;
-    m.ebits = (const uint32_t*)h->ws["EBITS"].p; m.WPe = h->WPe;
-    m.ybits = (const uint32_t*)h->ws["YBITS"].p; m.WPc = h->WPc;
+    m.ebits = (const uint32_t*)h->ws[h->bslot ? "EBITS1" : "EBITS0"].p; m.WPe = h->WPe;
+    m.ybits = (const uint32_t*)h->ws[h->bslot ? "YBITS1" : "YBITS0"].p; m.WPc = h->WPc;
     m.x = in.x; m.hmap = in.hmap; m.L = in.L;
     m.params = in.params; m.po = h->po; m.RS1 = F(h, "RS1"); m.CS1p = F(h, "CS1P");
     m.logits = logits; m.probs = probs; m.cep = F(h, "CEP");
@@ -678,9 +680,9 @@ int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out) {
     }
     h->pdl = env_int("HDGNN_PDL", 1) != 0 && !h->debug;
     h->fwd_nrg = env_int("HDGNN_FWD_NRG", 1);
-    h->bwd_nrg = env_int("HDGNN_BWD_NRG", 2);
+    h->bwd_nrg = env_int("HDGNN_BWD_NRG", 1);
     if (h->fwd_nrg != 1 && h->fwd_nrg != 2 && h->fwd_nrg != 4) h->fwd_nrg = 1;
-    if (h->bwd_nrg != 1 && h->bwd_nrg != 2 && h->bwd_nrg != 4) h->bwd_nrg = 2;
+    if (h->bwd_nrg != 1 && h->bwd_nrg != 2 && h->bwd_nrg != 4) h->bwd_nrg = 1;
     // the fused path needs the per-commit state of mid2 in one SM's shared memory and a hunk grid of <= 8 segments
     h->fused = !h->edge && !(cfg->flags & HDGNN_F_LEGACY) && h->Nc <= 256 &&
                mid2_smem_bytes(h->Ne, h->Nc, true) <= (size_t)prop.sharedMemPerBlockOptin;
@@ -716,7 +718,8 @@ int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out) {
         {"RS1D", B * Ne * HD * f, h->ent && lg}, {"CS1DP", B * Se * Ne * HD * f, h->ent && lg}, {"LS1P", B * Se * HD * f, h->ent && lg},
         {"GPART", B * (size_t)h->po.total * f, true},
         {"GPE", ((size_t)Gb_max + 1) * 4 * HD * f, h->fused && h->ent}, {"FIN_L2", 64 * f, h->fused}, {"FIN_CNT", 16, h->fused},
-        {"EBITS", B * Ne * (size_t)h->WPe * 4, h->fused}, {"YBITS", B * Nc * (size_t)h->WPc * 4, h->fused},
+        {"EBITS0", B * Ne * (size_t)h->WPe * 4, h->fused}, {"YBITS0", B * Nc * (size_t)h->WPc * 4, h->fused},
+        {"EBITS1", B * Ne * (size_t)h->WPe * 4, h->fused}, {"YBITS1", B * Nc * (size_t)h->WPc * 4, h->fused},
         {"DBG", B * mid2_dbg_floats(h->Ne, h->Nc) * f, h->fused && h->debug},
         {"CLK", B * 16 * sizeof(long long), h->fused && h->debug},
         {"RSE", B * Ne * HD * f, h->edge}, {"CSEP", B * Se * Ne * HD * f, h->edge}, {"CSEF", B * Ne * HD * f, h->edge},

@@ -43,6 +43,10 @@ __global__ void __launch_bounds__(256) pack_bits_kernel(const PackArgs a) {
         }
     }
     (void)lane;
+    // Launched with programmatic serialization right after the previous step's optimizer kernel: the packing
+    // above only reads this step's inputs and writes this step's bitmap buffer (two buffers alternate), so it
+    // overlaps that kernel; completing only after it has finished keeps every later kernel of this step ordered.
+    pdl_wait();
 }
 
 }  // namespace hdgnn
