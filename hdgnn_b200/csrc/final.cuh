@@ -49,16 +49,19 @@ __device__ __forceinline__ float rank1_extra(const Rank1Map& r, int p, int slice
     const bool two = i2 >= 0;
     if (!two) i2 = i1;
     float acc = 0.f;
-    const int n = r.n, step = nslice;
+    const int n = r.n;
+    const size_t stride = (size_t)nslice * 4 * HD;
+    constexpr int U = 16;                             // independent loads in flight; fixed summation order
     int t = slice;
-    for (; t + 3 * step < n; t += 4 * step) {        // four independent loads in flight; fixed summation order
+    for (; t + (U - 1) * nslice < n; t += U * nslice) {
         const float* g = r.gp + (size_t)t * 4 * HD;
-        const float a0 = g[i1], a1 = g[(size_t)step * 4 * HD + i1], a2 = g[(size_t)2 * step * 4 * HD + i1], a3 = g[(size_t)3 * step * 4 * HD + i1];
-        const float b0 = g[i2], b1 = g[(size_t)step * 4 * HD + i2], b2 = g[(size_t)2 * step * 4 * HD + i2], b3 = g[(size_t)3 * step * 4 * HD + i2];
-        acc += two ? fmaf(c2, b0, a0) : a0; acc += two ? fmaf(c2, b1, a1) : a1;
-        acc += two ? fmaf(c2, b2, a2) : a2; acc += two ? fmaf(c2, b3, a3) : a3;
+        float av[U], bv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { av[u] = g[u * stride + i1]; bv[u] = two ? g[u * stride + i2] : 0.f; }
+#pragma unroll
+        for (int u = 0; u < U; ++u) acc += two ? fmaf(c2, bv[u], av[u]) : av[u];
     }
-    for (; t < n; t += step) {
+    for (; t < n; t += nslice) {
         const float* g = r.gp + (size_t)t * 4 * HD;
         acc += two ? fmaf(c2, g[i2], g[i1]) : g[i1];
     }
@@ -85,15 +88,16 @@ __global__ void __launch_bounds__(FIN_P * FIN_SL) reduce_adam_kernel(const Final
     pdl_wait();                     // gradient partials come from mid2 / ent_bwd2
     float acc = 0.f;
     if (p < a.total) {
-        int bb = sl;
-        for (; bb + 7 * FIN_SL < a.B; bb += 8 * FIN_SL) {       // eight loads in flight, fixed summation order
-            float g[8];
+        for (int bb = sl; bb < a.B; bb += 16 * FIN_SL) {      // sixteen guarded loads in flight, fixed summation order
+            float g[16];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) g[u] = a.gpart[(size_t)(bb + u * FIN_SL) * a.total + p];
+            for (int u = 0; u < 16; ++u) {
+                const int idx = bb + u * FIN_SL;
+                g[u] = idx < a.B ? a.gpart[(size_t)idx * a.total + p] : 0.f;
+            }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) acc += g[u];
+            for (int u = 0; u < 16; ++u) acc += g[u];
         }
-        for (; bb < a.B; bb += FIN_SL) acc += a.gpart[(size_t)bb * a.total + p];
         acc += rank1_extra(a.ent, p, sl, FIN_SL);
         acc += rank1_extra(a.edge, p, sl, FIN_SL);
     }
