@@ -1,0 +1,34 @@
+"""BASELINE.json config 5: inference-only sweep (--Type test path), Ne = 200, Nc 74 -> 512, B = 100.
+Prints commits/s and hunk pairs/s for the device-resident forward (hdgnn_forward, probs only)."""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from hdgnn_b200.engine import Engine, DeviceBatch
+from hdgnn_b200.synthetic import make_commits
+
+B, Ne = 100, 200
+out = []
+for Nc in (74, 114, 150, 256, 384, 512):
+    eng = Engine(Ne, Nc, variant=2, max_batch=B)
+    pool = []
+    for i in range(8):
+        cb = make_commits(B, Ne, Nc, seed=20260 + i)
+        pool.append(DeviceBatch.from_numpy(cb.adj, cb.x, cb.hmap, cb.L, cb.Y, eng.tdev))
+    params = (0.1 * torch.randn(eng.n_params)).cuda()
+    for k in range(5):
+        eng.forward(pool[k % 8], params, want_logits=False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = 50
+    e0.record()
+    for k in range(steps):
+        eng.forward(pool[k % 8], params, want_logits=False)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    rec = {"Ne": Ne, "Nc": Nc, "B": B, "ms_per_batch": ms, "commits_per_s": B / ms * 1e3,
+           "hunk_pairs_per_s": B * Nc * (Nc - 1) / ms * 1e3, "launches": eng.last_launch_count(),
+           "probs_GBps": B * 8 * Nc * (Nc - 1) / ms / 1e6}
+    print(rec)
+    out.append(rec)
+    eng.close()
+json.dump(out, open(os.path.join(os.path.dirname(__file__), "..", "gpurun_out", "infer_sweep.json"), "w"), indent=1)
