@@ -14,6 +14,7 @@
 // bitmap is transposed with ballots when the reference's A^T form is asked for, and the propagation walks the
 // set bits (lanes = output channels).  HBM traffic = the adjacency bytes once + H in + out.
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <stdint.h>
 
 #include "../../include/hdgnn.h"
@@ -155,6 +156,205 @@ __global__ void __launch_bounds__(CONV_T) propagate_kernel(const ConvArgs a) {
     }
 }
 
+// ---- tcgen05 variant of the propagation ---------------------------------------------------------------------
+// The per-commit product  (A or A^T, N x N, entries 0/1)  x  (D^-1/2 H W, N x d_out)  is a dense contraction:
+// the adjacency is exact in bf16 and the scaled features are split into three bf16 terms (hi + mid + lo carries
+// 24 mantissa bits), so one tcgen05.mma chain with fp32 accumulation in TMEM reproduces the fp32 result whatever
+// the edge density.  Operands are written to shared memory by the CTA itself in the canonical no-swizzle K-major
+// layout ([K/8][rows][8] bf16: 8 x 16-byte core matrices, LBO = rows * 16 B, SBO = 128 B); one thread issues
+// the MMAs (M = 128 per tile, N = 4 d_out rounded to 16, K = 16 per instruction), tcgen05.commit signals an
+// mbarrier and the eight warps read their 32 TMEM lanes back with tcgen05.ld for the epilogue.
+constexpr int TC_T = 512;
+
+__host__ __device__ inline int tc_np(int d_out) { return round_up(4 * d_out, 16); }
+__host__ __device__ inline int tc_mp(int N) { return N <= 128 ? 128 : 256; }
+__host__ __device__ inline size_t tc_smem_bytes(int N, int pitch, int d_in, int d_out) {
+    const int WP = conv_words(N), NP32 = WP * 32, KP = round_up(N, 16);
+    const size_t tile = (size_t)round_up(N * pitch, 128), sa = (size_t)tc_mp(N) * KP * 2;
+    size_t off = 32 + (tile > sa ? tile : sa);                 // mbarrier + tmem slot | byte tile, later the A operand
+    off += (size_t)tc_np(d_out) * KP * 2;                      // B operand
+    off += (size_t)NP32 * WP * 4;                              // row bitmap
+    off += (size_t)round_up(N, 4) * 4 + (size_t)round_up(N * d_out, 4) * 4;     // dinv, Hs
+    off += (size_t)(CONV_MAXD * CONV_MAXD + CONV_MAXD) * 4;    // W
+    off += (size_t)round_up(N * d_in, 4) * 4;                  // H tile (TMA)
+    return off + 128;
+}
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    // cute/arch/mma_sm100_desc.hpp UMMA::SmemDescriptor: start >> 4 [0,14), LBO >> 4 [16,30), SBO >> 4 [32,46), version 1 [46,48)
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) |
+           ((uint64_t)1 << 46);
+}
+// UMMA::InstrDescriptor: D = F32 [4,6), A = B = BF16 [7,10) [10,13), K-major, N >> 3 [17,23), M >> 4 [24,29)
+__device__ __forceinline__ uint32_t umma_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(TC_T, 1) propagate_tc_kernel(const ConvArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int N = a.N, pitch = a.pitch, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int d_in = a.d_in, d_out = a.d_out, WP = conv_words(N), NP32 = WP * 32, KP = round_up(N, 16);
+    const int MP = tc_mp(N), NPc = tc_np(d_out), MT = MP / 128;
+    uint64_t* bar_tma = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* bar_mma = bar_tma + 1;
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(bar_tma + 2);
+    uint8_t* tile = smem + 32;
+    __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(smem + 32);                    // aliases the byte tile
+    const size_t tile_b = (size_t)round_up(N * pitch, 128), sa_b = (size_t)MP * KP * 2;
+    __nv_bfloat16* sB = reinterpret_cast<__nv_bfloat16*>(smem + 32 + (tile_b > sa_b ? tile_b : sa_b));
+    uint32_t* rbits = reinterpret_cast<uint32_t*>(sB + (size_t)NPc * KP);
+    float* dinv = reinterpret_cast<float*>(rbits + (size_t)NP32 * WP);
+    float* Hs = dinv + round_up(N, 4);
+    float* Ws = Hs + (size_t)round_up(N * d_out, 4);
+    float* Hin = Ws + CONV_MAXD * CONV_MAXD + CONV_MAXD;        // 16-byte aligned: every block above is a multiple of 4 floats
+    int tcols = 32;
+    while (tcols < MT * NPc) tcols <<= 1;
+    if (tid == 0) {
+        mbar_init(bar_tma, 1); mbar_init(bar_mma, 1);
+        fence_mbar_init();
+        const uint32_t hbytes = (uint32_t)N * d_in * 4;
+        const bool htma = (hbytes & 15u) == 0 && ((((size_t)b * N * d_in * 4) & 15) == 0) && (((uintptr_t)a.H & 15) == 0);
+        mbar_arrive_expect_tx(bar_tma, (uint32_t)N * pitch + (htma ? hbytes : 0u));
+        bulk_g2s(tile, a.adj + (size_t)b * N * pitch, (uint32_t)N * pitch, bar_tma);
+        if (htma) bulk_g2s(Hin, a.H + (size_t)b * N * d_in, hbytes, bar_tma);
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tslot)), "r"(tcols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (a.W) for (int i = tid; i < d_in * d_out; i += TC_T) Ws[i] = a.W[i];
+    {
+        const uint32_t hbytes = (uint32_t)N * d_in * 4;
+        const bool htma = (hbytes & 15u) == 0 && ((((size_t)b * N * d_in * 4) & 15) == 0) && (((uintptr_t)a.H & 15) == 0);
+        if (!htma) {            // odd shapes: plain coalesced copy of the feature tile
+            const float* Hb = a.H + (size_t)b * N * d_in;
+            for (int i = tid; i < N * d_in; i += TC_T) Hin[i] = Hb[i];
+        }
+    }
+    mbar_wait(bar_tma, 0);
+    __syncthreads();
+    for (int idx = tid; idx < N * d_out; idx += TC_T) {         // H W from shared memory
+        const int j = idx / d_out, c = idx - j * d_out;
+        float acc = 0.f;
+        if (a.W) { for (int k = 0; k < d_in; ++k) acc = fmaf(Hin[j * d_in + k], Ws[k * d_out + c], acc); }
+        else acc = Hin[j * d_in + c];
+        Hs[idx] = acc;
+    }
+    const bool self_loop = a.flags & HDGNN_P_SELF_LOOP, transpose = !(a.flags & HDGNN_P_NO_TRANSPOSE);
+    // degree scan + row bitmap while the byte tile is resident (same as conv_degree_scan, no transpose needed)
+    for (int j = warp; j < NP32; j += TC_T / 32) {
+        uint32_t m = 0u;
+        if (j < N && lane * 16 < pitch) {
+            const uint4 v = *reinterpret_cast<const uint4*>(tile + (size_t)j * pitch + lane * 16);
+            m = nz4(v.x) | (nz4(v.y) << 4) | (nz4(v.z) << 8) | (nz4(v.w) << 12);
+        }
+        const uint32_t hi = __shfl_down_sync(0xffffffffu, m, 1);
+        uint32_t w = 0u;
+        const int sg = lane >> 1;
+        if ((lane & 1) == 0 && sg < WP) {
+            w = m | (hi << 16);
+            const int c0 = sg * 32;
+            if (c0 + 32 > N) w &= (c0 >= N) ? 0u : (0xffffffffu >> (c0 + 32 - N));
+            if ((j >> 5) == sg) w &= ~(1u << (j & 31));
+            rbits[(size_t)j * WP + sg] = w;
+        }
+        const int deg = __reduce_add_sync(0xffffffffu, __popc(w));
+        if (lane == 0 && j < N) dinv[j] = 1.f / sqrtf((float)deg + (self_loop ? 1.f : 0.f) + a.eps);
+    }
+    __syncthreads();                    // the byte tile is dead from here on: sA overwrites it
+    if (a.dinv_out) for (int j = tid; j < N; j += TC_T) a.dinv_out[(size_t)b * N + j] = dinv[j];
+    // A operand: A_mma[m = i][k = j] = adj[j][i] (reference form) or adj[i][j]; + I with the self loop; zero padding
+    const uint32_t one = 0x3F80u;       // bf16 1.0
+    for (int t = tid; t < MP * (KP >> 3); t += TC_T) {
+        const int kk = t / MP, m = t - kk * MP;
+        uint32_t bits8 = 0u;
+        if (m < N) {
+            if (transpose) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int j = kk * 8 + u;
+                    bits8 |= ((rbits[(size_t)j * WP + (m >> 5)] >> (m & 31)) & 1u) << u;     // rows j >= N are zero (padded bitmap)
+                }
+            } else {
+                bits8 = (rbits[(size_t)m * WP + (kk >> 2)] >> ((kk & 3) * 8)) & 0xffu;
+            }
+            if (self_loop && (m >> 3) == kk) bits8 |= 1u << (m & 7);
+        }
+        uint4 v;
+        v.x = ((bits8 & 1u) ? one : 0u) | ((bits8 & 2u) ? one << 16 : 0u);
+        v.y = ((bits8 & 4u) ? one : 0u) | ((bits8 & 8u) ? one << 16 : 0u);
+        v.z = ((bits8 & 16u) ? one : 0u) | ((bits8 & 32u) ? one << 16 : 0u);
+        v.w = ((bits8 & 64u) ? one : 0u) | ((bits8 & 128u) ? one << 16 : 0u);
+        *reinterpret_cast<uint4*>(sA + ((size_t)kk * MP + m) * 8) = v;
+    }
+    // B operand: B_mma[n = 4 c + s][k = j] = s-th bf16 term of dinv_j * Hs[j][c] (s = 0, 1, 2), zero elsewhere
+    for (int t = tid; t < (NPc >> 2) * (KP >> 3); t += TC_T) {
+        const int kk = t / (NPc >> 2), c = t - kk * (NPc >> 2);
+        __nv_bfloat16 o0[8], o1[8], o2[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j = kk * 8 + u;
+            const float v = (c < d_out && j < N) ? Hs[(size_t)j * d_out + c] * dinv[j] : 0.f;
+            o0[u] = __float2bfloat16_rn(v);
+            const float r1 = v - __bfloat162float(o0[u]);
+            o1[u] = __float2bfloat16_rn(r1);
+            o2[u] = __float2bfloat16_rn(r1 - __bfloat162float(o1[u]));
+        }
+        uint4* dst = reinterpret_cast<uint4*>(sB + ((size_t)kk * NPc + 4 * c) * 8);
+        dst[0] = *reinterpret_cast<const uint4*>(o0); dst[1] = *reinterpret_cast<const uint4*>(o1);
+        dst[2] = *reinterpret_cast<const uint4*>(o2); dst[3] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async();                // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tslot;
+    if (tid == 0) {
+        const uint32_t idesc = umma_idesc(128, NPc);
+        for (int mt = 0; mt < MT; ++mt) {
+            for (int ks = 0; ks < (KP >> 4); ++ks) {
+                const uint64_t da = umma_desc(smem_u32(sA) + (uint32_t)(ks * 2 * MP + mt * 128) * 16, (uint32_t)MP * 16, 128);
+                const uint64_t db = umma_desc(smem_u32(sB) + (uint32_t)(ks * 2 * NPc) * 16, (uint32_t)NPc * 16, 128);
+                const uint32_t accum = ks > 0;
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                             ::"r"(tmem + (uint32_t)(mt * NPc)), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
+            }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar_mma)) : "memory");
+    }
+    mbar_wait(bar_mma, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // epilogue: warp w owns TMEM lanes 32 (w % 4) .. + 31 of M tile w / 4
+    if (warp / 4 < MT) {
+        const int mt = warp >> 2, i = mt * 128 + (warp & 3) * 32 + lane;
+        const float di = i < N ? dinv[i] : 0.f;
+        for (int c0 = 0; c0 < d_out; c0 += 4) {
+            uint32_t r[16];
+            const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mt * NPc + 4 * c0);
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                         : "r"(taddr) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (i < N) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int c = c0 + q;
+                    if (c < d_out) {
+                        const float acc = (__uint_as_float(r[4 * q]) + __uint_as_float(r[4 * q + 1])) + __uint_as_float(r[4 * q + 2]);
+                        float v = fmaf(di, acc, a.bias ? a.bias[c] : 0.f);
+                        if (a.flags & HDGNN_P_RELU) v = fmaxf(v, 0.f);
+                        a.out[((size_t)b * N + i) * d_out + c] = v;
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tcols) : "memory");
+}
+
 // per commit: q_b = x^T (t0 x + t1 ((2/lam)(x - A_hat x) - x)),  t = softmax(theta)
 __global__ void __launch_bounds__(CONV_T) map_conv_kernel(const ConvArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -228,15 +428,22 @@ extern "C" int hdgnn_normalize_propagate(int B, int N, const uint8_t* adj, int p
     if (rc) return rc;
     if (!H || !out || d_in < 1 || d_in > CONV_MAXD || d_out < 1 || d_out > CONV_MAXD) return HDGNN_E_INVALID;
     if (!W && d_in != d_out) return HDGNN_E_INVALID;
-    const size_t smem = conv_smem_bytes(N, pitch, d_out);
     int dev = 0, optin = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
         return HDGNN_E_CUDA;
-    if (smem > (size_t)optin) return HDGNN_E_UNSUPPORTED;       // the per-commit tile must fit one SM
-    if (cudaFuncSetAttribute(propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) != cudaSuccess) return HDGNN_E_CUDA;
     ConvArgs a{};
     a.B = B; a.N = N; a.pitch = pitch; a.d_in = d_in; a.d_out = d_out; a.flags = flags; a.eps = eps;
     a.adj = adj; a.H = H; a.W = W; a.bias = bias; a.out = out; a.dinv_out = dinv_out;
+    // tensor-core path (tcgen05): N <= 256 and the operands fit one SM; else the set-bit walk on the CUDA cores
+    const size_t smem_tc = tc_smem_bytes(N, pitch, d_in, d_out);
+    if (!(flags & HDGNN_P_NO_TENSOR) && N <= 256 && smem_tc <= (size_t)optin) {
+        if (cudaFuncSetAttribute(propagate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) != cudaSuccess) return HDGNN_E_CUDA;
+        propagate_tc_kernel<<<B, TC_T, smem_tc, (cudaStream_t)stream>>>(a);
+        return cudaGetLastError() == cudaSuccess ? HDGNN_OK : HDGNN_E_CUDA;
+    }
+    const size_t smem = conv_smem_bytes(N, pitch, d_out);
+    if (smem > (size_t)optin) return HDGNN_E_UNSUPPORTED;       // the per-commit tile must fit one SM
+    if (cudaFuncSetAttribute(propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) != cudaSuccess) return HDGNN_E_CUDA;
     propagate_kernel<<<B, CONV_T, smem, (cudaStream_t)stream>>>(a);
     return cudaGetLastError() == cudaSuccess ? HDGNN_OK : HDGNN_E_CUDA;
 }

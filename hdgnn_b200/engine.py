@@ -204,7 +204,7 @@ class Engine:
 
 
 # -- legacy operator of model.py (normalize_adj + propagation, Chebyshev map_conv) -------------------------------
-P_SELF_LOOP, P_RELU, P_NO_TRANSPOSE = 1, 2, 4
+P_SELF_LOOP, P_RELU, P_NO_TRANSPOSE, P_NO_TENSOR = 1, 2, 4, 8
 
 
 def _pitched(adj: torch.Tensor) -> torch.Tensor:

@@ -31,13 +31,13 @@ def _ref_propagate(adj, H, W, bias, eps, self_loop, relu, transpose):
 
 @pytest.mark.parametrize("B,N,d_in,d_out,p", [(3, 9, 4, 4, 0.3), (4, 50, 7, 20, 0.1), (2, 200, 20, 20, 0.05), (2, 250, 1, 1, 0.05),
                                               (1, 300, 20, 32, 0.02)])
-@pytest.mark.parametrize("flags", [0, 1, 2 | 4, 1 | 2])
+@pytest.mark.parametrize("flags", [0, 1, 2 | 4, 1 | 2, 8, 8 | 1 | 2 | 4])      # 8 = CUDA-core path, else tcgen05 when N <= 256
 def test_normalize_propagate(B, N, d_in, d_out, p, flags):
     from hdgnn_b200.engine import normalize_propagate
     rng = np.random.default_rng(N + flags)
     adj = _adj(B, N, p, N)
     H = rng.normal(size=(B, N, d_in)).astype(np.float32)
-    W = None if d_in == d_out and flags == 0 else rng.normal(scale=0.3, size=(d_in, d_out)).astype(np.float32)
+    W = None if d_in == d_out and flags in (0, 8) else rng.normal(scale=0.3, size=(d_in, d_out)).astype(np.float32)
     bias = rng.normal(size=d_out).astype(np.float32) if flags & 2 else None
     out, dinv = normalize_propagate(torch.tensor(adj).cuda(), torch.tensor(H).cuda(), None if W is None else torch.tensor(W).cuda(),
                                     None if bias is None else torch.tensor(bias).cuda(), eps=1e-3, flags=flags)
