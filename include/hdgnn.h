@@ -60,14 +60,14 @@ typedef struct {
                                3 = model_3 (HD-GNN/E), 4 = model_4 (HD-GNN) */
     int32_t max_batch;      /* largest B any later call will pass */
     int32_t device;         /* CUDA device ordinal */
-    int32_t rows_per_cta_e; /* tuning: entity-grid rows per CTA, 0 = default */
-    int32_t rows_per_cta_c; /* tuning: hunk-grid rows per CTA, 0 = default */
+    int32_t rows_per_cta_e; /* tuning of the multi-kernel path: entity-grid rows per CTA, 0 = default */
+    int32_t rows_per_cta_c; /* tuning of the multi-kernel path: hunk-grid rows per CTA, 0 = default */
     int32_t flags;          /* HDGNN_F_* */
 } hdgnn_config_t;
 
-#define HDGNN_F_GRAPH   1   /* cache the launch sequence of the *_host entry points as a CUDA graph */
+/* flag value 1 is reserved */
 #define HDGNN_F_DEBUG   2   /* keep named copies of intermediates for hdgnn_workspace (tests) */
-#define HDGNN_F_LEGACY  4   /* force the multi-kernel path (the only path for variant 4 / very large Nc) */
+#define HDGNN_F_LEGACY  4   /* force the multi-kernel path (the only path for variant 4 and for Nc above ~130) */
 
 /* number of fp32 parameters of a variant (2127 for variant 2, 3129 for variant 4) */
 int hdgnn_param_count(int variant);
