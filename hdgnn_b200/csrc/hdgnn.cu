@@ -102,6 +102,7 @@ struct hdgnn_handle_s {
     int fwd_occ = 1, bwd_occ = 1;                              // resident CTAs per SM
     bool pdl = true;                                           // programmatic dependent launch between the fused kernels
     int bslot = 0;                                             // bitmap buffer of the current step (two alternate)
+    bool dlt_global = false;                                   // mid2's dL/dlogit table in HBM instead of shared memory
     int Gf = 0, Gb = 0, Rf = 0, Rb = 0, SLf = 0;               // grids / rows per CTA / slots of the last launch
     std::map<std::string, Buf> ws;
     std::string err;
@@ -545,7 +546,9 @@ int fused_forward(hdgnn_handle_t h, int B, int B_global, const Inputs& in, float
     m.GE = F(h, "GE"); m.gpart = F(h, "GPART"); m.total = h->po.total;
     m.dbg = h->debug ? F(h, "DBG") : nullptr;
     m.clk = h->debug ? (long long*)h->ws["CLK"].p : nullptr;
-    const size_t smem = mid2_smem_bytes(h->Ne, h->Nc, train);
+    const bool dlt_g = train && h->dlt_global;
+    m.dlt_g = dlt_g ? F(h, "DLT") : nullptr;
+    const size_t smem = mid2_smem_bytes(h->Ne, h->Nc, train, !dlt_g);
     const int cwc = (h->Nc + 31) / 32;
     PROF_BEGIN(h, st);
     launch_mid2(cwc, train, B, smem, st, m, h->pdl && h->ent);
@@ -684,8 +687,11 @@ int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out) {
     if (h->fwd_nrg != 1 && h->fwd_nrg != 2 && h->fwd_nrg != 4) h->fwd_nrg = 1;
     if (h->bwd_nrg != 1 && h->bwd_nrg != 2 && h->bwd_nrg != 4) h->bwd_nrg = 1;
     // the fused path needs the per-commit state of mid2 in one SM's shared memory and a hunk grid of <= 8 segments
-    h->fused = !h->edge && !(cfg->flags & HDGNN_F_LEGACY) && h->Nc <= 256 &&
-               mid2_smem_bytes(h->Ne, h->Nc, true) <= (size_t)prop.sharedMemPerBlockOptin;
+    h->fused = !h->edge && !(cfg->flags & HDGNN_F_LEGACY) && h->Nc <= 256;
+    if (h->fused) {     // per-commit state of mid2 in one SM; the per-pair dL/dlogit table may spill to HBM (L2-resident)
+        h->dlt_global = mid2_smem_bytes(h->Ne, h->Nc, true, true) > (size_t)prop.sharedMemPerBlockOptin;
+        h->fused = mid2_smem_bytes(h->Ne, h->Nc, true, !h->dlt_global) <= (size_t)prop.sharedMemPerBlockOptin;
+    }
     cudaError_t e = set_attrs(h, (int)prop.sharedMemPerBlockOptin);
     if (e == cudaSuccess && h->fused) e = setup_fused(h, (int)prop.sharedMemPerBlockOptin);
     if (e != cudaSuccess) {
@@ -722,6 +728,7 @@ int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out) {
         {"EBITS1", B * Ne * (size_t)h->WPe * 4, h->fused}, {"YBITS1", B * Nc * (size_t)h->WPc * 4, h->fused},
         {"DBG", B * mid2_dbg_floats(h->Ne, h->Nc) * f, h->fused && h->debug},
         {"CLK", B * 16 * sizeof(long long), h->fused && h->debug},
+        {"DLT", B * Nc * (size_t)((h->Nc + 31) / 32 * 32) * f, h->fused && h->dlt_global},
         {"RSE", B * Ne * HD * f, h->edge}, {"CSEP", B * Se * Ne * HD * f, h->edge}, {"CSEF", B * Ne * HD * f, h->edge},
         {"PRE", B * Ne * HD * f, h->edge}, {"PCE", B * Ne * HD * f, h->edge},
         {"SOFT", B * Ne * Ne * 2 * f, h->edge}, {"DSOFT", B * Ne * Ne * 2 * f, h->edge},

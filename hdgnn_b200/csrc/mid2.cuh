@@ -45,6 +45,7 @@ struct Mid2Args {
     float* gpart; int total;                 // (B,total)
     float* dbg;                              // debug dumps (HDGNN_F_DEBUG) or null; layout below
     long long* clk;                          // per-phase clock64 stamps (B,16) or null
+    float* dlt_g;                            // (B, Nc, CW*32) dL/dlogit table in HBM when it does not fit smem, else null
 };
 // debug dump layout per commit (floats): S1[Ne*20] X2[Ne] NB[Nc*4] RS3[Nc*20] CS3[Nc*20] PR[Nc*20] PC[Nc*20]
 // DNB[Nc*4] DX2[Ne]
@@ -56,7 +57,8 @@ struct Mid2Smem {
     int x, x2, hm, SP, TP, dl, dx2, nb, dnb, ebits, ybits, scratch, red, uni, total;
 };
 
-__host__ __device__ inline Mid2Smem mid2_layout(int Ne, int Nc, bool train) {
+// dlt_smem: keep the per-pair dL/dlogit table of the training path in shared memory (else it lives in HBM / L2)
+__host__ __device__ inline Mid2Smem mid2_layout(int Ne, int Nc, bool train, bool dlt_smem = true) {
     Mid2Smem m;
     int o = 0;
     auto take = [&](int n) { int r = o; o += (n + 7) & ~7; return r; };      // 32-byte granules
@@ -73,15 +75,15 @@ __host__ __device__ inline Mid2Smem mid2_layout(int Ne, int Nc, bool train) {
     // union region: [hunk tables 12 Nc 20][dlt (training) | SP TP dl (pooling: dead while dlt is live)]; the
     // entity-state backward (after the pooling backward) reuses it from the start
     const int ent_phase = M2_CH * M2_NODE_F;
-    const int dlt = train ? Nc * cwc * 32 : 0, pool3 = 3 * ((4 * Ne + 7) & ~7);
+    const int dlt = (train && dlt_smem) ? Nc * cwc * 32 : 0, pool3 = 3 * ((4 * Ne + 7) & ~7);
     const int hunk_phase = ((12 * Nc * HD + 7) & ~7) + (dlt > pool3 ? dlt : pool3);
     m.SP = m.uni + ((12 * Nc * HD + 7) & ~7); m.TP = m.SP + ((4 * Ne + 7) & ~7); m.dl = m.TP + ((4 * Ne + 7) & ~7);
     o += ent_phase > hunk_phase ? ent_phase : hunk_phase;
     m.total = o;
     return m;
 }
-__host__ __device__ inline size_t mid2_smem_bytes(int Ne, int Nc, bool train) {
-    return (size_t)mid2_layout(Ne, Nc, train).total * 4 + 16;
+__host__ __device__ inline size_t mid2_smem_bytes(int Ne, int Nc, bool train, bool dlt_smem = true) {
+    return (size_t)mid2_layout(Ne, Nc, train, dlt_smem).total * 4 + 16;
 }
 
 // fixed-order block sum for M2_T threads; every thread gets the result
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
     const int Ne = a.Ne, Nc = a.Nc, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int kg = warp % KG, rg = warp / KG, k0 = kg * 4;
     const int WPe = a.WPe, WPc = a.WPc;
-    const Mid2Smem L_ = mid2_layout(Ne, Nc, TRAIN);
+    const Mid2Smem L_ = mid2_layout(Ne, Nc, TRAIN, a.dlt_g == nullptr);
     float* blk1 = sm + L_.blk1; float* blk2 = sm + L_.blk2;
     float* W5 = blk1; float* b5 = blk1 + 400; float* U1 = blk1 + 420; float* c1 = blk1 + 840;
     float* u2 = blk1 + 860; float* c2 = blk1 + 880;
@@ -474,8 +476,9 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
     float* PC = uni + 9 * T;        // later dc
     float* RSm = uni + 10 * T;      // later RS3d
     float* CSm = uni + 11 * T;      // later CS3d
-    float* dlt = uni + ((12 * T + 7) & ~7);     // [Nc][CWT*32] dL/dlogit-difference per pair (training); aliases SP/TP/dl
     constexpr int DW = CWT * 32;
+    // [Nc][CWT*32] dL/dlogit-difference per pair (training); in smem it aliases SP/TP/dl, else HBM (L2-resident)
+    float* dlt = a.dlt_g ? a.dlt_g + (size_t)b * Nc * DW : uni + ((12 * T + 7) & ~7);
     for (int idx = tid; idx < T; idx += M2_T) {
         const int c = idx / HD, k = idx - c * HD;
         float p = d1[k] + V1[8 * HD + k], q = 0.f;
@@ -627,12 +630,15 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             const float* prow0 = PR01 + (size_t)r * PROW + kg * 8;
             const float* prow1 = prow0 + 4;
             const float* drow = dlt + (size_t)r * DW + lane;
+            float dvs[CWT];
+#pragma unroll
+            for (int sg = 0; sg < CWT; ++sg) dvs[sg] = drow[sg * 32];      // all loads of the row in flight (HBM/L2 when spilled)
             rp0 = 0ull; rp1 = 0ull;
 #pragma unroll
             for (int sg = 0; sg < CWT; ++sg) {
                 const bool bit = (w[sg] & lmask) != 0u;
                 const ulonglong2 p = *reinterpret_cast<const ulonglong2*>(bit ? prow1 : prow0);
-                const float dv = drow[sg * 32];
+                const float dv = dvs[sg];
                 const u64 d2 = pk2(dv, dv);
                 const u64 v0 = gate2(add2(p.x, Q[sg][0]), d2), v1 = gate2(add2(p.y, Q[sg][1]), d2);
                 col[sg][0] = add2(col[sg][0], v0); col[sg][1] = add2(col[sg][1], v1);

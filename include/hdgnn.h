@@ -67,7 +67,7 @@ typedef struct {
 
 /* flag value 1 is reserved */
 #define HDGNN_F_DEBUG   2   /* keep named copies of intermediates for hdgnn_workspace (tests) */
-#define HDGNN_F_LEGACY  4   /* force the multi-kernel path (the only path for variant 4 and for Nc above ~130) */
+#define HDGNN_F_LEGACY  4   /* force the multi-kernel path (the only path for variant 4 and for Nc above ~160) */
 
 /* number of fp32 parameters of a variant (2127 for variant 2, 3129 for variant 4) */
 int hdgnn_param_count(int variant);
