@@ -397,29 +397,28 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         int nchunk = M2_T / Lb;
         nchunk = nchunk < 1 ? 1 : (nchunk > 4 ? 4 : nchunk);
         float* partC = scratch;                         // [nchunk][Lb][4]
+        int2* rowtab = reinterpret_cast<int2*>(scratch + 16 * Ne);      // [Lb] grid coordinates (row, offset) of flat index li m
+        for (int li = tid; li < Lb; li += M2_T) { const int q = li * m, g = q / n; rowtab[li] = make_int2(g, q - g * n); }
+        __syncthreads();
         for (int t = tid; t < nchunk * Lb; t += M2_T) {
             const int c = t / Lb, me = t - c * Lb;
             const int lo = (c * Lb) / nchunk, hi = ((c + 1) * Lb) / nchunk;
             float q0 = 0.f, q1 = 0.f;
-            int q3 = 0, cnt = 0;
-#pragma unroll
-            for (int part = 0; part < 2; ++part) {      // li < lj (flat column lj - 1), then li > lj (flat column lj)
-                const int l0 = part == 0 ? lo : max(lo, me + 1), l1 = part == 0 ? min(hi, me) : hi;
-                if (l0 >= l1) continue;
-                const int q = l0 * m + me - (part == 0 ? 1 : 0);
-                int gi = q / n, pp = q - gi * n;
-                const int trips = l1 - l0;
-                cnt += trips;
+            int q3 = 0;
+            const int cnt = (hi - lo) - ((me >= lo && me < hi) ? 1 : 0);
+            // no loop-carried index state: iteration li starts from the tabulated coordinates of li m (m < n: at most
+            // one row wrap), so the loads of several iterations overlap
 #pragma unroll 4
-                for (int it = 0; it < trips; ++it) {    // counted and branch-free: m < n, at most one row wrap per step
-                    const int gj = pp + (pp >= gi);
-                    q0 += x2[gi]; q1 += x2[gj];
-                    q3 += (ebits[gi * WPe + (gj >> 5)] >> (gj & 31)) & 1u;
-                    pp += m;
-                    const int w = pp >= n;
-                    pp -= w ? n : 0;
-                    gi += w;
-                }
+            for (int li = lo; li < hi; ++li) {
+                const int2 e = rowtab[li];
+                int pp = e.y + me - (li < me ? 1 : 0);
+                const int w = pp >= n;
+                pp -= w ? n : 0;
+                const int gi = e.x + w, gj = pp + (pp >= gi);
+                const bool valid = li != me;
+                const float xa = x2[gi], xb = x2[gj];
+                const uint32_t bit = (ebits[gi * WPe + (gj >> 5)] >> (gj & 31)) & 1u;
+                q0 += valid ? xa : 0.f; q1 += valid ? xb : 0.f; q3 += valid ? bit : 0u;
             }
             float* pc = partC + ((size_t)c * Lb + me) * 4;
             pc[0] = q0; pc[1] = q1; pc[2] = (float)(cnt - q3); pc[3] = (float)q3;
