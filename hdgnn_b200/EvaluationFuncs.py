@@ -101,3 +101,39 @@ def AUC(label, real, quirks=True):
         return last
     good = [v for v in vals if v is not None]
     return float(np.mean(good)) if good else float("nan")
+
+
+def metrics_from_counts(counts, quirks=True):
+    """The printed metrics of model_2.py:535-540 from the integer counters of hdgnn_eval_counts (include/hdgnn.h):
+    counts (N,8) = {arg-max hits, quirk tp fp fn, conventional tp fp fn, related pairs}.  Same conventions as the array
+    functions above (sklearn: 0 on an empty denominator); top_ACC = hits / (N Ncr)."""
+    c = np.asarray(counts, dtype=np.int64)
+    o = 1 if quirks else 4
+    tp, fp, fn = (c[:, o + k].astype(np.float64) for k in range(3))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        p = np.where(tp + fp > 0, tp / (tp + fp), 0.0)
+        r = np.where(tp + fn > 0, tp / (tp + fn), 0.0)
+        f = np.where(2 * tp + fp + fn > 0, 2 * tp / (2 * tp + fp + fn), 0.0)
+    out = dict(hits=int(c[:, 0].sum()), prec=float(p.mean()), recall=float(r.mean()), f1=float(f.mean()))
+    return out
+
+
+def _auc_from_counts(num, npos, ncr):
+    npos = npos.astype(np.float64)
+    den = 2.0 * npos * (ncr - npos)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.where(den > 0, num / den, np.nan)
+
+
+def auc_from_counts(counts, auc, ncr, quirks=True, first=0):
+    """AUC of EvaluationFuncs.py:119-153 from device counters: quirk form = the last commit's value
+    (ZeroDivisionError when it has one class), conventional = mean over the commits with both classes."""
+    c = np.asarray(counts, dtype=np.int64)
+    a = np.asarray(auc, dtype=np.int64)
+    vals = _auc_from_counts(a[:, 0 if quirks else 1], c[:, 7], ncr)
+    if quirks:
+        if np.isnan(vals[-1]):
+            raise ZeroDivisionError("float division by zero")
+        return float(vals[-1])
+    good = vals[first:][~np.isnan(vals[first:])]
+    return float(good.mean()) if good.size else float("nan")

@@ -46,6 +46,8 @@ def _load():
         "hdgnn_infer_host": ([vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp], i32),
         "hdgnn_normalize_propagate": ([i32, i32, vp, i32, vp, i32, vp, vp, i32, f32, i32, vp, vp, vp], i32),
         "hdgnn_map_conv": ([i32, i32, vp, i32, vp, vp, f32, f32, i32, vp, vp, vp], i32),
+        "hdgnn_compact_from_raw": ([i32, i32, vp, i32, vp, i32, vp, vp, vp], i32),
+        "hdgnn_eval_counts": ([i32, i32, vp, vp, i32, vp, vp, i32, vp], i32),
         "hdgnn_workspace": ([vp, C.c_char_p, C.POINTER(vp), C.POINTER(C.c_size_t)], i32),
         "hdgnn_workspace_copy": ([vp, C.c_char_p, vp, C.c_size_t, vp], i32),
         "hdgnn_profile": ([vp, i32], i32),

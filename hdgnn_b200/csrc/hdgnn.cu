@@ -932,7 +932,7 @@ int hdgnn_train_step_host(hdgnn_handle_t h, int B, const uint8_t* adj_host, cons
     if (rc) return rc;
     if ((rc = release_slot(h, st))) return rc;
     if (probs_host)
-        CK(h, cudaMemcpyAsync(probs_host, probs_d, (size_t)B * 2 * h->Nc * (h->Nc - 1) * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CK(h, cudaMemcpyAsync(probs_host, probs_d, (size_t)B * 2 * h->Nc * (h->Nc - 1) * sizeof(float), cudaMemcpyDefault, st));
     CK(h, cudaMemcpyAsync(loss3_host, loss_d, 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
     return HDGNN_OK;
 }
@@ -970,7 +970,7 @@ int hdgnn_infer_host(hdgnn_handle_t h, int B, const uint8_t* adj_host, const flo
     rc = run_step(h, B, B, in, nullptr, F(h, "H_PROBS"), F(h, "H_LOSS"), nullptr, nullptr, st);
     if (rc) return rc;
     if ((rc = release_slot(h, st))) return rc;
-    CK(h, cudaMemcpyAsync(probs_host, F(h, "H_PROBS"), (size_t)B * 2 * h->Nc * (h->Nc - 1) * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(h, cudaMemcpyAsync(probs_host, F(h, "H_PROBS"), (size_t)B * 2 * h->Nc * (h->Nc - 1) * sizeof(float), cudaMemcpyDefault, st));
     if (loss_host) CK(h, cudaMemcpyAsync(loss_host, F(h, "H_LOSS"), sizeof(float), cudaMemcpyDeviceToHost, st));
     return HDGNN_OK;
 }

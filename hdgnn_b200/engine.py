@@ -251,3 +251,44 @@ def map_conv(adj: torch.Tensor, x: torch.Tensor, theta: torch.Tensor, lam_max: f
     check(lib.hdgnn_map_conv(B, N, _p(a), pitch, _p(x.contiguous().float()), _p(theta.reshape(-1).contiguous().float()),
                              lam_max, eps, flags, _p(per), _p(loss), st))
     return loss, per
+
+
+# -- data formats either side of the hot path: device loader and device evaluation --------
+def compact_from_raw_device(raw: torch.Tensor, want_diag: bool = True):
+    """utils2.py:29-47 + the int() label indexing of :82,:105 on the device.  raw: (N,n,n) float64 / float32 CUDA tensor
+    as stored in CAdjs / CHunkAdjs.  Returns (grid u8 (N,n,pitch), diag f32 (N,n) or None); raises IndexError where
+    the reference would (an off-diagonal entry that does not truncate to -2, -1, 0 or 1)."""
+    if not raw.is_cuda:
+        raise RuntimeError("compact_from_raw_device needs a CUDA tensor; there is no CPU fallback")
+    if raw.dtype not in (torch.float64, torch.float32):
+        raw = raw.to(torch.float64)
+    raw = raw.contiguous()
+    N, n, n2 = raw.shape
+    assert n == n2
+    pitch = label_pitch(n)
+    grid = torch.empty(N, n, pitch, dtype=torch.uint8, device=raw.device)
+    diag = torch.empty(N, n, dtype=torch.float32, device=raw.device) if want_diag else None
+    err = torch.zeros(1, dtype=torch.int32, device=raw.device)
+    st = C.c_void_p(torch.cuda.current_stream(raw.device).cuda_stream)
+    check(lib.hdgnn_compact_from_raw(N, n, _p(raw), 1 if raw.dtype == torch.float64 else 0, _p(grid), pitch, _p(diag),
+                                     _p(err), st))
+    if int(err.item()):
+        raise IndexError("off-diagonal entries must truncate to 0 or 1 (utils2.py:82,105)")
+    return grid, diag
+
+
+def eval_counts(probs: torch.Tensor, Y: torch.Tensor, auc: bool = False, auc_first: int = 0):
+    """Evaluation counters of EvaluationFuncs.py on the device.  probs (B,2,Ncr) f32 CUDA, Y (B,Nc,Nc|pitch) u8 CUDA.
+    Returns (counts (B,8) int64, auc (B,2) int64 or None), see include/hdgnn.h; feed them to
+    EvaluationFuncs.metrics_from_counts."""
+    if not (probs.is_cuda and Y.is_cuda):
+        raise RuntimeError("eval_counts needs CUDA tensors; there is no CPU fallback")
+    probs = probs.contiguous()
+    Y = Y.contiguous()
+    B, Nc, pitch = Y.shape
+    assert probs.dtype == torch.float32 and probs.shape == (B, 2, Nc * (Nc - 1)) and Y.dtype == torch.uint8
+    counts = torch.empty(B, 8, dtype=torch.int64, device=probs.device)
+    a = torch.empty(B, 2, dtype=torch.int64, device=probs.device) if auc else None
+    st = C.c_void_p(torch.cuda.current_stream(probs.device).cuda_stream)
+    check(lib.hdgnn_eval_counts(B, Nc, _p(probs), _p(Y), pitch, _p(counts), _p(a), auc_first, st))
+    return counts, a

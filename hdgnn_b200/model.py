@@ -155,21 +155,22 @@ class graph2graph(object):
     def train_step(self, hb: HostBatch, want_probs: bool = False, probs_out: Optional[torch.Tensor] = None):
         """hb: this rank's shard of the global batch (pinned host tensors).  Returns the pinned
         3-vector {CE (this rank's share of the global mean), loss_map, loss_para}; valid after a
-        stream synchronize."""
+        stream synchronize.  probs_out: pinned host OR device tensor (>= (B,2,Ncr)) that receives the probabilities."""
         eng = self.engine
         if self.world == 1:
             eng.train_step_host(*hb.tensors(), self.params, self.m, self.v, self.step_counter, self.loss3,
                                 probs=probs_out if want_probs else None)
             return self.loss3
-        if want_probs and (not hasattr(self, "_probs_d") or self._probs_d.shape[0] < hb.B):
+        direct = want_probs and probs_out is not None and probs_out.is_cuda
+        if want_probs and not direct and (not hasattr(self, "_probs_d") or self._probs_d.shape[0] < hb.B):
             self._probs_d = torch.zeros(hb.B, 2, self.Ncr, dtype=torch.float32, device=eng.tdev)
-        eng.forward_backward_host(*hb.tensors(), self.params, self.grads, hb.B * self.world, loss=self.loss_d,
-                                  probs=self._probs_d if want_probs else None)
+        pd = (probs_out if direct else self._probs_d) if want_probs else None
+        eng.forward_backward_host(*hb.tensors(), self.params, self.grads, hb.B * self.world, loss=self.loss_d, probs=pd)
         torch.distributed.all_reduce(self.grads)        # the single collective of the step
         eng.adam_step(self.params, self.grads, self.m, self.v, self.step_counter, reg_losses=self.reg)
         self.loss3[0:1].copy_(self.loss_d, non_blocking=True)
         self.loss3[1:3].copy_(self.reg, non_blocking=True)
-        if want_probs and probs_out is not None:
+        if want_probs and probs_out is not None and not direct:
             probs_out.copy_(self._probs_d[:hb.B], non_blocking=True)
         return self.loss3
 
@@ -181,7 +182,7 @@ class graph2graph(object):
     # data
     def _load(self, root="."):
         from .utils2 import read_compact, split_half
-        cb = read_compact(self.Repo, self.Step, self.Ne, self.Nc, root=root)
+        cb = read_compact(self.Repo, self.Step, self.Ne, self.Nc, root=root, device=self.engine.tdev)
         return split_half(cb)
 
     def _batch(self, part: CommitBatch, maps: CommitBatch, j: int, quirk_q2: bool) -> CommitBatch:
@@ -202,8 +203,7 @@ class graph2graph(object):
     # ------------------------------------------------------------------------------------------
     def train(self, args=None, data=None, root=".", quirk_q2=True, log=print):
         """model_2.py:335-424.  `args` needs .Repo and .checkpoint_dir (main.py's namespace)."""
-        from .EvaluationFuncs import top_ACC
-        from .utils2 import edge_onehot
+        from .engine import eval_counts
         repo = getattr(args, "Repo", self.Repo)
         ckpt = getattr(args, "checkpoint_dir", self.checkpoint_dir)
         self.initialize()                                           # always from scratch (model_2.py:340-341)
@@ -212,37 +212,33 @@ class graph2graph(object):
         if self.world > 1 and mb % self.world:
             raise ValueError("Mini_batch must be divisible by the number of ranks")
         nb = int(train.B / mb)                                      # remainder batch dropped (model_2.py:364)
-        labels = edge_onehot(train.Y[:nb * mb])
         per = mb // self.world
-        probs_h = torch.zeros(per, 2, self.Ncr).pin_memory()
+        dev = self.engine.tdev
+        probs_d = torch.zeros(per, 2, self.Ncr, dtype=torch.float32, device=dev)
         counter = 1
         history = []
         start_time1 = time.time()
         for i in range(self.epoch):
             tr_loss_Hedge = 0.0
             tr_loss_map = 0.0
-            C_edge_t = []
+            hits = torch.zeros(1, dtype=torch.int64, device=dev)
             for j in range(nb):
                 hb = HostBatch(self._batch(train, train, j, quirk_q2))
-                l3 = self.train_step(hb, want_probs=True, probs_out=probs_h)
+                l3 = self.train_step(hb, want_probs=True, probs_out=probs_d)
+                # top_ACC (EvaluationFuncs.py:27-37) from device counters: the probabilities never leave the GPU
+                counts, _ = eval_counts(probs_d[:hb.B], hb.Y.to(dev, non_blocking=True))
+                hits += counts[:, 0].sum()
                 torch.cuda.current_stream().synchronize()
                 ce = float(l3[0])
                 if self.world > 1:                                  # CE partials add up to the global mean
-                    t = torch.tensor([ce], device=self.engine.tdev)
+                    t = torch.tensor([ce], device=dev)
                     torch.distributed.all_reduce(t)
                     ce = float(t.item())
                 tr_loss_Hedge += ce
                 tr_loss_map += float(l3[1])
-                C_edge_t.append(probs_h.numpy().copy())
-            pred = np.concatenate(C_edge_t, 0)
             if self.world > 1:
-                lab = np.concatenate([labels[j * mb + self.rank * per: j * mb + (self.rank + 1) * per] for j in range(nb)], 0)
-                hit = torch.tensor([float(np.sum(np.argmax(pred, 1) == np.argmax(lab, 1))), float(lab.shape[0] * lab.shape[2])],
-                                   device=self.engine.tdev, dtype=torch.float64)
-                torch.distributed.all_reduce(hit)
-                acc_top = float(hit[0] / hit[1])
-            else:
-                acc_top = top_ACC(labels, pred)
+                torch.distributed.all_reduce(hits)
+            acc_top = float(int(hits.item()) / (nb * mb * self.Ncr)) if nb else float("nan")
             theta = self.named_params()["theta2"].numpy().reshape([2])
             resultString = "Epoch " + str(i + 1) + \
                            " acc: " + str(acc_top)[0:6] + \
@@ -267,8 +263,10 @@ class graph2graph(object):
 
     def test(self, args=None, data=None, root=".", quirk_q2=True, quirks=True, log=print):
         """model_2.py:453-544: inference over the test half, writes C_edge_t{Ne}.npy / C_edge_y{Ne}.npy and
-        prints the metric lines."""
-        from .EvaluationFuncs import top_ACC, prec, recall, f1, AUC, process_edge
+        prints the metric lines.  The metrics come from integer counters computed on the device
+        (hdgnn_eval_counts); the probabilities are copied back once, for the output file only."""
+        from .EvaluationFuncs import metrics_from_counts, auc_from_counts
+        from .engine import eval_counts
         from .utils2 import edge_onehot
         repo = getattr(args, "Repo", self.Repo)
         train, test = data if data is not None else self._load(root)
@@ -281,37 +279,42 @@ class graph2graph(object):
             log(" [!] Load failed...")
         mb = self.mini_batch_num
         nb = int(test.B / mb)
-        probs_h = torch.zeros(mb, 2, self.Ncr).pin_memory()
-        loss_h = torch.zeros(1).pin_memory()
-        te_loss_Hedge = 0.0
-        C_edge_t = []
+        n = nb * mb
+        dev = self.engine.tdev
+        probs_d = torch.zeros(max(n, 1), 2, self.Ncr, dtype=torch.float32, device=dev)
+        counts_d = torch.zeros(max(n, 1), 8, dtype=torch.int64, device=dev)
+        auc_d = torch.zeros(max(n, 1), 2, dtype=torch.int64, device=dev)
+        loss_h = torch.zeros(max(nb, 1)).pin_memory()
         start_time = time.time()
-        end_time = start_time
         for j in range(nb):
             saved = (self.world, self.rank)
             self.world, self.rank = 1, 0                            # inference is not sharded
             hb = HostBatch(self._batch(test, train, j, quirk_q2))
             self.world, self.rank = saved
-            self.infer(hb, probs_h, loss_h)
-            torch.cuda.current_stream().synchronize()
-            end_time = time.time()
-            te_loss_Hedge += float(loss_h[0])
-            C_edge_t.append(probs_h.numpy().copy())
-        n = nb * mb
-        C_edge_t1 = np.concatenate(C_edge_t, 0).reshape(n, self.Dr, self.Ncr) if nb else np.zeros((0, 2, self.Ncr), np.float32)
-        C_edge_test = edge_onehot(test.Y[:n])
+            pj = probs_d[j * mb:(j + 1) * mb]
+            self.infer(hb, pj, loss_h[j:j + 1])
+            # the reference's AUC keeps only the last commit of the whole test set (quirk Q7)
+            first = (mb - 1 if j == nb - 1 else mb) if quirks else 0
+            c, a = eval_counts(pj, hb.Y.to(dev, non_blocking=True), auc=True, auc_first=first)
+            counts_d[j * mb:(j + 1) * mb] = c
+            auc_d[j * mb:(j + 1) * mb] = a
+        torch.cuda.current_stream().synchronize()
+        end_time = time.time()
+        te_loss_Hedge = float(loss_h[:nb].sum())
+        C_edge_t1 = probs_d[:n].cpu().numpy().reshape(n, self.Dr, self.Ncr) if nb else np.zeros((0, 2, self.Ncr), np.float32)
         out = {}
         if self.rank == 0:
+            C_edge_test = edge_onehot(test.Y[:n])
             step_dir = os.path.join(root, 'outputSelf/' + repo + '/model_%d/' % self.variant + str(self.Step) + '/')
             os.makedirs(step_dir, exist_ok=True)
             np.save(step_dir + 'C_edge_t' + str(self.Ne) + '.npy', C_edge_t1)
             np.save(step_dir + 'C_edge_y' + str(self.Ne) + '.npy', C_edge_test)
-            C_edge_t2 = process_edge(C_edge_t1)
-            out = dict(topol_acc=top_ACC(C_edge_test, C_edge_t2), prec=prec(C_edge_test, C_edge_t2, quirks),
-                       recall=recall(C_edge_test, C_edge_t2, quirks), f1=f1(C_edge_test, C_edge_t2, quirks),
-                       hedge_loss=te_loss_Hedge / max(nb, 1))
+            counts, auc = counts_d[:n].cpu().numpy(), auc_d[:n].cpu().numpy()
+            m = metrics_from_counts(counts, quirks) if nb else dict(hits=0, prec=float("nan"), recall=float("nan"), f1=float("nan"))
+            out = dict(topol_acc=m["hits"] / max(n * self.Ncr, 1), prec=m["prec"], recall=m["recall"], f1=m["f1"],
+                       hedge_loss=te_loss_Hedge / max(nb, 1), counts=counts)
             try:
-                out["auc"] = AUC(C_edge_test, C_edge_t2, quirks)
+                out["auc"] = auc_from_counts(counts, auc, self.Ncr, quirks) if nb else float("nan")
             except ZeroDivisionError:
                 out["auc"] = float("nan")
             log('topol_acc: ' + str(out["topol_acc"]))

@@ -36,14 +36,8 @@ def _cache_path(root, repo, step, Ne, Nc):
     return os.path.join(root, "Intermediate_products", repo, f"compact_{step}_{Ne}_{Nc}.npz")
 
 
-def compact_from_raw(x_raw, y_raw, index_lines, hunk_maps, Ne, Nc) -> CommitBatch:
-    """x_raw (N,Ne,Ne), y_raw (N,Nc,Nc): arrays as stored; index_lines: per commit the list of lines of
-    its IndexPath file; hunk_maps: per commit dict key -> number."""
-    x_raw = np.asarray(x_raw)
-    y_raw = np.asarray(y_raw)
-    N = x_raw.shape[0]
-    if x_raw.shape[1:] != (Ne, Ne) or y_raw.shape != (N, Nc, Nc):
-        raise ValueError(f"adjacency shapes {x_raw.shape} / {y_raw.shape} do not match Ne={Ne}, Nc={Nc}")
+def _grids_host(x_raw, y_raw, Ne, Nc):
+    """Array half of the loader on the host (NumPy): the checker of the device loader and the form the CPU tests use."""
     ie, ic = np.arange(Ne), np.arange(Nc)
     x = x_raw[:, ie, ie].astype(np.float32)                      # utils2.py:31-36: node attribute = diagonal
     adj_f = np.array(x_raw, dtype=np.float64, copy=True)
@@ -52,11 +46,27 @@ def compact_from_raw(x_raw, y_raw, index_lines, hunk_maps, Ne, Nc) -> CommitBatc
     y_f[:, ic, ic] = 0                                            # utils2.py:47
     # utils2.py:82,105 index a size-2 axis with int(value): anything but 0/1 is an IndexError there
     for name, arr in (("CAdjs", adj_f), ("CHunkAdjs", y_f)):
+        if not np.isfinite(arr).all():
+            raise IndexError(f"{name}: off-diagonal entries must truncate to 0 or 1 (utils2.py:82,105)")
         iv = arr.astype(np.int64)                                 # int() truncates toward zero
         if iv.min() < -2 or iv.max() > 1:
             raise IndexError(f"{name}: off-diagonal entries must truncate to 0 or 1 (utils2.py:82,105)")
     adj = (adj_f.astype(np.int64) % 2).astype(np.uint8)           # int(v) in {-2,-1,0,1}; python index -1 == 1, -2 == 0
     Y = (y_f.astype(np.int64) % 2).astype(np.uint8)
+    return adj, x, Y
+
+
+def _grids_device(x_raw, y_raw, Ne, Nc, device):
+    """Array half of the loader on the GPU (hdgnn_compact_from_raw, csrc/k_io.cu); raises IndexError like the host form."""
+    import torch
+    from .engine import compact_from_raw_device
+    adj, x = compact_from_raw_device(torch.as_tensor(np.ascontiguousarray(x_raw)).to(device))
+    Y, _ = compact_from_raw_device(torch.as_tensor(np.ascontiguousarray(y_raw)).to(device), want_diag=False)
+    return adj[:, :, :Ne].cpu().numpy(), x.cpu().numpy(), Y[:, :, :Nc].cpu().numpy()
+
+
+def _index_maps(index_lines, hunk_maps, N, Ne, Nc):
+    """String half of the loader (utils2.py:111-137): per commit the hunk number of every index line."""
     hmap = np.full((N, Ne), -1, dtype=np.int32)
     L = np.zeros(N, dtype=np.int32)
     for b in range(N):
@@ -69,10 +79,24 @@ def compact_from_raw(x_raw, y_raw, index_lines, hunk_maps, Ne, Nc) -> CommitBatc
                 num = int(m[key])
                 if num < Nc:
                     hmap[b, i] = num if num >= 0 else num + Nc    # a negative number indexes from the end in numpy
+    return hmap, L
+
+
+def compact_from_raw(x_raw, y_raw, index_lines, hunk_maps, Ne, Nc, device=None) -> CommitBatch:
+    """x_raw (N,Ne,Ne), y_raw (N,Nc,Nc): arrays as stored; index_lines: per commit the list of lines of
+    its IndexPath file; hunk_maps: per commit dict key -> number.  device: CUDA device -> the array half runs on
+    the GPU (what graph2graph uses); None -> NumPy (CPU tests, the checker)."""
+    x_raw = np.asarray(x_raw)
+    y_raw = np.asarray(y_raw)
+    N = x_raw.shape[0]
+    if x_raw.shape[1:] != (Ne, Ne) or y_raw.shape != (N, Nc, Nc):
+        raise ValueError(f"adjacency shapes {x_raw.shape} / {y_raw.shape} do not match Ne={Ne}, Nc={Nc}")
+    adj, x, Y = _grids_host(x_raw, y_raw, Ne, Nc) if device is None else _grids_device(x_raw, y_raw, Ne, Nc, device)
+    hmap, L = _index_maps(index_lines, hunk_maps, N, Ne, Nc)
     return CommitBatch(adj, x, hmap, L, Y)
 
 
-def read_compact(repo: str, step: int, Ne: int, Nc: int, root: str = ".", cache: bool = True) -> CommitBatch:
+def read_compact(repo: str, step: int, Ne: int, Nc: int, root: str = ".", cache: bool = True, device=None) -> CommitBatch:
     cp = _cache_path(root, repo, step, Ne, Nc)
     if cache and os.path.exists(cp):
         z = np.load(cp)
@@ -93,7 +117,7 @@ def read_compact(repo: str, step: int, Ne: int, Nc: int, root: str = ".", cache:
         q = p if os.path.isabs(p) or os.path.exists(p) else os.path.join(root, p)
         with open(q) as f:
             lines.append(f.readlines())
-    cb = compact_from_raw(x_raw, y_raw, lines, hunk_maps, Ne, Nc)
+    cb = compact_from_raw(x_raw, y_raw, lines, hunk_maps, Ne, Nc, device=device)
     if cache:
         os.makedirs(os.path.dirname(cp), exist_ok=True)          # the reference needs this dir to pre-exist (Q14)
         np.savez_compressed(cp, adj=cb.adj, x=cb.x, hmap=cb.hmap, L=cb.L, Y=cb.Y)

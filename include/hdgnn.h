@@ -132,7 +132,8 @@ int hdgnn_train_step(hdgnn_handle_t h, int B,
  * loss3_host.  The kernels and the D2H copy are enqueued on `stream`; the H2D copies go through two staging
  * slots on a copy stream owned by the handle (ordered against `stream` by events), so the copies of one call
  * overlap the kernels of the previous one.  Host buffers must stay unchanged until `stream` has passed the call.  Un-pitched host layouts: adj (B,Ne,Ne), Y (B,Nc,Nc).
- * probs_host may be NULL (otherwise B*2*Ncr floats are copied back). */
+ * probs_host may be NULL (otherwise B*2*Ncr floats are copied out; the pointer may also be a DEVICE buffer, e.g. to feed
+ * hdgnn_eval_counts without a round trip through the host). */
 int hdgnn_train_step_host(hdgnn_handle_t h, int B,
                           const uint8_t* adj_host, const float* x_host, const int32_t* hmap_host,
                           const int32_t* L_host, const uint8_t* Y_host,
@@ -148,7 +149,7 @@ int hdgnn_forward_backward_host(hdgnn_handle_t h, int B, int B_global,
                                 const int32_t* L_host, const uint8_t* Y_host,
                                 const float* params, float* probs, float* loss, float* grads, void* stream);
 
-/* Inference from HOST buffers: H2D, forward, D2H of probs (B*2*Ncr floats) and CE. */
+/* Inference from HOST buffers: H2D, forward, copy-out of probs (B*2*Ncr floats; host or device pointer) and D2H of CE. */
 int hdgnn_infer_host(hdgnn_handle_t h, int B,
                      const uint8_t* adj_host, const float* x_host, const int32_t* hmap_host,
                      const int32_t* L_host, const uint8_t* Y_host,
@@ -175,6 +176,24 @@ int hdgnn_normalize_propagate(int B, int N, const uint8_t* adj, int adj_pitch, c
  * lam_max = 1.5, eps = 1e-3, flags = 0. */
 int hdgnn_map_conv(int B, int N, const uint8_t* adj, int adj_pitch, const float* x, const float* theta,
                    float lam_max, float eps, int flags, float* per_commit, float* loss, void* stream);
+
+/* ---- the data formats either side of the hot path; stateless, asynchronous on `stream` ----
+ * Device-side loader, replaces the array half of utils2.py:29-47 (diagonal -> node attribute, diagonal zeroed) and the
+ * int() label indexing of utils2.py:82,105.  raw: (N,n,n) float64 (raw_is_f64 != 0) or float32, exactly as stored in
+ * CAdjs_{step}.npy / CHunkAdjs_{step}.npy.  grid: (N,n,pitch) u8 in {0,1}, zero diagonal, zero padding (pitch as
+ * hdgnn_label_pitch(n)); diag: (N,n) f32 or NULL; err: device int32, OR-ed with 1 when an off-diagonal entry does
+ * not truncate to -2,-1,0 or 1 (an IndexError in the reference), may be NULL. */
+int hdgnn_compact_from_raw(int N, int n, const void* raw, int raw_is_f64, uint8_t* grid, int pitch, float* diag,
+                           int32_t* err, void* stream);
+
+/* Evaluation counters on the device, replaces the loops of EvaluationFuncs.py:27-37 (top_ACC), :92-117 (prec / recall /
+ * f1) and :119-153 (AUC) over the probs the relation head wrote.  probs (B,2,Ncr) f32, Y (B,Nc,y_pitch) u8.
+ * counts (B,8) int64: {arg-max hits, quirk tp, fp, fn (ceil of channel 0, as the reference scores), conventional tp, fp,
+ * fn (relation = channel 1, p1 > p0), related pairs}.  auc (B,2) int64 or NULL: Mann-Whitney numerators
+ * 2 #{s_neg < s_pos} + #{s_neg == s_pos} for {the reference's scoring, score = p1}, computed for commits >= auc_first
+ * (the reference's AUC only keeps the LAST commit, quirk Q7); AUC = auc / (2 npos nneg). */
+int hdgnn_eval_counts(int B, int Nc, const float* probs, const uint8_t* Y, int y_pitch, int64_t* counts, int64_t* auc,
+                      int auc_first, void* stream);
 
 /* Debug / test introspection: device pointer and size in bytes of a named scratch buffer
  * (RS1 CS1 S1 X2 NB PH QH RS3 CS3 PR PC GRH GCH RS3D CS3D DNB GE RS1D CS1D GPART ...). */

@@ -57,6 +57,16 @@ def test_train_loop_matches_oracle_training(tmp_path, variant):
     d = tmp_path / "outputSelf" / "toy" / f"model_{variant}" / "2"
     pt = np.load(d / f"C_edge_t{Ne}.npy"); py = np.load(d / f"C_edge_y{Ne}.npy")
     assert pt.shape == (test.B, 2, Nc * (Nc - 1)) and np.array_equal(py, edge_onehot(test.Y))
+    # the metric lines come from device counters: identical to the array functions pinned to EvaluationFuncs.py
+    from hdgnn_b200 import EvaluationFuncs as EV
+    assert out["topol_acc"] == EV.top_ACC(py, pt)
+    assert out["prec"] == EV.prec(py, pt) and out["recall"] == EV.recall(py, pt) and out["f1"] == EV.f1(py, pt)
+    try:
+        assert np.isclose(out["auc"], EV.AUC(py, pt), rtol=1e-13)
+    except ZeroDivisionError:
+        assert np.isnan(out["auc"])
+    # and the per-epoch accuracy of train() is a ratio of integers over the training half
+    assert all(0.0 <= h["acc"] <= 1.0 and (h["acc"] * train.B * Nc * (Nc - 1)) % 1 < 1e-6 for h in hist)
     # inference parity on the test half (maps of the first MB TRAIN commits, quirk Q2)
     P = O.unflatten(flat, variant)
     for j in range(test.B // MB):
@@ -64,6 +74,18 @@ def test_train_loop_matches_oracle_training(tmp_path, variant):
         ref = O.forward_closed(variant, P, b.adj, b.x, train.hmap[:MB], train.L[:MB], b.Y)["probs"].numpy()
         assert np.abs(pt[j * MB:(j + 1) * MB] - ref).max() < 1e-4
     model.engine.close()
+
+
+def test_device_loader_equals_host_loader(tmp_path):
+    """graph2graph._load runs the array half of the loader on the GPU (hdgnn_compact_from_raw)."""
+    cb = make_commits(N, Ne, Nc, seed=8, p_edge=0.2, p_short=0.4, p_noise=0.2)
+    write_dataset(cb, "toy", 2, root=str(tmp_path))
+    host = read_compact("toy", 2, Ne, Nc, root=str(tmp_path), cache=False)
+    dev = read_compact("toy", 2, Ne, Nc, root=str(tmp_path), cache=False, device=torch.device("cuda", 0))
+    for name in ("adj", "x", "hmap", "L", "Y"):
+        a, b = getattr(host, name), getattr(dev, name)
+        assert a.dtype == b.dtype and np.array_equal(a, b), name
+    assert np.array_equal(host.adj, cb.adj) and np.array_equal(host.Y, cb.Y)
 
 
 def test_main_cli_train_and_test(tmp_path, capsys):
