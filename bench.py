@@ -162,6 +162,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="commits per GPU per step (default: workload's)")
     ap.add_argument("--ref-sample", type=int, default=25, help="commits per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--collective", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N>1 gradient exchange: fused into the last kernel over NVLink peer memory, or NCCL all-reduce")
     ap.add_argument("--rows-e", type=int, default=0)
     ap.add_argument("--rows-c", type=int, default=0)
     args = ap.parse_args()
@@ -195,7 +197,7 @@ def main():
 
     Ne, Nc, B, variant = wl["Ne"], wl["Nc"], wl["B"], args.variant
     model = graph2graph(None, Ne=Ne, Nc=Nc, Mini_batch=B, Step=wl["step"], Repo="synthetic", variant=variant,
-                        device=local, seed=1234, max_batch=B)
+                        device=local, seed=1234, max_batch=B, collective=args.collective)
     eng = model.engine
     dev = eng.tdev
     # pool of distinct batches, larger than L2, generated globally (seed per pool slot and rank)
@@ -218,6 +220,9 @@ def main():
         db = dev_pool[k % pool_n]
         if world == 1:      # one fused call: forward, backward, gradient reduction + regularisers + Adam
             eng.train_step(db, model.params, model.m, model.v, model.step_counter, loss3, probs=probs)
+            return eng.last_launch_count()
+        if model.peer:      # same 5 launches: the all-reduce is fused into the reduce + Adam kernel (peer memory over NVLink)
+            eng.train_step_peer(db, model.params, model.m, model.v, model.step_counter, loss3, probs=probs)
             return eng.last_launch_count()
         eng.forward_backward(db, model.params, B_global=Bg, grads=model.grads, probs=probs, loss=loss)
         n = eng.last_launch_count()
@@ -335,13 +340,17 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["desc"], "variant": variant, "commits_per_gpu_per_step": B, "global_batch": Bg,
-                       "parallelism": f"commit-sharded dp{world}, one gradient all-reduce/step",
+                       "parallelism": f"commit-sharded dp{world}, " + (
+                           "no collective" if world == 1 else
+                           "gradient all-reduce fused into the reduce+Adam kernel over NVLink peer memory (no NCCL call in the step)"
+                           if model.peer else "one NCCL gradient all-reduce/step between backward and Adam"),
                        "l2": f"inputs rotate through {pool_n} distinct batches = {pool_n * batch_bytes / 2**20:.0f} MiB > 126 MiB L2"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "commits/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": host_pool[0].nbytes(), "d2h_bytes_per_step": 12,
                     "api": "hdgnn_b200.model.graph2graph.train_step: pinned host buffers -> hdgnn_train_step_host (1 GPU) / "
-                           "hdgnn_forward_backward_host + all-reduce + hdgnn_adam_step (N GPUs); H2D of step k+1 overlaps the kernels of step k"},
+                           "hdgnn_train_step_peer_host (N GPUs, peer exchange) or hdgnn_forward_backward_host + NCCL all-reduce + hdgnn_adam_step; "
+                           "H2D of step k+1 overlaps the kernels of step k"},
             "gpu_launches": launches,
             "roofline": roof,
             "cpu_baseline": cpu,

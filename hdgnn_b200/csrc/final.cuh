@@ -11,8 +11,45 @@ struct Rank1Map {            // where the four 20-vectors of an ent_bwd partial 
     int n, o_u, o_v, o_b, o_l;   // o_u == o_v: tied first-layer row (model_4.py:219-222)
 };
 
+// Peer exchange over NVLink / NVSwitch (commit sharding, one process per GPU): every rank owns a MAILBOX in its own
+// HBM that its peers write into directly (P2P stores through IPC-mapped pointers):
+//   inbox  [2][world][stride] u64   gradient slices by step parity and sending rank; each entry = {sequence number of
+//   lossin [2][world]         u64   the step : fp32 payload} written with ONE 8-byte store (single-copy atomic), so the
+//                                   payload needs no separate flag and no fence (the scheme of NCCL's LL protocol)
+// A CTA of reduce_adam_kernel pushes its 128-parameter slice to every rank, then every thread polls its own entry of
+// the rank's OWN mailbox until the step's sequence number shows up, and the slices are summed in rank order -- every
+// rank forms the bitwise identical sum, so the replicas never diverge.  Two parities suffice: a rank can only be one
+// step ahead of a peer (it needs that peer's slice to finish the step).
+constexpr int PEER_MAX = 8;
+typedef unsigned long long peer_word;
+struct PeerArgs {
+    int world, rank, stride, ncta;
+    peer_word* inbox[PEER_MAX];  // mailbox of rank r as mapped into this process (own entry = local pointer)
+    peer_word* lossin[PEER_MAX];
+    int* seq;                    // device counter: exchanges completed so far (local)
+    int* error;                  // set to 1 when a wait timed out
+};
+
+__device__ __forceinline__ void peer_push(peer_word* p, float v, int seq) {
+    const peer_word w = ((peer_word)(unsigned int)seq << 32) | (peer_word)__float_as_uint(v);
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+// Bounded wait: a lost peer traps instead of hanging the GPU.
+__device__ __forceinline__ float peer_pull(const peer_word* p, int seq, int* error) {
+    peer_word w;
+    unsigned int spin = 0;
+    for (;;) {
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+        if ((int)(w >> 32) == seq) break;
+        if (++spin > (1u << 24)) { *error = 1; __threadfence_system(); __trap(); }
+        __nanosleep(32);
+    }
+    return __uint_as_float((unsigned int)(w & 0xffffffffu));
+}
+
 struct FinalArgs {
     int B, total;
+    PeerArgs peer;           // peer.world <= 1: single GPU
     const float* gpart;      // (B,total)
     Rank1Map ent, edge;
     const float* cep; int ncep; float loss_denom; float* loss;
@@ -72,6 +109,7 @@ __global__ void __launch_bounds__(FIN_P * FIN_SL) reduce_adam_kernel(const Final
     __shared__ float part[FIN_SL][FIN_P];
     __shared__ float scratch[32];
     __shared__ float tn[3];
+    __shared__ float ce_sh;
     __shared__ int last;
     const int tid = threadIdx.x, pl = tid % FIN_P, sl = tid / FIN_P;
     const int p = blockIdx.x * FIN_P + pl;
@@ -102,19 +140,46 @@ __global__ void __launch_bounds__(FIN_P * FIN_SL) reduce_adam_kernel(const Final
         acc += rank1_extra(a.edge, p, sl, FIN_SL);
     }
     part[sl][pl] = acc;
+    float ce_local = 0.f;
     if (blockIdx.x == 0 && a.loss) {          // mean CE: fixed-order block sum of the per-commit partials
         float c = 0.f;
         for (int i = tid; i < a.ncep; i += blockDim.x) c += a.cep[i];
-        const float t = block_sum(c, scratch);
-        if (tid == 0) *a.loss = t / a.loss_denom;
+        ce_local = block_sum(c, scratch) / a.loss_denom;
+        if (tid == 0) *a.loss = ce_local;
     }
     __syncthreads();
     float g = 0.f;
     if (sl == 0 && p < a.total) {
 #pragma unroll
         for (int s = 0; s < FIN_SL; ++s) g += part[s][pl];
-        a.grads[p] = g;
     }
+    if (a.peer.world > 1) {
+        // ---- gradient all-reduce over peer memory, fused with the reduction above and the optimizer below ----
+        const PeerArgs& pr = a.peer;
+        const int W = pr.world, seq = *pr.seq + 1, par = seq & 1;
+        __syncthreads();                                   // part[][] has been consumed
+        if (sl == 0) part[0][pl] = g;
+        if (blockIdx.x == 0 && tid == 0) ce_sh = ce_local;
+        __syncthreads();
+        const float mine = part[0][pl];
+        const size_t slot = (size_t)par * W;
+        if (sl < W && p < a.total) peer_push(pr.inbox[sl] + (slot + pr.rank) * pr.stride + p, mine, seq);
+        if (blockIdx.x == 0 && tid < W && a.loss) peer_push(pr.lossin[tid] + slot + pr.rank, ce_sh, seq);
+        __syncthreads();                                   // part[0][] has been read
+        part[sl][pl] = (sl < W && p < a.total) ? peer_pull(pr.inbox[pr.rank] + (slot + sl) * pr.stride + p, seq, pr.error) : 0.f;
+        __syncthreads();
+        if (sl == 0 && p < a.total) {
+            g = 0.f;
+            for (int r = 0; r < W; ++r) g += part[r][pl];  // rank order: identical on every rank
+        }
+        if (blockIdx.x == 0 && tid == 0 && a.loss) {
+            float c = 0.f;
+            for (int r = 0; r < W; ++r) c += peer_pull(pr.lossin[pr.rank] + slot + r, seq, pr.error);
+            *a.loss = c;                                   // global mean CE
+        }
+        // *pr.seq is advanced by the last CTA of the optimizer tail below: by then every CTA has read it
+    }
+    if (sl == 0 && p < a.total) a.grads[p] = g;
     if (!a.apply_adam) return;
 
     // regularisers (evaluated at the pre-update parameters) + TF1 Adam
@@ -149,6 +214,7 @@ __global__ void __launch_bounds__(FIN_P * FIN_SL) reduce_adam_kernel(const Final
             a.reg_losses[1] = 0.001f * 0.5f * l2;
         }
         *a.step = t;
+        if (a.peer.world > 1) *a.peer.seq = *a.peer.seq + 1;
         *a.counter = 0u;
     }
     // loss_map = 0.01 (|theta1| + |theta2|): written by the CTA that read the thetas before updating them

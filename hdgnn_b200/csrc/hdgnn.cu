@@ -117,6 +117,13 @@ struct hdgnn_handle_s {
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     bool done_valid[2] = {false, false};
     int slot = 0, cur = 0;
+    // peer exchange (commit sharding over NVLink, final.cuh): own mailbox + the peers' mailboxes mapped through CUDA IPC
+    PeerArgs peer{};
+    void* peer_box = nullptr;              // own mailbox (cudaMalloc)
+    void* peer_map[PEER_MAX] = {};         // IPC mappings of the other ranks' mailboxes
+    size_t peer_bytes = 0;
+    int peer_world = 0;
+    bool peer_ready = false;
 };
 
 namespace {
@@ -464,7 +471,7 @@ __global__ void repitch_kernel(const uint8_t* __restrict__ src, uint8_t* __restr
 // fused path: pack_bits -> ent_fwd2 -> mid2 -> ent_bwd2 -> reduce (+ adam)
 // ================================================================================================
 
-struct AdamArgs { float* params; float* m; float* v; int32_t* step; float lr, b1, b2, eps; float* reg; };
+struct AdamArgs { float* params; float* m; float* v; int32_t* step; float lr, b1, b2, eps; float* reg; bool peer = false; };
 
 // column segments per pass of an entity sweep: the whole row when it fits 8 segments, else passes of 8
 int ent2_cwt(int N) { const int cw = (N + 31) / 32; return cw <= 8 ? cw : 8; }
@@ -578,10 +585,11 @@ int fused_backward(hdgnn_handle_t h, int B, int B_global, const Inputs& in, floa
         f.apply_adam = 1; f.params = adam->params; f.m = adam->m; f.v = adam->v; f.step = adam->step;
         f.o_t1 = h->po.theta1; f.o_t2 = h->po.theta2; f.lr = adam->lr; f.b1 = adam->b1; f.b2 = adam->b2; f.eps = adam->eps;
         f.reg_losses = adam->reg;
+        if (adam->peer) f.peer = h->peer;
     }
     PROF_BEGIN(h, st);
     launch_ex(reduce_adam_kernel, (h->po.total + FIN_P - 1) / FIN_P, FIN_P * FIN_SL, 0, st, h->pdl, f);
-    LAUNCH_CHECK(h, adam ? "reduce_adam" : "grad_reduce", st);
+    LAUNCH_CHECK(h, adam ? (adam->peer ? "reduce_allreduce_adam(peer)" : "reduce_adam") : "grad_reduce", st);
     return HDGNN_OK;
 }
 
@@ -773,7 +781,67 @@ int hdgnn_destroy(hdgnn_handle_t h) {
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
     for (int i = 0; i < 2; ++i) { if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]); if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]); }
     for (auto& kv : h->ws) cudaFree(kv.second.p);
+    for (int r = 0; r < PEER_MAX; ++r) if (h->peer_map[r]) cudaIpcCloseMemHandle(h->peer_map[r]);
+    if (h->peer_box) cudaFree(h->peer_box);
     delete h;
+    return HDGNN_OK;
+}
+
+// ---- peer exchange set-up ------------------------------------------------------------------------------------
+// mailbox layout (final.cuh): [inbox 2*W*stride u64][lossin 2*W u64]
+static void peer_layout(int world, int total, int* stride, int* ncta, size_t* off_loss, size_t* bytes) {
+    *ncta = (total + FIN_P - 1) / FIN_P;
+    *stride = *ncta * FIN_P;
+    *off_loss = (size_t)2 * world * *stride * sizeof(peer_word);
+    *bytes = *off_loss + (size_t)2 * world * sizeof(peer_word);
+}
+
+int hdgnn_peer_export(hdgnn_handle_t h, int world, unsigned char* ipc_handle_out) {
+    if (!h) return HDGNN_E_INVALID;
+    if (world < 2 || world > PEER_MAX || !ipc_handle_out) return fail(h, HDGNN_E_INVALID, "world must be 2..8");
+    if (!h->fused) return fail(h, HDGNN_E_UNSUPPORTED, "the peer exchange is fused into the reduce+Adam kernel of the fused path (variants 1-3, per-commit state within one SM)");
+    static_assert(sizeof(cudaIpcMemHandle_t) == HDGNN_IPC_HANDLE_BYTES, "IPC handle size");
+    CK(h, cudaSetDevice(h->cfg.device));
+    if (h->peer_box) return fail(h, HDGNN_E_INVALID, "hdgnn_peer_export was already called on this handle");
+    int stride, ncta; size_t ol, bytes;
+    peer_layout(world, h->po.total, &stride, &ncta, &ol, &bytes);
+    CK(h, cudaMalloc(&h->peer_box, bytes));
+    CK(h, cudaMemset(h->peer_box, 0, bytes));
+    CK(h, cudaDeviceSynchronize());
+    h->peer_bytes = bytes; h->peer_world = world;
+    cudaIpcMemHandle_t ih;
+    CK(h, cudaIpcGetMemHandle(&ih, h->peer_box));
+    memcpy(ipc_handle_out, &ih, sizeof(ih));
+    return HDGNN_OK;
+}
+
+int hdgnn_peer_attach(hdgnn_handle_t h, int rank, int world, const unsigned char* ipc_handles) {
+    if (!h) return HDGNN_E_INVALID;
+    if (!h->peer_box || world != h->peer_world) return fail(h, HDGNN_E_INVALID, "call hdgnn_peer_export(world) first");
+    if (rank < 0 || rank >= world || !ipc_handles) return fail(h, HDGNN_E_INVALID, "bad rank / handles");
+    if (h->peer_ready) return fail(h, HDGNN_E_INVALID, "peers are already attached");
+    CK(h, cudaSetDevice(h->cfg.device));
+    int rc;
+    if (!h->ws.count("PEER_SEQ") && (rc = alloc(h, "PEER_SEQ", 16))) return rc;      // [0] sequence number, [1] error flag
+    int stride, ncta; size_t ol, bytes;
+    peer_layout(world, h->po.total, &stride, &ncta, &ol, &bytes);
+    PeerArgs pa{};
+    pa.world = world; pa.rank = rank; pa.stride = stride; pa.ncta = ncta;
+    for (int r = 0; r < world; ++r) {
+        void* base = h->peer_box;
+        if (r != rank) {
+            cudaIpcMemHandle_t ih;
+            memcpy(&ih, ipc_handles + (size_t)r * sizeof(ih), sizeof(ih));
+            CK(h, cudaIpcOpenMemHandle(&h->peer_map[r], ih, cudaIpcMemLazyEnablePeerAccess));
+            base = h->peer_map[r];
+        }
+        pa.inbox[r] = (peer_word*)base;
+        pa.lossin[r] = (peer_word*)((char*)base + ol);
+    }
+    pa.seq = (int*)h->ws["PEER_SEQ"].p;
+    pa.error = pa.seq + 1;
+    h->peer = pa;
+    h->peer_ready = true;
     return HDGNN_OK;
 }
 
@@ -933,6 +1001,48 @@ int hdgnn_train_step_host(hdgnn_handle_t h, int B, const uint8_t* adj_host, cons
     if ((rc = release_slot(h, st))) return rc;
     if (probs_host)
         CK(h, cudaMemcpyAsync(probs_host, probs_d, (size_t)B * 2 * h->Nc * (h->Nc - 1) * sizeof(float), cudaMemcpyDefault, st));
+    CK(h, cudaMemcpyAsync(loss3_host, loss_d, 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    return HDGNN_OK;
+}
+
+int hdgnn_train_step_peer(hdgnn_handle_t h, int B, int B_global, const uint8_t* adj, int adj_pitch, const float* x,
+                          const int32_t* hmap, const int32_t* L, const uint8_t* Y, int y_pitch, float* params, float* m, float* v,
+                          int32_t* step_counter, float lr, float beta1, float beta2, float eps, float* logits, float* probs,
+                          float* loss3, void* stream) {
+    int rc = check_inputs(h, B, adj, adj_pitch, x, hmap, L, Y, y_pitch, params);
+    if (rc) return rc;
+    if (!m || !v || !step_counter || !loss3) return fail(h, HDGNN_E_INVALID, "null pointer");
+    if (!h->peer_ready) return fail(h, HDGNN_E_INVALID, "hdgnn_peer_attach has not been called");
+    if (B_global != B * h->peer.world) return fail(h, HDGNN_E_INVALID, "B_global must be B * world (equal shards)");
+    h->launches = 0;
+    Inputs in{adj, x, hmap, L, Y, params};
+    AdamArgs ad{params, m, v, step_counter, lr, beta1, beta2, eps, loss3 + 1, true};
+    return run_step(h, B, B_global, in, logits, probs, loss3, F(h, "H_GRADS"), &ad, (cudaStream_t)stream);
+}
+
+int hdgnn_train_step_peer_host(hdgnn_handle_t h, int B, int B_global, const uint8_t* adj_host, const float* x_host,
+                               const int32_t* hmap_host, const int32_t* L_host, const uint8_t* Y_host, float* params,
+                               float* m, float* v, int32_t* step_counter, float lr, float beta1, float beta2, float eps,
+                               float* probs_out, float* loss3_host, void* stream) {
+    if (!h) return HDGNN_E_INVALID;
+    if (B < 1 || B > h->cfg.max_batch) return fail(h, HDGNN_E_INVALID, "B out of range [1, max_batch]");
+    if (!adj_host || !x_host || !hmap_host || !L_host || !Y_host || !params || !m || !v || !step_counter || !loss3_host)
+        return fail(h, HDGNN_E_INVALID, "null pointer");
+    if (!h->peer_ready) return fail(h, HDGNN_E_INVALID, "hdgnn_peer_attach has not been called");
+    if (B_global != B * h->peer.world) return fail(h, HDGNN_E_INVALID, "B_global must be B * world (equal shards)");
+    cudaStream_t st = (cudaStream_t)stream;
+    h->launches = 0;
+    int rc = stage_inputs(h, B, adj_host, x_host, hmap_host, L_host, Y_host, st);
+    if (rc) return rc;
+    Inputs in = staged_inputs(h, params);
+    float* probs_d = probs_out ? F(h, "H_PROBS") : nullptr;
+    float* loss_d = F(h, "H_LOSS");
+    AdamArgs ad{params, m, v, step_counter, lr, beta1, beta2, eps, loss_d + 1, true};
+    rc = run_step(h, B, B_global, in, nullptr, probs_d, loss_d, F(h, "H_GRADS"), &ad, st);
+    if (rc) return rc;
+    if ((rc = release_slot(h, st))) return rc;
+    if (probs_out)
+        CK(h, cudaMemcpyAsync(probs_out, probs_d, (size_t)B * 2 * h->Nc * (h->Nc - 1) * sizeof(float), cudaMemcpyDefault, st));
     CK(h, cudaMemcpyAsync(loss3_host, loss_d, 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
     return HDGNN_OK;
 }

@@ -171,6 +171,48 @@ class Engine:
         check(lib.hdgnn_forward_backward_host(self._h, B, B_global, _p(adj), _p(x), _p(hmap), _p(L), _p(Y), _p(params),
                                               _p(probs), _p(loss), _p(grads), self._stream()), self._h)
 
+    # -- commit sharding with the all-reduce fused into the last kernel (peer memory over NVLink) ----------------
+    def peer_attach(self, collective: str = "peer") -> bool:
+        """Exchange the CUDA IPC handles of the ranks' mailboxes through torch.distributed and map them
+        (hdgnn_peer_export / hdgnn_peer_attach).  Collective call.  Returns True when every rank is attached; with
+        collective="auto" a failure on any rank (multi-kernel path, no P2P) returns False on all ranks instead of raising."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(), dist.get_rank()
+        buf = (C.c_ubyte * 64)()
+        rc = lib.hdgnn_peer_export(self._h, world, buf) if 2 <= world <= 8 else _lib.E_UNSUPPORTED
+        flag = torch.tensor([1 if rc == _lib.OK else 0], device=self.tdev, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if not int(flag.item()):
+            if collective == "auto":
+                return False
+            check(rc if rc != _lib.OK else _lib.E_UNSUPPORTED, self._h)
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(buf))
+        rc = lib.hdgnn_peer_attach(self._h, rank, world, b"".join(handles))
+        flag = torch.tensor([1 if rc == _lib.OK else 0], device=self.tdev, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)          # also the barrier the first exchange needs
+        if not int(flag.item()):
+            if collective == "auto":
+                return False
+            check(rc if rc != _lib.OK else _lib.E_CUDA, self._h)
+        self.peer_world = world
+        return True
+
+    def train_step_peer(self, b: DeviceBatch, params, m, v, step_counter, loss3, probs=None, logits=None,
+                        lr=3e-4, beta1=0.9, beta2=0.999, eps=1e-8):
+        """This rank's shard of one training step; gradients are exchanged inside the last kernel (no NCCL call)."""
+        self._check_batch(b, params)
+        check(lib.hdgnn_train_step_peer(self._h, b.B, b.B * self.peer_world, _p(b.adj), self.pe, _p(b.x), _p(b.hmap), _p(b.L),
+                                        _p(b.Y), self.pc, _p(params), _p(m), _p(v), _p(step_counter), lr, beta1, beta2, eps,
+                                        _p(logits), _p(probs), _p(loss3), self._stream()), self._h)
+
+    def train_step_peer_host(self, adj, x, hmap, L, Y, params, m, v, step_counter, loss3, probs=None,
+                             lr=3e-4, beta1=0.9, beta2=0.999, eps=1e-8):
+        B = adj.shape[0]
+        check(lib.hdgnn_train_step_peer_host(self._h, B, B * self.peer_world, _p(adj), _p(x), _p(hmap), _p(L), _p(Y), _p(params),
+                                             _p(m), _p(v), _p(step_counter), lr, beta1, beta2, eps, _p(probs), _p(loss3),
+                                             self._stream()), self._h)
+
     def infer_host(self, adj, x, hmap, L, Y, params, probs, loss=None):
         B = adj.shape[0]
         check(lib.hdgnn_infer_host(self._h, B, _p(adj), _p(x), _p(hmap), _p(L), _p(Y), _p(params), _p(probs),

@@ -84,7 +84,8 @@ class HostBatch:
 class graph2graph(object):
     def __init__(self, sess=None, Ds=1, Ne=200, Nc=74, Ner=None, Ncr=None, Dr=2, De_e=20, De_er=20, Mini_batch=50,
                  checkpoint_dir="./checkpoint40/", epoch=50, Ds_inter=1, Dr_inter=2, Step=2, Repo="glide",
-                 variant=2, device: Optional[int] = None, seed: Optional[int] = None, max_batch: Optional[int] = None):
+                 variant=2, device: Optional[int] = None, seed: Optional[int] = None, max_batch: Optional[int] = None,
+                 collective: str = "auto"):
         # `sess` is accepted and ignored: there is no TF session (main.py:54-56).
         Ner = Ne * (Ne - 1) if Ner is None else Ner
         Ncr = Nc * (Nc - 1) if Ncr is None else Ncr
@@ -111,6 +112,10 @@ class graph2graph(object):
             device = int(os.environ.get("LOCAL_RANK", "0")) if self.world > 1 else 0
         self.device = device
         self.max_batch = max_batch or Mini_batch
+        if collective not in ("auto", "peer", "nccl"):
+            raise ValueError("collective must be 'auto', 'peer' (all-reduce fused into the last kernel over NVLink peer "
+                             "memory) or 'nccl' (torch.distributed.all_reduce between backward and Adam)")
+        self.collective = collective
         self.build_model()
 
     # ------------------------------------------------------------------------------------------
@@ -128,6 +133,8 @@ class graph2graph(object):
         self.reg = torch.zeros(2, dtype=torch.float32, device=dev)
         self.loss_d = torch.zeros(1, dtype=torch.float32, device=dev)
         self.loss3 = torch.zeros(3, dtype=torch.float32).pin_memory()
+        # gradient exchange of the sharded step: peer memory (one fused kernel) when every rank can map its peers
+        self.peer = self.world > 1 and self.collective != "nccl" and self.engine.peer_attach(self.collective)
         self.initialize()
 
     def initialize(self, flat: Optional[torch.Tensor] = None):
@@ -160,6 +167,10 @@ class graph2graph(object):
         if self.world == 1:
             eng.train_step_host(*hb.tensors(), self.params, self.m, self.v, self.step_counter, self.loss3,
                                 probs=probs_out if want_probs else None)
+            return self.loss3
+        if self.peer:                                   # loss3[0] is already the global mean CE
+            eng.train_step_peer_host(*hb.tensors(), self.params, self.m, self.v, self.step_counter, self.loss3,
+                                     probs=probs_out if want_probs else None)
             return self.loss3
         direct = want_probs and probs_out is not None and probs_out.is_cuda
         if want_probs and not direct and (not hasattr(self, "_probs_d") or self._probs_d.shape[0] < hb.B):
@@ -230,7 +241,7 @@ class graph2graph(object):
                 hits += counts[:, 0].sum()
                 torch.cuda.current_stream().synchronize()
                 ce = float(l3[0])
-                if self.world > 1:                                  # CE partials add up to the global mean
+                if self.world > 1 and not self.peer:                # CE partials add up to the global mean
                     t = torch.tensor([ce], device=dev)
                     torch.distributed.all_reduce(t)
                     ce = float(t.item())

@@ -149,6 +149,34 @@ int hdgnn_forward_backward_host(hdgnn_handle_t h, int B, int B_global,
                                 const int32_t* L_host, const uint8_t* Y_host,
                                 const float* params, float* probs, float* loss, float* grads, void* stream);
 
+/* ---- commit sharding with the gradient all-reduce fused into the reduce + Adam kernel (one process per GPU) --------
+ * The reference is single-device; this replaces what a data-parallel port would do with an NCCL all-reduce between
+ * hdgnn_forward_backward and hdgnn_adam_step.  Every rank owns a mailbox in its HBM; the last kernel of the step pushes
+ * its 128-parameter gradient slices into every peer's mailbox over NVLink (P2P stores of {sequence number : value}
+ * words, no flag and no fence), polls its own mailbox for the peers' slices, sums them in rank order (bitwise identical
+ * on all ranks) and applies the regularisers + TF1 Adam -- the step has the same 5 launches as on one GPU and no NCCL call.
+ * Set-up: (1) every rank calls hdgnn_peer_export and receives a 64-byte CUDA IPC handle; (2) the handles are gathered by
+ * the caller (torch.distributed / MPI / files) into world*64 bytes ordered by rank; (3) every rank calls
+ * hdgnn_peer_attach, then the ranks synchronise once (barrier) before the first step.  Fused path only (variants 1-3
+ * with the per-commit state within one SM), world <= 8, equal shards. */
+#define HDGNN_IPC_HANDLE_BYTES 64
+int hdgnn_peer_export(hdgnn_handle_t h, int world, unsigned char* ipc_handle_out);
+int hdgnn_peer_attach(hdgnn_handle_t h, int rank, int world, const unsigned char* ipc_handles);
+/* As hdgnn_train_step / hdgnn_train_step_host for this rank's B commits of a global batch of B_global = B * world.
+ * loss3[0] receives the GLOBAL mean cross-entropy (the ranks' shares are exchanged with the gradients). */
+int hdgnn_train_step_peer(hdgnn_handle_t h, int B, int B_global,
+                          const uint8_t* adj, int adj_pitch, const float* x, const int32_t* hmap,
+                          const int32_t* L, const uint8_t* Y, int y_pitch,
+                          float* params, float* m, float* v, int32_t* step_counter,
+                          float lr, float beta1, float beta2, float eps,
+                          float* logits, float* probs, float* loss3, void* stream);
+int hdgnn_train_step_peer_host(hdgnn_handle_t h, int B, int B_global,
+                               const uint8_t* adj_host, const float* x_host, const int32_t* hmap_host,
+                               const int32_t* L_host, const uint8_t* Y_host,
+                               float* params, float* m, float* v, int32_t* step_counter,
+                               float lr, float beta1, float beta2, float eps,
+                               float* probs_out, float* loss3_host, void* stream);
+
 /* Inference from HOST buffers: H2D, forward, copy-out of probs (B*2*Ncr floats; host or device pointer) and D2H of CE. */
 int hdgnn_infer_host(hdgnn_handle_t h, int B,
                      const uint8_t* adj_host, const float* x_host, const int32_t* hmap_host,
