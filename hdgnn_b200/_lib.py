@@ -37,6 +37,7 @@ def _load():
         "hdgnn_destroy": ([vp], i32),
         "hdgnn_last_error": ([vp], C.c_char_p),
         "hdgnn_label_pitch": ([i32], i32),
+        "hdgnn_bit_words": ([i32], i32),
         "hdgnn_forward": ([vp, i32, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp], i32),
         "hdgnn_forward_backward": ([vp, i32, i32, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp], i32),
         "hdgnn_adam_step": ([vp, vp, vp, vp, vp, vp, f32, f32, f32, f32, vp, vp], i32),
@@ -51,6 +52,7 @@ def _load():
         "hdgnn_normalize_propagate": ([i32, i32, vp, i32, vp, i32, vp, vp, i32, f32, i32, vp, vp, vp], i32),
         "hdgnn_map_conv": ([i32, i32, vp, i32, vp, vp, f32, f32, i32, vp, vp, vp], i32),
         "hdgnn_compact_from_raw": ([i32, i32, vp, i32, vp, i32, vp, vp, vp], i32),
+        "hdgnn_pack_label_bits": ([i32, i32, vp, i32, vp, vp], i32),
         "hdgnn_eval_counts": ([i32, i32, vp, vp, i32, vp, vp, i32, vp], i32),
         "hdgnn_workspace": ([vp, C.c_char_p, C.POINTER(vp), C.POINTER(C.c_size_t)], i32),
         "hdgnn_workspace_copy": ([vp, C.c_char_p, vp, C.c_size_t, vp], i32),

@@ -124,6 +124,9 @@ struct hdgnn_handle_s {
     size_t peer_bytes = 0;
     int peer_world = 0;
     bool peer_ready = false;
+    // HDGNN_F_LABEL_BITS: the *_host entry points receive label bitmaps (bits.cuh layout) instead of byte grids
+    bool host_bits = false;
+    const uint32_t* eb = nullptr; const uint32_t* yb = nullptr;   // bitmaps of the current step
 };
 
 namespace {
@@ -269,16 +272,30 @@ int check_inputs(hdgnn_handle_t h, int B, const void* adj, int adj_pitch, const 
     if (!h) return HDGNN_E_INVALID;
     if (B < 1 || B > h->cfg.max_batch) return fail(h, HDGNN_E_INVALID, "B out of range [1, max_batch]");
     if (!adj || !x || !hmap || !L || !Y || !params) return fail(h, HDGNN_E_INVALID, "null input pointer");
-    if (adj_pitch != h->pe) return fail(h, HDGNN_E_INVALID, "adj_pitch must equal hdgnn_label_pitch(Ne)");
-    if (y_pitch != h->pc) return fail(h, HDGNN_E_INVALID, "y_pitch must equal hdgnn_label_pitch(Nc)");
+    if (h->host_bits) {
+        if (adj_pitch != h->WPe * 4) return fail(h, HDGNN_E_INVALID, "HDGNN_F_LABEL_BITS: adj_pitch must equal 4 * hdgnn_bit_words(Ne)");
+        if (y_pitch != h->WPc * 4) return fail(h, HDGNN_E_INVALID, "HDGNN_F_LABEL_BITS: y_pitch must equal 4 * hdgnn_bit_words(Nc)");
+    } else {
+        if (adj_pitch != h->pe) return fail(h, HDGNN_E_INVALID, "adj_pitch must equal hdgnn_label_pitch(Ne)");
+        if (y_pitch != h->pc) return fail(h, HDGNN_E_INVALID, "y_pitch must equal hdgnn_label_pitch(Nc)");
+    }
     if (((uintptr_t)adj & 15) || ((uintptr_t)Y & 15)) return fail(h, HDGNN_E_INVALID, "adj and Y must be 16-byte aligned");
     return HDGNN_OK;
 }
 
+struct Inputs;
+static void alias_bits(hdgnn_handle_t h, Inputs& in);
+
 struct Inputs {
     const uint8_t* adj; const float* x; const int32_t* hmap; const int32_t* L; const uint8_t* Y;
     const float* params;
+    const uint32_t* ebits = nullptr; const uint32_t* ybits = nullptr;   // set: bitmaps are given, adj / Y are not read (fused path)
 };
+
+// HDGNN_F_LABEL_BITS: the adj / Y arguments of the device entry points ARE the bitmaps
+static void alias_bits(hdgnn_handle_t h, Inputs& in) {
+    if (h->host_bits && !in.ebits) { in.ebits = (const uint32_t*)in.adj; in.ybits = (const uint32_t*)in.Y; }
+}
 
 int forward_impl(hdgnn_handle_t h, int B, int B_global, const Inputs& in, float* logits, float* probs,
                  float* loss, bool train, cudaStream_t st) {
@@ -500,7 +517,7 @@ int ent2_occupancy(hdgnn_handle_t h, int cwt, int nrg, bool bwd) {
 
 Ent2Args ent2_args(hdgnn_handle_t h, int B, const Inputs& in) {
     Ent2Args a{};
-    a.bits = (const uint32_t*)h->ws[h->bslot ? "EBITS1" : "EBITS0"].p; a.WP = h->WPe; a.N = h->Ne; a.B = B;
+    a.bits = h->eb; a.WP = h->WPe; a.N = h->Ne; a.B = B;
     a.params = in.params; a.x = in.x;
     a.o_u = h->po.ent_w1; a.o_v = h->po.ent_w1 + HD; a.o_b = h->po.ent_b1; a.o_l = h->po.ent_w1 + 2 * HD;
     return a;
@@ -520,8 +537,14 @@ int debug_scatter(hdgnn_handle_t h, int B, cudaStream_t st) {
 
 int fused_forward(hdgnn_handle_t h, int B, int B_global, const Inputs& in, float* logits, float* probs, bool train,
                   cudaStream_t st) {
-    {
+    bool first_pdl = h->pdl;
+    if (in.ebits) {     // bitmaps came from the host: nothing to pack.  The first kernel then follows the previous step's
+        h->eb = in.ebits; h->yb = in.ybits;     // optimizer kernel directly and reads the weights it updates: no early launch
+        first_pdl = false;
+    } else {
         h->bslot ^= 1;
+        h->eb = (const uint32_t*)h->ws[h->bslot ? "EBITS1" : "EBITS0"].p;
+        h->yb = (const uint32_t*)h->ws[h->bslot ? "YBITS1" : "YBITS0"].p;
         PackArgs p{};
         p.adj = in.adj; p.Ne = h->Ne; p.pe = h->pe; p.WPe = h->WPe; p.ebits = (uint32_t*)h->ws[h->bslot ? "EBITS1" : "EBITS0"].p;
         p.Y = in.Y; p.Nc = h->Nc; p.pc = h->pc; p.WPc = h->WPc; p.ybits = (uint32_t*)h->ws[h->bslot ? "YBITS1" : "YBITS0"].p;
@@ -539,13 +562,13 @@ int fused_forward(hdgnn_handle_t h, int B, int B_global, const Inputs& in, float
         a.R = h->Rf; a.SL = h->SLf; a.RS = F(h, "RS1"); a.CSp = F(h, "CS1P");
         const size_t smem = ent2_smem_bytes(h->fwd_cwt, h->fwd_nrg, h->Ne, h->Rf, h->WPe, false);
         PROF_BEGIN(h, st);
-        launch_ent2(h->fwd_cwt, h->fwd_nrg, false, h->Gf, smem, st, a, h->pdl);
+        launch_ent2(h->fwd_cwt, h->fwd_nrg, false, h->Gf, smem, st, a, first_pdl);
         LAUNCH_CHECK(h, "ent_fwd", st);
     }
     Mid2Args m{};
     m.Ne = h->Ne; m.Nc = h->Nc; m.ent = h->ent ? 1 : 0; m.R = h->Rf; m.SL = h->SLf;
-    m.ebits = (const uint32_t*)h->ws[h->bslot ? "EBITS1" : "EBITS0"].p; m.WPe = h->WPe;
-    m.ybits = (const uint32_t*)h->ws[h->bslot ? "YBITS1" : "YBITS0"].p; m.WPc = h->WPc;
+    m.ebits = h->eb; m.WPe = h->WPe;
+    m.ybits = h->yb; m.WPc = h->WPc;
     m.x = in.x; m.hmap = in.hmap; m.L = in.L;
     m.params = in.params; m.po = h->po; m.RS1 = F(h, "RS1"); m.CS1p = F(h, "CS1P");
     m.logits = logits; m.probs = probs; m.cep = F(h, "CEP");
@@ -640,6 +663,20 @@ int hdgnn_param_offset(int variant, const char* name) {
     return find_off(layout(variant), name);
 }
 
+int hdgnn_pack_label_bits(int N, int n, const uint8_t* grid, int pitch, uint32_t* bits, void* stream) {
+    if (N < 1 || n < 2 || n > HDGNN_MAX_N || !grid || !bits) return HDGNN_E_INVALID;
+    if (pitch < n || (pitch & 15) || pitch > 528 || ((uintptr_t)grid & 15) || ((uintptr_t)bits & 15)) return HDGNN_E_INVALID;
+    PackArgs p{};
+    p.adj = grid; p.Ne = n; p.pe = pitch; p.WPe = bit_words(n); p.ebits = bits; p.B = N;
+    p.Y = nullptr; p.Nc = 0; p.pc = 0; p.WPc = 0; p.ybits = nullptr;
+    const long long rows = (long long)N * n;
+    if (pitch <= 256) pack_bits_kernel<16><<<(int)((rows + 15) / 16), 256, 0, (cudaStream_t)stream>>>(p);
+    else pack_bits_kernel<32><<<(int)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(p);
+    return cudaGetLastError() == cudaSuccess ? HDGNN_OK : HDGNN_E_CUDA;
+}
+
+int hdgnn_bit_words(int n) { return n > 0 && n <= HDGNN_MAX_N ? bit_words(n) : -1; }
+
 int hdgnn_label_pitch(int n) { return n < 1 ? HDGNN_E_INVALID : round_up(n, 16); }
 
 const char* hdgnn_last_error(hdgnn_handle_t h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -700,6 +737,11 @@ int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out) {
         h->dlt_global = mid2_smem_bytes(h->Ne, h->Nc, true, true) > (size_t)prop.sharedMemPerBlockOptin;
         h->fused = mid2_smem_bytes(h->Ne, h->Nc, true, !h->dlt_global) <= (size_t)prop.sharedMemPerBlockOptin;
     }
+    h->host_bits = (cfg->flags & HDGNN_F_LABEL_BITS) != 0;
+    if (h->host_bits && !h->fused) {
+        delete h;
+        return fail(nullptr, HDGNN_E_UNSUPPORTED, "HDGNN_F_LABEL_BITS needs the fused path (variants 1-3, per-commit state within one SM)");
+    }
     cudaError_t e = set_attrs(h, (int)prop.sharedMemPerBlockOptin);
     if (e == cudaSuccess && h->fused) e = setup_fused(h, (int)prop.sharedMemPerBlockOptin);
     if (e != cudaSuccess) {
@@ -751,6 +793,8 @@ int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out) {
         {"H_ADJ1", B * Ne * (size_t)h->pe, true}, {"H_Y1", B * Nc * (size_t)h->pc, true}, {"H_X1", B * Ne * f, true},
         {"H_ADJ_RAW1", B * Ne * Ne, h->pe != h->Ne}, {"H_Y_RAW1", B * Nc * Nc, h->pc != h->Nc},
         {"H_HMAP1", B * Ne * sizeof(int32_t), true}, {"H_L1", B * sizeof(int32_t), true},
+        {"H_EBITS0", B * Ne * (size_t)h->WPe * 4, h->host_bits}, {"H_YBITS0", B * Nc * (size_t)h->WPc * 4, h->host_bits},
+        {"H_EBITS1", B * Ne * (size_t)h->WPe * 4, h->host_bits}, {"H_YBITS1", B * Nc * (size_t)h->WPc * 4, h->host_bits},
         {"H_PROBS", B * 2 * Nc * (Nc - 1) * f, true}, {"H_LOSS", 4 * f, true}, {"H_GRADS", (size_t)h->po.total * f, true},
     };
     for (auto& p : plan) {
@@ -879,6 +923,7 @@ int hdgnn_forward(hdgnn_handle_t h, int B, const uint8_t* adj, int adj_pitch, co
     if (rc) return rc;
     h->launches = 0;
     Inputs in{adj, x, hmap, L, Y, params};
+    alias_bits(h, in);
     return run_step(h, B, B, in, logits, probs, loss, nullptr, nullptr, (cudaStream_t)stream);
 }
 
@@ -891,6 +936,7 @@ int hdgnn_forward_backward(hdgnn_handle_t h, int B, int B_global, const uint8_t*
     if (B_global < B) return fail(h, HDGNN_E_INVALID, "B_global < B");
     h->launches = 0;
     Inputs in{adj, x, hmap, L, Y, params};
+    alias_bits(h, in);
     return run_step(h, B, B_global, in, logits, probs, loss, grads, nullptr, (cudaStream_t)stream);
 }
 
@@ -911,6 +957,7 @@ int hdgnn_train_step(hdgnn_handle_t h, int B, const uint8_t* adj, int adj_pitch,
     if (!m || !v || !step_counter || !loss3) return fail(h, HDGNN_E_INVALID, "null pointer");
     h->launches = 0;
     Inputs in{adj, x, hmap, L, Y, params};
+    alias_bits(h, in);
     AdamArgs ad{params, m, v, step_counter, lr, beta1, beta2, eps, loss3 + 1};
     return run_step(h, B, B, in, logits, probs, loss3, F(h, "H_GRADS"), &ad, (cudaStream_t)stream);
 }
@@ -931,12 +978,16 @@ static int stage_inputs(hdgnn_handle_t h, int B, const uint8_t* adj_host, const 
     h->slot ^= 1;
     cudaStream_t cs = side ? h->copy_stream : st;
     if (side && h->done_valid[slot]) CK(h, cudaStreamWaitEvent(cs, h->ev_done[slot], 0));
+    if (h->host_bits) {
+        CK(h, cudaMemcpyAsync(h->ws[slot_name("H_EBITS", slot)].p, adj_host, (size_t)B * Ne * h->WPe * 4, cudaMemcpyHostToDevice, cs));
+        CK(h, cudaMemcpyAsync(h->ws[slot_name("H_YBITS", slot)].p, Y_host, (size_t)B * Nc * h->WPc * 4, cudaMemcpyHostToDevice, cs));
+    }
     const uint8_t* srcs[2] = {adj_host, Y_host};
     const char* raw[2] = {"H_ADJ_RAW", "H_Y_RAW"};
     const char* dstn[2] = {"H_ADJ", "H_Y"};
     const size_t n[2] = {Ne, Nc};
     const int pitch[2] = {h->pe, h->pc};
-    for (int t = 0; t < 2; ++t) {
+    for (int t = 0; t < 2 && !h->host_bits; ++t) {
         const size_t rows = (size_t)B * n[t];
         void* dst = h->ws[slot_name(dstn[t], slot)].p;
         if (pitch[t] == (int)n[t]) {
@@ -965,9 +1016,14 @@ static int stage_inputs(hdgnn_handle_t h, int B, const uint8_t* adj_host, const 
 // device-side views of the staging slot filled by the last stage_inputs call
 static Inputs staged_inputs(hdgnn_handle_t h, const float* params) {
     const int s = h->cur;
-    return Inputs{(const uint8_t*)h->ws[slot_name("H_ADJ", s)].p, (const float*)h->ws[slot_name("H_X", s)].p,
-                  (const int32_t*)h->ws[slot_name("H_HMAP", s)].p, (const int32_t*)h->ws[slot_name("H_L", s)].p,
-                  (const uint8_t*)h->ws[slot_name("H_Y", s)].p, params};
+    Inputs in{(const uint8_t*)h->ws[slot_name("H_ADJ", s)].p, (const float*)h->ws[slot_name("H_X", s)].p,
+              (const int32_t*)h->ws[slot_name("H_HMAP", s)].p, (const int32_t*)h->ws[slot_name("H_L", s)].p,
+              (const uint8_t*)h->ws[slot_name("H_Y", s)].p, params};
+    if (h->host_bits) {
+        in.ebits = (const uint32_t*)h->ws[slot_name("H_EBITS", s)].p;
+        in.ybits = (const uint32_t*)h->ws[slot_name("H_YBITS", s)].p;
+    }
+    return in;
 }
 
 // the kernels reading slot h->cur have been enqueued on `st`: the slot may be refilled once they are done
@@ -978,6 +1034,16 @@ static int release_slot(hdgnn_handle_t h, cudaStream_t st) {
     CK(h, cudaEventRecord(h->ev_done[h->cur], st));
     h->done_valid[h->cur] = true;
     return HDGNN_OK;
+}
+
+// A pinned (page-locked, UVA-mapped) host buffer can be written by the kernels directly: the three loss floats then
+// need no device->host copy at the end of the step (a 12-byte DMA costs several microseconds of stream time and
+// breaks the launch overlap with the next step).  Returns the device-visible alias or nullptr.
+static float* host_alias(float* host_ptr) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, host_ptr) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+    return (float*)at.devicePointer;
 }
 
 int hdgnn_train_step_host(hdgnn_handle_t h, int B, const uint8_t* adj_host, const float* x_host,
@@ -994,14 +1060,15 @@ int hdgnn_train_step_host(hdgnn_handle_t h, int B, const uint8_t* adj_host, cons
     if (rc) return rc;
     Inputs in = staged_inputs(h, params);
     float* probs_d = probs_host ? F(h, "H_PROBS") : nullptr;
-    float* loss_d = F(h, "H_LOSS");
+    float* alias = h->fused ? host_alias(loss3_host) : nullptr;
+    float* loss_d = alias ? alias : F(h, "H_LOSS");
     AdamArgs ad{params, m, v, step_counter, lr, beta1, beta2, eps, loss_d + 1};
     rc = run_step(h, B, B, in, nullptr, probs_d, loss_d, F(h, "H_GRADS"), &ad, st);
     if (rc) return rc;
     if ((rc = release_slot(h, st))) return rc;
     if (probs_host)
         CK(h, cudaMemcpyAsync(probs_host, probs_d, (size_t)B * 2 * h->Nc * (h->Nc - 1) * sizeof(float), cudaMemcpyDefault, st));
-    CK(h, cudaMemcpyAsync(loss3_host, loss_d, 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (!alias) CK(h, cudaMemcpyAsync(loss3_host, loss_d, 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
     return HDGNN_OK;
 }
 
@@ -1016,6 +1083,7 @@ int hdgnn_train_step_peer(hdgnn_handle_t h, int B, int B_global, const uint8_t* 
     if (B_global != B * h->peer.world) return fail(h, HDGNN_E_INVALID, "B_global must be B * world (equal shards)");
     h->launches = 0;
     Inputs in{adj, x, hmap, L, Y, params};
+    alias_bits(h, in);
     AdamArgs ad{params, m, v, step_counter, lr, beta1, beta2, eps, loss3 + 1, true};
     return run_step(h, B, B_global, in, logits, probs, loss3, F(h, "H_GRADS"), &ad, (cudaStream_t)stream);
 }
@@ -1036,14 +1104,15 @@ int hdgnn_train_step_peer_host(hdgnn_handle_t h, int B, int B_global, const uint
     if (rc) return rc;
     Inputs in = staged_inputs(h, params);
     float* probs_d = probs_out ? F(h, "H_PROBS") : nullptr;
-    float* loss_d = F(h, "H_LOSS");
+    float* alias = host_alias(loss3_host);
+    float* loss_d = alias ? alias : F(h, "H_LOSS");
     AdamArgs ad{params, m, v, step_counter, lr, beta1, beta2, eps, loss_d + 1, true};
     rc = run_step(h, B, B_global, in, nullptr, probs_d, loss_d, F(h, "H_GRADS"), &ad, st);
     if (rc) return rc;
     if ((rc = release_slot(h, st))) return rc;
     if (probs_out)
         CK(h, cudaMemcpyAsync(probs_out, probs_d, (size_t)B * 2 * h->Nc * (h->Nc - 1) * sizeof(float), cudaMemcpyDefault, st));
-    CK(h, cudaMemcpyAsync(loss3_host, loss_d, 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (!alias) CK(h, cudaMemcpyAsync(loss3_host, loss_d, 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
     return HDGNN_OK;
 }
 

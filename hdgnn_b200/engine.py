@@ -41,6 +41,25 @@ def label_pitch(n: int) -> int:
     return lib.hdgnn_label_pitch(n)
 
 
+F_DEBUG, F_LEGACY, F_LABEL_BITS = 2, 4, 8
+
+
+def bit_words(n: int) -> int:
+    return lib.hdgnn_bit_words(n)
+
+
+def pack_label_bits(lab: np.ndarray) -> np.ndarray:
+    """(B,n,n) {0,1} label grid -> (B,n,bit_words(n)) uint32 bitmap, the wire format of HDGNN_F_LABEL_BITS
+    (include/hdgnn.h): word w of a row holds column 32 w + k at bit k; diagonal and padding bits zero."""
+    lab = np.asarray(lab)
+    B, n, _ = lab.shape
+    wp = bit_words(n)
+    wide = np.zeros((B, n, wp * 32), dtype=np.uint8)
+    wide[:, :, :n] = lab != 0
+    wide[:, np.arange(n), np.arange(n)] = 0
+    return np.ascontiguousarray(np.packbits(wide, axis=-1, bitorder="little")).view("<u4").reshape(B, n, wp)
+
+
 @dataclass
 class DeviceBatch:
     """Compact commit batch resident in HBM (layouts of include/hdgnn.h)."""
@@ -57,7 +76,8 @@ class DeviceBatch:
         return self.adj.shape[0]
 
     @staticmethod
-    def from_numpy(adj, x, hmap, L, Y, device) -> "DeviceBatch":
+    def from_numpy(adj, x, hmap, L, Y, device, bits: bool = False) -> "DeviceBatch":
+        """bits=True: label grids as bitmaps (engines created with F_LABEL_BITS), packed on the device."""
         B, Ne, _ = adj.shape
         Nc = Y.shape[1]
         pe, pc = label_pitch(Ne), label_pitch(Nc)
@@ -65,10 +85,23 @@ class DeviceBatch:
         a[:, :, :Ne] = torch.as_tensor(np.ascontiguousarray(adj, dtype=np.uint8)).to(device)
         y = torch.zeros(B, Nc, pc, dtype=torch.uint8, device=device)
         y[:, :, :Nc] = torch.as_tensor(np.ascontiguousarray(Y, dtype=np.uint8)).to(device)
+        if bits:
+            a, y = pack_label_bits_device(a), pack_label_bits_device(y)
         return DeviceBatch(
             a, torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32)).to(device),
             torch.as_tensor(np.ascontiguousarray(hmap, dtype=np.int32)).to(device),
             torch.as_tensor(np.ascontiguousarray(L, dtype=np.int32)).to(device), y, Ne, Nc)
+
+
+def pack_label_bits_device(grid: torch.Tensor) -> torch.Tensor:
+    """(N,n,pitch) u8 CUDA byte grid (pitch = label_pitch(n)) -> (N,n,bit_words(n)) int32 bitmap (hdgnn_pack_label_bits)."""
+    if not grid.is_cuda:
+        raise RuntimeError("pack_label_bits_device needs a CUDA tensor; pack_label_bits is the host form")
+    N, n, pitch = grid.shape
+    bits = torch.empty(N, n, bit_words(n), dtype=torch.int32, device=grid.device)
+    st = C.c_void_p(torch.cuda.current_stream(grid.device).cuda_stream)
+    check(lib.hdgnn_pack_label_bits(N, n, C.c_void_p(grid.data_ptr()), pitch, C.c_void_p(bits.data_ptr()), st))
+    return bits
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -88,7 +121,9 @@ class Engine:
         check(lib.hdgnn_create(C.byref(cfg), C.byref(h)))
         self._h = h
         self.tdev = torch.device("cuda", device)
-        self.pe, self.pc = label_pitch(Ne), label_pitch(Nc)
+        self.host_bits = bool(flags & F_LABEL_BITS)      # label grids travel as bitmaps (host and device entry points)
+        # row pitch in bytes of the label arrays the device entry points take
+        self.pe, self.pc = (4 * bit_words(Ne), 4 * bit_words(Nc)) if self.host_bits else (label_pitch(Ne), label_pitch(Nc))
 
     def close(self):
         if getattr(self, "_h", None):
@@ -159,7 +194,8 @@ class Engine:
     def train_step_host(self, adj, x, hmap, L, Y, params, m, v, step_counter, loss3, probs=None,
                         lr=3e-4, beta1=0.9, beta2=0.999, eps=1e-8):
         """adj (B,Ne,Ne) u8, x (B,Ne) f32, hmap (B,Ne) i32, L (B,) i32, Y (B,Nc,Nc) u8: pinned host
-        tensors; loss3 (3,) pinned float32 receives {CE, loss_map, loss_para}.  Asynchronous."""
+        tensors (adj / Y as pack_label_bits bitmaps when the engine was created with F_LABEL_BITS);
+        loss3 (3,) pinned float32 receives {CE, loss_map, loss_para}.  Asynchronous."""
         B = adj.shape[0]
         check(lib.hdgnn_train_step_host(self._h, B, _p(adj), _p(x), _p(hmap), _p(L), _p(Y), _p(params), _p(m), _p(v),
                                         _p(step_counter), lr, beta1, beta2, eps, _p(probs), _p(loss3),

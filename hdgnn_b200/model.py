@@ -15,7 +15,8 @@ from typing import Optional
 import numpy as np
 import torch
 
-from .engine import Engine, DeviceBatch, param_count, param_offsets, PARAM_NAMES
+from . import _lib
+from .engine import Engine, DeviceBatch, param_count, param_offsets, PARAM_NAMES, F_LABEL_BITS, pack_label_bits
 from .synthetic import CommitBatch
 
 H = 20
@@ -64,21 +65,40 @@ def truncated_normal_init(variant: int, seed: Optional[int] = None) -> torch.Ten
 
 
 class HostBatch:
-    """Pinned host copy of a compact commit batch (the wire format into the hot path)."""
+    """Pinned host copy of a compact commit batch (the wire format into the hot path).  bits=True: the two label
+    grids travel as bitmaps (HDGNN_F_LABEL_BITS, 1/8 of the bytes); Y is kept as bytes too for the evaluation kernel."""
 
-    def __init__(self, cb: CommitBatch):
+    def __init__(self, cb: CommitBatch, bits: bool = False):
         pin = torch.cuda.is_available()
         mk = lambda a, dt: (torch.as_tensor(np.ascontiguousarray(a, dtype=dt)).pin_memory() if pin
                             else torch.as_tensor(np.ascontiguousarray(a, dtype=dt)))
-        self.adj, self.x = mk(cb.adj, np.uint8), mk(cb.x, np.float32)
-        self.hmap, self.L, self.Y = mk(cb.hmap, np.int32), mk(cb.L, np.int32), mk(cb.Y, np.uint8)
+        self.bits = bits
+        self.Y = mk(cb.Y, np.uint8)
+        if bits:
+            self.adj = mk(pack_label_bits(cb.adj).view(np.int32), np.int32)
+            self.Yw = mk(pack_label_bits(cb.Y).view(np.int32), np.int32)
+        else:
+            self.adj, self.Yw = mk(cb.adj, np.uint8), self.Y
+        self.x = mk(cb.x, np.float32)
+        self.hmap, self.L = mk(cb.hmap, np.int32), mk(cb.L, np.int32)
         self.B = self.adj.shape[0]
 
+    def clone(self) -> "HostBatch":
+        """Same batch in freshly pinned buffers."""
+        c = object.__new__(HostBatch)
+        c.bits, c.B = self.bits, self.B
+        pin = torch.cuda.is_available()
+        for k in ("adj", "x", "hmap", "L", "Y", "Yw"):
+            t = getattr(self, k).clone()
+            setattr(c, k, t.pin_memory() if pin else t)
+        return c
+
     def nbytes(self):
-        return sum(t.numel() * t.element_size() for t in (self.adj, self.x, self.hmap, self.L, self.Y))
+        """bytes copied host -> device per step"""
+        return sum(t.numel() * t.element_size() for t in self.tensors())
 
     def tensors(self):
-        return self.adj, self.x, self.hmap, self.L, self.Y
+        return self.adj, self.x, self.hmap, self.L, self.Yw
 
 
 class graph2graph(object):
@@ -121,7 +141,14 @@ class graph2graph(object):
     # ------------------------------------------------------------------------------------------
     def build_model(self):
         torch.cuda.set_device(self.device)
-        self.engine = Engine(self.Ne, self.Nc, variant=self.variant, max_batch=self.max_batch, device=self.device)
+        try:        # label grids as bitmaps on the wire (1/8 of the H2D bytes, no packing kernel): fused path only
+            self.engine = Engine(self.Ne, self.Nc, variant=self.variant, max_batch=self.max_batch, device=self.device,
+                                 flags=F_LABEL_BITS)
+        except _lib.HdgnnError as e:
+            if e.code != _lib.E_UNSUPPORTED:
+                raise
+            self.engine = Engine(self.Ne, self.Nc, variant=self.variant, max_batch=self.max_batch, device=self.device)
+        self.host_bits = self.engine.host_bits
         self.n_params = param_count(self.variant)
         self.offsets = param_offsets(self.variant)
         dev = self.engine.tdev
@@ -148,6 +175,10 @@ class graph2graph(object):
         assert flat.numel() == self.n_params
         self.params.copy_(flat.to(torch.float32))
         self.m.zero_(); self.v.zero_(); self.step_counter.zero_()
+
+    def host_batch(self, cb: CommitBatch) -> HostBatch:
+        """Pinned host batch in the wire format this model's engine takes."""
+        return HostBatch(cb, bits=self.host_bits)
 
     def named_params(self):
         out = {}
@@ -228,13 +259,15 @@ class graph2graph(object):
         probs_d = torch.zeros(per, 2, self.Ncr, dtype=torch.float32, device=dev)
         counter = 1
         history = []
+        # the data set is static across epochs: pin (and bit-pack) every batch once
+        batches = [self.host_batch(self._batch(train, train, j, quirk_q2)) for j in range(nb)]
         start_time1 = time.time()
         for i in range(self.epoch):
             tr_loss_Hedge = 0.0
             tr_loss_map = 0.0
             hits = torch.zeros(1, dtype=torch.int64, device=dev)
             for j in range(nb):
-                hb = HostBatch(self._batch(train, train, j, quirk_q2))
+                hb = batches[j]
                 l3 = self.train_step(hb, want_probs=True, probs_out=probs_d)
                 # top_ACC (EvaluationFuncs.py:27-37) from device counters: the probabilities never leave the GPU
                 counts, _ = eval_counts(probs_d[:hb.B], hb.Y.to(dev, non_blocking=True))
@@ -300,7 +333,7 @@ class graph2graph(object):
         for j in range(nb):
             saved = (self.world, self.rank)
             self.world, self.rank = 1, 0                            # inference is not sharded
-            hb = HostBatch(self._batch(test, train, j, quirk_q2))
+            hb = self.host_batch(self._batch(test, train, j, quirk_q2))
             self.world, self.rank = saved
             pj = probs_d[j * mb:(j + 1) * mb]
             self.infer(hb, pj, loss_h[j:j + 1])

@@ -68,6 +68,12 @@ typedef struct {
 /* flag value 1 is reserved */
 #define HDGNN_F_DEBUG   2   /* keep named copies of intermediates for hdgnn_workspace (tests) */
 #define HDGNN_F_LEGACY  4   /* force the multi-kernel path (the only path for variant 4 and for Nc above ~160) */
+#define HDGNN_F_LABEL_BITS 8 /* every entry point receives LABEL BITMAPS instead of byte grids: adj (device) / adj_host is
+                               (B, Ne, hdgnn_bit_words(Ne)) uint32 and Y / Y_host (B, Nc, hdgnn_bit_words(Nc)) uint32, word w of a
+                               row holding column 32 w + k at bit k (little-endian np.packbits order), diagonal and padding
+                               bits ZERO; adj_pitch / y_pitch = 4 * hdgnn_bit_words(n).  1/8 of the bytes on the wire and
+                               in HBM and no packing kernel; fused path only (hdgnn_create fails with
+                               HDGNN_E_UNSUPPORTED otherwise).  hdgnn_pack_label_bits builds the format on the device. */
 
 /* number of fp32 parameters of a variant (2127 for variant 2, 3129 for variant 4) */
 int hdgnn_param_count(int variant);
@@ -82,6 +88,7 @@ int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out);
 int hdgnn_destroy(hdgnn_handle_t h);
 const char* hdgnn_last_error(hdgnn_handle_t h);       /* h may be NULL: last create() error */
 int hdgnn_label_pitch(int n);                         /* required row pitch for an n x n byte grid */
+int hdgnn_bit_words(int n);                           /* uint32 words per row of an n x n label bitmap (16-byte rows) */
 
 /* Forward only.  Replaces sess.run([loss_Hedge_mse, loss_map, C_edge_output2]) of
  * model_2.py:486-502 (graph of model_2.py:86-118).  `loss` receives the mean softmax
@@ -213,6 +220,10 @@ int hdgnn_map_conv(int B, int N, const uint8_t* adj, int adj_pitch, const float*
  * not truncate to -2,-1,0 or 1 (an IndexError in the reference), may be NULL. */
 int hdgnn_compact_from_raw(int N, int n, const void* raw, int raw_is_f64, uint8_t* grid, int pitch, float* diag,
                            int32_t* err, void* stream);
+
+/* Byte grids -> label bitmaps (the format of HDGNN_F_LABEL_BITS) on the device: grid (N,n,pitch) u8 as written by
+ * hdgnn_compact_from_raw, bits (N,n,hdgnn_bit_words(n)) uint32; diagonal and padding bits come out zero. */
+int hdgnn_pack_label_bits(int N, int n, const uint8_t* grid, int pitch, uint32_t* bits, void* stream);
 
 /* Evaluation counters on the device, replaces the loops of EvaluationFuncs.py:27-37 (top_ACC), :92-117 (prec / recall /
  * f1) and :119-153 (AUC) over the probs the relation head wrote.  probs (B,2,Ncr) f32, Y (B,Nc,y_pitch) u8.

@@ -28,7 +28,7 @@ def main():
         ces = []
         for t in range(steps):
             cb = make_commits(Bg, Ne, Nc, seed=100 + t)           # the global batch, generated identically on every rank
-            hb = HostBatch(cb.slice(rank * per, (rank + 1) * per))
+            hb = model.host_batch(cb.slice(rank * per, (rank + 1) * per))
             l3 = model.train_step(hb)
             torch.cuda.synchronize()
             ce = float(l3[0])
