@@ -33,6 +33,8 @@ struct Ent2Args {
     const float* GR; const float* GC;  // bwd: (B,N,20) d/dRS, d/dCS
     float* RS; float* CSp;             // fwd: (B,N,20), (B,SL,N,20)
     float* gpart;                      // bwd: (gridDim.x, 80)
+    int head;                          // fwd: first kernel of the step (bitmaps given): the weights come from the previous
+                                       // step's optimizer kernel, so they too are read after pdl_wait()
 };
 
 // number of chunks that intersect commit b = slots to sum
@@ -67,6 +69,7 @@ __global__ void __launch_bounds__(KG * NRG * 32, 4 / NRG) ent_fwd2_kernel(const 
     uint64_t* bar = reinterpret_cast<uint64_t*>(wts + 5 * HD + NRG * HD + 3 * 8 * HD + 4 * HD + 2 * HD);
 
     if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    if (a.head) pdl_wait();
     if (tid < HD) {
         const float* par = a.params;
         wts[tid] = par[a.o_u + tid]; wts[HD + tid] = par[a.o_v + tid];

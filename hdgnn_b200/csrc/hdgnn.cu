@@ -537,10 +537,11 @@ int debug_scatter(hdgnn_handle_t h, int B, cudaStream_t st) {
 
 int fused_forward(hdgnn_handle_t h, int B, int B_global, const Inputs& in, float* logits, float* probs, bool train,
                   cudaStream_t st) {
-    bool first_pdl = h->pdl;
-    if (in.ebits) {     // bitmaps came from the host: nothing to pack.  The first kernel then follows the previous step's
-        h->eb = in.ebits; h->yb = in.ybits;     // optimizer kernel directly and reads the weights it updates: no early launch
-        first_pdl = false;
+    // bitmaps given: nothing to pack.  The first kernel then follows the previous step's optimizer kernel directly and reads
+    // the weights it updates: ent_fwd2 defers those loads behind its pdl_wait (Ent2Args::head), mid2 is launched normally
+    const bool head = in.ebits != nullptr;
+    if (head) {
+        h->eb = in.ebits; h->yb = in.ybits;
     } else {
         h->bslot ^= 1;
         h->eb = (const uint32_t*)h->ws[h->bslot ? "EBITS1" : "EBITS0"].p;
@@ -559,10 +560,10 @@ int fused_forward(hdgnn_handle_t h, int B, int B_global, const Inputs& in, float
         Ent2Args a = ent2_args(h, B, in);
         ent2_grid(h, B, h->fwd_occ, &h->Gf, &h->Rf);
         h->SLf = ent2_max_slots(h->Ne, h->Rf);
-        a.R = h->Rf; a.SL = h->SLf; a.RS = F(h, "RS1"); a.CSp = F(h, "CS1P");
+        a.R = h->Rf; a.SL = h->SLf; a.RS = F(h, "RS1"); a.CSp = F(h, "CS1P"); a.head = head ? 1 : 0;
         const size_t smem = ent2_smem_bytes(h->fwd_cwt, h->fwd_nrg, h->Ne, h->Rf, h->WPe, false);
         PROF_BEGIN(h, st);
-        launch_ent2(h->fwd_cwt, h->fwd_nrg, false, h->Gf, smem, st, a, first_pdl);
+        launch_ent2(h->fwd_cwt, h->fwd_nrg, false, h->Gf, smem, st, a, h->pdl);
         LAUNCH_CHECK(h, "ent_fwd", st);
     }
     Mid2Args m{};
