@@ -310,6 +310,90 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         }
     }
     __syncthreads();
+    // ---- everything that depends on the inputs only (bitmaps, hunk ids, L) is done BEFORE the dependency on ent_fwd2:
+    // under programmatic dependent launch it overlaps that kernel's tail
+    const int nm1 = Ne - 1;
+    const bool ident = Lb == Ne;
+    int* horder = reinterpret_cast<int*>(dx2);          // index lines sorted by hunk id, ascending within a hunk (dx2 is dead until K)
+    int* hstart = reinterpret_cast<int*>(dnb);          // [Nc + 1] list offsets (dnb is dead until J)
+    mbar_wait(bar, 0);
+    {
+        // (1) stable counting sort of the index lines by hunk id.  Warp w owns the lines 32 w .. 32 w + 31: match_any
+        // gives every line its rank among the equal keys of the warp, the per-warp counts are laid out [warp][hunk],
+        // thread c turns them into bases, one warp scans the hunk totals.
+        const int WU = (Ne + 31) >> 5, NLW = (Lb + 31) >> 5;        // used bitmap words per row; warps holding index lines
+        uint32_t* cparts = reinterpret_cast<uint32_t*>(scratch);    // [8 row parts][WU][8] byte counters (column degrees)
+        int* wcnt = reinterpret_cast<int*>(scratch) + 8 * WU * 8;   // [NLW][Nc]
+        int* hcnt = reinterpret_cast<int*>(red);                    // [Nc]
+        for (int e = tid; e < NLW * Nc; e += M2_T) wcnt[e] = 0;
+        __syncthreads();
+        int key = -1, rank = 0;
+        for (int w0 = 0; w0 < NLW; w0 += M2_NW) {                   // one round unless L > 32 * 20
+            const int w = w0 + warp, i = w * 32 + lane;
+            if (w < NLW) {
+                key = i < Lb ? hm[i] : -1;
+                const uint32_t peers = __match_any_sync(0xffffffffu, key);
+                rank = __popc(peers & ((1u << lane) - 1u));
+                if (key >= 0 && rank == 0) wcnt[w * Nc + key] = __popc(peers);
+            }
+        }
+        // (2) degrees (only the closed-form pooling uses them).  Rows: one thread per row.  Columns, bit-sliced: thread
+        // (row part, word, k) adds (w >> k) & 0x01010101 over its rows -- four column counters in the bytes of one
+        // register -- and the eight row parts are summed per column afterwards.  No votes, no warp reductions.
+        if (ident) {
+            for (int i = tid; i < Ne; i += M2_T) {
+                int c = 0;
+                for (int w = 0; w < WU; ++w) c += __popc(ebits[i * WPe + w]);
+                SP[4 * i + 3] = (float)c;
+            }
+            const int rows_per = (Ne + 7) >> 3;                     // <= 64: no byte overflow
+            for (int t = tid; t < 8 * WU * 8; t += M2_T) {
+                const int k = t & 7, sg = (t >> 3) % WU, rp = t / (8 * WU);
+                const int r0 = rp * rows_per, r1 = min(r0 + rows_per, Ne);
+                uint32_t acc = 0u;
+                for (int r = r0; r < r1; ++r) acc += (ebits[r * WPe + sg] >> k) & 0x01010101u;
+                cparts[t] = acc;
+            }
+        }
+        __syncthreads();
+        if (ident) {
+            for (int j = tid; j < Ne; j += M2_T) {
+                const int sg = j >> 5, bit = j & 31, k = bit & 7, sh = (bit >> 3) * 8;
+                int cd = 0;
+#pragma unroll
+                for (int rp = 0; rp < 8; ++rp) cd += (cparts[(rp * WU + sg) * 8 + k] >> sh) & 0xffu;
+                TP[4 * j + 3] = (float)cd;
+            }
+        }
+        if (tid < Nc) {                                             // per-warp counts -> bases within the hunk, hunk total
+            int run = 0;
+            for (int w = 0; w < NLW; ++w) { const int c = wcnt[w * Nc + tid]; wcnt[w * Nc + tid] = run; run += c; }
+            hcnt[tid] = run;
+        }
+        __syncthreads();
+        if (warp == 0) {                                            // exclusive scan of the hunk totals (Nc <= 256: 8 per lane)
+            const int per = (Nc + 31) >> 5, lo = min(lane * per, Nc), hi = min(lo + per, Nc);
+            int sum = 0;
+            for (int c = lo; c < hi; ++c) sum += hcnt[c];
+            int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            int run = incl - sum;
+            for (int c = lo; c < hi; ++c) { hstart[c] = run; run += hcnt[c]; }
+            if (lane == 31) hstart[Nc] = incl;
+        }
+        __syncthreads();
+        if (NLW <= M2_NW) {
+            if (warp < NLW && key >= 0) horder[hstart[key] + wcnt[warp * Nc + key] + rank] = warp * 32 + lane;
+        } else {                                                    // more index lines than one round of warps: recompute the ranks
+            for (int w = warp; w < NLW; w += M2_NW) {
+                const int i = w * 32 + lane, ky = i < Lb ? hm[i] : -1;
+                const uint32_t peers = __match_any_sync(0xffffffffu, ky);
+                if (ky >= 0) horder[hstart[ky] + wcnt[w * Nc + ky] + __popc(peers & ((1u << lane) - 1u))] = i;
+            }
+        }
+    }
+    __syncthreads();
     pdl_wait();                     // RS1 / CS1p come from ent_fwd2 (everything above reads inputs, weights, bitmaps)
     pdl_launch_dependents();
     M2_PHASE(1);
@@ -358,31 +442,18 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         __syncthreads();
     }
     if (dbg) for (int i = tid; i < Ne; i += M2_T) dbg[(size_t)Ne * HD + i] = x2[i];
-    mbar_wait(bar, 0);
     M2_PHASE(2);
 
     // ---------------- D. pooling forward -------------------------------------------------------
     // B2[q] = [x2_gi, x2_gj, 1 - A, A] over the Ne-grid enumeration q; the L x L local grid selects
     // q = li (L-1) + lj - [lj > li]  (utils2.py:123-137, quirk Q3).  SP[li] = row sums, TP[lj] = column sums.
-    const int nm1 = Ne - 1;
-    const bool ident = Lb == Ne;
     if (ident) {
         float part = 0.f;
         for (int i = tid; i < Ne; i += M2_T) part += x2[i];
         const float X = mid2_block_sum(part, red);
-        for (int i = warp; i < Ne; i += M2_NW) {            // row degrees
-            const int c = __reduce_add_sync(0xffffffffu, lane < WPe ? __popc(ebits[i * WPe + lane]) : 0);
-            if (lane == 0) SP[4 * i + 3] = (float)c;
-        }
-        for (int j = tid; j < Ne; j += M2_T) {              // column degrees
-            const uint32_t* col = ebits + (j >> 5);
-            const int sh = j & 31;
-            int c = 0;
-            for (int i = 0; i < Ne; ++i) c += (col[i * WPe] >> sh) & 1u;
-            TP[4 * j + 3] = (float)c;
-        }
-        __syncthreads();
-        for (int i = tid; i < Ne; i += M2_T) {
+        M2_PHASE(13);
+        M2_PHASE(14);
+        for (int i = tid; i < Ne; i += M2_T) {              // degrees are in SP[.][3] / TP[.][3] (computed before the wait)
             const float xi = x2[i], fn = (float)nm1;
             SP[4 * i] = fn * xi; SP[4 * i + 1] = X - xi; SP[4 * i + 2] = fn - SP[4 * i + 3];
             TP[4 * i] = X - xi; TP[4 * i + 1] = fn * xi; TP[4 * i + 2] = fn - TP[4 * i + 3];
@@ -445,20 +516,14 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         }
     }
     __syncthreads();
-    // segmented reduce by hunk id in ascending entity-line order; two threads per (hunk, channel), halves in order
-    for (int base = 0; base < Nc * 8; base += M2_T) {
-        const int idx2 = base + tid, idx = idx2 >> 1, half = idx2 & 1;
-        const int c = idx >> 2, chn = idx & 3, mid_i = Lb >> 1;
+    // segmented reduce by hunk id over the sorted lists: one thread per (hunk, channel), ascending index-line order
+    M2_PHASE(15);
+    for (int idx = tid; idx < Nc * 4; idx += M2_T) {
+        const int c = idx >> 2, chn = idx & 3;
         float acc = 0.f;
-        if (idx2 < Nc * 8)
-            for (int i = half ? mid_i : 0; i < (half ? Lb : mid_i); ++i)
-                if (hm[i] == c) acc += SP[4 * i + chn] + TP[4 * i + chn];
-        const float other = __shfl_xor_sync(0xffffffffu, acc, 1);
-        if (idx2 < Nc * 8 && half == 0) {
-            const float v = acc + other;
-            nb[idx] = v;
-            if (dbg) dbg[(size_t)Ne * 21 + idx] = v;
-        }
+        for (int k = hstart[c]; k < hstart[c + 1]; ++k) { const int i = horder[k]; acc += SP[4 * i + chn] + TP[4 * i + chn]; }
+        nb[idx] = acc;
+        if (dbg) dbg[(size_t)Ne * 21 + idx] = acc;
     }
     __syncthreads();
     M2_PHASE(3);

@@ -26,6 +26,11 @@ if g.any():
     print("general commits: J (9->12) %.0f | K gather (12->13) %.0f | K rest (13->10) %.0f | D: scan+TP gather (2->14) %.0f, rest (14->3) %.0f" % (
         (clk[g, 12] - clk[g, 9]).mean(), (clk[g, 13] - clk[g, 12]).mean(), (clk[g, 10] - clk[g, 13]).mean(),
         (clk[g, 14] - clk[g, 2]).mean(), (clk[g, 3] - clk[g, 14]).mean()))
+print("ident D: X sum (2->13) %.0f | degrees (13->14) %.0f | fill (14->15) %.0f | seg reduce (15->3) %.0f" % (
+    (clk[ident, 13] - clk[ident, 2]).mean(), (clk[ident, 14] - clk[ident, 13]).mean(), (clk[ident, 15] - clk[ident, 14]).mean(),
+    (clk[ident, 3] - clk[ident, 15]).mean()))
+if g.any():
+    print("general D: seg reduce (15->3) %.0f" % (clk[g, 3] - clk[g, 15]).mean())
 print("ident commits: J (9->12) %.0f | K (12->10) %.0f" % ((clk[ident, 12] - clk[ident, 9]).mean(), (clk[ident, 10] - clk[ident, 12]).mean()))
 tot = clk[:, 11] - clk[:, 0]
 print(f"total mean {tot.mean():.0f} max {tot.max():.0f} cycles")
