@@ -458,6 +458,9 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             SP[4 * i] = fn * xi; SP[4 * i + 1] = X - xi; SP[4 * i + 2] = fn - SP[4 * i + 3];
             TP[4 * i] = X - xi; TP[4 * i + 1] = fn * xi; TP[4 * i + 2] = fn - TP[4 * i + 3];
         }
+    } else if (Lb < 2) {
+        // an index file with fewer than two lines has no local pair (utils2.py:123-137): nothing is pooled
+        for (int idx = tid; idx < 4 * Ne; idx += M2_T) { SP[idx] = 0.f; TP[idx] = 0.f; }
     } else {
         // general path: SP[li] = sum of the m = L-1 consecutive entries B2[li m .. li m + m) (closed form from
         // prefix sums and bit-range popcounts); TP[lj] = sum_li B2[li m + lj - (lj > li)] gathered with
@@ -920,6 +923,8 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             const float a0 = dl[4 * i], a1 = dl[4 * i + 1];
             dx2[i] = (fmaf(fn, a0, D0 - a0)) + (fmaf(fn, a1, D1 - a1));
         }
+    } else if (Lb < 2) {
+        for (int i = tid; i < Ne; i += M2_T) dx2[i] = 0.f;
     } else {
         // general path (mirror of the forward): the row part of dx2[gi] runs over the consecutive flat indices
         // [gi n, gi n + n) below qmax = L (L-1) -> closed form from prefix sums of dl; the column part is gathered

@@ -26,7 +26,7 @@
  *                                   is ignored.  Row pitch in bytes, multiple of 16, >= Ne.
  *   x    float  (B, Ne)             node attribute x_i = raw A_ii            (utils2.py:35)
  *   hmap int32  (B, Ne)             hunk id of index line i; <0 or >=Nc = none (utils2.py:129-136)
- *   L    int32  (B)                 index lines read, 2 <= L <= Ne           (utils2.py:121)
+ *   L    int32  (B)                 index lines read, 0 <= L <= Ne (fewer than 2: nothing is pooled)  (utils2.py:121)
  *   Y    uint8  (B, Nc, y_pitch)    off-diagonal hunk adjacency = label      (utils2.py:47,105)
  * Outputs
  *   logits, probs  float (B, 2, Ncr), Ncr = Nc(Nc-1), pair order p(s,t) = s(Nc-1)+t-[t>s]

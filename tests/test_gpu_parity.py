@@ -249,3 +249,69 @@ def test_fused_train_step_matches_separate_calls(variant):
         assert relerr(pa.cpu().numpy(), p_ref.numpy()) < TIGHT
         assert abs(loss3[0].item() - float(ce)) < TIGHT * float(ce)
     eng.close()
+
+
+def _edge_batches():
+    """Inputs at the edges of the domain (utils2.py:111-137): index files with 0, 1 or 2 lines, every line 'null',
+    every entity in ONE hunk, empty and complete adjacency / label grids, zero node attributes."""
+    Ne, Nc, B = 40, 12, 8
+    cb = make_commits(B, Ne, Nc, seed=77, p_edge=0.15, p_short=0.0, p_noise=0.1)
+    cb.L[0], cb.L[1], cb.L[2], cb.L[3] = 0, 1, 2, 3
+    cb.hmap[4, :] = -1                       # all lines 'null' (or cut by the Nc rule): nothing is pooled
+    cb.hmap[5, :] = 7                        # every entity in one hunk
+    cb.adj[6] = 0; cb.Y[6] = 0               # no entity edge, no related hunk pair
+    cb.adj[7] = 1; cb.Y[7] = 1               # complete graphs
+    idx = np.arange(Ne); cb.adj[7, idx, idx] = 0
+    cidx = np.arange(Nc); cb.Y[7, cidx, cidx] = 0
+    cb.x[3] = 0.0
+    return cb, Ne, Nc, B
+
+
+@pytest.mark.parametrize("path", ["default", "legacy"])
+@pytest.mark.parametrize("variant", [1, 2, 4])
+def test_domain_edge_cases_match_oracle(variant, path):
+    from hdgnn_b200.engine import Engine, DeviceBatch
+    cb, Ne, Nc, B = _edge_batches()
+    flat = _params(variant)
+    plan = PN.train_step_plan(variant, flat, cb.adj, cb.x, cb.hmap, cb.L, cb.Y)
+    _, ce, _, grad, out = O.train_loss_and_grad(variant, flat, cb.adj, cb.x, cb.hmap, cb.L, cb.Y)
+    assert relerr(plan["grad"], grad.numpy()) < 1e-9 and relerr(plan["probs"], out["probs"].numpy()) < 1e-10
+    eng = Engine(Ne, Nc, variant=variant, max_batch=B, flags=F_LEGACY if path == "legacy" else 0)
+    db = DeviceBatch.from_numpy(cb.adj, cb.x, cb.hmap, cb.L, cb.Y, eng.tdev)
+    params = flat.float().cuda()
+    probs, logits, loss, grads = eng.forward_backward(db, params, want_logits=True)
+    torch.cuda.synchronize()
+    assert torch.isfinite(probs).all() and torch.isfinite(grads).all()
+    pf = flat.numpy()
+    reg = 0.001 * pf
+    names = [s[0] for s in O.param_spec(variant)]
+    offs = dict(zip(names, np.cumsum([0] + [int(np.prod(s[2])) for s in O.param_spec(variant)])[:-1]))
+    for t in ("theta1", "theta2"):
+        th = pf[offs[t]:offs[t] + 2]
+        reg[offs[t]:offs[t] + 2] += 0.001 * th / np.sqrt((th ** 2).sum())
+    errs = {"probs": relerr(probs.cpu().numpy(), plan["probs"]), "logits": relerr(logits.cpu().numpy(), plan["logits"]),
+            "ce": relerr(loss.cpu().numpy()[0], plan["ce"]), "grad": relerr(grads.cpu().numpy(), plan["grad"] - reg)}
+    # per commit, so that a wrong degenerate commit cannot hide behind the others
+    for b in range(B):
+        errs[f"probs[{b}]"] = relerr(probs[b].cpu().numpy(), plan["probs"][b])
+    assert all(v < TIGHT for v in errs.values()), errs
+    # a single-commit batch through the same engine
+    one = DeviceBatch.from_numpy(cb.adj[1:2], cb.x[1:2], cb.hmap[1:2], cb.L[1:2], cb.Y[1:2], eng.tdev)
+    p1, _, _, _ = eng.forward_backward(one, params)
+    torch.cuda.synchronize()
+    assert relerr(p1.cpu().numpy(), plan["probs"][1:2]) < TIGHT
+    eng.close()
+
+
+@pytest.mark.parametrize("Ne,Nc", [(2, 2), (3, 2), (2, 5)])
+def test_smallest_grids(Ne, Nc):
+    from hdgnn_b200.engine import Engine, DeviceBatch
+    cb = make_commits(3, Ne, Nc, seed=5, p_edge=0.5, p_short=0.0, p_noise=0.5)
+    flat = _params(2)
+    plan = PN.train_step_plan(2, flat, cb.adj, cb.x, cb.hmap, cb.L, cb.Y)
+    eng = Engine(Ne, Nc, variant=2, max_batch=3)
+    db = DeviceBatch.from_numpy(cb.adj, cb.x, cb.hmap, cb.L, cb.Y, eng.tdev)
+    probs, _, loss, grads = eng.forward_backward(db, flat.float().cuda())
+    torch.cuda.synchronize()
+    assert relerr(probs.cpu().numpy(), plan["probs"]) < TIGHT and relerr(loss.cpu().numpy()[0], plan["ce"]) < TIGHT
+    eng.close()
