@@ -355,6 +355,225 @@ __global__ void __launch_bounds__(TC_T, 1) propagate_tc_kernel(const ConvArgs a)
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tcols) : "memory");
 }
 
+// ---- persistent tcgen05 variant: the adjacency is the wide operand ------------------------------------------------
+// out^T (4 d_out x N) = Z^T (4 d_out x N_j) . Adj (N_j x N_i): the feature terms are the (small) A operand, the adjacency
+// tile is the B operand with n = output node.  Every 8 consecutive bytes of adjacency row r become ONE 16-byte bf16
+// chunk stored at chunk index c8 * KP + r -- and that single image serves both forms of the normalisation, because the
+// canonical no-swizzle layouts only differ in which of LBO / SBO strides over which index:
+//   reference form  out_i = sum_j adj[j][i] z_j : k = r, n = 8 c8 + u  -> MN-major B (SBO = KP * 16 B, LBO = 128 B)
+//   un-transposed   out_i = sum_j adj[i][j] z_j : n = r, k = 8 c8 + u  -> K-major  B (LBO = KP * 16 B, SBO = 128 B)
+// so there is no bit transpose at all; the row degrees fall out of the same pass over the bytes.  A CTA is persistent
+// over commits: as soon as a byte tile has been converted the TMA for the CTA's next commit is issued into the same
+// buffer and lands while the operands are finished, the MMA chain runs and the epilogue drains TMEM.
+constexpr int TC2_T = 512;
+// four bytes -> four bits (bit i = byte i != 0): bytes to 0/1, then one multiply gathers them into the top nibble
+__device__ __forceinline__ uint32_t nzn(uint32_t v) {
+    const uint32_t t = ((((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v) >> 7) & 0x01010101u;
+    return (t * 0x01020408u) >> 24;
+}
+__host__ __device__ inline size_t tc2_adj_bytes(int KP) {
+    const size_t adj = (size_t)(KP / 8) * (KP + 1) * 16, stage = (size_t)3 * KP * 32 * 4;
+    return adj > stage ? adj : stage;
+}
+__host__ __device__ inline size_t tc2_smem_bytes(int N, int pitch, int d_in) {
+    const int KP = round_up(N, 16), K8 = KP / 8, KS = KP + 1;   // KS: chunk stride per c8 (odd: conflict-free 16-byte stores)
+    size_t off = 256;                                           // two mbarriers + TMEM slot, nibble table
+    off += (size_t)round_up(N * pitch, 128);                    // byte tile (TMA destination)
+    off += tc2_adj_bytes(KP);                                   // adjacency chunks [c8][r] | epilogue staging [3][KP][32] f32
+    off += (size_t)K8 * 128 * 16;                               // feature chunks   [k8][m], m = 4 c + term
+    off += (size_t)round_up(N * d_in, 4) * 4;                   // H tile (TMA destination)
+    off += (size_t)round_up(N, 4) * 4;                          // dinv
+    off += (size_t)(CONV_MAXD * CONV_MAXD + CONV_MAXD) * 4;     // W, bias
+    off += (size_t)KP * 32;                                     // edge-mask bytes
+    return off + 128;
+}
+
+__global__ void __launch_bounds__(TC2_T, 1) propagate_tc2_kernel(const ConvArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int N = a.N, pitch = a.pitch, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int d_in = a.d_in, d_out = a.d_out, KP = round_up(N, 16), K8 = KP / 8, KS = KP + 1;
+    uint64_t* bar_tma = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* bar_mma = bar_tma + 1;
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(bar_tma + 2);
+    uint8_t* tile = smem + 256;
+    uint4* sAdj = reinterpret_cast<uint4*>(tile + round_up(N * pitch, 128));
+    uint4* sZ = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(sAdj) + tc2_adj_bytes(KP));
+    float* Hin = reinterpret_cast<float*>(sZ + (size_t)K8 * 128);
+    float* dinv = Hin + round_up(N * d_in, 4);
+    float* Ws = dinv + round_up(N, 4);
+    float* bs = Ws + CONV_MAXD * CONV_MAXD;
+    uint2* lut = reinterpret_cast<uint2*>(smem + 32);           // [16] nibble -> four bf16 {0, 1}
+    uint8_t* mask8 = reinterpret_cast<uint8_t*>(bs + CONV_MAXD);    // [KP][32] edge masks of a row, one byte per 8 columns
+    const bool self_loop = a.flags & HDGNN_P_SELF_LOOP, transpose = !(a.flags & HDGNN_P_NO_TRANSPOSE);
+    const uint32_t tbytes = (uint32_t)N * pitch, hbytes = (uint32_t)N * d_in * 4;
+    const bool htma = (hbytes & 15u) == 0 && (((uintptr_t)a.H & 15) == 0);
+    constexpr int TCOLS = 256;
+    if (tid == 0) {
+        mbar_init(bar_tma, 1); mbar_init(bar_mma, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tslot)), "r"(TCOLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (a.W) for (int i = tid; i < d_in * d_out; i += TC2_T) Ws[i] = a.W[i];
+    if (tid < CONV_MAXD) bs[tid] = (a.bias && tid < d_out) ? a.bias[tid] : 0.f;
+    if (tid < 16) {
+        const uint32_t o1 = 0x3F80u;    // bf16 1.0
+        lut[tid] = make_uint2(((tid & 1) ? o1 : 0u) | ((tid & 2) ? o1 << 16 : 0u), ((tid & 4) ? o1 : 0u) | ((tid & 8) ? o1 << 16 : 0u));
+    }
+    for (int i = tid; i < K8 * 128; i += TC2_T) sZ[i] = make_uint4(0u, 0u, 0u, 0u);     // rows 32 s + c with c >= d_out and rows >= 96 stay zero
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tslot;
+    int b = blockIdx.x;
+    if (tid == 0 && b < a.B) {
+        mbar_arrive_expect_tx(bar_tma, tbytes + (htma ? hbytes : 0u));
+        bulk_g2s(tile, a.adj + (size_t)b * tbytes, tbytes, bar_tma);
+        if (htma) bulk_g2s(Hin, a.H + (size_t)b * N * d_in, hbytes, bar_tma);
+    }
+    // per-lane constants of the conversion: valid-column mask of the lane's 8 columns
+    const uint32_t colmask = lane * 8 + 8 <= N ? 0xffu : (lane * 8 >= N ? 0u : (0xffu >> (lane * 8 + 8 - N)));
+    uint32_t ph = 0;
+    for (; b < a.B; b += gridDim.x, ph ^= 1u) {
+        mbar_wait(bar_tma, ph);
+        // bytes -> bf16 chunks + row degrees: a warp takes four rows at a time (all loads first), a lane per 8 columns
+        for (int r0 = warp; r0 < KP; r0 += 4 * (TC2_T / 32)) {
+            uint32_t lo[4], hi[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int r = r0 + q * (TC2_T / 32);
+                lo[q] = 0u; hi[q] = 0u;
+                if (lane < K8 && r < N && lane * 8 < pitch) {
+                    const uint2 v = *reinterpret_cast<const uint2*>(tile + (size_t)r * pitch + lane * 8);
+                    lo[q] = v.x; hi[q] = v.y;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int r = r0 + q * (TC2_T / 32);
+                uint32_t m = (nzn(lo[q]) | (nzn(hi[q]) << 4)) & colmask;                 // bit u = column 8 lane + u is an edge
+                const bool dg = (r >> 3) == lane;
+                if (dg) m &= ~(1u << (r & 7));                                            // the diagonal is not an edge
+                if (r < KP) mask8[r * 32 + lane] = (uint8_t)m;                            // edge masks of the row, for the degree
+                if (dg && self_loop && r < N) m |= 1u << (r & 7);                         // A + I
+                if (lane < K8 && r < KP) {
+                    const uint2 a0 = lut[m & 15u], a1 = lut[m >> 4];
+                    sAdj[(size_t)lane * KS + r] = make_uint4(a0.x, a0.y, a1.x, a1.y);
+                }
+            }
+        }
+        __syncthreads();
+        for (int j = tid; j < N; j += TC2_T) {              // degree = popcount of the row's 32 mask bytes (no warp reductions: REDUX is slow)
+            const uint4 m0 = *reinterpret_cast<const uint4*>(mask8 + j * 32), m1 = *reinterpret_cast<const uint4*>(mask8 + j * 32 + 16);
+            const int deg = __popc(m0.x) + __popc(m0.y) + __popc(m0.z) + __popc(m0.w) + __popc(m1.x) + __popc(m1.y) + __popc(m1.z) + __popc(m1.w);
+            dinv[j] = 1.f / sqrtf((float)deg + (self_loop ? 1.f : 0.f) + a.eps);
+        }
+        fence_proxy_async();            // the generic reads of the byte tile are ordered before the next bulk copy into it
+        __syncthreads();
+        const int nb = b + gridDim.x;
+        if (tid == 0 && nb < a.B) {     // prefetch: the tile buffer is free, the H buffer after the operand build below
+            mbar_arrive_expect_tx(bar_tma, tbytes + (htma ? hbytes : 0u));
+            bulk_g2s(tile, a.adj + (size_t)nb * tbytes, tbytes, bar_tma);
+        }
+        if (a.dinv_out) for (int j = tid; j < N; j += TC2_T) a.dinv_out[(size_t)b * N + j] = dinv[j];
+        // feature operand: row m = 32 s + c holds the s-th bf16 term of dinv_j (H W)[j][c]; two threads per 16-byte chunk
+        const float* Hb = htma ? Hin : a.H + (size_t)b * N * d_in;
+        for (int t = tid; t < K8 * d_out * 2; t += TC2_T) {
+            const int half = t & 1, t2 = t >> 1, kk = t2 / d_out, c = t2 - kk * d_out;
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = kk * 8 + half * 4 + u;
+                v[u] = 0.f;
+                if (j < N) {
+                    float acc = 0.f;
+                    if (a.W) { for (int k = 0; k < d_in; ++k) acc = fmaf(Hb[(size_t)j * d_in + k], Ws[k * d_out + c], acc); }
+                    else acc = Hb[(size_t)j * d_in + c];
+                    v[u] = acc * dinv[j];
+                }
+            }
+            // hi / mid / lo bf16 terms, two values per conversion (cvt.rn.bf16x2.f32)
+            __nv_bfloat162 o0[2], o1[2], o2[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                o0[h] = __floats2bfloat162_rn(v[2 * h], v[2 * h + 1]);
+                const float ra = v[2 * h] - __low2float(o0[h]), rb = v[2 * h + 1] - __high2float(o0[h]);
+                o1[h] = __floats2bfloat162_rn(ra, rb);
+                o2[h] = __floats2bfloat162_rn(ra - __low2float(o1[h]), rb - __high2float(o1[h]));
+            }
+            uint2* dst = reinterpret_cast<uint2*>(sZ + (size_t)kk * 128 + c) + half;
+            dst[0] = *reinterpret_cast<const uint2*>(o0); dst[2 * 32] = *reinterpret_cast<const uint2*>(o1);
+            dst[2 * 64] = *reinterpret_cast<const uint2*>(o2);
+        }
+        fence_proxy_async();            // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (tid == 0) {
+            if (nb < a.B && htma) bulk_g2s(Hin, a.H + (size_t)nb * N * d_in, hbytes, bar_tma);
+            const uint32_t idesc = umma_idesc(128, KP) | (transpose ? (1u << 16) : 0u);       // bit 16: B is MN-major
+            const uint32_t za = smem_u32(sZ), ba = smem_u32(sAdj);
+            for (int ks = 0; ks < (KP >> 4); ++ks) {
+                const uint64_t da = umma_desc(za + (uint32_t)ks * 2u * 128u * 16u, 128u * 16u, 128u);
+                const uint64_t db = transpose ? umma_desc(ba + (uint32_t)ks * 256u, 128u, (uint32_t)KS * 16u)
+                                              : umma_desc(ba + (uint32_t)ks * 2u * (uint32_t)KS * 16u, (uint32_t)KS * 16u, 128u);
+                const uint32_t accum = ks > 0;
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                             ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar_mma)) : "memory");
+        }
+        mbar_wait(bar_mma, ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // epilogue: quadrant q of TMEM (lanes 32 q .. + 31) holds term q of channel c = lane for every output node.
+        // Warp w drains quadrant w & 3 for the column slice w >> 2 into shared memory (the adjacency operand is dead),
+        // then all threads add the three terms, scale and store the (N, d_out) tile fully coalesced.
+        float* stage = reinterpret_cast<float*>(sAdj);                  // [3][KP][32]
+        {
+            const int q = warp & 3, sl = warp >> 2;
+            if (q < 3) {
+                // all loads of the warp's column slice in flight, one wait
+                uint32_t r[4][16];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int n0 = sl * 16 + g * 16 * (TC2_T / 128);
+                    if (n0 < KP) {
+                        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)n0;
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                                     : "=r"(r[g][0]), "=r"(r[g][1]), "=r"(r[g][2]), "=r"(r[g][3]), "=r"(r[g][4]), "=r"(r[g][5]), "=r"(r[g][6]),
+                                       "=r"(r[g][7]), "=r"(r[g][8]), "=r"(r[g][9]), "=r"(r[g][10]), "=r"(r[g][11]), "=r"(r[g][12]),
+                                       "=r"(r[g][13]), "=r"(r[g][14]), "=r"(r[g][15])
+                                     : "r"(taddr) : "memory");
+                    }
+                }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int n0 = sl * 16 + g * 16 * (TC2_T / 128);
+                    if (n0 < KP) {
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) stage[((size_t)q * KP + n0 + u) * 32 + lane] = __uint_as_float(r[g][u]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = warp; i < N; i += TC2_T / 32) {            // lanes = channels: 3 conflict-free loads, one contiguous store per row
+            if (lane < d_out) {
+                const float acc = (stage[(size_t)i * 32 + lane] + stage[((size_t)KP + i) * 32 + lane]) + stage[((size_t)2 * KP + i) * 32 + lane];
+                float o = fmaf(dinv[i], acc, bs[lane]);
+                if (a.flags & HDGNN_P_RELU) o = fmaxf(o, 0.f);
+                a.out[((size_t)b * N + i) * d_out + lane] = o;
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();                // TMEM, dinv and both operand buffers are free for the next commit
+    }
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TCOLS) : "memory");
+}
+
 // per commit: q_b = x^T (t0 x + t1 ((2/lam)(x - A_hat x) - x)),  t = softmax(theta)
 __global__ void __launch_bounds__(CONV_T) map_conv_kernel(const ConvArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -434,7 +653,16 @@ extern "C" int hdgnn_normalize_propagate(int B, int N, const uint8_t* adj, int p
     ConvArgs a{};
     a.B = B; a.N = N; a.pitch = pitch; a.d_in = d_in; a.d_out = d_out; a.flags = flags; a.eps = eps;
     a.adj = adj; a.H = H; a.W = W; a.bias = bias; a.out = out; a.dinv_out = dinv_out;
-    // tensor-core path (tcgen05): N <= 256 and the operands fit one SM; else the set-bit walk on the CUDA cores
+    // tensor-core paths (tcgen05), N <= 256: the persistent kernel with the adjacency as the wide operand when its
+    // buffers fit one SM, else the one-CTA-per-commit kernel; else the set-bit walk on the CUDA cores
+    const size_t smem_tc2 = tc2_smem_bytes(N, pitch, d_in);
+    if (!(flags & (HDGNN_P_NO_TENSOR | HDGNN_P_TENSOR_V1)) && N <= 256 && smem_tc2 <= (size_t)optin) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaFuncSetAttribute(propagate_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) != cudaSuccess) return HDGNN_E_CUDA;
+        propagate_tc2_kernel<<<B < sms ? B : sms, TC2_T, smem_tc2, (cudaStream_t)stream>>>(a);
+        return cudaGetLastError() == cudaSuccess ? HDGNN_OK : HDGNN_E_CUDA;
+    }
     const size_t smem_tc = tc_smem_bytes(N, pitch, d_in, d_out);
     if (!(flags & HDGNN_P_NO_TENSOR) && N <= 256 && smem_tc <= (size_t)optin) {
         if (cudaFuncSetAttribute(propagate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) != cudaSuccess) return HDGNN_E_CUDA;

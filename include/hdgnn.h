@@ -201,6 +201,7 @@ int hdgnn_infer_host(hdgnn_handle_t h, int B,
 #define HDGNN_P_RELU          2
 #define HDGNN_P_NO_TRANSPOSE  4   /* A_hat = D^-1/2 A D^-1/2 */
 #define HDGNN_P_NO_TENSOR     8   /* force the CUDA-core set-bit walk (default for N <= 256: tcgen05, bf16 x 3 split, fp32 in TMEM) */
+#define HDGNN_P_TENSOR_V1    16   /* force the one-CTA-per-commit tcgen05 kernel (default: the persistent kernel when its buffers fit) */
 int hdgnn_normalize_propagate(int B, int N, const uint8_t* adj, int adj_pitch, const float* H, int d_in,
                               const float* W, const float* bias, int d_out, float eps, int flags,
                               float* out, float* dinv_out, void* stream);

@@ -31,7 +31,7 @@ def _ref_propagate(adj, H, W, bias, eps, self_loop, relu, transpose):
 
 @pytest.mark.parametrize("B,N,d_in,d_out,p", [(3, 9, 4, 4, 0.3), (4, 50, 7, 20, 0.1), (2, 200, 20, 20, 0.05), (2, 250, 1, 1, 0.05),
                                               (1, 300, 20, 32, 0.02)])
-@pytest.mark.parametrize("flags", [0, 1, 2 | 4, 1 | 2, 8, 8 | 1 | 2 | 4])      # 8 = CUDA-core path, else tcgen05 when N <= 256
+@pytest.mark.parametrize("flags", [0, 1, 2 | 4, 1 | 2, 8, 8 | 1 | 2 | 4, 16, 16 | 1 | 4])      # 8 = CUDA-core path, 16 = one-CTA-per-commit tcgen05 kernel, else the persistent tcgen05 kernel when N <= 256
 def test_normalize_propagate(B, N, d_in, d_out, p, flags):
     from hdgnn_b200.engine import normalize_propagate
     rng = np.random.default_rng(N + flags)
@@ -89,3 +89,20 @@ def test_tile_too_large_is_reported():
     with pytest.raises(HdgnnError) as e:
         normalize_propagate(adj, torch.zeros(1, 500, 20, device="cuda"))
     assert e.value.code == E_UNSUPPORTED
+
+
+@pytest.mark.parametrize("flags", [0, 4, 1 | 2])
+def test_normalize_propagate_persistent_many_commits(flags):
+    """More commits than SMs: every CTA of the persistent tcgen05 kernel walks several commits with the prefetch."""
+    from hdgnn_b200.engine import normalize_propagate
+    B, N, d = 450, 200, 20
+    rng = np.random.default_rng(3)
+    adj = _adj(B, N, 0.05, 9)
+    H = rng.normal(size=(B, N, d)).astype(np.float32)
+    bias = rng.normal(size=d).astype(np.float32) if flags & 2 else None
+    out, dinv = normalize_propagate(torch.tensor(adj).cuda(), torch.tensor(H).cuda(), None,
+                                    None if bias is None else torch.tensor(bias).cuda(), eps=1e-3, flags=flags)
+    torch.cuda.synchronize()
+    ref, dd = _ref_propagate(adj, H, None, bias, 1e-3, bool(flags & 1), bool(flags & 2), not (flags & 4))
+    assert np.abs(dinv.cpu().numpy() - dd).max() / dd.max() < 1e-6
+    assert np.abs(out.cpu().numpy() - ref).max() / np.abs(ref).max() < 1e-5
