@@ -622,6 +622,106 @@ __global__ void __launch_bounds__(CONV_T) map_conv_kernel(const ConvArgs a) {
     (void)lane; (void)warp;
 }
 
+// ---- map_conv for the reference's (transposed) form, straight on the byte tile ---------------------------------------
+// (A_hat x)_i = dinv_i sum_j A[j][i] dinv_j x_j is a weighted COLUMN sum of the byte tile: no bitmap, no transpose.
+// Pass 1: row degrees, one thread per row (16-byte loads; at pitch 208 the rows of 8 lanes fall on distinct banks).
+// Pass 2: one 4-byte word (4 columns) per thread and row, the rows split over the thread groups.  The quadratic form
+// is reduced in a fixed order.  The tile (one buffer, 1-D TMA bulk copy) is 42 KB at N = 200, so five CTAs share an SM
+// and cover each other's copy latency; a CTA walks commits b, b + grid, ...
+constexpr int MC2_T = 256;
+__host__ __device__ inline size_t mc2_smem_bytes(int N, int pitch) {
+    const int WR = pitch / 4, G = MC2_T / WR > 0 ? MC2_T / WR : 1;
+    return 64 + (size_t)round_up(N * pitch, 128) + (size_t)(2 * round_up(N, 4) + G * WR * 4 + 64) * 4 + 64;
+}
+__device__ __forceinline__ int nzcount4(uint32_t v) {      // number of non-zero bytes
+    return __popc((((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v) & 0x80808080u);
+}
+
+__global__ void __launch_bounds__(MC2_T) map_conv2_kernel(const ConvArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int N = a.N, pitch = a.pitch, tid = threadIdx.x;
+    const int WR = pitch >> 2;                              // words per tile row
+    const int G = MC2_T / WR > 0 ? MC2_T / WR : 1;          // row groups of pass 2 (4 at N = 200)
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+    const uint32_t tbytes = (uint32_t)N * pitch;
+    uint8_t* tile = smem + 64;
+    float* xs = reinterpret_cast<float*>(tile + round_up(N * pitch, 128));       // x_j dinv_j
+    float* dinv = xs + round_up(N, 4);
+    float* part = dinv + round_up(N, 4);                    // [G][WR * 4] column partials
+    float* red = part + (size_t)G * WR * 4;
+    const bool self_loop = a.flags & HDGNN_P_SELF_LOOP;
+    const float th0 = a.theta[0], th1 = a.theta[1], mx = fmaxf(th0, th1);
+    const float e0 = expf(th0 - mx), e1 = expf(th1 - mx), t0 = e0 / (e0 + e1), t1 = e1 / (e0 + e1);
+    if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    uint32_t ph = 0u;
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x, ph ^= 1u) {
+        if (tid == 0) {
+            mbar_arrive_expect_tx(bar, tbytes);
+            bulk_g2s(tile, a.adj + (size_t)b * tbytes, tbytes, bar);
+        }
+        const float* xb = a.x + (size_t)b * N;
+        const float xmine = tid < N ? xb[tid] : 0.f;        // in flight with the tile (N <= MC2_T; else re-read below)
+        mbar_wait(bar, ph);
+        // pass 1: row degrees, thread per row
+        for (int j = tid; j < N; j += MC2_T) {
+            const uint4* row = reinterpret_cast<const uint4*>(tile + (size_t)j * pitch);
+            int c = 0;
+            for (int q = 0; q * 16 < N; ++q) {
+                const uint4 v = row[q];
+                uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int c0 = q * 16 + k * 4;
+                    if (c0 + 4 > N) w[k] = c0 >= N ? 0u : (w[k] & (0xffffffffu >> (8 * (c0 + 4 - N))));     // columns >= N
+                    c += nzcount4(w[k]);
+                }
+            }
+            c -= tile[(size_t)j * pitch + j] != 0;          // the diagonal is not an edge
+            const float d = 1.f / sqrtf((float)c + (self_loop ? 1.f : 0.f) + a.eps);
+            dinv[j] = d; xs[j] = (j == tid ? xmine : xb[j]) * d;
+        }
+        __syncthreads();
+        // pass 2: weighted column sums; thread = (row group g, word w), 4 columns per thread
+        {
+            const int g = tid / WR, w = tid - g * WR;
+            if (g < G) {
+                const int r0 = (g * N) / G, r1 = ((g + 1) * N) / G;
+                float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+                const uint32_t* col = reinterpret_cast<const uint32_t*>(tile) + w;
+#pragma unroll 8
+                for (int j = r0; j < r1; ++j) {
+                    const uint32_t v = col[(size_t)j * WR];
+                    const float xj = xs[j];
+                    c0 += (v & 0x000000ffu) ? xj : 0.f; c1 += (v & 0x0000ff00u) ? xj : 0.f;
+                    c2 += (v & 0x00ff0000u) ? xj : 0.f; c3 += (v & 0xff000000u) ? xj : 0.f;
+                }
+                // the diagonal entry is not an edge: take it out again (row i of column i lies in exactly one group)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = 4 * w + u;
+                    if (i < N && i >= r0 && i < r1 && tile[(size_t)i * pitch + i]) {
+                        const float xi = xs[i];
+                        if (u == 0) c0 -= xi; else if (u == 1) c1 -= xi; else if (u == 2) c2 -= xi; else c3 -= xi;
+                    }
+                }
+                *reinterpret_cast<float4*>(part + ((size_t)g * WR + w) * 4) = make_float4(c0, c1, c2, c3);
+            }
+        }
+        fence_proxy_async();                                // generic reads of the tile are ordered before the next bulk copy into it
+        __syncthreads();
+        float pq = 0.f;
+        for (int i = tid; i < N; i += MC2_T) {
+            float acc = self_loop ? xs[i] : 0.f;
+            for (int g = 0; g < G; ++g) acc += part[(size_t)g * WR * 4 + i];
+            const float xi = i == tid ? xmine : xb[i], ax = dinv[i] * acc;
+            pq += xi * fmaf(t1, (2.f / a.lam_max) * (xi - ax) - xi, t0 * xi);
+        }
+        const float q = block_sum(pq, red);                 // two barriers inside: xs / dinv / part are free afterwards
+        if (tid == 0) a.per_commit[b] = q * q;
+    }
+}
+
 __global__ void mean_kernel(const float* v, int n, float* out) {
     __shared__ float scratch[32];
     float acc = 0.f;
@@ -685,6 +785,23 @@ extern "C" int hdgnn_map_conv(int B, int N, const uint8_t* adj, int pitch, const
     int dev = 0, optin = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
         return HDGNN_E_CUDA;
+    // the reference's (transposed) form: persistent kernel on the byte tile, two tiles in flight, two CTAs per SM
+    const size_t smem2 = mc2_smem_bytes(N, pitch);
+    if (!(flags & (HDGNN_P_NO_TRANSPOSE | HDGNN_P_TENSOR_V1)) && smem2 <= (size_t)optin) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaFuncSetAttribute(map_conv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2) != cudaSuccess) return HDGNN_E_CUDA;
+        ConvArgs a2{};
+        a2.B = B; a2.N = N; a2.pitch = pitch; a2.flags = flags; a2.eps = eps; a2.lam_max = lam_max;
+        a2.adj = adj; a2.x = x; a2.theta = theta; a2.per_commit = per_commit;
+        int per_sm = (int)((size_t)(228 * 1024) / (smem2 + 1024));       // resident CTAs an SM's shared memory allows
+        per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+        const int grid = B < sms * per_sm ? B : sms * per_sm;
+        if (!x || !theta || !per_commit || lam_max <= 0.f) return HDGNN_E_INVALID;
+        map_conv2_kernel<<<grid, MC2_T, smem2, (cudaStream_t)stream>>>(a2);
+        if (loss) mean_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(per_commit, B, loss);
+        return cudaGetLastError() == cudaSuccess ? HDGNN_OK : HDGNN_E_CUDA;
+    }
     if (smem > (size_t)optin) return HDGNN_E_UNSUPPORTED;
     if (cudaFuncSetAttribute(map_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) != cudaSuccess) return HDGNN_E_CUDA;
     ConvArgs a{};
