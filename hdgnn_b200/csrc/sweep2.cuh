@@ -156,6 +156,19 @@ __device__ __forceinline__ void sweep2_fwd(const float* P01, const uint32_t* bit
                                            int kg, const u64 (&Q)[CW][2], u64 (&col)[CW][2], float* rowacc, int lane) {
     const uint32_t lmask = 1u << lane;
     int r = rg;
+    // four rows per trip: the two transpose-reduces are independent, so one hides behind the other's shuffle latency
+    for (; r + 3 * nrg < nrows; r += 4 * nrg) {
+        u64 a0, a1, c0, c1, e0, e1, g0, g1;
+        sweep2_fwd_row<CW>(P01, bits, WP, r, kg, lmask, Q, col, a0, a1);
+        sweep2_fwd_row<CW>(P01, bits, WP, r + nrg, kg, lmask, Q, col, c0, c1);
+        sweep2_fwd_row<CW>(P01, bits, WP, r + 2 * nrg, kg, lmask, Q, col, e0, e1);
+        sweep2_fwd_row<CW>(P01, bits, WP, r + 3 * nrg, kg, lmask, Q, col, g0, g1);
+        const float tot = reduce8(a0, a1, c0, c1, lane), tot2 = reduce8(e0, e1, g0, g1, lane);
+        if ((lane & 3) == 0) {
+            row_store<ACCUM>(rowacc, (lane & 16) ? r + nrg : r, kg * 4 + reduce8_channel(lane), tot);
+            row_store<ACCUM>(rowacc, (lane & 16) ? r + 3 * nrg : r + 2 * nrg, kg * 4 + reduce8_channel(lane), tot2);
+        }
+    }
     for (; r + nrg < nrows; r += 2 * nrg) {
         u64 a0, a1, c0, c1;
         sweep2_fwd_row<CW>(P01, bits, WP, r, kg, lmask, Q, col, a0, a1);
@@ -205,6 +218,18 @@ __device__ __forceinline__ void sweep2_bwd(const float* P01, const float* GRt, c
                                            u64 (&col)[CW][2], u64 (&lacc)[2], float* rowacc, int lane) {
     const uint32_t lmask = 1u << lane;
     int r = rg;
+    for (; r + 3 * nrg < nrows; r += 4 * nrg) {      // four rows per trip (see sweep2_fwd)
+        u64 a0, a1, c0, c1, e0, e1, g0, g1;
+        sweep2_bwd_row<CW>(P01, GRt, bits, WP, r, kg, lmask, Q, GC, col, lacc, a0, a1);
+        sweep2_bwd_row<CW>(P01, GRt, bits, WP, r + nrg, kg, lmask, Q, GC, col, lacc, c0, c1);
+        sweep2_bwd_row<CW>(P01, GRt, bits, WP, r + 2 * nrg, kg, lmask, Q, GC, col, lacc, e0, e1);
+        sweep2_bwd_row<CW>(P01, GRt, bits, WP, r + 3 * nrg, kg, lmask, Q, GC, col, lacc, g0, g1);
+        const float tot = reduce8(a0, a1, c0, c1, lane), tot2 = reduce8(e0, e1, g0, g1, lane);
+        if ((lane & 3) == 0) {
+            row_store<ACCUM>(rowacc, (lane & 16) ? r + nrg : r, kg * 4 + reduce8_channel(lane), tot);
+            row_store<ACCUM>(rowacc, (lane & 16) ? r + 3 * nrg : r + 2 * nrg, kg * 4 + reduce8_channel(lane), tot2);
+        }
+    }
     for (; r + nrg < nrows; r += 2 * nrg) {
         u64 a0, a1, c0, c1;
         sweep2_bwd_row<CW>(P01, GRt, bits, WP, r, kg, lmask, Q, GC, col, lacc, a0, a1);
