@@ -716,6 +716,18 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             }
         };
         int r = rg;
+        for (; r + 3 * M2_NRG < Nc; r += 4 * M2_NRG) {       // four rows per trip: two independent transpose-reduces in flight
+            u64 a0, a1, c0, c1, e0, e1, g0, g1;
+            delta_row(r, a0, a1);
+            delta_row(r + M2_NRG, c0, c1);
+            delta_row(r + 2 * M2_NRG, e0, e1);
+            delta_row(r + 3 * M2_NRG, g0, g1);
+            const float tot = reduce8(a0, a1, c0, c1, lane), tot2 = reduce8(e0, e1, g0, g1, lane);
+            if ((lane & 3) == 0) {
+                RSm[((lane & 16) ? r + M2_NRG : r) * HD + k0 + reduce8_channel(lane)] = tot;
+                RSm[((lane & 16) ? r + 3 * M2_NRG : r + 2 * M2_NRG) * HD + k0 + reduce8_channel(lane)] = tot2;
+            }
+        }
         for (; r + M2_NRG < Nc; r += 2 * M2_NRG) {
             u64 a0, a1, c0, c1;
             delta_row(r, a0, a1);
