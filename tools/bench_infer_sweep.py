@@ -3,17 +3,22 @@ Prints commits/s and hunk pairs/s for the device-resident forward (hdgnn_forward
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from hdgnn_b200.engine import Engine, DeviceBatch
+from hdgnn_b200 import _lib
+from hdgnn_b200.engine import Engine, DeviceBatch, F_LABEL_BITS, eval_counts
 from hdgnn_b200.synthetic import make_commits
 
 B, Ne = 100, 200
 out = []
 for Nc in (74, 114, 150, 256, 384, 512):
-    eng = Engine(Ne, Nc, variant=2, max_batch=B)
-    pool = []
+    try:        # label bitmaps resident in HBM on the fused path, byte grids on the multi-kernel path
+        eng = Engine(Ne, Nc, variant=2, max_batch=B, flags=F_LABEL_BITS)
+    except _lib.HdgnnError:
+        eng = Engine(Ne, Nc, variant=2, max_batch=B)
+    pool, ybytes = [], []
     for i in range(8):
         cb = make_commits(B, Ne, Nc, seed=20260 + i)
-        pool.append(DeviceBatch.from_numpy(cb.adj, cb.x, cb.hmap, cb.L, cb.Y, eng.tdev))
+        pool.append(DeviceBatch.from_numpy(cb.adj, cb.x, cb.hmap, cb.L, cb.Y, eng.tdev, bits=eng.host_bits))
+        ybytes.append(torch.as_tensor(cb.Y).cuda())
     params = (0.1 * torch.randn(eng.n_params)).cuda()
     for k in range(5):
         eng.forward(pool[k % 8], params, want_logits=False)
@@ -25,7 +30,14 @@ for Nc in (74, 114, 150, 256, 384, 512):
         eng.forward(pool[k % 8], params, want_logits=False)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    rec = {"Ne": Ne, "Nc": Nc, "B": B, "ms_per_batch": ms, "commits_per_s": B / ms * 1e3,
+    # the same with the evaluation counters (top_ACC / P / R / F1) computed on the device after every batch
+    e0.record()
+    for k in range(steps):
+        probs, _, _ = eng.forward(pool[k % 8], params, want_logits=False)
+        eval_counts(probs, ybytes[k % 8])
+    e1.record(); torch.cuda.synchronize()
+    ms_eval = e0.elapsed_time(e1) / steps
+    rec = {"label_bits": eng.host_bits, "ms_per_batch_with_eval": ms_eval,"Ne": Ne, "Nc": Nc, "B": B, "ms_per_batch": ms, "commits_per_s": B / ms * 1e3,
            "hunk_pairs_per_s": B * Nc * (Nc - 1) / ms * 1e3, "launches": eng.last_launch_count(),
            "probs_GBps": B * 8 * Nc * (Nc - 1) / ms / 1e6}
     print(rec)
