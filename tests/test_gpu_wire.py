@@ -97,3 +97,39 @@ def test_host_bits_refused_on_the_multi_kernel_path():
     with pytest.raises(_lib.HdgnnError) as e:
         Engine(48, 20, variant=4, max_batch=4, flags=F_LABEL_BITS)
     assert e.value.code == _lib.E_UNSUPPORTED
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flags", [0, 8])        # byte grids (5 launches incl. pack_bits), label bitmaps (4 launches)
+def test_train_step_is_cuda_graph_capturable_and_replayable(flags):
+    """include/hdgnn.h promises asynchronous, capturable entry points: the whole training step (programmatic dependent
+    launches included) is captured once and replayed; Adam's step count lives on the device, so replays advance it."""
+    from hdgnn_b200.engine import Engine, DeviceBatch
+    from hdgnn_b200.model import truncated_normal_init
+    Ne, Nc, B, variant, steps = 64, 24, 6, 2, 4
+    cb = make_commits(B, Ne, Nc, seed=21)
+    res = []
+    for mode in ("eager", "graph"):
+        eng = Engine(Ne, Nc, variant=variant, max_batch=B, flags=flags)
+        db = DeviceBatch.from_numpy(cb.adj, cb.x, cb.hmap, cb.L, cb.Y, eng.tdev, bits=bool(flags))
+        params = truncated_normal_init(variant, 3).cuda()
+        m = torch.zeros_like(params); v = torch.zeros_like(params)
+        step = torch.zeros(1, dtype=torch.int32, device="cuda"); loss3 = torch.zeros(3, device="cuda")
+        probs = torch.zeros(B, 2, Nc * (Nc - 1), device="cuda")
+        if mode == "eager":
+            for _ in range(steps):
+                eng.train_step(db, params, m, v, step, loss3, probs=probs)
+        else:
+            eng.train_step(db, params, m, v, step, loss3, probs=probs)       # warm-up outside the capture (attributes, lazy init)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                eng.train_step(db, params, m, v, step, loss3, probs=probs)
+            # the capture only recorded: one eager + (steps - 1) replays = `steps` steps
+            for _ in range(steps - 1):
+                g.replay()
+        torch.cuda.synchronize()
+        res.append((params.cpu().numpy(), m.cpu().numpy(), int(step.item()), loss3.cpu().numpy(), probs.cpu().numpy()))
+        eng.close()
+    assert res[0][2] == res[1][2] == steps
+    for k in (0, 1, 3, 4):
+        assert np.array_equal(res[0][k], res[1][k]), k
