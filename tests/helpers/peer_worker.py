@@ -59,6 +59,42 @@ def main():
             ces.append(float(loss3[0]))
         res["single_params"] = params.cpu().numpy(); res["single_ce"] = np.array(ces)
         eng.close()
+    # graph2graph.train() sharded over the ranks (peer exchange, device evaluation counters) vs the same loop on one GPU
+    if Ne <= 64:
+        from hdgnn_b200.utils2 import write_dataset, read_compact, split_half
+        from hdgnn_b200.engine import eval_counts
+        N_all, MB, epochs = 8 * per * world, per * world, 2
+        if rank == 0:
+            write_dataset(make_commits(N_all, Ne, Nc, seed=77, p_edge=0.2, p_short=0.4, p_noise=0.2), "toy", 2, root=out_dir)
+        dist.barrier()
+        model = graph2graph(None, Ne=Ne, Nc=Nc, Mini_batch=MB, epoch=epochs, Step=2, Repo="toy", variant=variant, device=local,
+                            seed=9, checkpoint_dir=os.path.join(out_dir, "ck"), collective="peer")
+        hist = model.train(None, root=out_dir, log=lambda *_: None)
+        res["train_loss"] = np.array([h["hedge_loss"] for h in hist]); res["train_acc"] = np.array([h["acc"] for h in hist])
+        res["train_params"] = model.params.cpu().numpy()
+        model.engine.close()
+        if rank == 0:
+            from hdgnn_b200.model import truncated_normal_init
+            train, _ = split_half(read_compact("toy", 2, Ne, Nc, root=out_dir))
+            eng = Engine(Ne, Nc, variant=variant, max_batch=MB, device=local)
+            params = truncated_normal_init(variant, 9).cuda()
+            m = torch.zeros_like(params); v = torch.zeros_like(params)
+            step = torch.zeros(1, dtype=torch.int32, device="cuda"); loss3 = torch.zeros(3, device="cuda")
+            losses, accs = [], []
+            for ep in range(epochs):
+                ls, hits = [], 0
+                for j in range(train.B // MB):
+                    b = train.slice(j * MB, (j + 1) * MB)
+                    db = DeviceBatch.from_numpy(b.adj, b.x, train.hmap[:MB], train.L[:MB], b.Y, eng.tdev)      # quirk Q2
+                    probs = torch.zeros(MB, 2, Nc * (Nc - 1), device="cuda")
+                    eng.train_step(db, params, m, v, step, loss3, probs=probs)
+                    c, _ = eval_counts(probs, torch.as_tensor(b.Y).cuda())
+                    torch.cuda.synchronize()
+                    ls.append(float(loss3[0])); hits += int(c[:, 0].sum())
+                losses.append(np.mean(ls)); accs.append(hits / ((train.B // MB) * MB * Nc * (Nc - 1)))
+            res["single_train_loss"] = np.array(losses); res["single_train_acc"] = np.array(accs)
+            res["single_train_params"] = params.cpu().numpy()
+            eng.close()
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **res)
     dist.barrier()
     dist.destroy_process_group()

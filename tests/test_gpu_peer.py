@@ -34,5 +34,11 @@ def test_peer_exchange_matches_nccl_and_single_gpu(tmp_path, variant, Ne, Nc, pe
     assert np.abs(z[0]["peer_params"] - z[0]["single_params"]).max() / scale < 1e-5
     assert np.allclose(z[0]["peer_ce"], z[0]["single_ce"], rtol=1e-5) and np.allclose(z[0]["peer_ce"], z[0]["nccl_ce"], rtol=1e-5)
     assert np.allclose(z[0]["peer_reg"], z[0]["nccl_reg"], rtol=1e-6)
+    if "train_loss" in z[0].files:
+        # graph2graph.train() over two ranks == the same epochs on one GPU (loss, accuracy from device counters, weights)
+        assert np.array_equal(z[0]["train_loss"], z[1]["train_loss"]) and np.array_equal(z[0]["train_params"], z[1]["train_params"])
+        assert np.allclose(z[0]["train_loss"], z[0]["single_train_loss"], rtol=2e-5)
+        assert np.abs(z[0]["train_acc"] - z[0]["single_train_acc"]).max() < 1e-3
+        assert np.abs(z[0]["train_params"] - z[0]["single_train_params"]).max() / np.abs(z[0]["single_train_params"]).max() < 1e-5
     # the fused step (pack, ent_fwd, mid, ent_bwd, reduce+all-reduce+Adam) plus at most two re-pitch kernels of the host staging
     assert int(z[0]["peer_launches"]) <= 7 and int(z[0]["nccl_launches"]) == 1
