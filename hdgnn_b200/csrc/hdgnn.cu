@@ -103,6 +103,7 @@ struct hdgnn_handle_s {
     bool pdl = true;                                           // programmatic dependent launch between the fused kernels
     int bslot = 0;                                             // bitmap buffer of the current step (two alternate)
     bool dlt_global = false;                                   // mid2's dL/dlogit table in HBM instead of shared memory
+    bool mid_scache = false;                                   // mid2 keeps the entity effect sums in shared memory for its backward
     int Gf = 0, Gb = 0, Rf = 0, Rb = 0, SLf = 0;               // grids / rows per CTA / slots of the last launch
     std::map<std::string, Buf> ws;
     std::string err;
@@ -579,7 +580,8 @@ int fused_forward(hdgnn_handle_t h, int B, int B_global, const Inputs& in, float
     m.clk = h->debug ? (long long*)h->ws["CLK"].p : nullptr;
     const bool dlt_g = train && h->dlt_global;
     m.dlt_g = dlt_g ? F(h, "DLT") : nullptr;
-    const size_t smem = mid2_smem_bytes(h->Ne, h->Nc, train, !dlt_g);
+    m.scache = (train && h->ent && h->mid_scache) ? 1 : 0;
+    const size_t smem = mid2_smem_bytes(h->Ne, h->Nc, train, !dlt_g, m.scache != 0);
     const int cwc = (h->Nc + 31) / 32;
     PROF_BEGIN(h, st);
     launch_mid2(cwc, train, B, smem, st, m, h->pdl && h->ent);
@@ -737,6 +739,7 @@ int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out) {
     if (h->fused) {     // per-commit state of mid2 in one SM; the per-pair dL/dlogit table may spill to HBM (L2-resident)
         h->dlt_global = mid2_smem_bytes(h->Ne, h->Nc, true, true) > (size_t)prop.sharedMemPerBlockOptin;
         h->fused = mid2_smem_bytes(h->Ne, h->Nc, true, !h->dlt_global) <= (size_t)prop.sharedMemPerBlockOptin;
+        h->mid_scache = h->fused && mid2_smem_bytes(h->Ne, h->Nc, true, !h->dlt_global, true) <= (size_t)prop.sharedMemPerBlockOptin;
     }
     h->host_bits = (cfg->flags & HDGNN_F_LABEL_BITS) != 0;
     if (h->host_bits && !h->fused) {

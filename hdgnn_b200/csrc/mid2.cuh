@@ -46,6 +46,7 @@ struct Mid2Args {
     float* dbg;                              // debug dumps (HDGNN_F_DEBUG) or null; layout below
     long long* clk;                          // per-phase clock64 stamps (B,16) or null
     float* dlt_g;                            // (B, Nc, CW*32) dL/dlogit table in HBM when it does not fit smem, else null
+    int scache;                              // keep the entity effect sums S (Ne x 20) in shared memory from the forward to the backward
 };
 // debug dump layout per commit (floats): S1[Ne*20] X2[Ne] NB[Nc*4] RS3[Nc*20] CS3[Nc*20] PR[Nc*20] PC[Nc*20]
 // DNB[Nc*4] DX2[Ne]
@@ -54,11 +55,11 @@ __host__ __device__ inline size_t mid2_dbg_floats(int Ne, int Nc) { return (size
 struct Mid2Smem {
     // offsets in floats
     int blk1, blk2, gam, Dh, Dg, G1g, W5U, c1p;   // weight blocks (contiguous copies of the parameter blob), derived tables
-    int x, x2, hm, SP, TP, dl, dx2, nb, dnb, ebits, ybits, scratch, red, uni, total;
+    int x, x2, hm, SP, TP, dl, dx2, nb, dnb, ebits, ybits, scratch, red, uni, sc, total;
 };
 
 // dlt_smem: keep the per-pair dL/dlogit table of the training path in shared memory (else it lives in HBM / L2)
-__host__ __device__ inline Mid2Smem mid2_layout(int Ne, int Nc, bool train, bool dlt_smem = true) {
+__host__ __device__ inline Mid2Smem mid2_layout(int Ne, int Nc, bool train, bool dlt_smem = true, bool scache = false) {
     Mid2Smem m;
     int o = 0;
     auto take = [&](int n) { int r = o; o += (n + 7) & ~7; return r; };      // 32-byte granules
@@ -79,11 +80,13 @@ __host__ __device__ inline Mid2Smem mid2_layout(int Ne, int Nc, bool train, bool
     const int hunk_phase = ((12 * Nc * HD + 7) & ~7) + (dlt > pool3 ? dlt : pool3);
     m.SP = m.uni + ((12 * Nc * HD + 7) & ~7); m.TP = m.SP + ((4 * Ne + 7) & ~7); m.dl = m.TP + ((4 * Ne + 7) & ~7);
     o += ent_phase > hunk_phase ? ent_phase : hunk_phase;
+    m.sc = o;
+    if (scache) o += (Ne * HD + 7) & ~7;
     m.total = o;
     return m;
 }
-__host__ __device__ inline size_t mid2_smem_bytes(int Ne, int Nc, bool train, bool dlt_smem = true) {
-    return (size_t)mid2_layout(Ne, Nc, train, dlt_smem).total * 4 + 16;
+__host__ __device__ inline size_t mid2_smem_bytes(int Ne, int Nc, bool train, bool dlt_smem = true, bool scache = false) {
+    return (size_t)mid2_layout(Ne, Nc, train, dlt_smem, scache).total * 4 + 16;
 }
 
 // fixed-order block sum for M2_T threads; every thread gets the result
@@ -224,7 +227,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
     const int Ne = a.Ne, Nc = a.Nc, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int kg = warp % KG, rg = warp / KG, k0 = kg * 4;
     const int WPe = a.WPe, WPc = a.WPc;
-    const Mid2Smem L_ = mid2_layout(Ne, Nc, TRAIN, a.dlt_g == nullptr);
+    const Mid2Smem L_ = mid2_layout(Ne, Nc, TRAIN, a.dlt_g == nullptr, a.scache != 0);
     float* blk1 = sm + L_.blk1; float* blk2 = sm + L_.blk2;
     float* W5 = blk1; float* b5 = blk1 + 400; float* U1 = blk1 + 420; float* c1 = blk1 + 840;
     float* u2 = blk1 + 860; float* c2 = blk1 + 880;
@@ -410,6 +413,26 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             for (int k = 0; k < HD; ++k) S[k] += t[k];
         }
     };
+    // The same sums for `count` nodes at once, written to shared memory (row stride in floats): every thread takes one
+    // float4 of one node and has the loads of ALL slots in flight, so the block pays one or two global round trips
+    // instead of 1 + nsl dependent ones per thread (nsl = 6-7 at glide).  Same summation order as load_S.
+    auto coop_load_S = [&](float* dst, int stride, int node0, int count) {
+        const float4* rs = reinterpret_cast<const float4*>(a.RS1 + ((size_t)b * Ne + node0) * HD);
+        const float4* cs = reinterpret_cast<const float4*>(a.CS1p + ((size_t)b * a.SL * Ne + node0) * HD);
+        const size_t slot4 = (size_t)Ne * HD / 4;
+        for (int e = tid; e < count * 5; e += M2_T) {
+            float4 acc = rs[e];
+            for (int s0 = 0; s0 < nsl; s0 += 8) {
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = s0 + u < nsl ? cs[(size_t)(s0 + u) * slot4 + e] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+            }
+            const int n = e / 5, j = e - n * 5;
+            *reinterpret_cast<float4*>(dst + (size_t)n * stride + 4 * j) = acc;
+        }
+    };
     // Zh[j] = pre-activation of hidden unit 10 h + j of the entity-state MLP for effect sums S and attribute xv
     auto hidden_half = [&](float (&Zh)[10], const float (&S)[HD], float xv, int h) {
 #pragma unroll
@@ -424,13 +447,18 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         }
     };
     if (a.ent) {
+        // S for all nodes -> its own region (kept for the backward) or the still unused head of the union region (unless
+        // that would run into SP / TP)
+        const bool coopS = a.scache || Ne <= 12 * Nc;
+        float* Sall = a.scache ? sm + L_.sc : uni;
+        if (coopS) { coop_load_S(Sall, HD, 0, Ne); __syncthreads(); }
         for (int base = 0; base < 2 * Ne; base += M2_T) {
             const int t = base + tid, node = t >> 1, h = t & 1;
             const bool valid = node < Ne;
             float acc = 0.f;
             if (valid) {
                 float S[HD], Zh[10];
-                load_S(S, node);
+                if (coopS) load20s(S, Sall + (size_t)node * HD); else load_S(S, node);
                 if (dbg && h == 0) for (int k = 0; k < HD; ++k) dbg[(size_t)node * HD + k] = S[k];
                 hidden_half(Zh, S, xs[node], h);
 #pragma unroll
@@ -1015,6 +1043,16 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         float accA = 0.f, accC = 0.f;                  // one reduced output per thread, summed over the chunks
         for (int c0 = 0; c0 < Ne; c0 += M2_CH) {
             const int nn = min(M2_CH, Ne - c0);
+            if (a.scache) {                              // S rows of the chunk: from the forward's copy, else from HBM / L2 again
+                const float* Sall = sm + L_.sc;
+                for (int e = tid; e < nn * 5; e += M2_T) {
+                    const int n = e / 5, j = e - n * 5;
+                    *reinterpret_cast<float4*>(Sa + n * 24 + 4 * j) = *reinterpret_cast<const float4*>(Sall + (size_t)(c0 + n) * HD + 4 * j);
+                }
+            } else {
+                coop_load_S(Sa, 24, c0, nn);
+            }
+            __syncthreads();
             // step 1: two threads per entity: recompute the hidden layer, back-propagate, write GE
             for (int base = 0; base < 2 * nn; base += M2_T) {
                 const int t = base + tid, n = t >> 1, h = t & 1, node = c0 + n;
@@ -1024,7 +1062,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
                 for (int j = 0; j < 10; ++j) dzh[j] = 0.f;
                 if (valid) {
                     float S[HD], Zh[10];
-                    load_S(S, node);
+                    load20s(S, Sa + n * 24);
                     const float xv = xs[node];
                     hidden_half(Zh, S, xv, h);
                     const float du = x2[node] > 0.f ? dx2[node] : 0.f;
@@ -1038,7 +1076,6 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
                             make_float2(fmaxf(Zh[2 * j2], 0.f) * du, fmaxf(Zh[2 * j2 + 1], 0.f) * du);
                     }
                     if (h == 0) {
-                        store20s(Sa + n * 24, S);
                         *reinterpret_cast<float4*>(Sa + n * 24 + HD) = make_float4(xv, 1.f, 0.f, 0.f);
                         *reinterpret_cast<float4*>(ZD + n * 24 + HD) = make_float4(du, 0.f, 0.f, 0.f);
                     }
