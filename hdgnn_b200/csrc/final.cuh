@@ -70,8 +70,8 @@ __device__ __forceinline__ float adam_lr_t(float lr, float b1, float b2, int t) 
     return lr * sqrtf(omb2) / omb1;
 }
 
-constexpr int FIN_P = 128;   // parameters per CTA
-constexpr int FIN_SL = 8;    // commit slices per parameter
+constexpr int FIN_P = 64;    // parameters per CTA
+constexpr int FIN_SL = 16;   // commit slices per parameter
 
 __device__ __forceinline__ float rank1_extra(const Rank1Map& r, int p, int slice, int nslice) {
     if (!r.gp) return 0.f;

@@ -777,7 +777,7 @@ int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out) {
         {"DNB", B * Nc * 4 * f, dbgbuf}, {"GE", B * Ne * HD * f, true}, {"DX2", B * Ne * f, dbgbuf},
         {"RS1D", B * Ne * HD * f, h->ent && lg}, {"CS1DP", B * Se * Ne * HD * f, h->ent && lg}, {"LS1P", B * Se * HD * f, h->ent && lg},
         {"GPART", B * (size_t)h->po.total * f, true},
-        {"GPE", ((size_t)Gb_max + 1) * 4 * HD * f, h->fused && h->ent}, {"FIN_L2", 64 * f, h->fused}, {"FIN_CNT", 16, h->fused},
+        {"GPE", ((size_t)Gb_max + 1) * 4 * HD * f, h->fused && h->ent}, {"FIN_L2", 256 * f, h->fused}, {"FIN_CNT", 16, h->fused},
         {"EBITS0", B * Ne * (size_t)h->WPe * 4, h->fused}, {"YBITS0", B * Nc * (size_t)h->WPc * 4, h->fused},
         {"EBITS1", B * Ne * (size_t)h->WPe * 4, h->fused}, {"YBITS1", B * Nc * (size_t)h->WPc * 4, h->fused},
         {"DBG", B * mid2_dbg_floats(h->Ne, h->Nc) * f, h->fused && h->debug},
