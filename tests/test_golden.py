@@ -129,3 +129,29 @@ def test_cuda_matches_reference_model_files(variant):
     # predicted relation classes identical
     assert np.array_equal(np.argmax(probs.cpu().numpy(), 1), np.argmax(g["probs"], 1))
     eng.close()
+
+
+def test_metrics_from_integer_counters_equal_array_metrics():
+    """Host half of the device evaluation (hdgnn_eval_counts -> EvaluationFuncs.metrics_from_counts / auc_from_counts):
+    the counters are rebuilt here with NumPy from the golden arrays and must give the reference's numbers."""
+    z = np.load(os.path.join(G, "eval_toy.npz"))
+    label, real = z["label"], z["real"]
+    N, _, Ncr = label.shape
+    y = label[:, 1, :] > 0.5
+    am = real[:, 1, :] > real[:, 0, :]
+    qt, qp = ~y, real[:, 0, :] > 0
+    counts = np.stack([(am == y).sum(1), (qt & qp).sum(1), (~qt & qp).sum(1), (qt & ~qp).sum(1),
+                       (y & am).sum(1), (~y & am).sum(1), (y & ~am).sum(1), y.sum(1)], 1).astype(np.int64)
+    auc = np.zeros((N, 2), np.int64)
+    for b in range(N):
+        for col, pos_score in ((0, real[b, 0][y[b]]), (1, real[b, 1][y[b]])):
+            neg = real[b, 1][~y[b]]
+            auc[b, col] = 2 * (neg[None, :] < pos_score[:, None]).sum() + (neg[None, :] == pos_score[:, None]).sum()
+    m = EV.metrics_from_counts(counts, quirks=True)
+    assert np.isclose(m["hits"] / (N * Ncr), float(z["top_ACC"]), rtol=1e-14)
+    assert np.isclose(m["prec"], float(z["prec"]), rtol=1e-14) and np.isclose(m["recall"], float(z["recall"]), rtol=1e-14)
+    assert np.isclose(m["f1"], float(z["f1"]), rtol=1e-14)
+    assert np.isclose(EV.auc_from_counts(counts, auc, Ncr, quirks=True), float(z["AUC"]), rtol=1e-12)
+    mc = EV.metrics_from_counts(counts, quirks=False)
+    assert mc["prec"] == EV.prec(label, real, False) and mc["f1"] == EV.f1(label, real, False)
+    assert np.isclose(EV.auc_from_counts(counts, auc, Ncr, quirks=False), EV.AUC(label, real, False), rtol=1e-13)
