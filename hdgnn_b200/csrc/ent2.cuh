@@ -96,13 +96,22 @@ __global__ void __launch_bounds__(KG * NRG * 32, 4 / NRG) ent_fwd2_kernel(const 
             mbar_arrive_expect_tx(bar, bytes);
             bulk_g2s(sbits, a.bits + ((size_t)b * N + r0) * WP, bytes, bar);
         }
-        for (int idx = tid; idx < nr * HD; idx += NT) {
-            const int r = idx / HD, k = idx - r * HD;
-            const float xi = xb[r0 + r];
-            const float p0 = fmaf(xi, wts[k], wts[2 * HD + k]);
-            float* dst = P01 + (size_t)r * PROW + (k >> 2) * 8 + (k & 3);
-            dst[0] = p0; dst[4] = p0 + wts[3 * HD + k];
-            diag[idx] = fmaxf(fmaf(xi, wts[HD + k], p0), 0.f);
+        for (int base = tid; base < nr * HD; base += 4 * NT) {      // four elements per thread per trip: their loads overlap
+            float xv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int idx = base + u * NT; xv[u] = idx < nr * HD ? xb[r0 + idx / HD] : 0.f; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = base + u * NT;
+                if (idx < nr * HD) {
+                    const int r = idx / HD, k = idx - r * HD;
+                    const float xi = xv[u];
+                    const float p0 = fmaf(xi, wts[k], wts[2 * HD + k]);
+                    float* dst = P01 + (size_t)r * PROW + (k >> 2) * 8 + (k & 3);
+                    dst[0] = p0; dst[4] = p0 + wts[3 * HD + k];
+                    diag[idx] = fmaxf(fmaf(xi, wts[HD + k], p0), 0.f);
+                }
+            }
         }
         mbar_wait(bar, phase);
         phase ^= 1u;
@@ -196,15 +205,29 @@ __global__ void __launch_bounds__(KG * NRG * 32, NRG == 1 ? 3 : 1) ent_bwd2_kern
             mbar_arrive_expect_tx(bar, bytes);
             bulk_g2s(sbits, a.bits + ((size_t)b * N + r0) * WP, bytes, bar);
         }
-        for (int idx = tid; idx < nr * HD; idx += NT) {
-            const int r = idx / HD, k = idx - r * HD, i = r0 + r;
-            const float xi = xb[i];
-            const float p0 = fmaf(xi, wts[k], wts[2 * HD + k]);
-            float* dst = P01 + (size_t)r * PROW + (k >> 2) * 8 + (k & 3);
-            dst[0] = p0; dst[4] = p0 + wts[3 * HD + k];
-            const float g = grb[(size_t)i * HD + k];
-            GRt[idx] = g;
-            dgv[idx] = fmaf(xi, wts[HD + k], p0) > 0.f ? g + gcb[(size_t)i * HD + k] : 0.f;
+        for (int base = tid; base < nr * HD; base += 4 * NT) {      // four elements per thread per trip: their loads overlap
+            float xv[4], gv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = base + u * NT;
+                const bool ok = idx < nr * HD;
+                xv[u] = ok ? xb[r0 + idx / HD] : 0.f;
+                gv[u] = ok ? grb[(size_t)r0 * HD + idx] : 0.f;          // GR = GC = d/dS of row r0 + idx / HD, channel idx % HD
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = base + u * NT;
+                if (idx < nr * HD) {
+                    const int r = idx / HD, k = idx - r * HD;
+                    const float xi = xv[u];
+                    const float p0 = fmaf(xi, wts[k], wts[2 * HD + k]);
+                    float* dst = P01 + (size_t)r * PROW + (k >> 2) * 8 + (k & 3);
+                    dst[0] = p0; dst[4] = p0 + wts[3 * HD + k];
+                    const float g = gv[u];
+                    GRt[idx] = g;
+                    dgv[idx] = fmaf(xi, wts[HD + k], p0) > 0.f ? g + (gcb == grb ? g : gcb[(size_t)(r0 + r) * HD + k]) : 0.f;
+                }
+            }
         }
         if (tid < HD) dvw[tid] = 0.f;
         mbar_wait(bar, phase);
