@@ -260,6 +260,10 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         bulk_g2s(ebits, a.ebits + (size_t)b * Ne * WPe, be, bar);
         bulk_g2s(ybits, a.ybits + (size_t)b * Nc * WPc, bc, bar);
     }
+    // per-commit inputs: in flight together with the weight loads below (Ne <= 512 < M2_T: one element per thread)
+    const int Lb = a.L[b];
+    const int h_in = tid < Ne ? a.hmap[(size_t)b * Ne + tid] : -1;
+    const float x_in = tid < Ne ? a.x[(size_t)b * Ne + tid] : 0.f;
     {   // both weight blocks with all global loads in flight before the first store
         const float* p1 = par + (a.ent ? po.ent_w5 : po.hnk_w1);
         const float* p2 = par + po.hnk_w1;
@@ -278,13 +282,10 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             else if (idx < n1 + M2_BLK2) blk2[idx - n1] = v[u];
         }
     }
-    const int Lb = a.L[b];
-    for (int i = tid; i < Ne; i += M2_T) {
-        const int h = a.hmap[(size_t)b * Ne + i];
-        hm[i] = (h >= 0 && h < Nc) ? h : -1;
-        const float xv = a.x[(size_t)b * Ne + i];
-        xs[i] = xv;
-        if (!a.ent) x2[i] = xv;
+    if (tid < Ne) {
+        hm[tid] = (h_in >= 0 && h_in < Nc) ? h_in : -1;
+        xs[tid] = x_in;
+        if (!a.ent) x2[tid] = x_in;
     }
     __syncthreads();
     if (tid < HD) {
