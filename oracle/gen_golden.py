@@ -123,6 +123,41 @@ def main():
     np.savez_compressed(os.path.join(OUT, "eval_toy.npz"), label=label, real=real, **{k: np.float64(v) for k, v in res.items()})
     print("eval:", res)
 
+    # ---- (5) the legacy operator: model.py's own chebyshev_polynomials / map_conv over the shim -----------------
+    # (model.py:335-403).  The methods are called unbound on a stub `self`; Ra is the soft edge tensor
+    # the legacy network would produce (argmax makes it a hard adjacency, model.py:337), O the node output, theta the
+    # Chebyshev coefficients.  O and theta are shim Variables so that autograd gives the reference's backward
+    # (the argmax blocks any gradient to Ra).
+    legacy = importlib.import_module("model")
+    No, mb, k = 9, 4, 2
+    Nr = No * (No - 1)
+    rng = np.random.default_rng(11)
+    lab = (rng.random((mb, Nr)) < 0.3).astype(np.float64)
+    z = rng.standard_normal((mb, 2, Nr)) + 3.0 * (np.stack([1 - lab, lab], 1) - 0.5)
+    Ra = np.exp(z) / np.exp(z).sum(1, keepdims=True)                  # soft one-hots, (mb, 2, Nr)
+    O0 = rng.integers(0, 10, size=(mb, 1, No)).astype(np.float64) / 3.0
+    th0 = np.array([0.13, -0.21]).reshape(1, k, 1, 1)
+    tf1_shim.reset_default_graph()
+    stub = object.__new__(legacy.graph2graph)                         # no __init__: build_model needs the dead loaders
+    stub.mini_batch_num, stub.Nr, stub.No, stub.Ds = mb, Nr, No, 1
+    Ov = tf1_shim.Variable(O0, name="O_legacy")
+    thv = tf1_shim.Variable(th0, name="theta_legacy")
+    t_k = stub.chebyshev_polynomials(tf1_shim.constant(Ra), k)
+    loss_node = stub.map_conv(thv, tf1_shim.constant(Ra), Ov, k)
+    tk_val = tf1_shim._eval(t_k, {}, {}).detach().numpy()
+    val = tf1_shim._eval(loss_node, {}, {})
+    gO, gth = tf1_shim.torch.autograd.grad(val, [Ov.value, thv.value])
+    hard = np.argmax(Ra, 1)                                             # (mb, Nr) -> dense adjacency by the pair order p(i,j)
+    adj = np.zeros((mb, No, No), dtype=np.uint8)
+    q = 0
+    for i in range(No):
+        for j in range(No):
+            if i != j:
+                adj[:, i, j] = hard[:, q]; q += 1
+    np.savez_compressed(os.path.join(OUT, "legacy_toy.npz"), Ra=Ra, O=O0, theta=th0.reshape(k), adj=adj, t_k=tk_val,
+                        loss=np.float64(val.item()), dO=gO.numpy(), dtheta=gth.numpy().reshape(k))
+    print(f"legacy map_conv: loss {val.item():.6f}")
+
 
 if __name__ == "__main__":
     main()

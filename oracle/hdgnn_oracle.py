@@ -416,7 +416,7 @@ def map_conv_dense(theta, Ra, O, k=2):
             t[:, j, j + 1] = 1
         T[:, i * (No - 1):(i + 1) * (No - 1), :] = t
     adj = S @ T
-    rowsum = adj.sum(2) + 0.001                                            # model.py:362
+    rowsum = adj.sum(2) + float(np.float32(0.001))                         # model.py:362 (the constant is a float32 array)
     d = rowsum ** -0.5
     dm = torch.diag_embed(d)
     a = (adj @ dm).transpose(1, 2)
@@ -433,7 +433,7 @@ def map_conv_dense(theta, Ra, O, k=2):
     return (loss ** 2).mean()
 
 
-def map_conv_closed(theta, adj, x, self_loop=False, eps=1e-3, lam_max=1.5):
+def map_conv_closed(theta, adj, x, self_loop=False, eps=float(np.float32(1e-3)), lam_max=1.5):
     """Index form: adj (mb,No,No) zero diagonal, x (mb,No).  A_hat = D^-1/2 A^T D^-1/2,
     D = rowsum(A)+eps (reference: no self loop, model.py:360-367)."""
     dt = x.dtype

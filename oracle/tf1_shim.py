@@ -37,6 +37,8 @@ def set_seed(seed: int):
 
 
 class Node:
+    __array_ufunc__ = None          # `ndarray - Node` defers to Node.__rsub__ (as tf.Tensor does), model.py:372
+
     def __init__(self, fn, inputs=(), name=None):
         self.fn, self.inputs, self.name = fn, tuple(inputs), name
         with torch.no_grad():
@@ -154,7 +156,7 @@ def concat(values, axis, name=None):
 def tile(a, multiples, name=None): return Node(lambda t: t.repeat(*[int(m) for m in multiples]), (_n(a),))
 def sqrt(a, name=None): return Node(torch.sqrt, (_n(a),))
 def square(a, name=None): return Node(torch.square, (_n(a),))
-def pow(a, b, name=None): return Node(lambda t: torch.pow(t, b), (_n(a),))  # noqa: A001
+def pow(a, b, name=None): return Node(lambda t, e: torch.pow(t, e.to(DTYPE) if isinstance(e, torch.Tensor) else e), (_n(a), _n(b)))  # noqa: A001
 def cast(a, dtype, name=None): return _n(a)
 def argmax(a, axis=None, name=None): return Node(lambda t: torch.argmax(t, axis), (_n(a),))
 def matrix_diag(a, name=None): return Node(torch.diag_embed, (_n(a),))
@@ -370,6 +372,9 @@ def install():
     pkg.__path__, compat.__path__ = [], []
     pkg.compat = compat
     compat.v1 = me
+    for k, v in vars(me).items():          # the legacy model.py does `import tensorflow as tf` (model.py:6)
+        if not k.startswith("_") and k not in ("sys", "types", "np", "torch", "math"):
+            setattr(pkg, k, v)
     sys.modules["tensorflow"] = pkg
     sys.modules["tensorflow.compat"] = compat
     sys.modules["tensorflow.compat.v1"] = me

@@ -155,3 +155,27 @@ def test_metrics_from_integer_counters_equal_array_metrics():
     mc = EV.metrics_from_counts(counts, quirks=False)
     assert mc["prec"] == EV.prec(label, real, False) and mc["f1"] == EV.f1(label, real, False)
     assert np.isclose(EV.auc_from_counts(counts, auc, Ncr, quirks=False), EV.AUC(label, real, False), rtol=1e-13)
+
+
+def test_legacy_operator_oracle_matches_reference_model_py():
+    """the oracle's map_conv (literal and closed forms) and normalize_adj against the reference's own
+    model.py:335-403 executed over the shim (tests/golden/legacy_toy.npz), forward value and gradients."""
+    z = np.load(os.path.join(G, "legacy_toy.npz"))
+    Ra, O0, th, adj = (torch.as_tensor(z[k]) for k in ("Ra", "O", "theta", "adj"))
+    mb, _, No = O0.shape
+    lit = O.map_conv_dense(th.reshape(1, 2, 1, 1), Ra, O0)
+    assert abs(float(lit) - float(z["loss"])) <= 1e-12 * abs(float(z["loss"]))
+    x = O0.reshape(mb, No).clone().requires_grad_(True)
+    t = th.clone().requires_grad_(True)
+    closed = O.map_conv_closed(t, adj, x)
+    assert abs(float(closed) - float(z["loss"])) <= 1e-10 * abs(float(z["loss"]))
+    gx, gt = torch.autograd.grad(closed, [x, t])
+    assert np.allclose(gx.numpy(), z["dO"].reshape(mb, No), rtol=1e-9, atol=1e-12)
+    assert np.allclose(gt.numpy(), z["dtheta"], rtol=1e-9, atol=1e-12)
+    # normalize_adj (model.py:360-367): T_1 = (2/1.5)(I - A_hat) - I  =>  A_hat = I - 0.75 (T_1 + I)
+    Ahat_ref = np.eye(No) - 0.75 * (z["t_k"][:, 1] + np.eye(No))
+    A = z["adj"].astype(np.float64)
+    d = (A.sum(2) + float(np.float32(1e-3))) ** -0.5       # the reference's constant is a float32 array (model.py:362)
+    Ahat = d[:, :, None] * np.transpose(A, (0, 2, 1)) * d[:, None, :]
+    assert np.allclose(Ahat, Ahat_ref, rtol=1e-12, atol=1e-13)
+    assert np.array_equal(z["t_k"][:, 0], np.broadcast_to(np.eye(No), (mb, No, No)))

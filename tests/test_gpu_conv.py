@@ -106,3 +106,26 @@ def test_normalize_propagate_persistent_many_commits(flags):
     ref, dd = _ref_propagate(adj, H, None, bias, 1e-3, bool(flags & 1), bool(flags & 2), not (flags & 4))
     assert np.abs(dinv.cpu().numpy() - dd).max() / dd.max() < 1e-6
     assert np.abs(out.cpu().numpy() - ref).max() / np.abs(ref).max() < 1e-5
+
+
+def test_legacy_operator_matches_reference_model_py_golden():
+    """Row a16 pinned: the CUDA normalize+propagate and map_conv against the reference's own model.py:335-403 executed over
+    the shim (tests/golden/legacy_toy.npz, written by oracle/gen_golden.py)."""
+    import os
+    from hdgnn_b200.engine import map_conv, normalize_propagate
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "legacy_toy.npz"))
+    adj = torch.tensor(z["adj"]).cuda()
+    mb, No = z["adj"].shape[:2]
+    x = torch.tensor(z["O"].reshape(mb, No), dtype=torch.float32).cuda()
+    theta = torch.tensor(z["theta"], dtype=torch.float32).cuda()
+    loss, per = map_conv(adj, x, theta)
+    torch.cuda.synchronize()
+    assert abs(loss.item() - float(z["loss"])) <= 1e-5 * abs(float(z["loss"]))
+    # A_hat of normalize_adj recovered from the reference's T_1 = (2/1.5)(I - A_hat) - I, applied to random features
+    Ahat = np.eye(No) - 0.75 * (z["t_k"][:, 1] + np.eye(No))
+    H = np.random.default_rng(5).normal(size=(mb, No, 20)).astype(np.float32)
+    for flags in (0, 8, 16):
+        out, _ = normalize_propagate(adj, torch.tensor(H).cuda(), flags=flags)
+        torch.cuda.synchronize()
+        ref = Ahat @ H.astype(np.float64)
+        assert np.abs(out.cpu().numpy() - ref).max() / np.abs(ref).max() < 1e-5, flags
