@@ -104,6 +104,7 @@ struct hdgnn_handle_s {
     int bslot = 0;                                             // bitmap buffer of the current step (two alternate)
     bool dlt_global = false;                                   // mid2's dL/dlogit table in HBM instead of shared memory
     bool mid_scache = false;                                   // mid2 keeps the entity effect sums in shared memory for its backward
+    bool inl = false;                                          // entity pair layer inside mid2 (entsp.cuh): no ent_fwd2 / ent_bwd2 launch
     int Gf = 0, Gb = 0, Rf = 0, Rb = 0, SLf = 0;               // grids / rows per CTA / slots of the last launch
     std::map<std::string, Buf> ws;
     std::string err;
@@ -557,7 +558,7 @@ int fused_forward(hdgnn_handle_t h, int B, int B_global, const Inputs& in, float
         else launch_ex(pack_bits_kernel<32>, (int)((rows + 7) / 8), 256, 0, st, h->pdl, p);
         LAUNCH_CHECK(h, "pack_bits", st);
     }
-    if (h->ent) {
+    if (h->ent && !h->inl) {
         Ent2Args a = ent2_args(h, B, in);
         ent2_grid(h, B, h->fwd_occ, &h->Gf, &h->Rf);
         h->SLf = ent2_max_slots(h->Ne, h->Rf);
@@ -580,11 +581,15 @@ int fused_forward(hdgnn_handle_t h, int B, int B_global, const Inputs& in, float
     m.clk = h->debug ? (long long*)h->ws["CLK"].p : nullptr;
     const bool dlt_g = train && h->dlt_global;
     m.dlt_g = dlt_g ? F(h, "DLT") : nullptr;
-    m.scache = (train && h->ent && h->mid_scache) ? 1 : 0;
-    const size_t smem = mid2_smem_bytes(h->Ne, h->Nc, train, !dlt_g, m.scache != 0);
+    m.scache = ((train && h->ent && h->mid_scache) || h->inl) ? 1 : 0;
+    m.inl = h->inl ? 1 : 0;
+    m.dRS1 = (h->inl && h->debug) ? F(h, "RS1") : nullptr;
+    const size_t smem = mid2_smem_bytes(h->Ne, h->Nc, train, !dlt_g, m.scache != 0, h->inl);
     const int cwc = (h->Nc + 31) / 32;
     PROF_BEGIN(h, st);
-    launch_mid2(cwc, train, B, smem, st, m, h->pdl && h->ent);
+    // inline entity stage: this kernel reads the weights after its pdl_wait, so it may follow the previous step's optimizer
+    // kernel (or pack_bits) under programmatic dependent launch; otherwise PDL only behind ent_fwd2
+    launch_mid2(cwc, train, B, smem, st, m, h->pdl && (h->ent || h->inl));
     LAUNCH_CHECK(h, train ? "mid(train)" : "mid(infer)", st);
     if (h->debug) return debug_scatter(h, B, st);
     return HDGNN_OK;
@@ -592,7 +597,7 @@ int fused_forward(hdgnn_handle_t h, int B, int B_global, const Inputs& in, float
 
 int fused_backward(hdgnn_handle_t h, int B, int B_global, const Inputs& in, float* loss, float* grads,
                    const AdamArgs* adam, cudaStream_t st) {
-    if (h->ent) {
+    if (h->ent && !h->inl) {
         Ent2Args a = ent2_args(h, B, in);
         ent2_grid(h, B, h->bwd_occ, &h->Gb, &h->Rb);
         a.R = h->Rb; a.SL = 0; a.GR = F(h, "GE"); a.GC = F(h, "GE"); a.gpart = F(h, "GPE");
@@ -603,7 +608,7 @@ int fused_backward(hdgnn_handle_t h, int B, int B_global, const Inputs& in, floa
     }
     FinalArgs f{};
     f.B = B; f.total = h->po.total; f.gpart = F(h, "GPART");
-    if (h->ent) f.ent = {F(h, "GPE"), h->Gb, h->po.ent_w1, h->po.ent_w1 + HD, h->po.ent_b1, h->po.ent_w1 + 2 * HD};
+    if (h->ent && !h->inl) f.ent = {F(h, "GPE"), h->Gb, h->po.ent_w1, h->po.ent_w1 + HD, h->po.ent_b1, h->po.ent_w1 + 2 * HD};
     f.cep = F(h, "CEP"); f.ncep = B; f.loss_denom = (float)B_global * (float)(h->Nc * (h->Nc - 1)); f.loss = loss;
     f.grads = grads;
     f.l2part = F(h, "FIN_L2"); f.counter = (unsigned int*)h->ws["FIN_CNT"].p;
@@ -740,6 +745,14 @@ int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out) {
         h->dlt_global = mid2_smem_bytes(h->Ne, h->Nc, true, true) > (size_t)prop.sharedMemPerBlockOptin;
         h->fused = mid2_smem_bytes(h->Ne, h->Nc, true, !h->dlt_global) <= (size_t)prop.sharedMemPerBlockOptin;
         h->mid_scache = h->fused && mid2_smem_bytes(h->Ne, h->Nc, true, !h->dlt_global, true) <= (size_t)prop.sharedMemPerBlockOptin;
+    }
+    if (h->fused && h->ent && !(cfg->flags & HDGNN_F_DENSE_SWEEP) && env_int("HDGNN_DENSE_SWEEP", 0) == 0 &&
+        h->Ne * bit_words(h->Ne) <= 12 * h->Nc * HD) {
+        // entity pair layer inside mid2 (sorted prefix sums + edge walk) when its extra state fits beside mid2's
+        const size_t lim = (size_t)prop.sharedMemPerBlockOptin;
+        if (mid2_smem_bytes(h->Ne, h->Nc, true, true, true, true) <= lim) { h->inl = true; h->dlt_global = false; }
+        else if (mid2_smem_bytes(h->Ne, h->Nc, true, false, true, true) <= lim) { h->inl = true; h->dlt_global = true; }
+        if (h->inl) h->mid_scache = true;
     }
     h->host_bits = (cfg->flags & HDGNN_F_LABEL_BITS) != 0;
     if (h->host_bits && !h->fused) {

@@ -17,6 +17,7 @@
 #pragma once
 #include "sweep2.cuh"
 #include "ent2.cuh"
+#include "entsp.cuh"
 
 namespace hdgnn {
 
@@ -47,6 +48,10 @@ struct Mid2Args {
     long long* clk;                          // per-phase clock64 stamps (B,16) or null
     float* dlt_g;                            // (B, Nc, CW*32) dL/dlogit table in HBM when it does not fit smem, else null
     int scache;                              // keep the entity effect sums S (Ne x 20) in shared memory from the forward to the backward
+    int inl;                                 // entity pair layer and its backward INSIDE this kernel (entsp.cuh: sorted prefix sums +
+                                             // edge walk): RS1 / CS1p / GE are not used, the step has no ent_fwd2 / ent_bwd2 launch and
+                                             // this kernel follows the previous step's optimizer kernel (weights are read after pdl_wait)
+    float* dRS1;                             // debug dump of the row sums (B,Ne,20) when inl, else unused
 };
 // debug dump layout per commit (floats): S1[Ne*20] X2[Ne] NB[Nc*4] RS3[Nc*20] CS3[Nc*20] PR[Nc*20] PC[Nc*20]
 // DNB[Nc*4] DX2[Ne]
@@ -56,16 +61,20 @@ struct Mid2Smem {
     // offsets in floats
     int blk1, blk2, gam, Dh, Dg, G1g, W5U, c1p;   // weight blocks (contiguous copies of the parameter blob), derived tables
     int x, x2, hm, SP, TP, dl, dx2, nb, dnb, ebits, ybits, scratch, red, uni, sc, total;
+    int entw, xsort, ordv, sx;               // inline entity stage: U V c D, x sorted, rank -> node, suffix sums of sorted x
 };
 
 // dlt_smem: keep the per-pair dL/dlogit table of the training path in shared memory (else it lives in HBM / L2)
-__host__ __device__ inline Mid2Smem mid2_layout(int Ne, int Nc, bool train, bool dlt_smem = true, bool scache = false) {
+__host__ __device__ inline Mid2Smem mid2_layout(int Ne, int Nc, bool train, bool dlt_smem = true, bool scache = false, bool inl = false) {
     Mid2Smem m;
+    if (inl) scache = true;
     int o = 0;
     auto take = [&](int n) { int r = o; o += (n + 7) & ~7; return r; };      // 32-byte granules
     m.blk1 = take(M2_BLK1); m.blk2 = take(M2_BLK2); m.gam = take(20); m.Dh = take(20); m.Dg = take(20); m.G1g = take(400);
     m.W5U = take(400); m.c1p = take(20);
     m.x = take(Ne); m.x2 = take(Ne); m.hm = take(Ne);
+    m.entw = m.xsort = m.ordv = m.sx = 0;
+    if (inl) { m.entw = take(4 * HD); m.xsort = take(Ne); m.ordv = take(Ne); m.sx = take(Ne + 1); }
     m.dx2 = take(Ne); m.nb = take(4 * Nc); m.dnb = take(4 * Nc);
     m.ebits = take(Ne * bit_words(Ne)); m.ybits = take(Nc * bit_words(Nc));
     const int cwc = (Nc + 31) / 32;
@@ -75,6 +84,8 @@ __host__ __device__ inline Mid2Smem mid2_layout(int Ne, int Nc, bool train, bool
     m.uni = o;
     // union region: [hunk tables 12 Nc 20][dlt (training) | SP TP dl (pooling: dead while dlt is live)]; the
     // entity-state backward (after the pooling backward) reuses it from the start
+    // (the inline entity stage keeps its transposed bitmap, Ne * bit_words(Ne) words, resp. 20 suffix tables of Ne + 1 floats
+    // plus 8 partial sums per thread here: both below M2_CH * M2_NODE_F for Ne <= 512)
     const int ent_phase = M2_CH * M2_NODE_F;
     const int dlt = (train && dlt_smem) ? Nc * cwc * 32 : 0, pool3 = 3 * ((4 * Ne + 7) & ~7);
     const int hunk_phase = ((12 * Nc * HD + 7) & ~7) + (dlt > pool3 ? dlt : pool3);
@@ -85,8 +96,8 @@ __host__ __device__ inline Mid2Smem mid2_layout(int Ne, int Nc, bool train, bool
     m.total = o;
     return m;
 }
-__host__ __device__ inline size_t mid2_smem_bytes(int Ne, int Nc, bool train, bool dlt_smem = true, bool scache = false) {
-    return (size_t)mid2_layout(Ne, Nc, train, dlt_smem, scache).total * 4 + 16;
+__host__ __device__ inline size_t mid2_smem_bytes(int Ne, int Nc, bool train, bool dlt_smem = true, bool scache = false, bool inl = false) {
+    return (size_t)mid2_layout(Ne, Nc, train, dlt_smem, scache, inl).total * 4 + 16;
 }
 
 // fixed-order block sum for M2_T threads; every thread gets the result
@@ -227,7 +238,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
     const int Ne = a.Ne, Nc = a.Nc, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int kg = warp % KG, rg = warp / KG, k0 = kg * 4;
     const int WPe = a.WPe, WPc = a.WPc;
-    const Mid2Smem L_ = mid2_layout(Ne, Nc, TRAIN, a.dlt_g == nullptr, a.scache != 0);
+    const Mid2Smem L_ = mid2_layout(Ne, Nc, TRAIN, a.dlt_g == nullptr, a.scache != 0, a.inl != 0);
     float* blk1 = sm + L_.blk1; float* blk2 = sm + L_.blk2;
     float* W5 = blk1; float* b5 = blk1 + 400; float* U1 = blk1 + 420; float* c1 = blk1 + 840;
     float* u2 = blk1 + 860; float* c2 = blk1 + 880;
@@ -261,59 +272,72 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         bulk_g2s(ybits, a.ybits + (size_t)b * Nc * WPc, bc, bar);
     }
     // per-commit inputs: in flight together with the weight loads below (Ne <= 512 < M2_T: one element per thread)
-    const int Lb = a.L[b];
+    const int Lb = min(max(a.L[b], 0), Ne);      // 0 <= L <= Ne is the ABI's contract; clamped so a bad value cannot index out of the tile
     const int h_in = tid < Ne ? a.hmap[(size_t)b * Ne + tid] : -1;
     const float x_in = tid < Ne ? a.x[(size_t)b * Ne + tid] : 0.f;
-    {   // both weight blocks with all global loads in flight before the first store
-        const float* p1 = par + (a.ent ? po.ent_w5 : po.hnk_w1);
-        const float* p2 = par + po.hnk_w1;
-        const int n1 = a.ent ? M2_BLK1 : 0;
-        constexpr int NLD = (M2_BLK1 + M2_BLK2 + M2_T - 1) / M2_T;
-        float v[NLD];
+    // Weights -> shared memory and the tables derived from them.  With the entity stage inline this kernel follows the
+    // previous step's optimizer kernel, so the weights are read after pdl_wait (below); otherwise its predecessor is
+    // ent_fwd2, which does not write them, and the loads overlap that kernel's tail.
+    float* wE = sm + L_.entw;                   // inline entity stage: U[20] V[20] c[20] D[20] (model_2.py:167-170)
+    const float nb5 = 2.f * (float)(Ne - 1);
+    auto load_weights = [&]() {
+        {   // both weight blocks with all global loads in flight before the first store
+            const float* p1 = par + (a.ent ? po.ent_w5 : po.hnk_w1);
+            const float* p2 = par + po.hnk_w1;
+            const int n1 = a.ent ? M2_BLK1 : 0;
+            constexpr int NLD = (M2_BLK1 + M2_BLK2 + M2_T - 1) / M2_T;
+            float v[NLD];
 #pragma unroll
-        for (int u = 0; u < NLD; ++u) {
-            const int idx = tid + u * M2_T;
-            v[u] = idx < n1 ? p1[idx] : (idx < n1 + M2_BLK2 ? p2[idx - n1] : 0.f);
-        }
+            for (int u = 0; u < NLD; ++u) {
+                const int idx = tid + u * M2_T;
+                v[u] = idx < n1 ? p1[idx] : (idx < n1 + M2_BLK2 ? p2[idx - n1] : 0.f);
+            }
+            float e0 = 0.f, e1 = 0.f, e2 = 0.f;
+            if (a.inl && tid < HD) {
+                e0 = par[po.ent_w1 + 2 * HD + tid]; e1 = par[po.ent_w1 + 3 * HD + tid]; e2 = par[po.ent_b1 + tid];
+                wE[tid] = par[po.ent_w1 + tid]; wE[HD + tid] = par[po.ent_w1 + HD + tid];
+                wE[2 * HD + tid] = e2 + e0; wE[3 * HD + tid] = e1 - e0;
+            }
 #pragma unroll
-        for (int u = 0; u < NLD; ++u) {
-            const int idx = tid + u * M2_T;
-            if (idx < n1) blk1[idx] = v[u];
-            else if (idx < n1 + M2_BLK2) blk2[idx - n1] = v[u];
+            for (int u = 0; u < NLD; ++u) {
+                const int idx = tid + u * M2_T;
+                if (idx < n1) blk1[idx] = v[u];
+                else if (idx < n1 + M2_BLK2) blk2[idx - n1] = v[u];
+            }
         }
-    }
+        __syncthreads();
+        if (tid < HD) {
+            gam[tid] = G2[2 * tid + 1] - G2[2 * tid];
+            Dh[tid] = V1[9 * HD + tid] - V1[8 * HD + tid];
+            Dg[tid] = G1[HD + tid] - G1[tid];
+        }
+        if (TRAIN) for (int e = tid; e < 400; e += M2_T) G1g[e] = G1[2 * HD + e] * (G2[2 * (e % HD) + 1] - G2[2 * (e % HD)]);
+        if (a.ent) {
+            // the entity effect layer (x W5 + (Ne-1) 2 b5, model_2.py:172-175 after aggregation) and the first layer of
+            // the entity-state MLP compose into one 20 x 20 map: Z = c1' + x U1[0] + S W5U
+            for (int e = tid; e < 420; e += M2_T) {
+                float acc = 0.f;
+                if (e < 400) {
+                    const int q = e / HD, k = e - q * HD;
+#pragma unroll
+                    for (int m = 0; m < HD; ++m) acc = fmaf(W5[q * HD + m], U1[(1 + m) * HD + k], acc);
+                    W5U[e] = acc;
+                } else {
+                    const int k = e - 400;
+#pragma unroll
+                    for (int m = 0; m < HD; ++m) acc = fmaf(b5[m], U1[(1 + m) * HD + k], acc);
+                    c1p[k] = fmaf(nb5, acc, c1[k]);
+                }
+            }
+        }
+        __syncthreads();
+    };
     if (tid < Ne) {
         hm[tid] = (h_in >= 0 && h_in < Nc) ? h_in : -1;
         xs[tid] = x_in;
         if (!a.ent) x2[tid] = x_in;
     }
-    __syncthreads();
-    if (tid < HD) {
-        gam[tid] = G2[2 * tid + 1] - G2[2 * tid];
-        Dh[tid] = V1[9 * HD + tid] - V1[8 * HD + tid];
-        Dg[tid] = G1[HD + tid] - G1[tid];
-    }
-    if (TRAIN) for (int e = tid; e < 400; e += M2_T) G1g[e] = G1[2 * HD + e] * (G2[2 * (e % HD) + 1] - G2[2 * (e % HD)]);
-    const float nb5 = 2.f * (float)(Ne - 1);
-    if (a.ent) {
-        // the entity effect layer (x W5 + (Ne-1) 2 b5, model_2.py:172-175 after aggregation) and the first layer of
-        // the entity-state MLP compose into one 20 x 20 map: Z = c1' + x U1[0] + S W5U
-        for (int e = tid; e < 420; e += M2_T) {
-            float acc = 0.f;
-            if (e < 400) {
-                const int q = e / HD, k = e - q * HD;
-#pragma unroll
-                for (int m = 0; m < HD; ++m) acc = fmaf(W5[q * HD + m], U1[(1 + m) * HD + k], acc);
-                W5U[e] = acc;
-            } else {
-                const int k = e - 400;
-#pragma unroll
-                for (int m = 0; m < HD; ++m) acc = fmaf(b5[m], U1[(1 + m) * HD + k], acc);
-                c1p[k] = fmaf(nb5, acc, c1[k]);
-            }
-        }
-    }
-    __syncthreads();
+    if (!a.inl) load_weights(); else __syncthreads();
     // ---- everything that depends on the inputs only (bitmaps, hunk ids, L) is done BEFORE the dependency on ent_fwd2:
     // under programmatic dependent launch it overlaps that kernel's tail
     const int nm1 = Ne - 1;
@@ -397,10 +421,97 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             }
         }
     }
+    // ---- inline entity stage, input-only half (entsp.cuh): nodes sorted by attribute, suffix sums, transposed bitmap
+    float* xsort = sm + L_.xsort; int* ordv = reinterpret_cast<int*>(sm + L_.ordv); float* SXs = sm + L_.sx;
+    uint32_t* ebT = reinterpret_cast<uint32_t*>(uni);      // [Ne][WPe]: bit i of row j = A_ij; dead after the entity forward
+    if (a.inl) {
+        for (int i = tid; i < Ne; i += M2_T) {               // stable rank sort: N broadcast reads per node
+            const float xi = xs[i];
+            int r = 0;
+            for (int j = 0; j < Ne; ++j) { const float xj = xs[j]; r += (xj < xi || (xj == xi && j < i)) ? 1 : 0; }
+            xsort[r] = xi; ordv[r] = i;
+        }
+        for (int blk = warp; blk < WPe * ((Ne + 31) >> 5); blk += M2_NW) {       // 32 x 32 bit blocks (row block, column word)
+            const int rb = blk / WPe, cw = blk - rb * WPe, row = rb * 32 + lane;
+            const uint32_t w = warp_transpose32(row < Ne ? ebits[row * WPe + cw] : 0u, lane);
+            const int col = cw * 32 + lane;
+            if (col < Ne) ebT[col * WPe + rb] = w;
+        }
+        __syncthreads();
+        if (warp == 0) {                                     // SXs[r] = sum of the sorted attributes from rank r on, SXs[Ne] = 0
+            const int per = (Ne + 31) >> 5, lo = min(lane * per, Ne), hi = min(lo + per, Ne);
+            float sum = 0.f;
+            for (int r = hi - 1; r >= lo; --r) sum += xsort[r];
+            float incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_down_sync(0xffffffffu, incl, o); if (lane + o < 32) incl += t; }
+            float run = incl - sum;
+            for (int r = hi - 1; r >= lo; --r) { run += xsort[r]; SXs[r] = run; }
+            if (lane == 0) SXs[Ne] = 0.f;
+        }
+    }
     __syncthreads();
-    pdl_wait();                     // RS1 / CS1p come from ent_fwd2 (everything above reads inputs, weights, bitmaps)
+    pdl_wait();                     // RS1 / CS1p come from ent_fwd2, or (inline entity stage) the weights from the previous step's optimizer
     pdl_launch_dependents();
     M2_PHASE(1);
+    if (a.inl) {
+        load_weights();
+        // ---------------- entity pair layer forward: S_n = sum_{j != n} relu(pre_nj) + sum_{i != n} relu(pre_in) -------------
+        // one owner thread per (node, channel pair): two binary searches per channel, the row walk (edges n -> j) and the
+        // column walk (edges i -> n, transposed bitmap)
+        float* Sall = sm + L_.sc;
+        int P2 = 1;
+        while (P2 <= Ne) P2 <<= 1;
+        const int c0 = 2 * (tid % 10);
+        const float Uc[2] = {wE[c0], wE[c0 + 1]}, Vc[2] = {wE[HD + c0], wE[HD + c0 + 1]};
+        const float Cc[2] = {wE[2 * HD + c0], wE[2 * HD + c0 + 1]}, Dc[2] = {wE[3 * HD + c0], wE[3 * HD + c0 + 1]};
+        const int WU = (Ne + 31) >> 5;
+        for (int n = tid / 10; n < Ne; n += M2_T / 10) {
+            const float xn = xs[n];
+            float pb[2], qb[2], accR[2], accC[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) { pb[h] = fmaf(xn, Uc[h], Cc[h]); qb[h] = fmaf(xn, Vc[h], Cc[h]); }
+            int r[4] = {0, 0, 0, 0};
+            const float sw[4] = {Vc[0], Vc[1], Uc[0], Uc[1]}, sb[4] = {pb[0], pb[1], qb[0], qb[1]};
+            for (int step = P2 >> 1; step > 0; step >>= 1) {        // the four searches advance together
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int probe = r[u] + step - 1;
+                    const float xv = xsort[probe < Ne ? probe : Ne - 1];
+                    const bool act = fmaf(xv, sw[u], sb[u]) > 0.f;
+                    if (probe < Ne && act != (sw[u] >= 0.f)) r[u] += step;
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float cnt, sx;
+                entsp_active(r[h], Ne, Vc[h] >= 0.f, SXs, cnt, sx);
+                accR[h] = fmaf(cnt, pb[h], Vc[h] * sx) - fmaxf(fmaf(xn, Vc[h], pb[h]), 0.f);
+                entsp_active(r[2 + h], Ne, Uc[h] >= 0.f, SXs, cnt, sx);
+                accC[h] = fmaf(cnt, qb[h], Uc[h] * sx) - fmaxf(fmaf(xn, Uc[h], qb[h]), 0.f);
+            }
+            for (int w = 0; w < WU; ++w) {
+                uint32_t rowb = ebits[n * WPe + w], colb = ebT[n * WPe + w];
+                while (rowb) {
+                    const int j = (w << 5) + __ffs(rowb) - 1;
+                    rowb &= rowb - 1;
+                    const float xj = xs[j];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) { const float t0 = fmaf(xj, Vc[h], pb[h]); accR[h] += fmaxf(t0 + Dc[h], 0.f) - fmaxf(t0, 0.f); }
+                }
+                while (colb) {
+                    const int i = (w << 5) + __ffs(colb) - 1;
+                    colb &= colb - 1;
+                    const float xi = xs[i];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) { const float t0 = fmaf(xi, Uc[h], qb[h]); accC[h] += fmaxf(t0 + Dc[h], 0.f) - fmaxf(t0, 0.f); }
+                }
+            }
+            *reinterpret_cast<float2*>(Sall + (size_t)n * HD + c0) = make_float2(accR[0] + accC[0], accR[1] + accC[1]);
+            if (dbg && a.dRS1) *reinterpret_cast<float2*>(a.dRS1 + ((size_t)b * Ne + n) * HD + c0) = make_float2(accR[0], accR[1]);
+        }
+        __syncthreads();
+    }
 
     // ---------------- B/C. entity-state MLP forward: two threads per entity (10 hidden units each) ----------
     const int nsl = a.ent ? ent2_slots(b, Ne, a.R) : 0;
@@ -452,7 +563,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         // that would run into SP / TP)
         const bool coopS = a.scache || Ne <= 12 * Nc;
         float* Sall = a.scache ? sm + L_.sc : uni;
-        if (coopS) { coop_load_S(Sall, HD, 0, Ne); __syncthreads(); }
+        if (coopS && !a.inl) { coop_load_S(Sall, HD, 0, Ne); __syncthreads(); }
         for (int base = 0; base < 2 * Ne; base += M2_T) {
             const int t = base + tid, node = t >> 1, h = t & 1;
             const bool valid = node < Ne;
@@ -1088,7 +1199,9 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
                     dz[j] = h ? o : dzh[j]; dz[10 + j] = h ? dzh[j] : o;
                 }
                 if (valid) {                           // GE_n[q] = sum_k W5U[q][k] dz[k], q = 10 h .. 10 h + 9
-                    float* ge = a.GE + ((size_t)b * Ne + node) * HD + 10 * h;
+                    // inline entity stage: GE takes the place of S in shared memory (this chunk's S rows were copied to Sa)
+                    float* ge = (a.inl ? sm + L_.sc + (size_t)node * HD : a.GE + ((size_t)b * Ne + node) * HD) + 10 * h;
+                    float* ge_dbg = (a.inl && dbg) ? a.GE + ((size_t)b * Ne + node) * HD + 10 * h : nullptr;
 #pragma unroll
                     for (int j2 = 0; j2 < 5; ++j2) {
                         float g0 = 0.f, g1 = 0.f;
@@ -1103,6 +1216,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
                             g1 = fmaf(v.z, dz[4 * k4 + 2], g1); g1 = fmaf(v.w, dz[4 * k4 + 3], g1);
                         }
                         *reinterpret_cast<float2*>(ge + 2 * j2) = make_float2(g0, g1);
+                        if (ge_dbg) *reinterpret_cast<float2*>(ge_dbg + 2 * j2) = make_float2(g0, g1);
                     }
                 }
             }
@@ -1161,6 +1275,102 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             } else {
                 gp[po.nod_b1 + (e - 840)] = dc1v[e - 840];
             }
+        }
+    }
+    if (a.inl) {
+        // ---------------- entity pair layer backward (entsp.cuh): first-layer weight gradients from GE ---------------------
+        // v_ij[k] = [pre_ij[k] > 0] (GE_i[k] + GE_j[k]);  db = sum v, dU = sum x_i v, dV = sum x_j v, LS = sum over l_ij = 1
+        __syncthreads();
+        const float* GEs = sm + L_.sc;
+        float* SGs = uni;                                   // [20][Ne + 1] suffix sums of GE over the sorted order, per channel
+        float* part = uni + 20 * (Ne + 1) + ((20 * (Ne + 1)) & 1);   // [M2_T][8] per-thread partial sums (8-byte aligned)
+        {
+            const int k = warp;                             // M2_NW == HD: one warp per channel
+            const int per = (Ne + 31) >> 5, lo = min(lane * per, Ne), hi = min(lo + per, Ne);
+            float sum = 0.f;
+            for (int r = hi - 1; r >= lo; --r) sum += GEs[(size_t)ordv[r] * HD + k];
+            float incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_down_sync(0xffffffffu, incl, o); if (lane + o < 32) incl += t; }
+            float run = incl - sum;
+            float* dst = SGs + (size_t)k * (Ne + 1);
+            for (int r = hi - 1; r >= lo; --r) { run += GEs[(size_t)ordv[r] * HD + k]; dst[r] = run; }
+            if (lane == 0) dst[Ne] = 0.f;
+        }
+        __syncthreads();
+        int P2 = 1;
+        while (P2 <= Ne) P2 <<= 1;
+        const int c0 = 2 * (tid % 10);
+        const float Uc[2] = {wE[c0], wE[c0 + 1]}, Vc[2] = {wE[HD + c0], wE[HD + c0 + 1]};
+        const float Cc[2] = {wE[2 * HD + c0], wE[2 * HD + c0 + 1]}, Dc[2] = {wE[3 * HD + c0], wE[3 * HD + c0 + 1]};
+        const int WU = (Ne + 31) >> 5;
+        float db[2] = {0.f, 0.f}, dU[2] = {0.f, 0.f}, dV[2] = {0.f, 0.f}, LS[2] = {0.f, 0.f};
+        for (int n = tid / 10; n < Ne; n += M2_T / 10) {
+            const float xn = xs[n];
+            const float2 gn2 = *reinterpret_cast<const float2*>(GEs + (size_t)n * HD + c0);
+            const float gn[2] = {gn2.x, gn2.y};
+            float pb[2], qb[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) { pb[h] = fmaf(xn, Uc[h], Cc[h]); qb[h] = fmaf(xn, Vc[h], Cc[h]); }
+            int r[4] = {0, 0, 0, 0};
+            const float sw[4] = {Vc[0], Vc[1], Uc[0], Uc[1]}, sb[4] = {pb[0], pb[1], qb[0], qb[1]};
+            for (int step = P2 >> 1; step > 0; step >>= 1) {        // same predicate as the forward: identical gates
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int probe = r[u] + step - 1;
+                    const float xv = xsort[probe < Ne ? probe : Ne - 1];
+                    const bool act = fmaf(xv, sw[u], sb[u]) > 0.f;
+                    if (probe < Ne && act != (sw[u] >= 0.f)) r[u] += step;
+                }
+            }
+            float rsd[2], csd[2], dvx[2] = {0.f, 0.f}, ls[2] = {0.f, 0.f};
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float cnt, sg;
+                entsp_active(r[h], Ne, Vc[h] >= 0.f, SGs + (size_t)(c0 + h) * (Ne + 1), cnt, sg);
+                rsd[h] = fmaf(cnt, gn[h], sg) - (fmaf(xn, Vc[h], pb[h]) > 0.f ? 2.f * gn[h] : 0.f);
+                entsp_active(r[2 + h], Ne, Uc[h] >= 0.f, SGs + (size_t)(c0 + h) * (Ne + 1), cnt, sg);
+                csd[h] = fmaf(cnt, gn[h], sg) - (fmaf(xn, Uc[h], qb[h]) > 0.f ? 2.f * gn[h] : 0.f);
+            }
+            for (int w = 0; w < WU; ++w) {
+                uint32_t rowb = ebits[n * WPe + w];
+                while (rowb) {
+                    const int j = (w << 5) + __ffs(rowb) - 1;
+                    rowb &= rowb - 1;
+                    const float xj = xs[j];
+                    const float2 gj = *reinterpret_cast<const float2*>(GEs + (size_t)j * HD + c0);
+                    const float gjv[2] = {gj.x, gj.y};
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const float t0 = fmaf(xj, Vc[h], pb[h]), g = gn[h] + gjv[h];
+                        const float v1 = (t0 + Dc[h]) > 0.f ? g : 0.f, v0 = t0 > 0.f ? g : 0.f;
+                        const float dlt_e = v1 - v0;
+                        rsd[h] += dlt_e; dvx[h] = fmaf(xj, dlt_e, dvx[h]); ls[h] += v1;
+                    }
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                db[h] += rsd[h]; dU[h] = fmaf(xn, rsd[h], dU[h]); dV[h] += fmaf(xn, csd[h], dvx[h]); LS[h] += ls[h];
+            }
+        }
+        *reinterpret_cast<float4*>(part + (size_t)tid * 8) = make_float4(db[0], db[1], dU[0], dU[1]);
+        *reinterpret_cast<float4*>(part + (size_t)tid * 8 + 4) = make_float4(dV[0], dV[1], LS[0], LS[1]);
+        __syncthreads();
+        if (tid < 4 * HD) {                                 // fixed-order sum over the 64 threads that own a channel pair
+            const int qn = tid / HD, k = tid - qn * HD, kp = k >> 1, hh = k & 1;
+            float t = 0.f;
+            for (int s2 = 0; s2 < M2_T / 10; ++s2) t += part[(size_t)(kp + 10 * s2) * 8 + 2 * qn + hh];
+            red[tid] = t;
+        }
+        __syncthreads();
+        if (tid < HD) {
+            const float dbk = red[tid], lsk = red[3 * HD + tid];
+            gp[po.ent_b1 + tid] = dbk;
+            gp[po.ent_w1 + tid] = red[HD + tid];
+            gp[po.ent_w1 + HD + tid] = red[2 * HD + tid];
+            gp[po.ent_w1 + 2 * HD + tid] = dbk - lsk;
+            gp[po.ent_w1 + 3 * HD + tid] = lsk;
         }
     }
     M2_PHASE(11);

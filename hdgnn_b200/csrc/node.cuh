@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(NODE_THREADS) pool_fwd_kernel(const PoolFwdArg
         copy_to_smem(u2, par + po.nod_w2, 20);  copy_to_smem(c2, par + po.nod_b2, 1);
     }
     copy_to_smem(V1, par + po.hnk_w1, 200); copy_to_smem(d1, par + po.hnk_b1, 20);
-    const int Lb = a.L[b];
+    const int Lb = min(max(a.L[b], 0), Ne);      // 0 <= L <= Ne is the ABI's contract; clamped so a bad value cannot index out of the tile
     for (int i = tid; i < Ne; i += blockDim.x) {
         const int h = a.hmap[(size_t)b * Ne + i];
         hm[i] = (h >= 0 && h < Nc) ? h : -1;
@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(NODE_THREADS) pool_bwd_kernel(const PoolBwdArg
     }
     copy_to_smem(V1, par + po.hnk_w1, 200);
     copy_to_smem(nbs, a.NB + (size_t)b * Nc * 4, Nc * 4);
-    const int Lb = a.L[b];
+    const int Lb = min(max(a.L[b], 0), Ne);      // 0 <= L <= Ne is the ABI's contract; clamped so a bad value cannot index out of the tile
     for (int i = tid; i < Ne; i += blockDim.x) {
         const int h = a.hmap[(size_t)b * Ne + i];
         hm[i] = (h >= 0 && h < Nc) ? h : -1;

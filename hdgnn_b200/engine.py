@@ -41,7 +41,7 @@ def label_pitch(n: int) -> int:
     return lib.hdgnn_label_pitch(n)
 
 
-F_DEBUG, F_LEGACY, F_LABEL_BITS = 2, 4, 8
+F_DEBUG, F_LEGACY, F_LABEL_BITS, F_DENSE_SWEEP = 2, 4, 8, 16
 
 
 def bit_words(n: int) -> int:

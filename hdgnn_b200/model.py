@@ -136,6 +136,7 @@ class graph2graph(object):
             raise ValueError("collective must be 'auto', 'peer' (all-reduce fused into the last kernel over NVLink peer "
                              "memory) or 'nccl' (torch.distributed.all_reduce between backward and Adam)")
         self.collective = collective
+        self._saved = {}                 # checkpoint dir -> names written by THIS object (the Saver's max_to_keep list)
         self.build_model()
 
     # ------------------------------------------------------------------------------------------
@@ -330,11 +331,13 @@ class graph2graph(object):
         auc_d = torch.zeros(max(n, 1), 2, dtype=torch.int64, device=dev)
         loss_h = torch.zeros(max(nb, 1)).pin_memory()
         start_time = time.time()
+        alive = []       # the library DMAs from these pinned buffers asynchronously: keep them until the final synchronize
         for j in range(nb):
             saved = (self.world, self.rank)
             self.world, self.rank = 1, 0                            # inference is not sharded
             hb = self.host_batch(self._batch(test, train, j, quirk_q2))
             self.world, self.rank = saved
+            alive.append(hb)
             pj = probs_d[j * mb:(j + 1) * mb]
             self.infer(hb, pj, loss_h[j:j + 1])
             # the reference's AUC keeps only the last commit of the whole test set (quirk Q7)
@@ -343,6 +346,7 @@ class graph2graph(object):
             counts_d[j * mb:(j + 1) * mb] = c
             auc_d[j * mb:(j + 1) * mb] = a
         torch.cuda.current_stream().synchronize()
+        alive.clear()
         end_time = time.time()
         te_loss_Hedge = float(loss_h[:nb].sum())
         C_edge_t1 = probs_d[:n].cpu().numpy().reshape(n, self.Dr, self.Ncr) if nb else np.zeros((0, 2, self.Ncr), np.float32)
@@ -381,17 +385,21 @@ class graph2graph(object):
                  __adam_m__=self.m.cpu().numpy(), __adam_v__=self.v.cpu().numpy(),
                  __adam_t__=self.step_counter.cpu().numpy(), **named)
         index = os.path.join(checkpoint_dir, "checkpoint")
-        kept = []
-        if os.path.exists(index):
-            kept = [l.strip() for l in open(index) if l.strip()]
-        kept.append(os.path.basename(path))
-        for old in kept[:-5]:                                        # max_to_keep = 5 (tf.train.Saver default)
+        # max_to_keep = 5 is tracked IN MEMORY per model object, as tf.train.Saver does: files of an earlier run are
+        # never deleted, and a name that is still among the last five is never removed (a rerun writes the same names)
+        kept = self._saved.setdefault(checkpoint_dir, [])
+        name = os.path.basename(path)
+        if name in kept:
+            kept.remove(name)
+        kept.append(name)
+        while len(kept) > 5:
+            old = kept.pop(0)
             try:
                 os.remove(os.path.join(checkpoint_dir, old))
             except OSError:
                 pass
         with open(index, "w") as f:
-            f.write("\n".join(kept[-5:]) + "\n")
+            f.write("\n".join(kept) + "\n")
         return path
 
     def load(self, checkpoint_dir, note=None, restore_adam=False):
@@ -404,7 +412,10 @@ class graph2graph(object):
         names = [l.strip() for l in open(index) if l.strip()]
         if not names:
             return False
-        z = np.load(os.path.join(checkpoint_dir, names[-1]))
+        latest = os.path.join(checkpoint_dir, names[-1])
+        if not os.path.exists(latest):
+            return False
+        z = np.load(latest)
         if int(z["__variant__"]) != self.variant or z["__flat__"].size != self.n_params:
             return False
         if note:

@@ -118,9 +118,12 @@ def read_compact(repo: str, step: int, Ne: int, Nc: int, root: str = ".", cache:
         with open(q) as f:
             lines.append(f.readlines())
     cb = compact_from_raw(x_raw, y_raw, lines, hunk_maps, Ne, Nc, device=device)
-    if cache:
+    if cache and int(os.environ.get("RANK", "0")) == 0:
+        # one writer (rank 0), temporary file + atomic rename: a rank arriving later never sees a half-written zip
         os.makedirs(os.path.dirname(cp), exist_ok=True)          # the reference needs this dir to pre-exist (Q14)
-        np.savez_compressed(cp, adj=cb.adj, x=cb.x, hmap=cb.hmap, L=cb.L, Y=cb.Y)
+        tmp = f"{cp}.{os.getpid()}.tmp.npz"
+        np.savez_compressed(tmp, adj=cb.adj, x=cb.x, hmap=cb.hmap, L=cb.L, Y=cb.Y)
+        os.replace(tmp, cp)
     return cb
 
 

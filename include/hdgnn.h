@@ -75,6 +75,10 @@ typedef struct {
                                in HBM and no packing kernel; fused path only (hdgnn_create fails with
                                HDGNN_E_UNSUPPORTED otherwise).  hdgnn_pack_label_bits builds the format on the device. */
 
+#define HDGNN_F_DENSE_SWEEP 16 /* variants 2 / 3: run the entity pair layer (model_2.py:161-188) as the dense Ne x Ne sweep kernels
+                               (ent_fwd2 / ent_bwd2) instead of the default sorted-prefix + edge-walk form inside the per-commit
+                               kernel, whose cost grows with the number of edges: choose this for adjacency densities above ~25 % */
+
 /* number of fp32 parameters of a variant (2127 for variant 2, 3129 for variant 4) */
 int hdgnn_param_count(int variant);
 /* offset (in floats) of a named block in the flat parameter blob, or -1.  Names:

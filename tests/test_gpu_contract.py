@@ -1,0 +1,119 @@
+"""GPU parity at the CONTRACT shapes of BASELINE.json (the sizes the bench and the driver actually launch), against
+the fp64 oracle plan (oracle/plan_numpy.py, itself pinned to the reference's model files by tests/test_golden.py):
+
+  * glide B=100 (Ne=200, Nc=74) through hdgnn_train_step with label bitmaps for three Adam steps -- the exact launch
+    geometry of bench.py (row chunks of the entity sweeps straddling commits, fused reduce + Adam);
+  * cfg2 (250,114), cfg3 (250,150: the per-pair dL/dlogit table spills to HBM), cfg4 (512,256), variant 4 at Ne=200;
+  * the inference sweep of config 5: Ne=200, Nc in {256, 384, 512}, forward only.
+
+Tolerance: north-star budget max|cuda - oracle| / max|oracle| <= 1e-3 per tensor; the fp32 path is held to 1e-4 on
+logits, losses, gradients and parameters.  Probabilities are held to the 1e-3 budget only: with the perturbed weights of
+these cases the logits reach several thousand at Nc >= 74, one fp32 ulp of such a logit is ~2e-4, and a probability
+moves by up to a quarter of the logit difference's absolute error (the logits themselves agree to ~5e-7 relative)."""
+import numpy as np
+import pytest
+import torch
+
+from hdgnn_b200.synthetic import make_commits
+from oracle import hdgnn_oracle as O
+from oracle import plan_numpy as PN
+
+pytestmark = pytest.mark.gpu
+TOL, TIGHT = 1e-3, 1e-4
+F_LABEL_BITS = 8
+
+
+def relerr(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def _params(variant, seed=7):
+    flat = O.init_params(variant, seed=seed, dtype=torch.float64)
+    g = torch.Generator().manual_seed(seed + 1)
+    return flat + 0.05 * torch.randn(flat.numel(), generator=g, dtype=torch.float64)
+
+
+def _ce_grad(plan, flat, variant):
+    """plan['grad'] holds d(10 CE + regularisers); the library's forward_backward returns the CE part only."""
+    pf = flat.numpy()
+    reg = 0.001 * pf
+    names = [s[0] for s in O.param_spec(variant)]
+    offs = dict(zip(names, np.cumsum([0] + [int(np.prod(s[2])) for s in O.param_spec(variant)])[:-1]))
+    for t in ("theta1", "theta2"):
+        th = pf[offs[t]:offs[t] + 2]
+        reg[offs[t]:offs[t] + 2] += 0.001 * th / np.sqrt((th ** 2).sum())
+    return plan["grad"] - reg, offs
+
+
+def test_glide_bench_launch_shape_three_adam_steps():
+    """B=100, Ne=200, Nc=74, variant 2, label bitmaps, hdgnn_train_step: what bench.py times."""
+    from hdgnn_b200.engine import Engine, DeviceBatch
+    B, Ne, Nc, variant = 100, 200, 74, 2
+    cb = make_commits(B, Ne, Nc, seed=20260)                       # the bench's generator settings (20 % short index files)
+    flat = _params(variant)
+    eng = Engine(Ne, Nc, variant=variant, max_batch=B, flags=F_LABEL_BITS)
+    db = DeviceBatch.from_numpy(cb.adj, cb.x, cb.hmap, cb.L, cb.Y, eng.tdev, bits=True)
+    p = flat.float().cuda(); m = torch.zeros_like(p); v = torch.zeros_like(p)
+    step = torch.zeros(1, dtype=torch.int32, device="cuda"); loss3 = torch.zeros(3, device="cuda")
+    probs = torch.zeros(B, 2, eng.Ncr, device="cuda")
+    p_ref = flat.numpy().copy(); m_ref = np.zeros_like(p_ref); v_ref = np.zeros_like(p_ref)
+    for t in range(1, 4):
+        eng.train_step(db, p, m, v, step, loss3, probs=probs)
+        torch.cuda.synchronize()
+        assert eng.last_launch_count() <= 4
+        plan = PN.train_step_plan(variant, torch.as_tensor(p_ref), cb.adj, cb.x, cb.hmap, cb.L, cb.Y)
+        lm, lp = O.reg_loss(torch.as_tensor(p_ref), variant)
+        p_ref, m_ref, v_ref = O.tf_adam_step(p_ref, plan["grad"], m_ref, v_ref, t)
+        errs = {"probs": relerr(probs.cpu().numpy(), plan["probs"]), "ce": relerr(loss3[0].item(), plan["ce"]),
+                "reg": relerr(loss3[1:].cpu().numpy(), np.array([float(lm), float(lp)])),
+                "params": relerr(p.cpu().numpy(), p_ref), "m": relerr(m.cpu().numpy(), m_ref)}
+        assert all(e < (TOL if k == "probs" else TIGHT) for k, e in errs.items()), (t, errs)
+        pc, pp = probs.cpu().numpy(), plan["probs"]
+        sure = np.abs(pp[:, 1] - pp[:, 0]) > 1e-4
+        assert np.array_equal((pc[:, 1] > pc[:, 0])[sure], (pp[:, 1] > pp[:, 0])[sure])      # identical predicted classes
+    eng.close()
+
+
+@pytest.mark.parametrize("B,Ne,Nc,variant", [(2, 250, 114, 2), (2, 250, 150, 2), (1, 512, 256, 2), (2, 200, 74, 4),
+                                             (3, 200, 74, 1), (2, 200, 74, 3), (2, 250, 150, 4)])
+def test_contract_shapes_forward_backward(B, Ne, Nc, variant):
+    from hdgnn_b200.engine import Engine, DeviceBatch
+    cb = make_commits(B, Ne, Nc, seed=300 + Nc, p_short=0.5)
+    flat = _params(variant)
+    plan = PN.train_step_plan(variant, flat, cb.adj, cb.x, cb.hmap, cb.L, cb.Y)
+    eng = Engine(Ne, Nc, variant=variant, max_batch=B)
+    db = DeviceBatch.from_numpy(cb.adj, cb.x, cb.hmap, cb.L, cb.Y, eng.tdev)
+    probs, logits, loss, grads = eng.forward_backward(db, flat.float().cuda(), want_logits=True)
+    torch.cuda.synchronize()
+    g_ce, offs = _ce_grad(plan, flat, variant)
+    g_cuda = grads.cpu().numpy()
+    errs = {"probs": relerr(probs.cpu().numpy(), plan["probs"]), "logits": relerr(logits.cpu().numpy(), plan["logits"]),
+            "ce": relerr(loss.cpu().numpy()[0], plan["ce"]), "grad": relerr(g_cuda, g_ce)}
+    for (name, _, shape) in O.param_spec(variant):              # per block, relative to the block's own scale
+        n = int(np.prod(shape)); o = offs[name]
+        if np.abs(g_ce[o:o + n]).max() > 0:
+            errs["g_" + name] = relerr(g_cuda[o:o + n], g_ce[o:o + n])
+    assert all(e < (TOL if k == "probs" else TIGHT) for k, e in errs.items()), errs
+    pc, pp = probs.cpu().numpy(), plan["probs"]
+    sure = np.abs(pp[:, 1] - pp[:, 0]) > 1e-4
+    assert np.array_equal((pc[:, 1] > pc[:, 0])[sure], (pp[:, 1] > pp[:, 0])[sure])
+    eng.close()
+
+
+@pytest.mark.parametrize("Nc", [256, 384, 512])
+def test_inference_sweep_shapes(Nc):
+    """BASELINE.json config 5: Ne=200, forward only."""
+    from hdgnn_b200.engine import Engine, DeviceBatch
+    B, Ne, variant = 2, 200, 2
+    cb = make_commits(B, Ne, Nc, seed=400 + Nc, p_short=0.5)
+    flat = _params(variant)
+    plan = PN.train_step_plan(variant, flat, cb.adj, cb.x, cb.hmap, cb.L, cb.Y)
+    eng = Engine(Ne, Nc, variant=variant, max_batch=B)
+    db = DeviceBatch.from_numpy(cb.adj, cb.x, cb.hmap, cb.L, cb.Y, eng.tdev)
+    probs, logits, loss = eng.forward(db, flat.float().cuda())
+    torch.cuda.synchronize()
+    errs = {"probs": relerr(probs.cpu().numpy(), plan["probs"]), "logits": relerr(logits.cpu().numpy(), plan["logits"]),
+            "ce": relerr(loss.cpu().numpy()[0], plan["ce"])}
+    assert all(e < (TOL if k == "probs" else TIGHT) for k, e in errs.items()), errs
+    eng.close()
