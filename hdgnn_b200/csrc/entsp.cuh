@@ -54,4 +54,33 @@ __device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
     return x;
 }
 
+// in-place exclusive prefix sum of p[0..n) by ONE warp; p[n] receives the total
+__device__ __forceinline__ void warp_excl_scan_int(int* p, int n, int lane) {
+    const int per = (n + 31) >> 5, lo = min(lane * per, n), hi = min(lo + per, n);
+    int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += p[i];
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    int run = incl - sum;
+    for (int i = lo; i < hi; ++i) { const int v = p[i]; p[i] = run; run += v; }
+    if (lane == 31) p[n] = incl;
+}
+
+// Cursor over the set bits of an n-row bitmap in row-major order, positioned at the edge with index e0 given the
+// exclusive prefix counts ptr[0..n] (ptr[n] = number of edges > e0).  P2 = smallest power of two > n.
+struct EdgeCursor { int row, w; uint32_t bits; };
+__device__ __forceinline__ EdgeCursor edge_seek(const uint32_t* bm, int WP, const int* ptr, int n, int P2, int e0) {
+    int row = 0;                                           // largest row with ptr[row] <= e0 (that row holds edge e0)
+    for (int step = P2 >> 1; step > 0; step >>= 1) {
+        const int probe = row + step;
+        if (probe < n && ptr[probe] <= e0) row = probe;
+    }
+    int skip = e0 - ptr[row], w = 0;
+    uint32_t bits = bm[(size_t)row * WP];
+    for (int c = __popc(bits); skip >= c; c = __popc(bits)) { skip -= c; ++w; bits = bm[(size_t)row * WP + w]; }
+    for (; skip > 0; --skip) bits &= bits - 1;
+    return {row, w, bits};
+}
+
 }  // namespace hdgnn

@@ -583,7 +583,6 @@ int fused_forward(hdgnn_handle_t h, int B, int B_global, const Inputs& in, float
     m.dlt_g = dlt_g ? F(h, "DLT") : nullptr;
     m.scache = ((train && h->ent && h->mid_scache) || h->inl) ? 1 : 0;
     m.inl = h->inl ? 1 : 0;
-    m.dRS1 = (h->inl && h->debug) ? F(h, "RS1") : nullptr;
     const size_t smem = mid2_smem_bytes(h->Ne, h->Nc, train, !dlt_g, m.scache != 0, h->inl);
     const int cwc = (h->Nc + 31) / 32;
     PROF_BEGIN(h, st);
@@ -746,8 +745,7 @@ int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out) {
         h->fused = mid2_smem_bytes(h->Ne, h->Nc, true, !h->dlt_global) <= (size_t)prop.sharedMemPerBlockOptin;
         h->mid_scache = h->fused && mid2_smem_bytes(h->Ne, h->Nc, true, !h->dlt_global, true) <= (size_t)prop.sharedMemPerBlockOptin;
     }
-    if (h->fused && h->ent && !(cfg->flags & HDGNN_F_DENSE_SWEEP) && env_int("HDGNN_DENSE_SWEEP", 0) == 0 &&
-        h->Ne * bit_words(h->Ne) <= 12 * h->Nc * HD) {
+    if (h->fused && h->ent && !(cfg->flags & HDGNN_F_DENSE_SWEEP) && env_int("HDGNN_DENSE_SWEEP", 0) == 0) {
         // entity pair layer inside mid2 (sorted prefix sums + edge walk) when its extra state fits beside mid2's
         const size_t lim = (size_t)prop.sharedMemPerBlockOptin;
         if (mid2_smem_bytes(h->Ne, h->Nc, true, true, true, true) <= lim) { h->inl = true; h->dlt_global = false; }
@@ -794,7 +792,7 @@ int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out) {
         {"EBITS0", B * Ne * (size_t)h->WPe * 4, h->fused}, {"YBITS0", B * Nc * (size_t)h->WPc * 4, h->fused},
         {"EBITS1", B * Ne * (size_t)h->WPe * 4, h->fused}, {"YBITS1", B * Nc * (size_t)h->WPc * 4, h->fused},
         {"DBG", B * mid2_dbg_floats(h->Ne, h->Nc) * f, h->fused && h->debug},
-        {"CLK", B * 16 * sizeof(long long), h->fused && h->debug},
+        {"CLK", B * 24 * sizeof(long long), h->fused && h->debug},
         {"DLT", B * Nc * (size_t)((h->Nc + 31) / 32 * 32) * f, h->fused && h->dlt_global},
         {"RSE", B * Ne * HD * f, h->edge}, {"CSEP", B * Se * Ne * HD * f, h->edge}, {"CSEF", B * Ne * HD * f, h->edge},
         {"PRE", B * Ne * HD * f, h->edge}, {"PCE", B * Ne * HD * f, h->edge},

@@ -29,6 +29,7 @@ constexpr int M2_NODE_F = 24 + 20 + 24;   // floats per node of that chunk: [S|x
 // The entity block ent_w5 .. nod_b2 and the hunk block hnk_w1 .. scr_b2 are each contiguous in the
 // parameter blob (TF creation order, hdgnn.cu) with every array at a multiple of 4 floats from the
 // block start, so one copy per block keeps every matrix 16-byte aligned in shared memory.
+constexpr int M2_MCLS = 16;               // inline entity stage: most distinct node-attribute values served by the class tables
 constexpr int M2_BLK1 = 400 + 20 + 420 + 20 + 20 + 1;              // 881
 constexpr int M2_BLK2 = 200 + 20 + 400 + 20 + 440 + 20 + 40 + 2;   // 1142
 
@@ -45,13 +46,12 @@ struct Mid2Args {
     float* GE;                               // (B,Ne,20) d/dS1
     float* gpart; int total;                 // (B,total)
     float* dbg;                              // debug dumps (HDGNN_F_DEBUG) or null; layout below
-    long long* clk;                          // per-phase clock64 stamps (B,16) or null
+    long long* clk;                          // per-phase clock64 stamps (B,24) or null
     float* dlt_g;                            // (B, Nc, CW*32) dL/dlogit table in HBM when it does not fit smem, else null
     int scache;                              // keep the entity effect sums S (Ne x 20) in shared memory from the forward to the backward
     int inl;                                 // entity pair layer and its backward INSIDE this kernel (entsp.cuh: sorted prefix sums +
                                              // edge walk): RS1 / CS1p / GE are not used, the step has no ent_fwd2 / ent_bwd2 launch and
                                              // this kernel follows the previous step's optimizer kernel (weights are read after pdl_wait)
-    float* dRS1;                             // debug dump of the row sums (B,Ne,20) when inl, else unused
 };
 // debug dump layout per commit (floats): S1[Ne*20] X2[Ne] NB[Nc*4] RS3[Nc*20] CS3[Nc*20] PR[Nc*20] PC[Nc*20]
 // DNB[Nc*4] DX2[Ne]
@@ -62,6 +62,8 @@ struct Mid2Smem {
     int blk1, blk2, gam, Dh, Dg, G1g, W5U, c1p;   // weight blocks (contiguous copies of the parameter blob), derived tables
     int x, x2, hm, SP, TP, dl, dx2, nb, dnb, ebits, ybits, scratch, red, uni, sc, total;
     int entw, xsort, ordv, sx;               // inline entity stage: U V c D, x sorted, rank -> node, suffix sums of sorted x
+    int rptr, cptr, headrow, headp;          // edge prefix counts by row / by column, head partials of the edge-walk slots
+    int ebt, cls, cval, csize, cmask, cmeta;  // transposed bitmap; attribute classes: class of a node, value / size / node mask of a class
 };
 
 // dlt_smem: keep the per-pair dL/dlogit table of the training path in shared memory (else it lives in HBM / L2)
@@ -73,8 +75,14 @@ __host__ __device__ inline Mid2Smem mid2_layout(int Ne, int Nc, bool train, bool
     m.blk1 = take(M2_BLK1); m.blk2 = take(M2_BLK2); m.gam = take(20); m.Dh = take(20); m.Dg = take(20); m.G1g = take(400);
     m.W5U = take(400); m.c1p = take(20);
     m.x = take(Ne); m.x2 = take(Ne); m.hm = take(Ne);
-    m.entw = m.xsort = m.ordv = m.sx = 0;
-    if (inl) { m.entw = take(4 * HD); m.xsort = take(Ne); m.ordv = take(Ne); m.sx = take(Ne + 1); }
+    m.entw = m.xsort = m.ordv = m.sx = m.rptr = m.cptr = m.headrow = m.headp = 0;
+    m.ebt = m.cls = m.cval = m.csize = m.cmask = m.cmeta = 0;
+    if (inl) {
+        m.entw = take(4 * HD); m.xsort = take(Ne); m.ordv = take(Ne); m.sx = take(Ne + 1);
+        m.rptr = take(Ne + 1); m.cptr = take(Ne + 1); m.headrow = take(M2_T / 10); m.headp = take(M2_T / 10 * HD);
+        m.ebt = take(Ne * bit_words(Ne)); m.cls = take(Ne); m.cval = take(M2_MCLS); m.csize = take(M2_MCLS);
+        m.cmask = take(M2_MCLS * bit_words(Ne)); m.cmeta = take(8);
+    }
     m.dx2 = take(Ne); m.nb = take(4 * Nc); m.dnb = take(4 * Nc);
     m.ebits = take(Ne * bit_words(Ne)); m.ybits = take(Nc * bit_words(Nc));
     const int cwc = (Nc + 31) / 32;
@@ -229,7 +237,7 @@ __device__ __forceinline__ float offdiag_prefix(const float* PV, const float* v,
 // element k of row n of a [n][KG][2][4] table (half 0)
 __device__ __forceinline__ int p01_idx(int n, int k) { return n * PROW + (k >> 2) * 8 + (k & 3); }
 
-#define M2_PHASE(i) do { if (a.clk && tid == 0) a.clk[(size_t)b * 16 + (i)] = clock64(); } while (0)
+#define M2_PHASE(i) do { if (a.clk && tid == 0) a.clk[(size_t)b * 24 + (i)] = clock64(); } while (0)
 
 template <int CWT, bool TRAIN>
 __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
@@ -368,7 +376,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         // (2) degrees (only the closed-form pooling uses them).  Rows: one thread per row.  Columns, bit-sliced: thread
         // (row part, word, k) adds (w >> k) & 0x01010101 over its rows -- four column counters in the bytes of one
         // register -- and the eight row parts are summed per column afterwards.  No votes, no warp reductions.
-        if (ident) {
+        if (ident && !a.inl) {
             for (int i = tid; i < Ne; i += M2_T) {
                 int c = 0;
                 for (int w = 0; w < WU; ++w) c += __popc(ebits[i * WPe + w]);
@@ -384,7 +392,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             }
         }
         __syncthreads();
-        if (ident) {
+        if (ident && !a.inl) {
             for (int j = tid; j < Ne; j += M2_T) {
                 const int sg = j >> 5, bit = j & 31, k = bit & 7, sh = (bit >> 3) * 8;
                 int cd = 0;
@@ -421,23 +429,75 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             }
         }
     }
-    // ---- inline entity stage, input-only half (entsp.cuh): nodes sorted by attribute, suffix sums, transposed bitmap
+    // ---- inline entity stage, input-only half (entsp.cuh): nodes sorted by attribute, suffix sums, transposed bitmap,
+    // edge prefix counts by row and by column
     float* xsort = sm + L_.xsort; int* ordv = reinterpret_cast<int*>(sm + L_.ordv); float* SXs = sm + L_.sx;
-    uint32_t* ebT = reinterpret_cast<uint32_t*>(uni);      // [Ne][WPe]: bit i of row j = A_ij; dead after the entity forward
+    int* rptr = reinterpret_cast<int*>(sm + L_.rptr); int* cptr = reinterpret_cast<int*>(sm + L_.cptr);
+    uint32_t* ebT = reinterpret_cast<uint32_t*>(sm + L_.ebt);      // [Ne][WPe]: bit i of row j = A_ij
+    // attribute classes: the distinct values of x in ascending order.  With at most m_max of them the pair layer is evaluated
+    // from per-class tables and per-(node, class) neighbour counts (popcounts), see below; otherwise by search + edge walk
+    int* clsv = reinterpret_cast<int*>(sm + L_.cls); float* cval = sm + L_.cval; int* csize = reinterpret_cast<int*>(sm + L_.csize);
+    uint32_t* cmask = reinterpret_cast<uint32_t*>(sm + L_.cmask); int* cmeta = reinterpret_cast<int*>(sm + L_.cmeta);
+    // tables (2 m^2 20 floats) + counts (Ne m words) + 8 partial sums per thread must fit the union region
+    const int uni_floats = L_.sc - L_.uni;
+    int m_max = M2_MCLS;
+    while (m_max > 0 && 2 * m_max * m_max * HD + Ne * m_max + 8 * M2_T > uni_floats) --m_max;
     if (a.inl) {
-        for (int i = tid; i < Ne; i += M2_T) {               // stable rank sort: N broadcast reads per node
-            const float xi = xs[i];
-            int r = 0;
-            for (int j = 0; j < Ne; ++j) { const float xj = xs[j]; r += (xj < xi || (xj == xi && j < i)) ? 1 : 0; }
-            xsort[r] = xi; ordv[r] = i;
+        const int WU = (Ne + 31) >> 5;
+        {   // stable rank sort: three threads per node count over a third of the nodes each (integer atomics: exact)
+            int* rk = ordv;                                  // ranks accumulate here, then the rank -> node map replaces them
+            for (int i = tid; i < Ne; i += M2_T) rk[i] = 0;
+            __syncthreads();
+            const int third = (Ne + 2) / 3;
+            for (int t = tid; t < 3 * Ne; t += M2_T) {
+                const int i = t % Ne, part = t / Ne, j0 = part * third, j1 = min(j0 + third, Ne);
+                const float xi = xs[i];
+                int r = 0;
+                for (int j = j0; j < j1; ++j) { const float xj = xs[j]; r += (xj < xi || (xj == xi && j < i)) ? 1 : 0; }
+                atomicAdd(&rk[i], r);
+            }
         }
-        for (int blk = warp; blk < WPe * ((Ne + 31) >> 5); blk += M2_NW) {       // 32 x 32 bit blocks (row block, column word)
+        for (int blk = warp; blk < WPe * WU; blk += M2_NW) {  // 32 x 32 bit blocks (row block, column word)
             const int rb = blk / WPe, cw = blk - rb * WPe, row = rb * 32 + lane;
             const uint32_t w = warp_transpose32(row < Ne ? ebits[row * WPe + cw] : 0u, lane);
             const int col = cw * 32 + lane;
             if (col < Ne) ebT[col * WPe + rb] = w;
         }
         __syncthreads();
+        int myrank = 0;
+        if (tid < Ne) myrank = ordv[tid];
+        for (int i = tid; i < Ne; i += M2_T) {               // out- and in-degrees
+            int rc = 0, cc = 0;
+            for (int w = 0; w < WU; ++w) { rc += __popc(ebits[i * WPe + w]); cc += __popc(ebT[i * WPe + w]); }
+            rptr[i] = rc; cptr[i] = cc;
+        }
+        __syncthreads();
+        if (tid < Ne) { xsort[myrank] = xs[tid]; ordv[myrank] = tid; }
+        if (warp == 1) warp_excl_scan_int(rptr, Ne, lane);
+        if (warp == 2) warp_excl_scan_int(cptr, Ne, lane);
+        for (int e = tid; e < M2_MCLS * WPe; e += M2_T) cmask[e] = 0u;
+        __syncthreads();
+        if (warp == 3) {                                     // class of every rank: runs of equal values in the sorted order
+            const int per = (Ne + 31) >> 5, lo = min(lane * per, Ne), hi = min(lo + per, Ne);
+            int cnt = 0;
+            for (int r = lo; r < hi; ++r) cnt += (r == 0 || xsort[r] != xsort[r - 1]) ? 1 : 0;
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            int c = incl - cnt - 1;                          // class of the rank before this lane's chunk
+            for (int r = lo; r < hi; ++r) {
+                if (r == 0 || xsort[r] != xsort[r - 1]) { ++c; if (c < M2_MCLS) { cval[c] = xsort[r]; csize[c] = r; } }
+                clsv[ordv[r]] = c;
+            }
+            const int m = __shfl_sync(0xffffffffu, incl, 31);
+            __syncwarp();
+            if (lane < M2_MCLS && lane < m) {                // run starts -> sizes
+                const int start = csize[lane], next = lane + 1 < m && lane + 1 < M2_MCLS ? csize[lane + 1] : Ne;
+                __syncwarp();
+                csize[lane] = next - start;
+            } else { __syncwarp(); }
+            if (lane == 0) { cmeta[0] = m; cmeta[1] = (m <= m_max) ? 1 : 0; }
+        }
         if (warp == 0) {                                     // SXs[r] = sum of the sorted attributes from rank r on, SXs[Ne] = 0
             const int per = (Ne + 31) >> 5, lo = min(lane * per, Ne), hi = min(lo + per, Ne);
             float sum = 0.f;
@@ -449,6 +509,17 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             for (int r = hi - 1; r >= lo; --r) { run += xsort[r]; SXs[r] = run; }
             if (lane == 0) SXs[Ne] = 0.f;
         }
+        __syncthreads();
+        if (cmeta[1]) {                                      // node masks of the classes: one ballot per (32 nodes, class)
+            const int m = cmeta[0];
+            for (int w = warp; w < WU; w += M2_NW) {
+                const int node = w * 32 + lane, c = node < Ne ? clsv[node] : -1;
+                for (int bcl = 0; bcl < m; ++bcl) {
+                    const uint32_t bal = __ballot_sync(0xffffffffu, c == bcl);
+                    if (lane == 0) cmask[bcl * WPe + w] = bal;
+                }
+            }
+        }
     }
     __syncthreads();
     pdl_wait();                     // RS1 / CS1p come from ent_fwd2, or (inline entity stage) the weights from the previous step's optimizer
@@ -456,61 +527,148 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
     M2_PHASE(1);
     if (a.inl) {
         load_weights();
+        M2_PHASE(16);
         // ---------------- entity pair layer forward: S_n = sum_{j != n} relu(pre_nj) + sum_{i != n} relu(pre_in) -------------
-        // one owner thread per (node, channel pair): two binary searches per channel, the row walk (edges n -> j) and the
-        // column walk (edges i -> n, transposed bitmap)
-        float* Sall = sm + L_.sc;
-        int P2 = 1;
-        while (P2 <= Ne) P2 <<= 1;
-        const int c0 = 2 * (tid % 10);
-        const float Uc[2] = {wE[c0], wE[c0 + 1]}, Vc[2] = {wE[HD + c0], wE[HD + c0 + 1]};
-        const float Cc[2] = {wE[2 * HD + c0], wE[2 * HD + c0 + 1]}, Dc[2] = {wE[3 * HD + c0], wE[3 * HD + c0 + 1]};
-        const int WU = (Ne + 31) >> 5;
-        for (int n = tid / 10; n < Ne; n += M2_T / 10) {
-            const float xn = xs[n];
-            float pb[2], qb[2], accR[2], accC[2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) { pb[h] = fmaf(xn, Uc[h], Cc[h]); qb[h] = fmaf(xn, Vc[h], Cc[h]); }
-            int r[4] = {0, 0, 0, 0};
-            const float sw[4] = {Vc[0], Vc[1], Uc[0], Uc[1]}, sb[4] = {pb[0], pb[1], qb[0], qb[1]};
-            for (int step = P2 >> 1; step > 0; step >>= 1) {        // the four searches advance together
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int probe = r[u] + step - 1;
-                    const float xv = xsort[probe < Ne ? probe : Ne - 1];
-                    const bool act = fmaf(xv, sw[u], sb[u]) > 0.f;
-                    if (probe < Ne && act != (sw[u] >= 0.f)) r[u] += step;
-                }
+        const bool use_cls = cmeta[1] != 0;
+        if (use_cls) {
+            // CLASS TABLES (at most m_max distinct attribute values).  relu(pre_ij[k]) depends on (class of i, class of j,
+            // l_ij, k) only: H_l[a][b][k] = relu(U_k val_a + V_k val_b + c_k + l D_k).  With c1o(n,b) / c1i(n,b) = number of
+            // out- / in-neighbours of n in class b (popcounts of bitmap row AND class mask) and c0 = |b| - [a == b] - c1,
+            //     S_n[k] = sum_b  c0o H_0[a][b] + c1o H_1[a][b] + c0i H_0[b][a] + c1i H_1[b][a],      a = class of n:
+            // no search, no edge walk, every sum in class order.
+            const int m = cmeta[0];
+            float* H0 = uni; float* H1 = uni + m * m * HD;
+            uint32_t* cnt = reinterpret_cast<uint32_t*>(uni + 2 * m * m * HD);      // [Ne][m]  c1o | c1i << 16
+            for (int e = tid; e < m * m * HD; e += M2_T) {
+                const int k = e % HD, ab = e / HD, bq = ab % m, aq = ab / m;
+                const float t0 = fmaf(cval[bq], wE[HD + k], fmaf(cval[aq], wE[k], wE[2 * HD + k]));
+                H0[e] = fmaxf(t0, 0.f); H1[e] = fmaxf(t0 + wE[3 * HD + k], 0.f);
             }
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                float cnt, sx;
-                entsp_active(r[h], Ne, Vc[h] >= 0.f, SXs, cnt, sx);
-                accR[h] = fmaf(cnt, pb[h], Vc[h] * sx) - fmaxf(fmaf(xn, Vc[h], pb[h]), 0.f);
-                entsp_active(r[2 + h], Ne, Uc[h] >= 0.f, SXs, cnt, sx);
-                accC[h] = fmaf(cnt, qb[h], Uc[h] * sx) - fmaxf(fmaf(xn, Uc[h], qb[h]), 0.f);
-            }
-            for (int w = 0; w < WU; ++w) {
-                uint32_t rowb = ebits[n * WPe + w], colb = ebT[n * WPe + w];
-                while (rowb) {
-                    const int j = (w << 5) + __ffs(rowb) - 1;
-                    rowb &= rowb - 1;
-                    const float xj = xs[j];
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) { const float t0 = fmaf(xj, Vc[h], pb[h]); accR[h] += fmaxf(t0 + Dc[h], 0.f) - fmaxf(t0, 0.f); }
+            const int WU = (Ne + 31) >> 5;
+            for (int e = tid; e < Ne * m; e += M2_T) {
+                const int n = e / m, bq = e - n * m;
+                int co = 0, ci = 0;
+                for (int w = 0; w < WU; ++w) {
+                    const uint32_t mk = cmask[bq * WPe + w];
+                    co += __popc(ebits[n * WPe + w] & mk); ci += __popc(ebT[n * WPe + w] & mk);
                 }
-                while (colb) {
-                    const int i = (w << 5) + __ffs(colb) - 1;
-                    colb &= colb - 1;
-                    const float xi = xs[i];
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) { const float t0 = fmaf(xi, Uc[h], qb[h]); accC[h] += fmaxf(t0 + Dc[h], 0.f) - fmaxf(t0, 0.f); }
-                }
+                cnt[e] = (uint32_t)co | ((uint32_t)ci << 16);
             }
-            *reinterpret_cast<float2*>(Sall + (size_t)n * HD + c0) = make_float2(accR[0] + accC[0], accR[1] + accC[1]);
-            if (dbg && a.dRS1) *reinterpret_cast<float2*>(a.dRS1 + ((size_t)b * Ne + n) * HD + c0) = make_float2(accR[0], accR[1]);
+            __syncthreads();
+            float* Sall = sm + L_.sc;
+            const int c0 = 2 * (tid % 10);
+            for (int n = tid / 10; n < Ne; n += M2_T / 10) {
+                const int aq = clsv[n];
+                float s0 = 0.f, s1 = 0.f;
+                for (int bq = 0; bq < m; ++bq) {
+                    const uint32_t pk = cnt[n * m + bq];
+                    const int c1o = (int)(pk & 0xffffu), c1i = (int)(pk >> 16), tot = csize[bq] - (aq == bq ? 1 : 0);
+                    const float f1o = (float)c1o, f1i = (float)c1i, f0o = (float)(tot - c1o), f0i = (float)(tot - c1i);
+                    const float2 h0ab = *reinterpret_cast<const float2*>(H0 + (aq * m + bq) * HD + c0);
+                    const float2 h1ab = *reinterpret_cast<const float2*>(H1 + (aq * m + bq) * HD + c0);
+                    const float2 h0ba = *reinterpret_cast<const float2*>(H0 + (bq * m + aq) * HD + c0);
+                    const float2 h1ba = *reinterpret_cast<const float2*>(H1 + (bq * m + aq) * HD + c0);
+                    s0 = fmaf(f0o, h0ab.x, s0); s0 = fmaf(f1o, h1ab.x, s0); s0 = fmaf(f0i, h0ba.x, s0); s0 = fmaf(f1i, h1ba.x, s0);
+                    s1 = fmaf(f0o, h0ab.y, s1); s1 = fmaf(f1o, h1ab.y, s1); s1 = fmaf(f0i, h0ba.y, s1); s1 = fmaf(f1i, h1ba.y, s1);
+                }
+                *reinterpret_cast<float2*>(Sall + (size_t)n * HD + c0) = make_float2(s0, s1);
+            }
+            __syncthreads();
+        } else {
+            // GENERAL attributes: sorted prefix sums for the l = 0 part, edge walk for the l = 1 pairs (entsp.cuh)
+            // dense (l = 0) part: one owner thread per (node, channel pair), two binary searches per channel
+            float* Sall = sm + L_.sc;
+            int* headrow = reinterpret_cast<int*>(sm + L_.headrow); float* headp = sm + L_.headp;
+            int P2 = 1;
+            while (P2 <= Ne) P2 <<= 1;
+            constexpr int NSLOT = M2_T / 10;
+            const int slot = tid / 10, c0 = 2 * (tid % 10);
+            const float Uc[2] = {wE[c0], wE[c0 + 1]}, Vc[2] = {wE[HD + c0], wE[HD + c0 + 1]};
+            const float Cc[2] = {wE[2 * HD + c0], wE[2 * HD + c0 + 1]}, Dc[2] = {wE[3 * HD + c0], wE[3 * HD + c0 + 1]};
+            const int WU = (Ne + 31) >> 5;
+            for (int n = slot; n < Ne; n += NSLOT) {
+                const float xn = xs[n];
+                float pb[2], qb[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) { pb[h] = fmaf(xn, Uc[h], Cc[h]); qb[h] = fmaf(xn, Vc[h], Cc[h]); }
+                int r[4] = {0, 0, 0, 0};
+                const float sw[4] = {Vc[0], Vc[1], Uc[0], Uc[1]}, sb[4] = {pb[0], pb[1], qb[0], qb[1]};
+                for (int step = P2 >> 1; step > 0; step >>= 1) {        // the four searches advance together
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int probe = r[u] + step - 1;
+                        const float xv = xsort[probe < Ne ? probe : Ne - 1];
+                        const bool act = fmaf(xv, sw[u], sb[u]) > 0.f;
+                        if (probe < Ne && act != (sw[u] >= 0.f)) r[u] += step;
+                    }
+                }
+                float acc[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float cnt, sx;
+                    entsp_active(r[h], Ne, Vc[h] >= 0.f, SXs, cnt, sx);
+                    acc[h] = fmaf(cnt, pb[h], Vc[h] * sx) - fmaxf(fmaf(xn, Vc[h], pb[h]), 0.f);
+                    entsp_active(r[2 + h], Ne, Uc[h] >= 0.f, SXs, cnt, sx);
+                    acc[h] += fmaf(cnt, qb[h], Uc[h] * sx) - fmaxf(fmaf(xn, Uc[h], qb[h]), 0.f);
+                }
+                *reinterpret_cast<float2*>(Sall + (size_t)n * HD + c0) = make_float2(acc[0], acc[1]);
+            }
+            __syncthreads();
+            M2_PHASE(20);
+            // l = 1 pairs, edge by edge: pass 0 walks the rows (edges n -> j add to S_n), pass 1 the transposed bitmap (edges
+            // i -> n).  Every slot of 10 threads takes an equal share of the edges in row-major order; a slot adds the sums of
+            // the rows that START inside its share directly, the partial sum of its first row goes through headp and is
+            // added afterwards in slot order (fixed order, one writer per row at a time).
+            for (int pass = 0; pass < 2; ++pass) {
+                const uint32_t* bm = pass ? ebT : ebits;
+                const int* ptr = pass ? cptr : rptr;
+                const float Wo[2] = {pass ? Vc[0] : Uc[0], pass ? Vc[1] : Uc[1]}, Wn[2] = {pass ? Uc[0] : Vc[0], pass ? Uc[1] : Vc[1]};
+                const int nnz = ptr[Ne], per = (nnz + NSLOT - 1) / NSLOT, e0 = min(slot * per, nnz), e1 = min(e0 + per, nnz);
+                int hrow = -1;
+                float h0 = 0.f, h1 = 0.f;
+                if (e1 > e0) {
+                    const EdgeCursor cur = edge_seek(bm, WPe, ptr, Ne, P2, e0);
+                    int row = cur.row, w = cur.w;
+                    uint32_t bits = cur.bits;
+                    float xo = xs[row], b0 = fmaf(xo, Wo[0], Cc[0]), b1 = fmaf(xo, Wo[1], Cc[1]), a0 = 0.f, a1 = 0.f;
+                    bool first = true;
+                    for (int e = e0; e < e1; ++e) {
+                        while (!bits) {
+                            if (++w == WU) {
+                                if (first) { hrow = row; h0 = a0; h1 = a1; first = false; }
+                                else { float2* d = reinterpret_cast<float2*>(Sall + (size_t)row * HD + c0); const float2 o = *d; *d = make_float2(o.x + a0, o.y + a1); }
+                                a0 = 0.f; a1 = 0.f; w = 0; ++row;
+                                xo = xs[row]; b0 = fmaf(xo, Wo[0], Cc[0]); b1 = fmaf(xo, Wo[1], Cc[1]);
+                            }
+                            bits = bm[row * WPe + w];
+                        }
+                        const float xv = xs[(w << 5) + __ffs(bits) - 1];
+                        bits &= bits - 1;
+                        const float t0 = fmaf(xv, Wn[0], b0), t1 = fmaf(xv, Wn[1], b1);
+                        a0 += fmaxf(t0 + Dc[0], 0.f) - fmaxf(t0, 0.f);
+                        a1 += fmaxf(t1 + Dc[1], 0.f) - fmaxf(t1, 0.f);
+                    }
+                    if (first) { hrow = row; h0 = a0; h1 = a1; }
+                    else { float2* d = reinterpret_cast<float2*>(Sall + (size_t)row * HD + c0); const float2 o = *d; *d = make_float2(o.x + a0, o.y + a1); }
+                }
+                if (c0 == 0) headrow[slot] = hrow;
+                *reinterpret_cast<float2*>(headp + slot * HD + c0) = make_float2(h0, h1);
+                __syncthreads();
+                if (hrow >= 0 && (slot == 0 || headrow[slot - 1] != hrow)) {
+                    float s0 = 0.f, s1 = 0.f;
+                    for (int t = slot; t < NSLOT && headrow[t] == hrow; ++t) {
+                        const float2 v = *reinterpret_cast<const float2*>(headp + t * HD + c0);
+                        s0 += v.x; s1 += v.y;
+                    }
+                    float2* d = reinterpret_cast<float2*>(Sall + (size_t)hrow * HD + c0);
+                    const float2 o = *d;
+                    *d = make_float2(o.x + s0, o.y + s1);
+                }
+                __syncthreads();
+                M2_PHASE(21 + pass);
+            }
         }
-        __syncthreads();
+        M2_PHASE(17);
     }
 
     // ---------------- B/C. entity-state MLP forward: two threads per entity (10 hidden units each) ----------
@@ -593,8 +751,9 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         const float X = mid2_block_sum(part, red);
         M2_PHASE(13);
         M2_PHASE(14);
-        for (int i = tid; i < Ne; i += M2_T) {              // degrees are in SP[.][3] / TP[.][3] (computed before the wait)
-            const float xi = x2[i], fn = (float)nm1;
+        for (int i = tid; i < Ne; i += M2_T) {              // degrees: SP[.][3] / TP[.][3] (computed before the wait), or the edge
+            const float xi = x2[i], fn = (float)nm1;        // prefix counts of the inline entity stage
+            if (a.inl) { SP[4 * i + 3] = (float)(rptr[i + 1] - rptr[i]); TP[4 * i + 3] = (float)(cptr[i + 1] - cptr[i]); }
             SP[4 * i] = fn * xi; SP[4 * i + 1] = X - xi; SP[4 * i + 2] = fn - SP[4 * i + 3];
             TP[4 * i] = X - xi; TP[4 * i + 1] = fn * xi; TP[4 * i + 2] = fn - TP[4 * i + 3];
         }
@@ -1281,77 +1440,153 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         // ---------------- entity pair layer backward (entsp.cuh): first-layer weight gradients from GE ---------------------
         // v_ij[k] = [pre_ij[k] > 0] (GE_i[k] + GE_j[k]);  db = sum v, dU = sum x_i v, dV = sum x_j v, LS = sum over l_ij = 1
         __syncthreads();
+        M2_PHASE(18);
         const float* GEs = sm + L_.sc;
-        float* SGs = uni;                                   // [20][Ne + 1] suffix sums of GE over the sorted order, per channel
-        float* part = uni + 20 * (Ne + 1) + ((20 * (Ne + 1)) & 1);   // [M2_T][8] per-thread partial sums (8-byte aligned)
-        {
-            const int k = warp;                             // M2_NW == HD: one warp per channel
-            const int per = (Ne + 31) >> 5, lo = min(lane * per, Ne), hi = min(lo + per, Ne);
-            float sum = 0.f;
-            for (int r = hi - 1; r >= lo; --r) sum += GEs[(size_t)ordv[r] * HD + k];
-            float incl = sum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_down_sync(0xffffffffu, incl, o); if (lane + o < 32) incl += t; }
-            float run = incl - sum;
-            float* dst = SGs + (size_t)k * (Ne + 1);
-            for (int r = hi - 1; r >= lo; --r) { run += GEs[(size_t)ordv[r] * HD + k]; dst[r] = run; }
-            if (lane == 0) dst[Ne] = 0.f;
-        }
-        __syncthreads();
-        int P2 = 1;
-        while (P2 <= Ne) P2 <<= 1;
-        const int c0 = 2 * (tid % 10);
-        const float Uc[2] = {wE[c0], wE[c0 + 1]}, Vc[2] = {wE[HD + c0], wE[HD + c0 + 1]};
-        const float Cc[2] = {wE[2 * HD + c0], wE[2 * HD + c0 + 1]}, Dc[2] = {wE[3 * HD + c0], wE[3 * HD + c0 + 1]};
-        const int WU = (Ne + 31) >> 5;
+        const bool use_cls = cmeta[1] != 0;
+        const int mcl = cmeta[0];
+        float* SGs = uni;                                   // general path: [20][Ne + 1] suffix sums of GE over the sorted order, per channel
+        // [M2_T][8] per-thread partial sums behind the path's tables
+        float* part = uni + (use_cls ? ((2 * mcl * mcl * HD + Ne * mcl + 3) & ~3) : 20 * (Ne + 1));
         float db[2] = {0.f, 0.f}, dU[2] = {0.f, 0.f}, dV[2] = {0.f, 0.f}, LS[2] = {0.f, 0.f};
-        for (int n = tid / 10; n < Ne; n += M2_T / 10) {
-            const float xn = xs[n];
-            const float2 gn2 = *reinterpret_cast<const float2*>(GEs + (size_t)n * HD + c0);
-            const float gn[2] = {gn2.x, gn2.y};
-            float pb[2], qb[2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) { pb[h] = fmaf(xn, Uc[h], Cc[h]); qb[h] = fmaf(xn, Vc[h], Cc[h]); }
-            int r[4] = {0, 0, 0, 0};
-            const float sw[4] = {Vc[0], Vc[1], Uc[0], Uc[1]}, sb[4] = {pb[0], pb[1], qb[0], qb[1]};
-            for (int step = P2 >> 1; step > 0; step >>= 1) {        // same predicate as the forward: identical gates
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int probe = r[u] + step - 1;
-                    const float xv = xsort[probe < Ne ? probe : Ne - 1];
-                    const bool act = fmaf(xv, sw[u], sb[u]) > 0.f;
-                    if (probe < Ne && act != (sw[u] >= 0.f)) r[u] += step;
+        if (use_cls) {
+            // CLASS TABLES: v_ij[k] = g_l[a][b][k] (GE_i[k] + GE_j[k]) with the 0/1 gates g_l[a][b][k] = [H_l[a][b][k] > 0].  All four
+            // results are sums over pairs, so with the number of active pairs per node,
+            //   Wrow_i = sum_j g_ij,  XWrow_i = sum_j x_j g_ij,  W1row_i = sum_{l_ij = 1} g_ij   (and the column forms over i),
+            //   db = sum_n GE_n (Wrow_n + Wcol_n),      dU = sum_n GE_n (x_n Wrow_n + XWcol_n),
+            //   dV = sum_n GE_n (XWrow_n + x_n Wcol_n), LS = sum_n GE_n (W1row_n + W1col_n),
+            // and the W's come from the same neighbour counts as the forward.
+            const int m = mcl;
+            float* G0 = uni; float* G1t = uni + m * m * HD;
+            uint32_t* cnt = reinterpret_cast<uint32_t*>(uni + 2 * m * m * HD);
+            for (int e = tid; e < m * m * HD; e += M2_T) {
+                const int k = e % HD, ab = e / HD, bq = ab % m, aq = ab / m;
+                const float t0 = fmaf(cval[bq], wE[HD + k], fmaf(cval[aq], wE[k], wE[2 * HD + k]));      // as in the forward: same gates
+                G0[e] = t0 > 0.f ? 1.f : 0.f; G1t[e] = (t0 + wE[3 * HD + k]) > 0.f ? 1.f : 0.f;
+            }
+            const int WU = (Ne + 31) >> 5;
+            for (int e = tid; e < Ne * m; e += M2_T) {
+                const int n = e / m, bq = e - n * m;
+                int co = 0, ci = 0;
+                for (int w = 0; w < WU; ++w) {
+                    const uint32_t mk = cmask[bq * WPe + w];
+                    co += __popc(ebits[n * WPe + w] & mk); ci += __popc(ebT[n * WPe + w] & mk);
                 }
+                cnt[e] = (uint32_t)co | ((uint32_t)ci << 16);
             }
-            float rsd[2], csd[2], dvx[2] = {0.f, 0.f}, ls[2] = {0.f, 0.f};
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                float cnt, sg;
-                entsp_active(r[h], Ne, Vc[h] >= 0.f, SGs + (size_t)(c0 + h) * (Ne + 1), cnt, sg);
-                rsd[h] = fmaf(cnt, gn[h], sg) - (fmaf(xn, Vc[h], pb[h]) > 0.f ? 2.f * gn[h] : 0.f);
-                entsp_active(r[2 + h], Ne, Uc[h] >= 0.f, SGs + (size_t)(c0 + h) * (Ne + 1), cnt, sg);
-                csd[h] = fmaf(cnt, gn[h], sg) - (fmaf(xn, Uc[h], qb[h]) > 0.f ? 2.f * gn[h] : 0.f);
-            }
-            for (int w = 0; w < WU; ++w) {
-                uint32_t rowb = ebits[n * WPe + w];
-                while (rowb) {
-                    const int j = (w << 5) + __ffs(rowb) - 1;
-                    rowb &= rowb - 1;
-                    const float xj = xs[j];
-                    const float2 gj = *reinterpret_cast<const float2*>(GEs + (size_t)j * HD + c0);
-                    const float gjv[2] = {gj.x, gj.y};
+            __syncthreads();
+            M2_PHASE(19);
+            const int c0 = 2 * (tid % 10);
+            for (int n = tid / 10; n < Ne; n += M2_T / 10) {
+                const int aq = clsv[n];
+                const float xn = xs[n];
+                const float2 gn = *reinterpret_cast<const float2*>(GEs + (size_t)n * HD + c0);
+                float wr[2] = {0.f, 0.f}, xwr[2] = {0.f, 0.f}, w1r[2] = {0.f, 0.f}, wc[2] = {0.f, 0.f}, xwc[2] = {0.f, 0.f}, w1c[2] = {0.f, 0.f};
+                for (int bq = 0; bq < m; ++bq) {
+                    const uint32_t pk = cnt[n * m + bq];
+                    const int c1o = (int)(pk & 0xffffu), c1i = (int)(pk >> 16), tot = csize[bq] - (aq == bq ? 1 : 0);
+                    const float f1o = (float)c1o, f1i = (float)c1i, f0o = (float)(tot - c1o), f0i = (float)(tot - c1i), vb = cval[bq];
+                    const float2 g0ab = *reinterpret_cast<const float2*>(G0 + (aq * m + bq) * HD + c0);
+                    const float2 g1ab = *reinterpret_cast<const float2*>(G1t + (aq * m + bq) * HD + c0);
+                    const float2 g0ba = *reinterpret_cast<const float2*>(G0 + (bq * m + aq) * HD + c0);
+                    const float2 g1ba = *reinterpret_cast<const float2*>(G1t + (bq * m + aq) * HD + c0);
+                    const float a0[2] = {g0ab.x, g0ab.y}, a1[2] = {g1ab.x, g1ab.y}, b0[2] = {g0ba.x, g0ba.y}, b1[2] = {g1ba.x, g1ba.y};
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const float t0 = fmaf(xj, Vc[h], pb[h]), g = gn[h] + gjv[h];
-                        const float v1 = (t0 + Dc[h]) > 0.f ? g : 0.f, v0 = t0 > 0.f ? g : 0.f;
-                        const float dlt_e = v1 - v0;
-                        rsd[h] += dlt_e; dvx[h] = fmaf(xj, dlt_e, dvx[h]); ls[h] += v1;
+                        const float l1o = f1o * a1[h], ro = fmaf(f0o, a0[h], l1o), l1i = f1i * b1[h], ci2 = fmaf(f0i, b0[h], l1i);
+                        wr[h] += ro; xwr[h] = fmaf(vb, ro, xwr[h]); w1r[h] += l1o;
+                        wc[h] += ci2; xwc[h] = fmaf(vb, ci2, xwc[h]); w1c[h] += l1i;
                     }
                 }
-            }
+                const float gv[2] = {gn.x, gn.y};
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                db[h] += rsd[h]; dU[h] = fmaf(xn, rsd[h], dU[h]); dV[h] += fmaf(xn, csd[h], dvx[h]); LS[h] += ls[h];
+                for (int h = 0; h < 2; ++h) {
+                    db[h] = fmaf(gv[h], wr[h] + wc[h], db[h]);
+                    dU[h] = fmaf(gv[h], fmaf(xn, wr[h], xwc[h]), dU[h]);
+                    dV[h] = fmaf(gv[h], fmaf(xn, wc[h], xwr[h]), dV[h]);
+                    LS[h] = fmaf(gv[h], w1r[h] + w1c[h], LS[h]);
+                }
+            }
+        } else {
+            {
+                const int k = warp;                             // M2_NW == HD: one warp per channel
+                const int per = (Ne + 31) >> 5, lo = min(lane * per, Ne), hi = min(lo + per, Ne);
+                float sum = 0.f;
+                for (int r = hi - 1; r >= lo; --r) sum += GEs[(size_t)ordv[r] * HD + k];
+                float incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_down_sync(0xffffffffu, incl, o); if (lane + o < 32) incl += t; }
+                float run = incl - sum;
+                float* dst = SGs + (size_t)k * (Ne + 1);
+                for (int r = hi - 1; r >= lo; --r) { run += GEs[(size_t)ordv[r] * HD + k]; dst[r] = run; }
+                if (lane == 0) dst[Ne] = 0.f;
+            }
+            __syncthreads();
+            M2_PHASE(19);
+            int P2 = 1;
+            while (P2 <= Ne) P2 <<= 1;
+            constexpr int NSLOT = M2_T / 10;
+            const int slot = tid / 10, c0 = 2 * (tid % 10);
+            const float Uc[2] = {wE[c0], wE[c0 + 1]}, Vc[2] = {wE[HD + c0], wE[HD + c0 + 1]};
+            const float Cc[2] = {wE[2 * HD + c0], wE[2 * HD + c0 + 1]}, Dc[2] = {wE[3 * HD + c0], wE[3 * HD + c0 + 1]};
+            const int WU = (Ne + 31) >> 5;
+            for (int n = slot; n < Ne; n += NSLOT) {             // dense (l = 0) part
+                const float xn = xs[n];
+                const float2 gn2 = *reinterpret_cast<const float2*>(GEs + (size_t)n * HD + c0);
+                const float gn[2] = {gn2.x, gn2.y};
+                float pb[2], qb[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) { pb[h] = fmaf(xn, Uc[h], Cc[h]); qb[h] = fmaf(xn, Vc[h], Cc[h]); }
+                int r[4] = {0, 0, 0, 0};
+                const float sw[4] = {Vc[0], Vc[1], Uc[0], Uc[1]}, sb[4] = {pb[0], pb[1], qb[0], qb[1]};
+                for (int step = P2 >> 1; step > 0; step >>= 1) {        // same predicate as the forward: identical gates
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int probe = r[u] + step - 1;
+                        const float xv = xsort[probe < Ne ? probe : Ne - 1];
+                        const bool act = fmaf(xv, sw[u], sb[u]) > 0.f;
+                        if (probe < Ne && act != (sw[u] >= 0.f)) r[u] += step;
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float cnt, sg;
+                    entsp_active(r[h], Ne, Vc[h] >= 0.f, SGs + (size_t)(c0 + h) * (Ne + 1), cnt, sg);
+                    const float rsd = fmaf(cnt, gn[h], sg) - (fmaf(xn, Vc[h], pb[h]) > 0.f ? 2.f * gn[h] : 0.f);
+                    entsp_active(r[2 + h], Ne, Uc[h] >= 0.f, SGs + (size_t)(c0 + h) * (Ne + 1), cnt, sg);
+                    const float csd = fmaf(cnt, gn[h], sg) - (fmaf(xn, Uc[h], qb[h]) > 0.f ? 2.f * gn[h] : 0.f);
+                    db[h] += rsd; dU[h] = fmaf(xn, rsd, dU[h]); dV[h] = fmaf(xn, csd, dV[h]);
+                }
+            }
+            {   // l = 1 pairs: every slot walks an equal share of the edges; all four results are sums over edges
+                const int nnz = rptr[Ne], per = (nnz + NSLOT - 1) / NSLOT, e0 = min(slot * per, nnz), e1 = min(e0 + per, nnz);
+                if (e1 > e0) {
+                    const EdgeCursor cur = edge_seek(ebits, WPe, rptr, Ne, P2, e0);
+                    int row = cur.row, w = cur.w;
+                    uint32_t bits = cur.bits;
+                    float xo = xs[row], b0 = fmaf(xo, Uc[0], Cc[0]), b1 = fmaf(xo, Uc[1], Cc[1]);
+                    float2 go = *reinterpret_cast<const float2*>(GEs + (size_t)row * HD + c0);
+                    for (int e = e0; e < e1; ++e) {
+                        while (!bits) {
+                            if (++w == WU) {
+                                w = 0; ++row;
+                                xo = xs[row]; b0 = fmaf(xo, Uc[0], Cc[0]); b1 = fmaf(xo, Uc[1], Cc[1]);
+                                go = *reinterpret_cast<const float2*>(GEs + (size_t)row * HD + c0);
+                            }
+                            bits = ebits[row * WPe + w];
+                        }
+                        const int j = (w << 5) + __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        const float xj = xs[j];
+                        const float2 gj = *reinterpret_cast<const float2*>(GEs + (size_t)j * HD + c0);
+                        const float t0 = fmaf(xj, Vc[0], b0), t1 = fmaf(xj, Vc[1], b1), g0 = go.x + gj.x, g1 = go.y + gj.y;
+                        const float v10 = (t0 + Dc[0]) > 0.f ? g0 : 0.f, v11 = (t1 + Dc[1]) > 0.f ? g1 : 0.f;
+                        const float d0 = v10 - (t0 > 0.f ? g0 : 0.f), d1 = v11 - (t1 > 0.f ? g1 : 0.f);
+                        db[0] += d0; db[1] += d1;
+                        dU[0] = fmaf(xo, d0, dU[0]); dU[1] = fmaf(xo, d1, dU[1]);
+                        dV[0] = fmaf(xj, d0, dV[0]); dV[1] = fmaf(xj, d1, dV[1]);
+                        LS[0] += v10; LS[1] += v11;
+                    }
+                }
             }
         }
         *reinterpret_cast<float4*>(part + (size_t)tid * 8) = make_float4(db[0], db[1], dU[0], dU[1]);
@@ -1360,7 +1595,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         if (tid < 4 * HD) {                                 // fixed-order sum over the 64 threads that own a channel pair
             const int qn = tid / HD, k = tid - qn * HD, kp = k >> 1, hh = k & 1;
             float t = 0.f;
-            for (int s2 = 0; s2 < M2_T / 10; ++s2) t += part[(size_t)(kp + 10 * s2) * 8 + 2 * qn + hh];
+            for (int s2 = 0; s2 < M2_T / 10; ++s2) t += part[(size_t)(kp + 10 * s2) * 8 + 2 * qn + hh];      // slot order
             red[tid] = t;
         }
         __syncthreads();

@@ -13,7 +13,7 @@ params = (0.1 * torch.randn(eng.n_params)).cuda()
 for _ in range(3):
     eng.forward_backward(db, params)
 torch.cuda.synchronize()
-clk = eng.workspace("CLK", (B, 16), dtype=torch.int64).cpu().numpy()
+clk = eng.workspace("CLK", (B, 24), dtype=torch.int64).cpu().numpy()
 names = ["A load", "B node fwd", "D pool fwd", "tables+E hunk fwd", "F head tables", "G1 head", "G2 delta sums", "H head bwd",
          "I hunk bwd", "J+K pool bwd", "L node bwd"]
 d = np.diff(clk[:, :12], axis=1)
@@ -32,5 +32,12 @@ print("ident D: X sum (2->13) %.0f | degrees (13->14) %.0f | fill (14->15) %.0f 
 if g.any():
     print("general D: seg reduce (15->3) %.0f" % (clk[g, 3] - clk[g, 15]).mean())
 print("ident commits: J (9->12) %.0f | K (12->10) %.0f" % ((clk[ident, 12] - clk[ident, 9]).mean(), (clk[ident, 10] - clk[ident, 12]).mean()))
+if clk[:, 16].any():
+    print("inline entity stage: prologue incl. sort (0->1) %.0f | weights (1->16) %.0f | fwd items (16->17) %.0f | node fwd (17->2) %.0f | L (10->18) %.0f | SG scan (18->19) %.0f | bwd items+reduce (19->11) %.0f" % (
+        (clk[:, 1] - clk[:, 0]).mean(), (clk[:, 16] - clk[:, 1]).mean(), (clk[:, 17] - clk[:, 16]).mean(), (clk[:, 2] - clk[:, 17]).mean(),
+        (clk[:, 18] - clk[:, 10]).mean(), (clk[:, 19] - clk[:, 18]).mean(), (clk[:, 11] - clk[:, 19]).mean()))
+if clk[:, 16].any():
+    print("  fwd items: dense part (16->20) %.0f | row walk (20->21) %.0f | column walk (21->22) %.0f" % (
+        (clk[:, 20] - clk[:, 16]).mean(), (clk[:, 21] - clk[:, 20]).mean(), (clk[:, 22] - clk[:, 21]).mean()))
 tot = clk[:, 11] - clk[:, 0]
 print(f"total mean {tot.mean():.0f} max {tot.max():.0f} cycles")
