@@ -7,7 +7,7 @@ import os
 
 from .build import LIB
 
-OK, E_INVALID, E_CUDA, E_NOMEM, E_UNSUPPORTED = 0, -1, -2, -3, -4
+OK, E_INVALID, E_CUDA, E_NOMEM, E_UNSUPPORTED, E_PEER = 0, -1, -2, -3, -4, -5
 MAX_N = 512
 
 
@@ -46,6 +46,8 @@ def _load():
         "hdgnn_forward_backward_host": ([vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp], i32),
         "hdgnn_peer_export": ([vp, i32, vp], i32),
         "hdgnn_peer_attach": ([vp, i32, i32, vp], i32),
+        "hdgnn_peer_status": ([vp], i32),
+        "hdgnn_set_hits_accumulator": ([vp, vp], i32),
         "hdgnn_train_step_peer": ([vp, i32, i32, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, f32, f32, f32, f32, vp, vp, vp, vp], i32),
         "hdgnn_train_step_peer_host": ([vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, f32, f32, f32, vp, vp, vp], i32),
         "hdgnn_infer_host": ([vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp], i32),
@@ -60,6 +62,7 @@ def _load():
         "hdgnn_profile_count": ([vp], i32),
         "hdgnn_profile_get": ([vp, i32, C.c_char_p, i32, C.POINTER(f32)], i32),
         "hdgnn_last_launch_count": ([vp], i32),
+        "hdgnn_measure_fp32_peak": ([i32, C.POINTER(f32)], i32),
     }
     for name, (argtypes, restype) in sig.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported

@@ -27,22 +27,24 @@ struct PeerArgs {
     peer_word* inbox[PEER_MAX];  // mailbox of rank r as mapped into this process (own entry = local pointer)
     peer_word* lossin[PEER_MAX];
     int* seq;                    // device counter: exchanges completed so far (local)
-    int* error;                  // set to 1 when a wait timed out
+    int* error;                  // set to 1 when a wait timed out (hdgnn_peer_status reads it)
+    unsigned int max_spins;      // polls of ~1 us before a wait gives up (HDGNN_PEER_TIMEOUT_MS, default 20 s)
 };
 
 __device__ __forceinline__ void peer_push(peer_word* p, float v, int seq) {
     const peer_word w = ((peer_word)(unsigned int)seq << 32) | (peer_word)__float_as_uint(v);
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
 }
-// Bounded wait: a lost peer traps instead of hanging the GPU.
-__device__ __forceinline__ float peer_pull(const peer_word* p, int seq, int* error) {
+// Bounded wait: a lost or very late peer sets the error flag and the wait returns 0 (the step's result is then
+// meaningless, but the context survives: the host sees the flag through hdgnn_peer_status and raises).
+__device__ __forceinline__ float peer_pull(const peer_word* p, int seq, int* error, unsigned int max_spins) {
     peer_word w;
     unsigned int spin = 0;
     for (;;) {
         asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
         if ((int)(w >> 32) == seq) break;
-        if (++spin > (1u << 24)) { *error = 1; __threadfence_system(); __trap(); }
-        __nanosleep(32);
+        if (++spin > max_spins || *reinterpret_cast<volatile int*>(error)) { *error = 1; return 0.f; }
+        __nanosleep(spin < 64 ? 32 : 1000);
     }
     return __uint_as_float((unsigned int)(w & 0xffffffffu));
 }
@@ -70,7 +72,7 @@ __device__ __forceinline__ float adam_lr_t(float lr, float b1, float b2, int t) 
     return lr * sqrtf(omb2) / omb1;
 }
 
-constexpr int FIN_P = 64;    // parameters per CTA
+constexpr int FIN_P = 16;    // parameters per CTA: ~133 small CTAs, every thread has all its loads in flight at once (one L2 round trip)
 constexpr int FIN_SL = 16;   // commit slices per parameter
 
 __device__ __forceinline__ float rank1_extra(const Rank1Map& r, int p, int slice, int nslice) {
@@ -166,7 +168,7 @@ __global__ void __launch_bounds__(FIN_P * FIN_SL) reduce_adam_kernel(const Final
         if (sl < W && p < a.total) peer_push(pr.inbox[sl] + (slot + pr.rank) * pr.stride + p, mine, seq);
         if (blockIdx.x == 0 && tid < W && a.loss) peer_push(pr.lossin[tid] + slot + pr.rank, ce_sh, seq);
         __syncthreads();                                   // part[0][] has been read
-        part[sl][pl] = (sl < W && p < a.total) ? peer_pull(pr.inbox[pr.rank] + (slot + sl) * pr.stride + p, seq, pr.error) : 0.f;
+        part[sl][pl] = (sl < W && p < a.total) ? peer_pull(pr.inbox[pr.rank] + (slot + sl) * pr.stride + p, seq, pr.error, pr.max_spins) : 0.f;
         __syncthreads();
         if (sl == 0 && p < a.total) {
             g = 0.f;
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(FIN_P * FIN_SL) reduce_adam_kernel(const Final
         }
         if (blockIdx.x == 0 && tid == 0 && a.loss) {
             float c = 0.f;
-            for (int r = 0; r < W; ++r) c += peer_pull(pr.lossin[pr.rank] + slot + r, seq, pr.error);
+            for (int r = 0; r < W; ++r) c += peer_pull(pr.lossin[pr.rank] + slot + r, seq, pr.error, pr.max_spins);
             *a.loss = c;                                   // global mean CE
         }
         // *pr.seq is advanced by the last CTA of the optimizer tail below: by then every CTA has read it

@@ -126,6 +126,12 @@ struct hdgnn_handle_s {
     size_t peer_bytes = 0;
     int peer_world = 0;
     bool peer_ready = false;
+    // host-fed steps whose first kernel is mid2: that kernel polls a tag the copy stream's last DMA writes (no event wait on
+    // the caller's stream, which would break the programmatic launch chain optimizer -> mid2)
+    unsigned long long* hits_acc = nullptr;   // hdgnn_set_hits_accumulator
+    uint32_t* tag_table = nullptr;         // pinned, tag_table[i] = i: immutable DMA source
+    unsigned int slot_uses[2] = {0, 0};
+    int cur_tag = -1;                      // tag of the staging slot filled by the last stage_inputs call, -1 = ordered by event
     // HDGNN_F_LABEL_BITS: the *_host entry points receive label bitmaps (bits.cuh layout) instead of byte grids
     bool host_bits = false;
     const uint32_t* eb = nullptr; const uint32_t* yb = nullptr;   // bitmaps of the current step
@@ -292,6 +298,7 @@ struct Inputs {
     const uint8_t* adj; const float* x; const int32_t* hmap; const int32_t* L; const uint8_t* Y;
     const float* params;
     const uint32_t* ebits = nullptr; const uint32_t* ybits = nullptr;   // set: bitmaps are given, adj / Y are not read (fused path)
+    const int* wait_flag = nullptr; int wait_tag = 0;                    // staged inputs ordered by a DMA-written tag (mid2 polls it)
 };
 
 // HDGNN_F_LABEL_BITS: the adj / Y arguments of the device entry points ARE the bitmaps
@@ -583,6 +590,8 @@ int fused_forward(hdgnn_handle_t h, int B, int B_global, const Inputs& in, float
     m.dlt_g = dlt_g ? F(h, "DLT") : nullptr;
     m.scache = ((train && h->ent && h->mid_scache) || h->inl) ? 1 : 0;
     m.inl = h->inl ? 1 : 0;
+    m.wait_flag = in.wait_flag; m.wait_tag = in.wait_tag;
+    m.hits_acc = h->hits_acc;
     const size_t smem = mid2_smem_bytes(h->Ne, h->Nc, train, !dlt_g, m.scache != 0, h->inl);
     const int cwc = (h->Nc + 31) / 32;
     PROF_BEGIN(h, st);
@@ -810,7 +819,7 @@ int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out) {
         {"H_HMAP1", B * Ne * sizeof(int32_t), true}, {"H_L1", B * sizeof(int32_t), true},
         {"H_EBITS0", B * Ne * (size_t)h->WPe * 4, h->host_bits}, {"H_YBITS0", B * Nc * (size_t)h->WPc * 4, h->host_bits},
         {"H_EBITS1", B * Ne * (size_t)h->WPe * 4, h->host_bits}, {"H_YBITS1", B * Nc * (size_t)h->WPc * 4, h->host_bits},
-        {"H_PROBS", B * 2 * Nc * (Nc - 1) * f, true}, {"H_LOSS", 4 * f, true}, {"H_GRADS", (size_t)h->po.total * f, true},
+        {"H_FLAG", 16, true}, {"H_PROBS", B * 2 * Nc * (Nc - 1) * f, true}, {"H_LOSS", 4 * f, true}, {"H_GRADS", (size_t)h->po.total * f, true},
     };
     for (auto& p : plan) {
         if (!p.need) continue;
@@ -822,6 +831,9 @@ int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out) {
         }
     }
     bool ok = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    if (ok && env_int("HDGNN_TAG_WAIT", 1) != 0 && cudaHostAlloc((void**)&h->tag_table, 256 * sizeof(uint32_t), cudaHostAllocDefault) == cudaSuccess) {
+        for (int i = 0; i < 256; ++i) h->tag_table[i] = (uint32_t)i;
+    } else { cudaGetLastError(); h->tag_table = nullptr; }
     for (int i = 0; i < 2 && ok; ++i)
         ok = cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming) == cudaSuccess;
@@ -840,6 +852,7 @@ int hdgnn_destroy(hdgnn_handle_t h) {
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
     for (int i = 0; i < 2; ++i) { if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]); if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]); }
     for (auto& kv : h->ws) cudaFree(kv.second.p);
+    if (h->tag_table) cudaFreeHost(h->tag_table);
     for (int r = 0; r < PEER_MAX; ++r) if (h->peer_map[r]) cudaIpcCloseMemHandle(h->peer_map[r]);
     if (h->peer_box) cudaFree(h->peer_box);
     delete h;
@@ -899,8 +912,29 @@ int hdgnn_peer_attach(hdgnn_handle_t h, int rank, int world, const unsigned char
     }
     pa.seq = (int*)h->ws["PEER_SEQ"].p;
     pa.error = pa.seq + 1;
+    {
+        const long long ms = env_int("HDGNN_PEER_TIMEOUT_MS", 20000);
+        const long long spins = (ms < 1 ? 1 : ms) * 1000;            // ~1 us per poll after the first 64
+        pa.max_spins = spins > 0xfffffff0ll ? 0xfffffff0u : (unsigned int)spins;
+    }
     h->peer = pa;
     h->peer_ready = true;
+    return HDGNN_OK;
+}
+
+int hdgnn_set_hits_accumulator(hdgnn_handle_t h, uint64_t* acc) {
+    if (!h) return HDGNN_E_INVALID;
+    if (acc && !h->fused) return fail(h, HDGNN_E_UNSUPPORTED, "the hit counter lives in the fused per-commit kernel (variants 1-3, per-commit state within one SM); use hdgnn_eval_counts");
+    h->hits_acc = (unsigned long long*)acc;
+    return HDGNN_OK;
+}
+
+int hdgnn_peer_status(hdgnn_handle_t h) {
+    if (!h) return HDGNN_E_INVALID;
+    if (!h->peer_ready) return HDGNN_OK;
+    int flag = 0;
+    CK(h, cudaMemcpy(&flag, h->peer.error, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) return fail(h, HDGNN_E_PEER, "a peer's gradient slice did not arrive within HDGNN_PEER_TIMEOUT_MS: the replicas are out of step");
     return HDGNN_OK;
 }
 
@@ -1021,9 +1055,17 @@ static int stage_inputs(hdgnn_handle_t h, int B, const uint8_t* adj_host, const 
     CK(h, cudaMemcpyAsync(h->ws[slot_name("H_X", slot)].p, x_host, (size_t)B * Ne * sizeof(float), cudaMemcpyHostToDevice, cs));
     CK(h, cudaMemcpyAsync(h->ws[slot_name("H_HMAP", slot)].p, hmap_host, (size_t)B * Ne * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
     CK(h, cudaMemcpyAsync(h->ws[slot_name("H_L", slot)].p, L_host, (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
+    h->cur_tag = -1;
     if (side) {
-        CK(h, cudaEventRecord(h->ev_copy[slot], cs));
-        CK(h, cudaStreamWaitEvent(st, h->ev_copy[slot], 0));
+        if (h->tag_table && h->host_bits && h->fused && (h->inl || !h->ent)) {
+            // mid2 is the first kernel of the step and reads every staged input: order it by a tag instead of an event
+            const int tag = (int)(++h->slot_uses[slot] & 0xffu);
+            CK(h, cudaMemcpyAsync((int*)h->ws["H_FLAG"].p + slot, h->tag_table + tag, sizeof(int), cudaMemcpyHostToDevice, cs));
+            h->cur_tag = tag;
+        } else {
+            CK(h, cudaEventRecord(h->ev_copy[slot], cs));
+            CK(h, cudaStreamWaitEvent(st, h->ev_copy[slot], 0));
+        }
     }
     return HDGNN_OK;
 }
@@ -1038,6 +1080,7 @@ static Inputs staged_inputs(hdgnn_handle_t h, const float* params) {
         in.ebits = (const uint32_t*)h->ws[slot_name("H_EBITS", s)].p;
         in.ybits = (const uint32_t*)h->ws[slot_name("H_YBITS", s)].p;
     }
+    if (h->cur_tag >= 0) { in.wait_flag = (const int*)h->ws["H_FLAG"].p + s; in.wait_tag = h->cur_tag; }
     return in;
 }
 

@@ -185,3 +185,66 @@ extern "C" int hdgnn_eval_counts(int B, int Nc, const float* probs, const uint8_
                                           auc_first < 0 ? 0 : auc_first);
     return cudaGetLastError() == cudaSuccess ? HDGNN_OK : HDGNN_E_CUDA;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Measured fp32 CUDA-core peaks for bench.py's roofline denominators (not part of the hot path): a register-resident chain
+// of independent fused multiply-adds, scalar (FFMA) or packed (fma.rn.f32x2, SASS FFMA2 -- the form the pair sweeps use).
+namespace hdgnn {
+template <bool PACKED>
+__global__ void __launch_bounds__(256) fma_peak_kernel(int iters, float seed, float* sink) {
+    constexpr int NA = 8;
+    if (PACKED) {
+        unsigned long long acc[NA], m, c;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(m) : "f"(1.0f + seed * 1e-7f));
+        asm("mov.b64 %0, {%1, %1};" : "=l"(c) : "f"(seed * 1e-3f));
+#pragma unroll
+        for (int i = 0; i < NA; ++i) asm("mov.b64 %0, {%1, %2};" : "=l"(acc[i]) : "f"((float)(threadIdx.x + i)), "f"((float)i));
+        for (int it = 0; it < iters; ++it)
+#pragma unroll
+            for (int i = 0; i < NA; ++i) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(acc[i]) : "l"(m), "l"(c));
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < NA; ++i) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[i])); s += lo + hi; }
+        if (s == 12345.678f) sink[0] = s;
+    } else {
+        float acc[NA];
+        const float m = 1.0f + seed * 1e-7f, c = seed * 1e-3f;
+#pragma unroll
+        for (int i = 0; i < NA; ++i) acc[i] = (float)(threadIdx.x + i);
+        for (int it = 0; it < iters; ++it)
+#pragma unroll
+            for (int i = 0; i < NA; ++i) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(acc[i]) : "f"(m), "f"(c));
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < NA; ++i) s += acc[i];
+        if (s == 12345.678f) sink[0] = s;
+    }
+}
+}  // namespace hdgnn
+
+extern "C" int hdgnn_measure_fp32_peak(int packed, float* tflops_out) {
+    if (!tflops_out) return HDGNN_E_INVALID;
+    int dev = 0, nsm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return HDGNN_E_CUDA;
+    float* sink = nullptr;
+    if (cudaMalloc(&sink, 16) != cudaSuccess) return HDGNN_E_NOMEM;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int iters = 20000, grid = nsm * 8, block = 256;
+    float best = 0.f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        if (packed) hdgnn::fma_peak_kernel<true><<<grid, block>>>(iters, 1.f, sink);
+        else hdgnn::fma_peak_kernel<false><<<grid, block>>>(iters, 1.f, sink);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(sink); return HDGNN_E_CUDA; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = (double)grid * block * iters * 8.0 * 2.0 * (packed ? 2.0 : 1.0);
+        const float tf = (float)(flops / (ms * 1e-3) / 1e12);
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    *tflops_out = best;
+    return HDGNN_OK;
+}

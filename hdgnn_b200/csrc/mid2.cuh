@@ -49,6 +49,9 @@ struct Mid2Args {
     long long* clk;                          // per-phase clock64 stamps (B,24) or null
     float* dlt_g;                            // (B, Nc, CW*32) dL/dlogit table in HBM when it does not fit smem, else null
     int scache;                              // keep the entity effect sums S (Ne x 20) in shared memory from the forward to the backward
+    unsigned long long* hits_acc;            // running count of arg-max hits (EvaluationFuncs.py:27-37) over all commits, or null
+    const int* wait_flag; int wait_tag;      // host-fed step: the staging copies of this step are complete once *wait_flag == wait_tag
+                                             // (written by the copy stream's DMA after the data); null = inputs already ordered
     int inl;                                 // entity pair layer and its backward INSIDE this kernel (entsp.cuh: sorted prefix sums +
                                              // edge walk): RS1 / CS1p / GE are not used, the step has no ent_fwd2 / ent_bwd2 launch and
                                              // this kernel follows the previous step's optimizer kernel (weights are read after pdl_wait)
@@ -271,6 +274,20 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
     M2_PHASE(0);
 
     // ---------------- A. label bitmaps (TMA), weights and per-commit vectors -> shared memory ------
+    if (a.wait_flag) {
+        // Host-fed step: the inputs are copied on the library's copy stream.  A cross-stream event wait in front of this
+        // kernel would undo its programmatic launch behind the optimizer kernel, so the copy stream's LAST DMA writes a tag
+        // and the kernel polls it here (the copies were enqueued a whole step earlier: the first poll normally succeeds).
+        if (tid == 0) {
+            unsigned int spin = 0;
+            while (*reinterpret_cast<const volatile int*>(a.wait_flag) != a.wait_tag) {
+                __nanosleep(spin < 16 ? 64 : 2000);
+                if (++spin > (1u << 22)) __trap();          // ~8 s without the copy: a lost DMA traps instead of hanging the GPU
+            }
+            __threadfence_system();
+        }
+        __syncthreads();
+    }
     if (tid == 0) {
         mbar_init(bar, 1);
         fence_mbar_init();
@@ -912,7 +929,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
     M2_PHASE(5);
 
     // ---------------- G1. relation head: logits, softmax, CE (lanes = columns, all 20 channels) ---------
-    float ce_acc = 0.f, d_acc = 0.f;
+    float ce_acc = 0.f, d_acc = 0.f, hit_acc = 0.f;
     {
         const size_t npair = (size_t)Nc * (Nc - 1);
         const float bd = gb2[1] - gb2[0], b20 = gb2[0];
@@ -959,6 +976,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
                     }
                     const float z = lab ? -d : d;
                     ce_acc += fmaxf(z, 0.f) + __logf(1.f + e);     // e in (0, 1]: absolute error ~1e-7
+                    hit_acc += ((p1 > p0) == lab) ? 1.f : 0.f;      // np.argmax over the two channels: a tie is class 0
                 }
                 if (TRAIN) {
                     const float dv = valid ? a.scale * (p1 - (lab ? 1.f : 0.f)) : 0.f;
@@ -971,6 +989,10 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
     {
         const float ce_tot = mid2_block_sum(ce_acc, red);
         if (tid == 0 && a.cep) a.cep[b] = ce_tot;
+        if (a.hits_acc) {                                    // per-commit counts are below 2^24: exact in float; integer atomic: order independent
+            const float hit_tot = mid2_block_sum(hit_acc, red);
+            if (tid == 0) atomicAdd(a.hits_acc, (unsigned long long)(hit_tot + 0.5f));
+        }
     }
     M2_PHASE(6);
     if (!TRAIN) return;

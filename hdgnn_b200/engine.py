@@ -234,6 +234,20 @@ class Engine:
         self.peer_world = world
         return True
 
+    def set_hits_accumulator(self, acc: Optional[torch.Tensor]) -> bool:
+        """acc: one-element int64 CUDA tensor that every later step adds its arg-max hits to (None: off).  Returns False when
+        this engine runs the multi-kernel path, which has no in-kernel counter (use eval_counts)."""
+        rc = lib.hdgnn_set_hits_accumulator(self._h, _p(acc))
+        if rc == _lib.E_UNSUPPORTED:
+            return False
+        check(rc, self._h)
+        self._hits_ref = acc            # keep the tensor alive while the handle points at it
+        return True
+
+    def peer_status(self):
+        """Raises HdgnnError(E_PEER) if a gradient exchange timed out since peer_attach (synchronises with the device)."""
+        check(lib.hdgnn_peer_status(self._h), self._h)
+
     def train_step_peer(self, b: DeviceBatch, params, m, v, step_counter, loss3, probs=None, logits=None,
                         lr=3e-4, beta1=0.9, beta2=0.999, eps=1e-8):
         """This rank's shard of one training step; gradients are exchanged inside the last kernel (no NCCL call)."""

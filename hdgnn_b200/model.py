@@ -244,8 +244,11 @@ class graph2graph(object):
         return "%s" % (self.Repo + '/model_%d/' % self.variant + str(self.Step))
 
     # ------------------------------------------------------------------------------------------
-    def train(self, args=None, data=None, root=".", quirk_q2=True, log=print):
-        """model_2.py:335-424.  `args` needs .Repo and .checkpoint_dir (main.py's namespace)."""
+    def train(self, args=None, data=None, root=".", quirk_q2=True, log=print, save_checkpoints=True):
+        """model_2.py:335-424.  `args` needs .Repo and .checkpoint_dir (main.py's namespace).
+        The loop body is one asynchronous library call per batch: the batches are pinned (and bit-packed) once, the losses of
+        an epoch land in a pinned ring, top_ACC (EvaluationFuncs.py:27-37) is counted inside the relation-head phase of the
+        step (hdgnn_set_hits_accumulator), and the host synchronises once per epoch to print the reference's log line."""
         from .engine import eval_counts
         repo = getattr(args, "Repo", self.Repo)
         ckpt = getattr(args, "checkpoint_dir", self.checkpoint_dir)
@@ -257,51 +260,67 @@ class graph2graph(object):
         nb = int(train.B / mb)                                      # remainder batch dropped (model_2.py:364)
         per = mb // self.world
         dev = self.engine.tdev
-        probs_d = torch.zeros(per, 2, self.Ncr, dtype=torch.float32, device=dev)
+        hits = torch.zeros(1, dtype=torch.int64, device=dev)
+        in_kernel_hits = self.engine.set_hits_accumulator(hits)     # False on the multi-kernel path (variant 4, very large grids)
+        probs_d = None if in_kernel_hits else torch.zeros(per, 2, self.Ncr, dtype=torch.float32, device=dev)
+        ring = torch.zeros(max(nb, 1), 3, dtype=torch.float32).pin_memory()
+        keep3 = self.loss3
         counter = 1
         history = []
         # the data set is static across epochs: pin (and bit-pack) every batch once
         batches = [self.host_batch(self._batch(train, train, j, quirk_q2)) for j in range(nb)]
+        y_dev = None if in_kernel_hits else [hb.Y.to(dev) for hb in batches]
+        if self.world > 1:
+            torch.distributed.barrier()          # data preparation can skew the ranks by seconds: line up before the first exchange
         start_time1 = time.time()
-        for i in range(self.epoch):
-            tr_loss_Hedge = 0.0
-            tr_loss_map = 0.0
-            hits = torch.zeros(1, dtype=torch.int64, device=dev)
-            for j in range(nb):
-                hb = batches[j]
-                l3 = self.train_step(hb, want_probs=True, probs_out=probs_d)
-                # top_ACC (EvaluationFuncs.py:27-37) from device counters: the probabilities never leave the GPU
-                counts, _ = eval_counts(probs_d[:hb.B], hb.Y.to(dev, non_blocking=True))
-                hits += counts[:, 0].sum()
-                torch.cuda.current_stream().synchronize()
-                ce = float(l3[0])
+        try:
+            for i in range(self.epoch):
+                hits.zero_()
+                for j in range(nb):
+                    hb = batches[j]
+                    self.loss3 = ring[j]
+                    if in_kernel_hits:
+                        self.train_step(hb)
+                    else:
+                        self.train_step(hb, want_probs=True, probs_out=probs_d)
+                        counts, _ = eval_counts(probs_d[:hb.B], y_dev[j])
+                        hits += counts[:, 0].sum()
+                torch.cuda.current_stream().synchronize()           # once per epoch
+                if self.peer:
+                    self.engine.peer_status()        # a timed-out exchange raises here instead of training on with diverged replicas
+                ce_steps = ring[:nb, 0].double()
                 if self.world > 1 and not self.peer:                # CE partials add up to the global mean
-                    t = torch.tensor([ce], device=dev)
+                    t = ce_steps.to(dev)
                     torch.distributed.all_reduce(t)
-                    ce = float(t.item())
-                tr_loss_Hedge += ce
-                tr_loss_map += float(l3[1])
-            if self.world > 1:
-                torch.distributed.all_reduce(hits)
-            acc_top = float(int(hits.item()) / (nb * mb * self.Ncr)) if nb else float("nan")
-            theta = self.named_params()["theta2"].numpy().reshape([2])
-            resultString = "Epoch " + str(i + 1) + \
-                           " acc: " + str(acc_top)[0:6] + \
-                           " Hedge loss: " + str(tr_loss_Hedge / nb)[0:6] + \
-                           " map MSE: " + str(tr_loss_map / nb)[0:6] + \
-                           " theta: " + str(theta[0]) + ' ' + str(theta[1]) + '\n'
-            history.append(dict(epoch=i + 1, acc=acc_top, hedge_loss=tr_loss_Hedge / nb, map_loss=tr_loss_map / nb))
-            if self.rank == 0:
-                filepath = r'outputSelf/{}/model_{}/{}/result_{}.npy'.format(repo, self.variant, self.Step, self.Step)
-                filepath = os.path.join(root, filepath)
-                os.makedirs(os.path.dirname(filepath), exist_ok=True)
-                with open(filepath, "a", encoding='utf-8') as f:
-                    f.write(resultString)
-                log(resultString)
-            counter += 1
-            if self.rank == 0:
-                self.save(os.path.join(root, ckpt) if not os.path.isabs(ckpt) else ckpt, counter)
+                    ce_steps = t.cpu()
+                tr_loss_Hedge = float(ce_steps.sum())
+                tr_loss_map = float(ring[:nb, 1].double().sum())
+                if self.world > 1:
+                    torch.distributed.all_reduce(hits)
+                acc_top = float(int(hits.item()) / (nb * mb * self.Ncr)) if nb else float("nan")
+                theta = self.named_params()["theta2"].numpy().reshape([2])
+                resultString = "Epoch " + str(i + 1) + \
+                               " acc: " + str(acc_top)[0:6] + \
+                               " Hedge loss: " + str(tr_loss_Hedge / nb)[0:6] + \
+                               " map MSE: " + str(tr_loss_map / nb)[0:6] + \
+                               " theta: " + str(theta[0]) + ' ' + str(theta[1]) + '\n'
+                history.append(dict(epoch=i + 1, acc=acc_top, hedge_loss=tr_loss_Hedge / nb, map_loss=tr_loss_map / nb))
+                if self.rank == 0 and save_checkpoints:
+                    filepath = r'outputSelf/{}/model_{}/{}/result_{}.npy'.format(repo, self.variant, self.Step, self.Step)
+                    filepath = os.path.join(root, filepath)
+                    os.makedirs(os.path.dirname(filepath), exist_ok=True)
+                    with open(filepath, "a", encoding='utf-8') as f:
+                        f.write(resultString)
+                if self.rank == 0:
+                    log(resultString)
+                counter += 1
+                if self.rank == 0 and save_checkpoints:
+                    self.save(os.path.join(root, ckpt) if not os.path.isabs(ckpt) else ckpt, counter)
+        finally:
+            self.loss3 = keep3
+            self.engine.set_hits_accumulator(None)
         end_time1 = time.time()
+        self.last_train_seconds = end_time1 - start_time1          # the epoch loop alone, as the reference times it (model_2.py:358,423)
         if self.rank == 0:
             log('test time:' + str(end_time1 - start_time1))       # sic (model_2.py:424)
         return history

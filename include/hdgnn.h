@@ -47,6 +47,7 @@ extern "C" {
 #define HDGNN_E_CUDA         -2   /* a CUDA runtime call failed; see hdgnn_last_error */
 #define HDGNN_E_NOMEM        -3
 #define HDGNN_E_UNSUPPORTED  -4   /* e.g. Ne or Nc above the compiled limit */
+#define HDGNN_E_PEER         -5   /* a peer's share of the gradient exchange did not arrive in time (hdgnn_peer_status) */
 
 #define HDGNN_MAX_N          512  /* largest Ne / Nc the kernels are instantiated for */
 #define HDGNN_HIDDEN         20   /* hidden / effect width: h_size, De_e, De_er (main.py:31-32) */
@@ -173,6 +174,10 @@ int hdgnn_forward_backward_host(hdgnn_handle_t h, int B, int B_global,
 #define HDGNN_IPC_HANDLE_BYTES 64
 int hdgnn_peer_export(hdgnn_handle_t h, int world, unsigned char* ipc_handle_out);
 int hdgnn_peer_attach(hdgnn_handle_t h, int rank, int world, const unsigned char* ipc_handles);
+/* Synchronises with the device and reports whether any exchange since hdgnn_peer_attach timed out (HDGNN_E_PEER): a wait
+ * that sees no data for HDGNN_PEER_TIMEOUT_MS (environment, default 20000) gives up WITHOUT killing the context; the
+ * parameters are then out of step with the peers' and training must stop.  Cheap enough for once per epoch. */
+int hdgnn_peer_status(hdgnn_handle_t h);
 /* As hdgnn_train_step / hdgnn_train_step_host for this rank's B commits of a global batch of B_global = B * world.
  * loss3[0] receives the GLOBAL mean cross-entropy (the ranks' shares are exchanged with the gradients). */
 int hdgnn_train_step_peer(hdgnn_handle_t h, int B, int B_global,
@@ -239,6 +244,12 @@ int hdgnn_pack_label_bits(int N, int n, const uint8_t* grid, int pitch, uint32_t
 int hdgnn_eval_counts(int B, int Nc, const float* probs, const uint8_t* Y, int y_pitch, int64_t* counts, int64_t* auc,
                       int auc_first, void* stream);
 
+/* Accuracy counter of the training loop without a second kernel: while `acc` (device, one uint64, caller-owned) is set, every
+ * forward / training call ADDS the number of hunk pairs whose arg-max class equals the label (EvaluationFuncs.py:27-37, a
+ * tie is class 0) for all commits of the call; the caller zeroes it when a new epoch starts.  NULL switches it off.  Fused
+ * path only (HDGNN_E_UNSUPPORTED otherwise: use hdgnn_eval_counts). */
+int hdgnn_set_hits_accumulator(hdgnn_handle_t h, uint64_t* acc);
+
 /* Debug / test introspection: device pointer and size in bytes of a named scratch buffer
  * (RS1 CS1 S1 X2 NB PH QH RS3 CS3 PR PC GRH GCH RS3D CS3D DNB GE RS1D CS1D GPART ...). */
 int hdgnn_workspace(hdgnn_handle_t h, const char* name, void** ptr, size_t* bytes);
@@ -252,6 +263,10 @@ int hdgnn_workspace_copy(hdgnn_handle_t h, const char* name, void* dst, size_t b
 int hdgnn_profile(hdgnn_handle_t h, int enable);
 int hdgnn_profile_count(hdgnn_handle_t h);
 int hdgnn_profile_get(hdgnn_handle_t h, int idx, char* name, int name_cap, float* ms);
+
+/* Measurement utility for the roofline denominators (synchronous, current device): sustained fp32 TFLOP/s of the CUDA cores
+ * with scalar FFMA (packed = 0) or the packed fma.rn.f32x2 form the pair sweeps use (packed = 1). */
+int hdgnn_measure_fp32_peak(int packed, float* tflops_out);
 
 /* number of kernel launches the last forward / forward_backward / adam call enqueued */
 int hdgnn_last_launch_count(hdgnn_handle_t h);
