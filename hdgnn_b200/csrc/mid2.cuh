@@ -455,10 +455,11 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
     // from per-class tables and per-(node, class) neighbour counts (popcounts), see below; otherwise by search + edge walk
     int* clsv = reinterpret_cast<int*>(sm + L_.cls); float* cval = sm + L_.cval; int* csize = reinterpret_cast<int*>(sm + L_.csize);
     uint32_t* cmask = reinterpret_cast<uint32_t*>(sm + L_.cmask); int* cmeta = reinterpret_cast<int*>(sm + L_.cmeta);
-    // tables (2 m^2 20 floats) + counts (Ne m words) + 8 partial sums per thread must fit the union region
+    // the union region must hold: forward 2 m^2 20 table floats + 4 Ne m count floats; backward the tables + Ne m packed counts +
+    // 16 partial sums per thread
     const int uni_floats = L_.sc - L_.uni;
     int m_max = M2_MCLS;
-    while (m_max > 0 && 2 * m_max * m_max * HD + Ne * m_max + 8 * M2_T > uni_floats) --m_max;
+    while (m_max > 0 && (2 * m_max * m_max * HD + 4 * Ne * m_max > uni_floats || 2 * m_max * m_max * HD + Ne * m_max + 16 * M2_T > uni_floats)) --m_max;
     if (a.inl) {
         const int WU = (Ne + 31) >> 5;
         {   // stable rank sort: three threads per node count over a third of the nodes each (integer atomics: exact)
@@ -555,7 +556,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             // no search, no edge walk, every sum in class order.
             const int m = cmeta[0];
             float* H0 = uni; float* H1 = uni + m * m * HD;
-            uint32_t* cnt = reinterpret_cast<uint32_t*>(uni + 2 * m * m * HD);      // [Ne][m]  c1o | c1i << 16
+            float4* cntf = reinterpret_cast<float4*>(uni + 2 * m * m * HD);      // [Ne][m]  {c0o, c1o, c0i, c1i} as floats
             for (int e = tid; e < m * m * HD; e += M2_T) {
                 const int k = e % HD, ab = e / HD, bq = ab % m, aq = ab / m;
                 const float t0 = fmaf(cval[bq], wE[HD + k], fmaf(cval[aq], wE[k], wE[2 * HD + k]));
@@ -569,26 +570,28 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
                     const uint32_t mk = cmask[bq * WPe + w];
                     co += __popc(ebits[n * WPe + w] & mk); ci += __popc(ebT[n * WPe + w] & mk);
                 }
-                cnt[e] = (uint32_t)co | ((uint32_t)ci << 16);
+                const int tot = csize[bq] - (clsv[n] == bq ? 1 : 0);
+                cntf[e] = make_float4((float)(tot - co), (float)co, (float)(tot - ci), (float)ci);
             }
             __syncthreads();
             float* Sall = sm + L_.sc;
-            const int c0 = 2 * (tid % 10);
-            for (int n = tid / 10; n < Ne; n += M2_T / 10) {
+            const int k4 = 4 * (tid % KG);
+            for (int n = tid / KG; n < Ne; n += M2_T / KG) {        // one owner per (node, 4 channels); every sum in class order
                 const int aq = clsv[n];
-                float s0 = 0.f, s1 = 0.f;
+                float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float* hab0 = H0 + aq * m * HD + k4; const float* hab1 = H1 + aq * m * HD + k4;
+                const float* hba0 = H0 + aq * HD + k4;     const float* hba1 = H1 + aq * HD + k4;
+                const float4* cf = cntf + n * m;
                 for (int bq = 0; bq < m; ++bq) {
-                    const uint32_t pk = cnt[n * m + bq];
-                    const int c1o = (int)(pk & 0xffffu), c1i = (int)(pk >> 16), tot = csize[bq] - (aq == bq ? 1 : 0);
-                    const float f1o = (float)c1o, f1i = (float)c1i, f0o = (float)(tot - c1o), f0i = (float)(tot - c1i);
-                    const float2 h0ab = *reinterpret_cast<const float2*>(H0 + (aq * m + bq) * HD + c0);
-                    const float2 h1ab = *reinterpret_cast<const float2*>(H1 + (aq * m + bq) * HD + c0);
-                    const float2 h0ba = *reinterpret_cast<const float2*>(H0 + (bq * m + aq) * HD + c0);
-                    const float2 h1ba = *reinterpret_cast<const float2*>(H1 + (bq * m + aq) * HD + c0);
-                    s0 = fmaf(f0o, h0ab.x, s0); s0 = fmaf(f1o, h1ab.x, s0); s0 = fmaf(f0i, h0ba.x, s0); s0 = fmaf(f1i, h1ba.x, s0);
-                    s1 = fmaf(f0o, h0ab.y, s1); s1 = fmaf(f1o, h1ab.y, s1); s1 = fmaf(f0i, h0ba.y, s1); s1 = fmaf(f1i, h1ba.y, s1);
+                    const float4 c = cf[bq];
+                    const float4 a0 = *reinterpret_cast<const float4*>(hab0 + bq * HD), a1 = *reinterpret_cast<const float4*>(hab1 + bq * HD);
+                    const float4 b0 = *reinterpret_cast<const float4*>(hba0 + bq * m * HD), b1 = *reinterpret_cast<const float4*>(hba1 + bq * m * HD);
+                    s4.x = fmaf(c.x, a0.x, s4.x); s4.x = fmaf(c.y, a1.x, s4.x); s4.x = fmaf(c.z, b0.x, s4.x); s4.x = fmaf(c.w, b1.x, s4.x);
+                    s4.y = fmaf(c.x, a0.y, s4.y); s4.y = fmaf(c.y, a1.y, s4.y); s4.y = fmaf(c.z, b0.y, s4.y); s4.y = fmaf(c.w, b1.y, s4.y);
+                    s4.z = fmaf(c.x, a0.z, s4.z); s4.z = fmaf(c.y, a1.z, s4.z); s4.z = fmaf(c.z, b0.z, s4.z); s4.z = fmaf(c.w, b1.z, s4.z);
+                    s4.w = fmaf(c.x, a0.w, s4.w); s4.w = fmaf(c.y, a1.w, s4.w); s4.w = fmaf(c.z, b0.w, s4.w); s4.w = fmaf(c.w, b1.w, s4.w);
                 }
-                *reinterpret_cast<float2*>(Sall + (size_t)n * HD + c0) = make_float2(s0, s1);
+                *reinterpret_cast<float4*>(Sall + (size_t)n * HD + k4) = s4;
             }
             __syncthreads();
         } else {
@@ -1468,7 +1471,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         const int mcl = cmeta[0];
         float* SGs = uni;                                   // general path: [20][Ne + 1] suffix sums of GE over the sorted order, per channel
         // [M2_T][8] per-thread partial sums behind the path's tables
-        float* part = uni + (use_cls ? ((2 * mcl * mcl * HD + Ne * mcl + 3) & ~3) : 20 * (Ne + 1));
+        float* part = uni + (use_cls ? ((2 * mcl * mcl * HD + Ne * mcl + 3) & ~3) : 20 * (Ne + 1));      // per-thread partial sums
         float db[2] = {0.f, 0.f}, dU[2] = {0.f, 0.f}, dV[2] = {0.f, 0.f}, LS[2] = {0.f, 0.f};
         if (use_cls) {
             // CLASS TABLES: v_ij[k] = g_l[a][b][k] (GE_i[k] + GE_j[k]) with the 0/1 gates g_l[a][b][k] = [H_l[a][b][k] > 0].  All four
@@ -1479,7 +1482,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             // and the W's come from the same neighbour counts as the forward.
             const int m = mcl;
             float* G0 = uni; float* G1t = uni + m * m * HD;
-            uint32_t* cnt = reinterpret_cast<uint32_t*>(uni + 2 * m * m * HD);
+            uint32_t* cnt = reinterpret_cast<uint32_t*>(uni + 2 * m * m * HD);      // [Ne][m]  c1o | c1i << 16
             for (int e = tid; e < m * m * HD; e += M2_T) {
                 const int k = e % HD, ab = e / HD, bq = ab % m, aq = ab / m;
                 const float t0 = fmaf(cval[bq], wE[HD + k], fmaf(cval[aq], wE[k], wE[2 * HD + k]));      // as in the forward: same gates
@@ -1497,36 +1500,49 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             }
             __syncthreads();
             M2_PHASE(19);
-            const int c0 = 2 * (tid % 10);
-            for (int n = tid / 10; n < Ne; n += M2_T / 10) {
+            const int k4 = 4 * (tid % KG);
+            float a_db[4] = {0.f, 0.f, 0.f, 0.f}, a_dU[4] = {0.f, 0.f, 0.f, 0.f}, a_dV[4] = {0.f, 0.f, 0.f, 0.f}, a_LS[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int n = tid / KG; n < Ne; n += M2_T / KG) {
                 const int aq = clsv[n];
                 const float xn = xs[n];
-                const float2 gn = *reinterpret_cast<const float2*>(GEs + (size_t)n * HD + c0);
-                float wr[2] = {0.f, 0.f}, xwr[2] = {0.f, 0.f}, w1r[2] = {0.f, 0.f}, wc[2] = {0.f, 0.f}, xwc[2] = {0.f, 0.f}, w1c[2] = {0.f, 0.f};
+                const float4 gn4 = *reinterpret_cast<const float4*>(GEs + (size_t)n * HD + k4);
+                float wr[4] = {0.f, 0.f, 0.f, 0.f}, xwr[4] = {0.f, 0.f, 0.f, 0.f}, w1r[4] = {0.f, 0.f, 0.f, 0.f};
+                float wc[4] = {0.f, 0.f, 0.f, 0.f}, xwc[4] = {0.f, 0.f, 0.f, 0.f}, w1c[4] = {0.f, 0.f, 0.f, 0.f};
+                const float* gab0 = G0 + aq * m * HD + k4; const float* gab1 = G1t + aq * m * HD + k4;
+                const float* gba0 = G0 + aq * HD + k4;     const float* gba1 = G1t + aq * HD + k4;
                 for (int bq = 0; bq < m; ++bq) {
                     const uint32_t pk = cnt[n * m + bq];
                     const int c1o = (int)(pk & 0xffffu), c1i = (int)(pk >> 16), tot = csize[bq] - (aq == bq ? 1 : 0);
                     const float f1o = (float)c1o, f1i = (float)c1i, f0o = (float)(tot - c1o), f0i = (float)(tot - c1i), vb = cval[bq];
-                    const float2 g0ab = *reinterpret_cast<const float2*>(G0 + (aq * m + bq) * HD + c0);
-                    const float2 g1ab = *reinterpret_cast<const float2*>(G1t + (aq * m + bq) * HD + c0);
-                    const float2 g0ba = *reinterpret_cast<const float2*>(G0 + (bq * m + aq) * HD + c0);
-                    const float2 g1ba = *reinterpret_cast<const float2*>(G1t + (bq * m + aq) * HD + c0);
-                    const float a0[2] = {g0ab.x, g0ab.y}, a1[2] = {g1ab.x, g1ab.y}, b0[2] = {g0ba.x, g0ba.y}, b1[2] = {g1ba.x, g1ba.y};
+                    const float4 q0 = *reinterpret_cast<const float4*>(gab0 + bq * HD), q1 = *reinterpret_cast<const float4*>(gab1 + bq * HD);
+                    const float4 r0 = *reinterpret_cast<const float4*>(gba0 + bq * m * HD), r1 = *reinterpret_cast<const float4*>(gba1 + bq * m * HD);
+                    const float a0[4] = {q0.x, q0.y, q0.z, q0.w}, a1[4] = {q1.x, q1.y, q1.z, q1.w};
+                    const float b0[4] = {r0.x, r0.y, r0.z, r0.w}, b1[4] = {r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const float l1o = f1o * a1[h], ro = fmaf(f0o, a0[h], l1o), l1i = f1i * b1[h], ci2 = fmaf(f0i, b0[h], l1i);
-                        wr[h] += ro; xwr[h] = fmaf(vb, ro, xwr[h]); w1r[h] += l1o;
-                        wc[h] += ci2; xwc[h] = fmaf(vb, ci2, xwc[h]); w1c[h] += l1i;
+                    for (int c = 0; c < 4; ++c) {
+                        const float l1o = f1o * a1[c], ro = fmaf(f0o, a0[c], l1o), l1i = f1i * b1[c], ci2 = fmaf(f0i, b0[c], l1i);
+                        wr[c] += ro; xwr[c] = fmaf(vb, ro, xwr[c]); w1r[c] += l1o;
+                        wc[c] += ci2; xwc[c] = fmaf(vb, ci2, xwc[c]); w1c[c] += l1i;
                     }
                 }
-                const float gv[2] = {gn.x, gn.y};
+                const float gv[4] = {gn4.x, gn4.y, gn4.z, gn4.w};
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    db[h] = fmaf(gv[h], wr[h] + wc[h], db[h]);
-                    dU[h] = fmaf(gv[h], fmaf(xn, wr[h], xwc[h]), dU[h]);
-                    dV[h] = fmaf(gv[h], fmaf(xn, wc[h], xwr[h]), dV[h]);
-                    LS[h] = fmaf(gv[h], w1r[h] + w1c[h], LS[h]);
+                for (int c = 0; c < 4; ++c) {
+                    a_db[c] = fmaf(gv[c], wr[c] + wc[c], a_db[c]);
+                    a_dU[c] = fmaf(gv[c], fmaf(xn, wr[c], xwc[c]), a_dU[c]);
+                    a_dV[c] = fmaf(gv[c], fmaf(xn, wc[c], xwr[c]), a_dV[c]);
+                    a_LS[c] = fmaf(gv[c], w1r[c] + w1c[c], a_LS[c]);
                 }
+            }
+            float4* p4 = reinterpret_cast<float4*>(part + (size_t)tid * 16);
+            p4[0] = make_float4(a_db[0], a_db[1], a_db[2], a_db[3]); p4[1] = make_float4(a_dU[0], a_dU[1], a_dU[2], a_dU[3]);
+            p4[2] = make_float4(a_dV[0], a_dV[1], a_dV[2], a_dV[3]); p4[3] = make_float4(a_LS[0], a_LS[1], a_LS[2], a_LS[3]);
+            __syncthreads();
+            if (tid < 4 * HD) {                             // fixed-order sum over the 128 node slots of a channel group
+                const int qn = tid / HD, k = tid - qn * HD, kgq = k >> 2, cc2 = k & 3;
+                float t = 0.f;
+                for (int s2 = 0; s2 < M2_T / KG; ++s2) t += part[(size_t)(s2 * KG + kgq) * 16 + 4 * qn + cc2];
+                red[tid] = t;
             }
         } else {
             {
@@ -1610,15 +1626,15 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
                     }
                 }
             }
-        }
-        *reinterpret_cast<float4*>(part + (size_t)tid * 8) = make_float4(db[0], db[1], dU[0], dU[1]);
-        *reinterpret_cast<float4*>(part + (size_t)tid * 8 + 4) = make_float4(dV[0], dV[1], LS[0], LS[1]);
-        __syncthreads();
-        if (tid < 4 * HD) {                                 // fixed-order sum over the 64 threads that own a channel pair
-            const int qn = tid / HD, k = tid - qn * HD, kp = k >> 1, hh = k & 1;
-            float t = 0.f;
-            for (int s2 = 0; s2 < M2_T / 10; ++s2) t += part[(size_t)(kp + 10 * s2) * 8 + 2 * qn + hh];      // slot order
-            red[tid] = t;
+                    *reinterpret_cast<float4*>(part + (size_t)tid * 8) = make_float4(db[0], db[1], dU[0], dU[1]);
+            *reinterpret_cast<float4*>(part + (size_t)tid * 8 + 4) = make_float4(dV[0], dV[1], LS[0], LS[1]);
+            __syncthreads();
+            if (tid < 4 * HD) {                                 // fixed-order sum over the 64 threads that own a channel pair
+                const int qn = tid / HD, k = tid - qn * HD, kp = k >> 1, hh = k & 1;
+                float t = 0.f;
+                for (int s2 = 0; s2 < M2_T / 10; ++s2) t += part[(size_t)(kp + 10 * s2) * 8 + 2 * qn + hh];      // slot order
+                red[tid] = t;
+            }
         }
         __syncthreads();
         if (tid < HD) {
