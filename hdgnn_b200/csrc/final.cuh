@@ -206,18 +206,18 @@ __global__ void __launch_bounds__(FIN_P * FIN_SL) reduce_adam_kernel(const Final
         last = (done == gridDim.x - 1);
     }
     __syncthreads();
-    if (last && tid == 0) {
+    if (last && tid < 32) {
+        // the last CTA's first warp: the per-CTA partials with all loads in flight (lane-strided, then a fixed shuffle tree)
         __threadfence();
         float l2 = 0.f;
-        for (unsigned int i = 0; i < gridDim.x; ++i) l2 += a.l2part[i];
-        if (a.reg_losses) {
-            // theta norms at the pre-update values: this CTA may already have updated them, so they
-            // are recomputed from l2part-independent saved values by the CTA owning them (below)
-            a.reg_losses[1] = 0.001f * 0.5f * l2;
+        for (unsigned int i = tid; i < gridDim.x; i += 32) l2 += __ldcg(a.l2part + i);
+        l2 = warp_sum(l2);
+        if (tid == 0) {
+            if (a.reg_losses) a.reg_losses[1] = 0.001f * 0.5f * l2;
+            *a.step = t;
+            if (a.peer.world > 1) *a.peer.seq = *a.peer.seq + 1;
+            *a.counter = 0u;
         }
-        *a.step = t;
-        if (a.peer.world > 1) *a.peer.seq = *a.peer.seq + 1;
-        *a.counter = 0u;
     }
     // loss_map = 0.01 (|theta1| + |theta2|): written by the CTA that read the thetas before updating them
     if (a.reg_losses && tid == 0 && a.o_t1 >= (int)(blockIdx.x * FIN_P) && a.o_t1 < (int)((blockIdx.x + 1) * FIN_P))

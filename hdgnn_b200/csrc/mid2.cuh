@@ -150,6 +150,34 @@ __device__ __forceinline__ void gemv20t(float (&y)[HD], const float (&x)[HD], co
         y[q] = acc;
     }
 }
+// y[k4 .. k4+3] = init + sum_q x[q] W[q][k4 ..]      (x: 20 floats in shared memory, 16-byte aligned; one quarter-row per thread)
+__device__ __forceinline__ float4 gemv20_k4(const float* x, const float* W, int k4, float4 acc) {
+#pragma unroll
+    for (int q4 = 0; q4 < 5; ++q4) {
+        const float4 xv = *reinterpret_cast<const float4*>(x + 4 * q4);
+        const float xr[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 w = *reinterpret_cast<const float4*>(W + (4 * q4 + j) * HD + k4);
+            acc.x = fmaf(xr[j], w.x, acc.x); acc.y = fmaf(xr[j], w.y, acc.y); acc.z = fmaf(xr[j], w.z, acc.z); acc.w = fmaf(xr[j], w.w, acc.w);
+        }
+    }
+    return acc;
+}
+// y[k4 + j] = sum_m W[k4 + j][m] x[m]               (multiply by W^T)
+__device__ __forceinline__ float4 gemv20t_k4(const float* x, const float* W, int k4) {
+    float out[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int m4 = 0; m4 < 5; ++m4) {
+        const float4 xv = *reinterpret_cast<const float4*>(x + 4 * m4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 w = *reinterpret_cast<const float4*>(W + (k4 + j) * HD + 4 * m4);
+            out[j] = fmaf(w.x, xv.x, out[j]); out[j] = fmaf(w.y, xv.y, out[j]); out[j] = fmaf(w.z, xv.z, out[j]); out[j] = fmaf(w.w, xv.w, out[j]);
+        }
+    }
+    return make_float4(out[0], out[1], out[2], out[3]);
+}
 __device__ __forceinline__ void load20s(float (&v)[HD], const float* src) {      // 16-byte aligned source
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
@@ -505,7 +533,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             int c = incl - cnt - 1;                          // class of the rank before this lane's chunk
             for (int r = lo; r < hi; ++r) {
                 if (r == 0 || xsort[r] != xsort[r - 1]) { ++c; if (c < M2_MCLS) { cval[c] = xsort[r]; csize[c] = r; } }
-                clsv[ordv[r]] = c;
+                clsv[ordv[r]] = (c & 0xffff) | (r << 16);        // class of the node | its rank in the sorted order
             }
             const int m = __shfl_sync(0xffffffffu, incl, 31);
             __syncwarp();
@@ -531,7 +559,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         if (cmeta[1]) {                                      // node masks of the classes: one ballot per (32 nodes, class)
             const int m = cmeta[0];
             for (int w = warp; w < WU; w += M2_NW) {
-                const int node = w * 32 + lane, c = node < Ne ? clsv[node] : -1;
+                const int node = w * 32 + lane, c = node < Ne ? (clsv[node] & 0xffff) : -1;
                 for (int bcl = 0; bcl < m; ++bcl) {
                     const uint32_t bal = __ballot_sync(0xffffffffu, c == bcl);
                     if (lane == 0) cmask[bcl * WPe + w] = bal;
@@ -570,20 +598,23 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
                     const uint32_t mk = cmask[bq * WPe + w];
                     co += __popc(ebits[n * WPe + w] & mk); ci += __popc(ebT[n * WPe + w] & mk);
                 }
-                const int tot = csize[bq] - (clsv[n] == bq ? 1 : 0);
-                cntf[e] = make_float4((float)(tot - co), (float)co, (float)(tot - ci), (float)ci);
+                const int cr = clsv[n], tot = csize[bq] - ((cr & 0xffff) == bq ? 1 : 0);
+                cntf[bq * Ne + (cr >> 16)] = make_float4((float)(tot - co), (float)co, (float)(tot - ci), (float)ci);      // [class][rank]
             }
             __syncthreads();
+            // One owner per (node, 4 channels); the lanes of a warp take CONSECUTIVE RANKS of the sorted order, i.e. mostly one
+            // class: the four table loads of an iteration are (near-)uniform across the warp and the count loads are contiguous,
+            // so the loop is not bound by shared-memory bandwidth.  Every sum runs in class order.
             float* Sall = sm + L_.sc;
-            const int k4 = 4 * (tid % KG);
-            for (int n = tid / KG; n < Ne; n += M2_T / KG) {        // one owner per (node, 4 channels); every sum in class order
-                const int aq = clsv[n];
+            const int k4 = 4 * (tid / (M2_T / KG));
+            for (int r = tid % (M2_T / KG); r < Ne; r += M2_T / KG) {
+                const int n = ordv[r], aq = clsv[n] & 0xffff;
                 float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 const float* hab0 = H0 + aq * m * HD + k4; const float* hab1 = H1 + aq * m * HD + k4;
                 const float* hba0 = H0 + aq * HD + k4;     const float* hba1 = H1 + aq * HD + k4;
-                const float4* cf = cntf + n * m;
+                const float4* cf = cntf + r;
                 for (int bq = 0; bq < m; ++bq) {
-                    const float4 c = cf[bq];
+                    const float4 c = cf[bq * Ne];
                     const float4 a0 = *reinterpret_cast<const float4*>(hab0 + bq * HD), a1 = *reinterpret_cast<const float4*>(hab1 + bq * HD);
                     const float4 b0 = *reinterpret_cast<const float4*>(hba0 + bq * m * HD), b1 = *reinterpret_cast<const float4*>(hba1 + bq * m * HD);
                     s4.x = fmaf(c.x, a0.x, s4.x); s4.x = fmaf(c.y, a1.x, s4.x); s4.x = fmaf(c.z, b0.x, s4.x); s4.x = fmaf(c.w, b1.x, s4.x);
@@ -909,24 +940,36 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
     M2_PHASE(4);
 
     // ---------------- F. linear second layer on the sums + head tables (model_2.py:263-275, 311-315) --
-    // one thread per (hunk, side): r_n = (Nc-1) b2 + RS3_n W2 and PR_n = g1b + G1[0] + r_n G1e, or the c / PC side
-    for (int t = tid; t < 2 * Nc; t += M2_T) {
-        const bool cside = t >= Nc;
+    // five threads per (hunk, side), four output channels each: r_n = (Nc-1) b2 + RS3_n W2, then (after the block has the whole
+    // r_n) PR_n = g1b + G1[0] + r_n G1e, or the c / PC side
+    for (int it0 = 0; it0 < 2 * Nc; it0 += M2_T / KG) {
+        const int t = it0 + tid / KG, k4 = 4 * (tid % KG);
+        const bool live = t < 2 * Nc, cside = t >= Nc;
         const int n = cside ? t - Nc : t;
-        float in[HD], r[HD], pq[HD];
-        load20s(in, (cside ? CS3 : RS3) + n * HD);
-#pragma unroll
-        for (int k = 0; k < HD; ++k) { r[k] = (float)(Nc - 1) * b2[k]; pq[k] = cside ? 0.f : g1b[k] + G1[k]; }
-        gemv20(r, in, W2);
-        gemv20(pq, r, G1 + 2 * HD);
-        store20s((cside ? cc : rr) + n * HD, r);
-        if (cside) {
-            store20s(PC + n * HD, pq);
-        } else {
-#pragma unroll
-            for (int k = 0; k < HD; ++k) { const int pi = p01_idx(n, k); PR01[pi] = pq[k]; PR01[pi + 4] = pq[k] + Dg[k]; }
+        if (live) {
+            const float fn1 = (float)(Nc - 1);
+            const float4 bb = *reinterpret_cast<const float4*>(b2 + k4);
+            const float4 r4 = gemv20_k4((cside ? CS3 : RS3) + n * HD, W2, k4, make_float4(fn1 * bb.x, fn1 * bb.y, fn1 * bb.z, fn1 * bb.w));
+            *reinterpret_cast<float4*>((cside ? cc : rr) + n * HD + k4) = r4;
         }
-        if (dbg) for (int k = 0; k < HD; ++k) dbg[(size_t)Ne * 21 + Nc * 4 + (cside ? 3 : 2) * T + n * HD + k] = pq[k];
+        __syncthreads();
+        if (live) {
+            float4 init = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!cside) {
+                const float4 g = *reinterpret_cast<const float4*>(g1b + k4), g0 = *reinterpret_cast<const float4*>(G1 + k4);
+                init = make_float4(g.x + g0.x, g.y + g0.y, g.z + g0.z, g.w + g0.w);
+            }
+            const float4 pq = gemv20_k4((cside ? cc : rr) + n * HD, G1 + 2 * HD, k4, init);
+            if (cside) {
+                *reinterpret_cast<float4*>(PC + n * HD + k4) = pq;
+            } else {
+                const float4 d = *reinterpret_cast<const float4*>(Dg + k4);
+                float* dst = PR01 + (size_t)n * PROW + 2 * k4;        // [n][kg][2][4]
+                *reinterpret_cast<float4*>(dst) = pq;
+                *reinterpret_cast<float4*>(dst + 4) = make_float4(pq.x + d.x, pq.y + d.y, pq.z + d.z, pq.w + d.w);
+            }
+            if (dbg) { float* dd = dbg + (size_t)Ne * 21 + Nc * 4 + (cside ? 3 : 2) * T + n * HD + k4; dd[0] = pq.x; dd[1] = pq.y; dd[2] = pq.z; dd[3] = pq.w; }
+        }
     }
     __syncthreads();
     M2_PHASE(5);
@@ -1496,14 +1539,14 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
                     const uint32_t mk = cmask[bq * WPe + w];
                     co += __popc(ebits[n * WPe + w] & mk); ci += __popc(ebT[n * WPe + w] & mk);
                 }
-                cnt[e] = (uint32_t)co | ((uint32_t)ci << 16);
+                cnt[bq * Ne + (clsv[n] >> 16)] = (uint32_t)co | ((uint32_t)ci << 16);      // [class][rank]
             }
             __syncthreads();
             M2_PHASE(19);
-            const int k4 = 4 * (tid % KG);
+            const int k4 = 4 * (tid / (M2_T / KG));
             float a_db[4] = {0.f, 0.f, 0.f, 0.f}, a_dU[4] = {0.f, 0.f, 0.f, 0.f}, a_dV[4] = {0.f, 0.f, 0.f, 0.f}, a_LS[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int n = tid / KG; n < Ne; n += M2_T / KG) {
-                const int aq = clsv[n];
+            for (int r = tid % (M2_T / KG); r < Ne; r += M2_T / KG) {      // lanes = consecutive ranks (see the forward)
+                const int n = ordv[r], aq = clsv[n] & 0xffff;
                 const float xn = xs[n];
                 const float4 gn4 = *reinterpret_cast<const float4*>(GEs + (size_t)n * HD + k4);
                 float wr[4] = {0.f, 0.f, 0.f, 0.f}, xwr[4] = {0.f, 0.f, 0.f, 0.f}, w1r[4] = {0.f, 0.f, 0.f, 0.f};
@@ -1511,7 +1554,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
                 const float* gab0 = G0 + aq * m * HD + k4; const float* gab1 = G1t + aq * m * HD + k4;
                 const float* gba0 = G0 + aq * HD + k4;     const float* gba1 = G1t + aq * HD + k4;
                 for (int bq = 0; bq < m; ++bq) {
-                    const uint32_t pk = cnt[n * m + bq];
+                    const uint32_t pk = cnt[bq * Ne + r];
                     const int c1o = (int)(pk & 0xffffu), c1i = (int)(pk >> 16), tot = csize[bq] - (aq == bq ? 1 : 0);
                     const float f1o = (float)c1o, f1i = (float)c1i, f0o = (float)(tot - c1o), f0i = (float)(tot - c1i), vb = cval[bq];
                     const float4 q0 = *reinterpret_cast<const float4*>(gab0 + bq * HD), q1 = *reinterpret_cast<const float4*>(gab1 + bq * HD);
@@ -1541,7 +1584,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             if (tid < 4 * HD) {                             // fixed-order sum over the 128 node slots of a channel group
                 const int qn = tid / HD, k = tid - qn * HD, kgq = k >> 2, cc2 = k & 3;
                 float t = 0.f;
-                for (int s2 = 0; s2 < M2_T / KG; ++s2) t += part[(size_t)(s2 * KG + kgq) * 16 + 4 * qn + cc2];
+                for (int s2 = 0; s2 < M2_T / KG; ++s2) t += part[(size_t)(kgq * (M2_T / KG) + s2) * 16 + 4 * qn + cc2];
                 red[tid] = t;
             }
         } else {
