@@ -53,6 +53,9 @@ def _load():
         "hdgnn_infer_host": ([vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp], i32),
         "hdgnn_normalize_propagate": ([i32, i32, vp, i32, vp, i32, vp, vp, i32, f32, i32, vp, vp, vp], i32),
         "hdgnn_map_conv": ([i32, i32, vp, i32, vp, vp, f32, f32, i32, vp, vp, vp], i32),
+        "hdgnn_propagate_backward_work": ([i32, i32, i32, i32], C.c_size_t),
+        "hdgnn_normalize_propagate_backward": ([i32, i32, vp, i32, vp, i32, vp, i32, f32, i32, vp, vp, vp, vp, vp, vp, vp], i32),
+        "hdgnn_map_conv_backward": ([i32, i32, vp, i32, vp, vp, f32, f32, i32, f32, vp, vp, vp, vp], i32),
         "hdgnn_compact_from_raw": ([i32, i32, vp, i32, vp, i32, vp, vp, vp], i32),
         "hdgnn_pack_label_bits": ([i32, i32, vp, i32, vp, vp], i32),
         "hdgnn_eval_counts": ([i32, i32, vp, vp, i32, vp, vp, i32, vp], i32),

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhdgnn.so")
-SOURCES = ["hdgnn.cu", "k_ent.cu", "k_mid.cu", "k_conv.cu", "k_io.cu"]
+SOURCES = ["hdgnn.cu", "k_ent.cu", "k_mid.cu", "k_conv.cu", "k_conv_bwd.cu", "k_io.cu"]
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh")) + [os.path.join("..", "..", "include", "hdgnn.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]

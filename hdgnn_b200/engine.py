@@ -345,6 +345,43 @@ def map_conv(adj: torch.Tensor, x: torch.Tensor, theta: torch.Tensor, lam_max: f
     return loss, per
 
 
+def normalize_propagate_backward(adj: torch.Tensor, H: torch.Tensor, dOut: torch.Tensor, W: Optional[torch.Tensor] = None,
+                                 out: Optional[torch.Tensor] = None, eps: float = 1e-3, flags: int = 0):
+    """Backward of normalize_propagate w.r.t. H, W and the bias (the adjacency carries no gradient: model.py:337 takes its
+    argmax).  `out` = the forward's output, needed with P_RELU.  Returns (dH (B,N,d_in), dW (d_in,d_out) or None, dbias (d_out))."""
+    if not (adj.is_cuda and H.is_cuda and dOut.is_cuda):
+        raise RuntimeError("normalize_propagate_backward needs CUDA tensors; there is no CPU fallback")
+    a = _pitched(adj)
+    B, N, pitch = a.shape
+    H = H.contiguous().float(); dOut = dOut.contiguous().float()
+    d_in, d_out = H.shape[2], dOut.shape[2]
+    dH = torch.empty(B, N, d_in, dtype=torch.float32, device=a.device)
+    dW = torch.empty(d_in, d_out, dtype=torch.float32, device=a.device) if W is not None else None
+    db = torch.empty(d_out, dtype=torch.float32, device=a.device)
+    work = torch.empty(lib.hdgnn_propagate_backward_work(B, N, d_in, d_out), dtype=torch.float32, device=a.device)
+    st = C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream)
+    check(lib.hdgnn_normalize_propagate_backward(B, N, _p(a), pitch, _p(H), d_in, _p(None if W is None else W.contiguous().float()), d_out,
+                                                 eps, flags, _p(None if out is None else out.contiguous().float()), _p(dOut),
+                                                 _p(dH), _p(dW), _p(db), _p(work), st))
+    return dH, dW, db
+
+
+def map_conv_backward(adj: torch.Tensor, x: torch.Tensor, theta: torch.Tensor, lam_max: float = 1.5, eps: float = 1e-3,
+                      flags: int = 0, gscale: float = 1.0):
+    """Gradient of map_conv's loss w.r.t. x (B,N) and theta (2) (model.py:394-403; no gradient to the adjacency)."""
+    if not (adj.is_cuda and x.is_cuda):
+        raise RuntimeError("map_conv_backward needs CUDA tensors; there is no CPU fallback")
+    a = _pitched(adj)
+    B, N, pitch = a.shape
+    dx = torch.empty(B, N, dtype=torch.float32, device=a.device)
+    dth = torch.empty(2, dtype=torch.float32, device=a.device)
+    work = torch.empty(2 * B, dtype=torch.float32, device=a.device)
+    st = C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream)
+    check(lib.hdgnn_map_conv_backward(B, N, _p(a), pitch, _p(x.contiguous().float()), _p(theta.reshape(-1).contiguous().float()),
+                                      lam_max, eps, flags, gscale, _p(dx), _p(dth), _p(work), st))
+    return dx, dth
+
+
 # -- data formats either side of the hot path: device loader and device evaluation (SURVEY 8(f) rows 1, 2) --------
 def compact_from_raw_device(raw: torch.Tensor, want_diag: bool = True):
     """utils2.py:29-47 + the int() label indexing of :82,:105 on the device.  raw: (N,n,n) float64 / float32 CUDA tensor

@@ -222,6 +222,23 @@ int hdgnn_normalize_propagate(int B, int N, const uint8_t* adj, int adj_pitch, c
 int hdgnn_map_conv(int B, int N, const uint8_t* adj, int adj_pitch, const float* x, const float* theta,
                    float lam_max, float eps, int flags, float* per_commit, float* loss, void* stream);
 
+/* Backward of the legacy operator.  The reference trains through map_conv (model.py:150-155, 405-417), but the edge tensor
+ * enters chebyshev_polynomials through tf.argmax (model.py:337): the adjacency is a hard {0,1} grid without gradient, so the
+ * backward runs w.r.t. the node features / weights / Chebyshev coefficients only.
+ *
+ * hdgnn_normalize_propagate_backward: out = act(A_hat (H W) + bias).  dOut (B,N,d_out); `out` is the forward's output (read
+ * only with HDGNN_P_RELU, for the mask).  dH (B,N,d_in), dW (d_in,d_out), dbias (d_out): each may be NULL.  dZ = A_hat^T dPre is
+ * computed by the forward's own kernel with the transposition flipped (same tcgen05 path).  work: device scratch of
+ * hdgnn_propagate_backward_work(B,N,d_in,d_out) floats.  Same flags as the forward. */
+size_t hdgnn_propagate_backward_work(int B, int N, int d_in, int d_out);
+int hdgnn_normalize_propagate_backward(int B, int N, const uint8_t* adj, int adj_pitch, const float* H, int d_in, const float* W,
+                                       int d_out, float eps, int flags, const float* out, const float* dOut,
+                                       float* dH, float* dW, float* dbias, float* work, void* stream);
+/* hdgnn_map_conv_backward: gscale * d loss / d x -> dx (B,N) and gscale * d loss / d theta -> dtheta (2) for the loss of
+ * hdgnn_map_conv (either output may be NULL).  work: 2*B floats (needed for dtheta). */
+int hdgnn_map_conv_backward(int B, int N, const uint8_t* adj, int adj_pitch, const float* x, const float* theta, float lam_max,
+                            float eps, int flags, float gscale, float* dx, float* dtheta, float* work, void* stream);
+
 /* ---- the data formats either side of the hot path; stateless, asynchronous on `stream` ----
  * Device-side loader, replaces the array half of utils2.py:29-47 (diagonal -> node attribute, diagonal zeroed) and the
  * int() label indexing of utils2.py:82,105.  raw: (N,n,n) float64 (raw_is_f64 != 0) or float32, exactly as stored in

@@ -129,3 +129,79 @@ def test_legacy_operator_matches_reference_model_py_golden():
         torch.cuda.synchronize()
         ref = Ahat @ H.astype(np.float64)
         assert np.abs(out.cpu().numpy() - ref).max() / np.abs(ref).max() < 1e-5, flags
+
+
+def test_legacy_operator_backward_matches_reference_gradients():
+    """map_conv backward against the gradients autograd gives for the reference's own model.py:394-403 (golden dO, dtheta)."""
+    import os
+    from hdgnn_b200.engine import map_conv_backward
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "legacy_toy.npz"))
+    mb, No = z["adj"].shape[:2]
+    adj = torch.tensor(z["adj"]).cuda()
+    x = torch.tensor(z["O"].reshape(mb, No), dtype=torch.float32).cuda()
+    theta = torch.tensor(z["theta"], dtype=torch.float32).cuda()
+    dx, dth = map_conv_backward(adj, x, theta)
+    torch.cuda.synchronize()
+    ref_dx, ref_dth = z["dO"].reshape(mb, No), z["dtheta"]
+    assert np.abs(dx.cpu().numpy() - ref_dx).max() / np.abs(ref_dx).max() < 1e-5
+    assert np.abs(dth.cpu().numpy() - ref_dth).max() / np.abs(ref_dth).max() < 1e-5
+
+
+@pytest.mark.parametrize("B,N,p", [(3, 6, 0.4), (4, 200, 0.05), (2, 333, 0.03)])
+@pytest.mark.parametrize("flags", [0, 1, 4, 1 | 4])
+def test_map_conv_backward_matches_autograd(B, N, p, flags):
+    """dx, dtheta against autograd of an fp64 restatement with the same switches (self loop, un-transposed form); flags = 0 is
+    the reference's form, which test_legacy_operator_backward_matches_reference_gradients pins to model.py itself."""
+    from hdgnn_b200.engine import map_conv_backward
+    rng = np.random.default_rng(N + flags)
+    adj = _adj(B, N, p, N + 2)
+    x = rng.integers(0, 10, size=(B, N)).astype(np.float64) / 3.0
+    th = torch.tensor([0.13, -0.21], dtype=torch.float64, requires_grad=True)
+    xt = torch.tensor(x, requires_grad=True)
+    A = torch.tensor(adj, dtype=torch.float64)
+    if flags & 1:
+        A = A + torch.eye(N, dtype=torch.float64)
+    d = (A.sum(2) + float(np.float32(1e-3))) ** -0.5
+    Ahat = d[:, :, None] * (A if flags & 4 else A.transpose(1, 2)) * d[:, None, :]
+    t = torch.softmax(th, 0)
+    Lx = (2.0 / 1.5) * (xt - (Ahat @ xt[..., None])[..., 0]) - xt
+    loss = (((xt * (t[0] * xt + t[1] * Lx)).sum(1)) ** 2).mean()
+    if flags == 0:
+        assert abs(float(loss) - float(O.map_conv_closed(th, torch.tensor(adj), xt))) <= 1e-10 * abs(float(loss))
+    gx, gt = torch.autograd.grad(loss, [xt, th])
+    dx, dth = map_conv_backward(torch.tensor(adj).cuda(), torch.tensor(x, dtype=torch.float32).cuda(), th.detach().float().cuda(),
+                                flags=flags, gscale=0.7)
+    torch.cuda.synchronize()
+    assert np.abs(dx.cpu().numpy() - 0.7 * gx.numpy()).max() / np.abs(gx.numpy()).max() < 5e-5
+    assert np.abs(dth.cpu().numpy() - 0.7 * gt.numpy()).max() / np.abs(gt.numpy()).max() < 5e-5
+
+
+@pytest.mark.parametrize("B,N,d_in,d_out,p", [(3, 9, 4, 4, 0.3), (4, 50, 7, 20, 0.1), (2, 200, 20, 20, 0.05), (2, 300, 20, 32, 0.02)])
+@pytest.mark.parametrize("flags", [0, 2, 1 | 2, 4, 8 | 2, 16])
+def test_normalize_propagate_backward_matches_autograd(B, N, d_in, d_out, p, flags):
+    """dH, dW, dbias of act(A_hat (H W) + b) against autograd of the fp64 restatement; A_hat^T dPre runs on the forward's kernels."""
+    from hdgnn_b200.engine import normalize_propagate, normalize_propagate_backward
+    rng = np.random.default_rng(N + 3 * flags)
+    adj = _adj(B, N, p, N + 5)
+    H = rng.normal(size=(B, N, d_in))
+    W = rng.normal(scale=0.3, size=(d_in, d_out))
+    bias = rng.normal(size=d_out) if flags & 2 else np.zeros(d_out)
+    dOut = rng.normal(size=(B, N, d_out))
+    A = torch.tensor(adj, dtype=torch.float64)
+    if flags & 1:
+        A = A + torch.eye(N, dtype=torch.float64)
+    d = (A.sum(2) + float(np.float32(1e-3))) ** -0.5
+    M = A if flags & 4 else A.transpose(1, 2)
+    Ahat = d[:, :, None] * M * d[:, None, :]
+    Ht = torch.tensor(H, requires_grad=True); Wt = torch.tensor(W, requires_grad=True); bt = torch.tensor(bias, requires_grad=True)
+    pre = Ahat @ (Ht @ Wt) + bt
+    out_ref = torch.relu(pre) if flags & 2 else pre
+    gH, gW, gb = torch.autograd.grad((out_ref * torch.tensor(dOut)).sum(), [Ht, Wt, bt])
+    adj_d = torch.tensor(adj).cuda()
+    Hd, Wd = torch.tensor(H, dtype=torch.float32).cuda(), torch.tensor(W, dtype=torch.float32).cuda()
+    bd = torch.tensor(bias, dtype=torch.float32).cuda() if flags & 2 else None
+    out, _ = normalize_propagate(adj_d, Hd, Wd, bd, eps=1e-3, flags=flags)
+    dH, dW, db = normalize_propagate_backward(adj_d, Hd, torch.tensor(dOut, dtype=torch.float32).cuda(), W=Wd, out=out, eps=1e-3, flags=flags)
+    torch.cuda.synchronize()
+    rel = lambda a, r: float(np.abs(a.cpu().numpy() - r.numpy()).max() / max(np.abs(r.numpy()).max(), 1e-30))
+    assert rel(dH, gH) < 2e-5 and rel(dW, gW) < 2e-5 and rel(db, gb) < 2e-5
