@@ -592,6 +592,7 @@ int fused_forward(hdgnn_handle_t h, int B, int B_global, const Inputs& in, float
     m.inl = h->inl ? 1 : 0;
     m.wait_flag = in.wait_flag; m.wait_tag = in.wait_tag;
     m.hits_acc = h->hits_acc;
+    m.lay = mid2_layout(h->Ne, h->Nc, train, !dlt_g, m.scache != 0, h->inl);
     const size_t smem = mid2_smem_bytes(h->Ne, h->Nc, train, !dlt_g, m.scache != 0, h->inl);
     const int cwc = (h->Nc + 31) / 32;
     PROF_BEGIN(h, st);

@@ -33,29 +33,6 @@ constexpr int M2_MCLS = 16;               // inline entity stage: most distinct 
 constexpr int M2_BLK1 = 400 + 20 + 420 + 20 + 20 + 1;              // 881
 constexpr int M2_BLK2 = 200 + 20 + 400 + 20 + 440 + 20 + 40 + 2;   // 1142
 
-struct Mid2Args {
-    int Ne, Nc, ent, R, SL;                  // R, SL: row-chunk decomposition of ent_fwd2 (ent2.cuh)
-    const uint32_t* ebits; int WPe;          // (B,Ne,WPe)
-    const uint32_t* ybits; int WPc;          // (B,Nc,WPc)
-    const float* x; const int* hmap; const int* L;
-    const float* params; ParamOff po;
-    const float* RS1; const float* CS1p;     // (B,Ne,20), (B,SL,Ne,20)
-    float* logits; float* probs;             // (B,2,Ncr) or null
-    float* cep;                              // (B) sum of CE over the commit's pairs
-    float scale;                             // dL/dlogit scale: 10 / (B_global * Ncr)
-    float* GE;                               // (B,Ne,20) d/dS1
-    float* gpart; int total;                 // (B,total)
-    float* dbg;                              // debug dumps (HDGNN_F_DEBUG) or null; layout below
-    long long* clk;                          // per-phase clock64 stamps (B,24) or null
-    float* dlt_g;                            // (B, Nc, CW*32) dL/dlogit table in HBM when it does not fit smem, else null
-    int scache;                              // keep the entity effect sums S (Ne x 20) in shared memory from the forward to the backward
-    unsigned long long* hits_acc;            // running count of arg-max hits (EvaluationFuncs.py:27-37) over all commits, or null
-    const int* wait_flag; int wait_tag;      // host-fed step: the staging copies of this step are complete once *wait_flag == wait_tag
-                                             // (written by the copy stream's DMA after the data); null = inputs already ordered
-    int inl;                                 // entity pair layer and its backward INSIDE this kernel (entsp.cuh: sorted prefix sums +
-                                             // edge walk): RS1 / CS1p / GE are not used, the step has no ent_fwd2 / ent_bwd2 launch and
-                                             // this kernel follows the previous step's optimizer kernel (weights are read after pdl_wait)
-};
 // debug dump layout per commit (floats): S1[Ne*20] X2[Ne] NB[Nc*4] RS3[Nc*20] CS3[Nc*20] PR[Nc*20] PC[Nc*20]
 // DNB[Nc*4] DX2[Ne]
 __host__ __device__ inline size_t mid2_dbg_floats(int Ne, int Nc) { return (size_t)Ne * 22 + (size_t)Nc * 88; }
@@ -110,6 +87,32 @@ __host__ __device__ inline Mid2Smem mid2_layout(int Ne, int Nc, bool train, bool
 __host__ __device__ inline size_t mid2_smem_bytes(int Ne, int Nc, bool train, bool dlt_smem = true, bool scache = false, bool inl = false) {
     return (size_t)mid2_layout(Ne, Nc, train, dlt_smem, scache, inl).total * 4 + 16;
 }
+
+struct Mid2Args {
+    int Ne, Nc, ent, R, SL;                  // R, SL: row-chunk decomposition of ent_fwd2 (ent2.cuh)
+    const uint32_t* ebits; int WPe;          // (B,Ne,WPe)
+    const uint32_t* ybits; int WPc;          // (B,Nc,WPc)
+    const float* x; const int* hmap; const int* L;
+    const float* params; ParamOff po;
+    const float* RS1; const float* CS1p;     // (B,Ne,20), (B,SL,Ne,20)
+    float* logits; float* probs;             // (B,2,Ncr) or null
+    float* cep;                              // (B) sum of CE over the commit's pairs
+    float scale;                             // dL/dlogit scale: 10 / (B_global * Ncr)
+    float* GE;                               // (B,Ne,20) d/dS1
+    float* gpart; int total;                 // (B,total)
+    float* dbg;                              // debug dumps (HDGNN_F_DEBUG) or null; layout below
+    long long* clk;                          // per-phase clock64 stamps (B,24) or null
+    float* dlt_g;                            // (B, Nc, CW*32) dL/dlogit table in HBM when it does not fit smem, else null
+    int scache;                              // keep the entity effect sums S (Ne x 20) in shared memory from the forward to the backward
+    unsigned long long* hits_acc;            // running count of arg-max hits (EvaluationFuncs.py:27-37) over all commits, or null
+    const int* wait_flag; int wait_tag;      // host-fed step: the staging copies of this step are complete once *wait_flag == wait_tag
+                                             // (written by the copy stream's DMA after the data); null = inputs already ordered
+    Mid2Smem lay;                            // shared-memory layout (mid2_layout), computed once on the host: the offsets are kernel
+                                             // arguments (constant bank) instead of per-thread arithmetic
+    int inl;                                 // entity pair layer and its backward INSIDE this kernel (entsp.cuh: sorted prefix sums +
+                                             // edge walk): RS1 / CS1p / GE are not used, the step has no ent_fwd2 / ent_bwd2 launch and
+                                             // this kernel follows the previous step's optimizer kernel (weights are read after pdl_wait)
+};
 
 // fixed-order block sum for M2_T threads; every thread gets the result
 __device__ __forceinline__ float mid2_block_sum(float v, float* scratch) {
@@ -277,7 +280,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
     const int Ne = a.Ne, Nc = a.Nc, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int kg = warp % KG, rg = warp / KG, k0 = kg * 4;
     const int WPe = a.WPe, WPc = a.WPc;
-    const Mid2Smem L_ = mid2_layout(Ne, Nc, TRAIN, a.dlt_g == nullptr, a.scache != 0, a.inl != 0);
+    const Mid2Smem& L_ = a.lay;
     float* blk1 = sm + L_.blk1; float* blk2 = sm + L_.blk2;
     float* W5 = blk1; float* b5 = blk1 + 400; float* U1 = blk1 + 420; float* c1 = blk1 + 840;
     float* u2 = blk1 + 860; float* c2 = blk1 + 880;
