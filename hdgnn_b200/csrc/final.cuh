@@ -29,8 +29,14 @@ struct PeerArgs {
     int* seq;                    // device counter: exchanges completed so far (local)
     int* error;                  // set to 1 when a wait timed out (hdgnn_peer_status reads it)
     unsigned int max_spins;      // polls of ~1 us before a wait gives up (HDGNN_PEER_TIMEOUT_MS, default 20 s)
+    unsigned long long* stamps;  // debug (HDGNN_PEER_STAMPS=1): [4096][2] globaltimer ns of CTA 0 at its push and after its last pull
 };
 
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void peer_push(peer_word* p, float v, int seq) {
     const peer_word w = ((peer_word)(unsigned int)seq << 32) | (peer_word)__float_as_uint(v);
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
@@ -165,11 +171,13 @@ __global__ void __launch_bounds__(FIN_P * FIN_SL) reduce_adam_kernel(const Final
         __syncthreads();
         const float mine = part[0][pl];
         const size_t slot = (size_t)par * W;
+        if (pr.stamps && blockIdx.x == 0 && tid == 0) pr.stamps[2 * (seq & 4095)] = global_ns();
         if (sl < W && p < a.total) peer_push(pr.inbox[sl] + (slot + pr.rank) * pr.stride + p, mine, seq);
         if (blockIdx.x == 0 && tid < W && a.loss) peer_push(pr.lossin[tid] + slot + pr.rank, ce_sh, seq);
         __syncthreads();                                   // part[0][] has been read
         part[sl][pl] = (sl < W && p < a.total) ? peer_pull(pr.inbox[pr.rank] + (slot + sl) * pr.stride + p, seq, pr.error, pr.max_spins) : 0.f;
         __syncthreads();
+        if (pr.stamps && blockIdx.x == 0 && tid == 0) pr.stamps[2 * (seq & 4095) + 1] = global_ns();
         if (sl == 0 && p < a.total) {
             g = 0.f;
             for (int r = 0; r < W; ++r) g += part[r][pl];  // rank order: identical on every rank

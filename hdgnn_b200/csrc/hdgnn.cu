@@ -918,6 +918,11 @@ int hdgnn_peer_attach(hdgnn_handle_t h, int rank, int world, const unsigned char
         const long long spins = (ms < 1 ? 1 : ms) * 1000;            // ~1 us per poll after the first 64
         pa.max_spins = spins > 0xfffffff0ll ? 0xfffffff0u : (unsigned int)spins;
     }
+    pa.stamps = nullptr;
+    if (env_int("HDGNN_PEER_STAMPS", 0)) {
+        if (!h->ws.count("PEER_STAMPS") && (rc = alloc(h, "PEER_STAMPS", 4096 * 2 * sizeof(unsigned long long)))) return rc;
+        pa.stamps = (unsigned long long*)h->ws["PEER_STAMPS"].p;
+    }
     h->peer = pa;
     h->peer_ready = true;
     return HDGNN_OK;

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .engine import Engine, DeviceBatch, param_count, param_offsets, PARAM_NAMES, F_LABEL_BITS, pack_label_bits
+from .engine import Engine, DeviceBatch, param_count, param_offsets, PARAM_NAMES, F_LABEL_BITS, F_DENSE_SWEEP, pack_label_bits
 from .synthetic import CommitBatch
 
 H = 20
@@ -105,7 +105,7 @@ class graph2graph(object):
     def __init__(self, sess=None, Ds=1, Ne=200, Nc=74, Ner=None, Ncr=None, Dr=2, De_e=20, De_er=20, Mini_batch=50,
                  checkpoint_dir="./checkpoint40/", epoch=50, Ds_inter=1, Dr_inter=2, Step=2, Repo="glide",
                  variant=2, device: Optional[int] = None, seed: Optional[int] = None, max_batch: Optional[int] = None,
-                 collective: str = "auto"):
+                 collective: str = "auto", entity_sweep: str = "auto"):
         # `sess` is accepted and ignored: there is no TF session (main.py:54-56).
         Ner = Ne * (Ne - 1) if Ner is None else Ner
         Ncr = Nc * (Nc - 1) if Ncr is None else Ncr
@@ -136,19 +136,25 @@ class graph2graph(object):
             raise ValueError("collective must be 'auto', 'peer' (all-reduce fused into the last kernel over NVLink peer "
                              "memory) or 'nccl' (torch.distributed.all_reduce between backward and Adam)")
         self.collective = collective
+        if entity_sweep not in ("auto", "inline", "dense"):
+            raise ValueError("entity_sweep must be 'auto', 'inline' (sorted prefix sums / class tables inside the per-commit kernel) "
+                             "or 'dense' (the Ne x Ne sweep kernels, HDGNN_F_DENSE_SWEEP)")
+        self.entity_sweep = entity_sweep
+        self._dense = entity_sweep == "dense"
         self._saved = {}                 # checkpoint dir -> names written by THIS object (the Saver's max_to_keep list)
         self.build_model()
 
     # ------------------------------------------------------------------------------------------
     def build_model(self):
         torch.cuda.set_device(self.device)
+        extra = F_DENSE_SWEEP if self._dense else 0
         try:        # label grids as bitmaps on the wire (1/8 of the H2D bytes, no packing kernel): fused path only
             self.engine = Engine(self.Ne, self.Nc, variant=self.variant, max_batch=self.max_batch, device=self.device,
-                                 flags=F_LABEL_BITS)
+                                 flags=F_LABEL_BITS | extra)
         except _lib.HdgnnError as e:
             if e.code != _lib.E_UNSUPPORTED:
                 raise
-            self.engine = Engine(self.Ne, self.Nc, variant=self.variant, max_batch=self.max_batch, device=self.device)
+            self.engine = Engine(self.Ne, self.Nc, variant=self.variant, max_batch=self.max_batch, device=self.device, flags=extra)
         self.host_bits = self.engine.host_bits
         self.n_params = param_count(self.variant)
         self.offsets = param_offsets(self.variant)
@@ -240,6 +246,23 @@ class graph2graph(object):
             b = b.slice(self.rank * per, (self.rank + 1) * per)
         return b
 
+    def _choose_entity_sweep(self, cb: CommitBatch):
+        """entity_sweep='auto': the inline entity stage costs O(edges) when the node attribute has more than 16 distinct
+        values per commit (class tables otherwise), the dense sweeps O(Ne^2): measured break-even near 15-20 % edge density
+        (tools/step_probe.py).  Decided from the data set, identically on every rank; rebuilds the engine if it changes."""
+        if self.entity_sweep != "auto" or self.variant != 2 or cb.B == 0:
+            return
+        n = min(cb.B, 64)
+        distinct = max(len(np.unique(cb.x[b])) for b in range(n))
+        density = float(np.asarray(cb.adj[:n], dtype=np.float32).mean())
+        dense = distinct > 16 and density > 0.15
+        if dense != self._dense:
+            self._dense = dense
+            params = self.params.clone()
+            self.engine.close()
+            self.build_model()
+            self.params.copy_(params)
+
     def _model_dir(self):
         return "%s" % (self.Repo + '/model_%d/' % self.variant + str(self.Step))
 
@@ -254,6 +277,7 @@ class graph2graph(object):
         ckpt = getattr(args, "checkpoint_dir", self.checkpoint_dir)
         self.initialize()                                           # always from scratch (model_2.py:340-341)
         train, _ = data if data is not None else self._load(root)
+        self._choose_entity_sweep(train)
         mb = self.mini_batch_num
         if self.world > 1 and mb % self.world:
             raise ValueError("Mini_batch must be divisible by the number of ranks")

@@ -1,5 +1,5 @@
 """Commit sharding with the gradient all-reduce fused into the reduce + Adam kernel over NVLink peer memory
-(hdgnn_peer_export / hdgnn_peer_attach / hdgnn_train_step_peer_host): 2 ranks on 2 GPUs against the NCCL path and
+(hdgnn_peer_export / hdgnn_peer_attach / hdgnn_train_step_peer_host): 2, 4 and 8 ranks against the NCCL path and
 against the same global batches trained on one GPU.  Needs >= 2 GPUs (gpurun --gpus 2); skipped on a 1-GPU box."""
 import os
 import subprocess
@@ -13,12 +13,15 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+@pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("variant,Ne,Nc,per", [(2, 48, 20, 6), (1, 30, 12, 3), (2, 200, 74, 10)])
-def test_peer_exchange_matches_nccl_and_single_gpu(tmp_path, variant, Ne, Nc, per):
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    world, steps = 2, 4
-    port = 29600 + (os.getpid() % 300)
+def test_peer_exchange_matches_nccl_and_single_gpu(tmp_path, variant, Ne, Nc, per, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    if world > 2 and Ne == 30:
+        pytest.skip("covered at world 2")
+    steps = 4
+    port = 29600 + (os.getpid() % 300) + world
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "helpers", "peer_worker.py"), str(tmp_path), str(variant),
            str(Ne), str(Nc), str(per), str(steps)]
@@ -26,8 +29,9 @@ def test_peer_exchange_matches_nccl_and_single_gpu(tmp_path, variant, Ne, Nc, pe
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     z = [np.load(tmp_path / f"rank{k}.npz") for k in range(world)]
     # replicas stay bitwise identical (every rank sums the slices in rank order)
-    assert np.array_equal(z[0]["peer_params"], z[1]["peer_params"]) and np.array_equal(z[0]["peer_m"], z[1]["peer_m"])
-    assert np.array_equal(z[0]["peer_ce"], z[1]["peer_ce"])                   # every rank gets the GLOBAL mean CE
+    for k in range(1, world):
+        assert np.array_equal(z[0]["peer_params"], z[k]["peer_params"]) and np.array_equal(z[0]["peer_m"], z[k]["peer_m"])
+        assert np.array_equal(z[0]["peer_ce"], z[k]["peer_ce"])               # every rank gets the GLOBAL mean CE
     scale = np.abs(z[0]["single_params"]).max()
     # same numbers as the NCCL path and as one GPU on the whole batch (summation order differs: fp32 round-off)
     assert np.abs(z[0]["peer_params"] - z[0]["nccl_params"]).max() / scale < 1e-5
@@ -36,7 +40,8 @@ def test_peer_exchange_matches_nccl_and_single_gpu(tmp_path, variant, Ne, Nc, pe
     assert np.allclose(z[0]["peer_reg"], z[0]["nccl_reg"], rtol=1e-6)
     if "train_loss" in z[0].files:
         # graph2graph.train() over two ranks == the same epochs on one GPU (loss, accuracy from device counters, weights)
-        assert np.array_equal(z[0]["train_loss"], z[1]["train_loss"]) and np.array_equal(z[0]["train_params"], z[1]["train_params"])
+        for k in range(1, world):
+            assert np.array_equal(z[0]["train_loss"], z[k]["train_loss"]) and np.array_equal(z[0]["train_params"], z[k]["train_params"])
         assert np.allclose(z[0]["train_loss"], z[0]["single_train_loss"], rtol=2e-5)
         assert np.abs(z[0]["train_acc"] - z[0]["single_train_acc"]).max() < 1e-3
         assert np.abs(z[0]["train_params"] - z[0]["single_train_params"]).max() / np.abs(z[0]["single_train_params"]).max() < 1e-5
