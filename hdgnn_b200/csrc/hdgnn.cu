@@ -105,6 +105,8 @@ struct hdgnn_handle_s {
     bool dlt_global = false;                                   // mid2's dL/dlogit table in HBM instead of shared memory
     bool mid_scache = false;                                   // mid2 keeps the entity effect sums in shared memory for its backward
     bool inl = false;                                          // entity pair layer inside mid2 (entsp.cuh): no ent_fwd2 / ent_bwd2 launch
+    bool edge_fused = false;                                   // variant 4: the entity-edge branch inside mid2 as well
+    bool edge_fused_train = false;                             // ... including its backward
     int Gf = 0, Gb = 0, Rf = 0, Rb = 0, SLf = 0;               // grids / rows per CTA / slots of the last launch
     std::map<std::string, Buf> ws;
     std::string err;
@@ -171,6 +173,10 @@ namespace {
             (h)->prof_ev.push_back({what, {(h)->prof_start, stop_}});                             \
         }                                                                                         \
     } while (0)
+
+// which path a call takes: variant 4 runs its forward on the fused path as soon as the edge branch fits (edge_fused), its
+// training step only with edge_fused_train; everything else follows h->fused
+bool fused_for(hdgnn_handle_t h, bool train) { return h->fused && (!h->edge || (train ? h->edge_fused_train : h->edge_fused)); }
 
 int fail(hdgnn_handle_t h, int code, const std::string& msg) {
     if (h) h->err = msg; else g_create_error = msg;
@@ -592,8 +598,10 @@ int fused_forward(hdgnn_handle_t h, int B, int B_global, const Inputs& in, float
     m.inl = h->inl ? 1 : 0;
     m.wait_flag = in.wait_flag; m.wait_tag = in.wait_tag;
     m.hits_acc = h->hits_acc;
-    m.lay = mid2_layout(h->Ne, h->Nc, train, !dlt_g, m.scache != 0, h->inl);
-    const size_t smem = mid2_smem_bytes(h->Ne, h->Nc, train, !dlt_g, m.scache != 0, h->inl);
+    m.edge = h->edge_fused ? 1 : 0;
+    if (m.edge) { m.RSEg = F(h, "RSEG"); m.CSEg = F(h, "CSEG"); m.REg = F(h, "REG"); m.CEg = F(h, "CEG"); m.A1F = F(h, "A1F"); }
+    m.lay = mid2_layout(h->Ne, h->Nc, train, !dlt_g, m.scache != 0, h->inl, h->edge_fused);
+    const size_t smem = mid2_smem_bytes(h->Ne, h->Nc, train, !dlt_g, m.scache != 0, h->inl, h->edge_fused);
     const int cwc = (h->Nc + 31) / 32;
     PROF_BEGIN(h, st);
     // inline entity stage: this kernel reads the weights after its pdl_wait, so it may follow the previous step's optimizer
@@ -749,7 +757,7 @@ int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out) {
     if (h->fwd_nrg != 1 && h->fwd_nrg != 2 && h->fwd_nrg != 4) h->fwd_nrg = 1;
     if (h->bwd_nrg != 1 && h->bwd_nrg != 2 && h->bwd_nrg != 4) h->bwd_nrg = 1;
     // the fused path needs the per-commit state of mid2 in one SM's shared memory and a hunk grid of <= 8 segments
-    h->fused = !h->edge && !(cfg->flags & HDGNN_F_LEGACY) && h->Nc <= 256;
+    h->fused = !(cfg->flags & HDGNN_F_LEGACY) && h->Nc <= 256;
     if (h->fused) {     // per-commit state of mid2 in one SM; the per-pair dL/dlogit table may spill to HBM (L2-resident)
         h->dlt_global = mid2_smem_bytes(h->Ne, h->Nc, true, true) > (size_t)prop.sharedMemPerBlockOptin;
         h->fused = mid2_smem_bytes(h->Ne, h->Nc, true, !h->dlt_global) <= (size_t)prop.sharedMemPerBlockOptin;
@@ -762,8 +770,22 @@ int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out) {
         else if (mid2_smem_bytes(h->Ne, h->Nc, true, false, true, true) <= lim) { h->inl = true; h->dlt_global = true; }
         if (h->inl) h->mid_scache = true;
     }
+    if (h->edge) {
+        // variant 4 on the fused path: needs the inline entity stage, the soft-edge head tables (Ne x 60 floats + a 128-row
+        // staging tile) and the edge branch's pair sums (2 Ne x 20) side by side in mid2's union region
+        bool ok = h->fused && h->inl && env_int("HDGNN_V4_FUSED", 1) != 0;
+        if (ok) {
+            const size_t lim = (size_t)prop.sharedMemPerBlockOptin;
+            h->dlt_global = mid2_smem_bytes(h->Ne, h->Nc, true, true, true, true, true) > lim;
+            const Mid2Smem L = mid2_layout(h->Ne, h->Nc, true, !h->dlt_global, true, true, true);
+            ok = (size_t)L.total * 4 + 16 <= lim && h->Ne * 60 + (M2_T / KG) * HD <= (L.sc - L.uni) - 2 * h->Ne * HD;
+        }
+        h->edge_fused = ok;
+        h->edge_fused_train = ok && env_int("HDGNN_V4_FUSED_TRAIN", 0) != 0;
+        if (!ok) { h->fused = false; h->inl = false; }
+    }
     h->host_bits = (cfg->flags & HDGNN_F_LABEL_BITS) != 0;
-    if (h->host_bits && !h->fused) {
+    if (h->host_bits && !fused_for(h, true)) {
         delete h;
         return fail(nullptr, HDGNN_E_UNSUPPORTED, "HDGNN_F_LABEL_BITS needs the fused path (variants 1-3, per-commit state within one SM)");
     }
@@ -783,8 +805,10 @@ int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out) {
 
     const size_t B = cfg->max_batch, Ne = h->Ne, Nc = h->Nc, Se = h->Se, Sc = h->Sc, f = sizeof(float);
     // (B, SL, Ne, 20) column partials of ent_fwd2: B * SL <= grid + 2 B for every batch size <= max_batch
-    const size_t cs1p = h->fused ? ((size_t)Gf_max + 2 * B + 2) * Ne * HD * f : B * Se * Ne * HD * f;
-    const bool lg = !h->fused;     // buffers only the multi-kernel path needs (kept when debugging: dump targets)
+    const size_t cs1p_f = ((size_t)Gf_max + 2 * B + 2) * Ne * HD * f, cs1p_l = B * Se * Ne * HD * f;
+    const bool mixed = h->fused && !fused_for(h, true);        // variant 4: fused forward, multi-kernel training
+    const size_t cs1p = !h->fused ? cs1p_l : (mixed && cs1p_l > cs1p_f ? cs1p_l : cs1p_f);
+    const bool lg = !fused_for(h, true) || !fused_for(h, false);     // buffers only the multi-kernel path needs (kept when debugging: dump targets)
     const bool dbgbuf = lg || h->debug;
     struct { const char* n; size_t bytes; bool need; } plan[] = {
         {"RS1", B * Ne * HD * f, h->ent}, {"CS1P", cs1p, h->ent}, {"S1", B * Ne * HD * f, dbgbuf},
@@ -804,6 +828,8 @@ int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out) {
         {"DBG", B * mid2_dbg_floats(h->Ne, h->Nc) * f, h->fused && h->debug},
         {"CLK", B * 24 * sizeof(long long), h->fused && h->debug},
         {"DLT", B * Nc * (size_t)((h->Nc + 31) / 32 * 32) * f, h->fused && h->dlt_global},
+        {"RSEG", B * Ne * HD * f, h->edge_fused}, {"CSEG", B * Ne * HD * f, h->edge_fused}, {"REG", B * Ne * HD * f, h->edge_fused},
+        {"CEG", B * Ne * HD * f, h->edge_fused}, {"A1F", B * Ne * (Ne - 1) * f, h->edge_fused},
         {"RSE", B * Ne * HD * f, h->edge}, {"CSEP", B * Se * Ne * HD * f, h->edge}, {"CSEF", B * Ne * HD * f, h->edge},
         {"PRE", B * Ne * HD * f, h->edge}, {"PCE", B * Ne * HD * f, h->edge},
         {"SOFT", B * Ne * Ne * 2 * f, h->edge}, {"DSOFT", B * Ne * Ne * 2 * f, h->edge},
@@ -872,7 +898,7 @@ static void peer_layout(int world, int total, int* stride, int* ncta, size_t* of
 int hdgnn_peer_export(hdgnn_handle_t h, int world, unsigned char* ipc_handle_out) {
     if (!h) return HDGNN_E_INVALID;
     if (world < 2 || world > PEER_MAX || !ipc_handle_out) return fail(h, HDGNN_E_INVALID, "world must be 2..8");
-    if (!h->fused) return fail(h, HDGNN_E_UNSUPPORTED, "the peer exchange is fused into the reduce+Adam kernel of the fused path (variants 1-3, per-commit state within one SM)");
+    if (!fused_for(h, true)) return fail(h, HDGNN_E_UNSUPPORTED, "the peer exchange is fused into the reduce+Adam kernel of the fused path (variants 1-3, per-commit state within one SM)");
     static_assert(sizeof(cudaIpcMemHandle_t) == HDGNN_IPC_HANDLE_BYTES, "IPC handle size");
     CK(h, cudaSetDevice(h->cfg.device));
     if (h->peer_box) return fail(h, HDGNN_E_INVALID, "hdgnn_peer_export was already called on this handle");
@@ -930,7 +956,7 @@ int hdgnn_peer_attach(hdgnn_handle_t h, int rank, int world, const unsigned char
 
 int hdgnn_set_hits_accumulator(hdgnn_handle_t h, uint64_t* acc) {
     if (!h) return HDGNN_E_INVALID;
-    if (acc && !h->fused) return fail(h, HDGNN_E_UNSUPPORTED, "the hit counter lives in the fused per-commit kernel (variants 1-3, per-commit state within one SM); use hdgnn_eval_counts");
+    if (acc && !fused_for(h, true)) return fail(h, HDGNN_E_UNSUPPORTED, "the hit counter lives in the fused per-commit kernel (variants 1-3, per-commit state within one SM); use hdgnn_eval_counts");
     h->hits_acc = (unsigned long long*)acc;
     return HDGNN_OK;
 }
@@ -950,7 +976,7 @@ static int run_step(hdgnn_handle_t h, int B, int B_global, const Inputs& in, flo
                     float* grads, const AdamArgs* adam, cudaStream_t st) {
     const bool train = grads != nullptr;
     int rc;
-    if (h->fused) {
+    if (fused_for(h, train)) {
         rc = fused_forward(h, B, B_global, in, logits, probs, train, st);
         if (rc) return rc;
         if (!train) {
@@ -1124,7 +1150,7 @@ int hdgnn_train_step_host(hdgnn_handle_t h, int B, const uint8_t* adj_host, cons
     if (rc) return rc;
     Inputs in = staged_inputs(h, params);
     float* probs_d = probs_host ? F(h, "H_PROBS") : nullptr;
-    float* alias = h->fused ? host_alias(loss3_host) : nullptr;
+    float* alias = fused_for(h, true) ? host_alias(loss3_host) : nullptr;
     float* loss_d = alias ? alias : F(h, "H_LOSS");
     AdamArgs ad{params, m, v, step_counter, lr, beta1, beta2, eps, loss_d + 1};
     rc = run_step(h, B, B, in, nullptr, probs_d, loss_d, F(h, "H_GRADS"), &ad, st);

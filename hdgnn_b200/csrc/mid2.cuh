@@ -32,6 +32,8 @@ constexpr int M2_NODE_F = 24 + 20 + 24;   // floats per node of that chunk: [S|x
 constexpr int M2_MCLS = 16;               // inline entity stage: most distinct node-attribute values served by the class tables
 constexpr int M2_BLK1 = 400 + 20 + 420 + 20 + 20 + 1;              // 881
 constexpr int M2_BLK2 = 200 + 20 + 400 + 20 + 440 + 20 + 40 + 2;   // 1142
+// variant 4's edge block edg_w11 .. eup_b2 (model_4.py:219-229, 292-297): offsets 0 20 60 80 480 500 940 960 1000
+constexpr int M2_BLKE = 20 + 40 + 20 + 400 + 20 + 440 + 20 + 40 + 2;    // 1002
 
 // debug dump layout per commit (floats): S1[Ne*20] X2[Ne] NB[Nc*4] RS3[Nc*20] CS3[Nc*20] PR[Nc*20] PC[Nc*20]
 // DNB[Nc*4] DX2[Ne]
@@ -44,10 +46,11 @@ struct Mid2Smem {
     int entw, xsort, ordv, sx;               // inline entity stage: U V c D, x sorted, rank -> node, suffix sums of sorted x
     int rptr, cptr, headrow, headp;          // edge prefix counts by row / by column, head partials of the edge-walk slots
     int ebt, cls, cval, csize, cmask, cmeta;  // transposed bitmap; attribute classes: class of a node, value / size / node mask of a class
+    int blkE, wEe, gamE, DgE, RA, CA, cpart; // variant 4: edge-branch weight block, its first layer (U V c D), head tables, row / column sums of a1
 };
 
 // dlt_smem: keep the per-pair dL/dlogit table of the training path in shared memory (else it lives in HBM / L2)
-__host__ __device__ inline Mid2Smem mid2_layout(int Ne, int Nc, bool train, bool dlt_smem = true, bool scache = false, bool inl = false) {
+__host__ __device__ inline Mid2Smem mid2_layout(int Ne, int Nc, bool train, bool dlt_smem = true, bool scache = false, bool inl = false, bool edge = false) {
     Mid2Smem m;
     if (inl) scache = true;
     int o = 0;
@@ -62,6 +65,8 @@ __host__ __device__ inline Mid2Smem mid2_layout(int Ne, int Nc, bool train, bool
         m.rptr = take(Ne + 1); m.cptr = take(Ne + 1); m.headrow = take(M2_T / 10); m.headp = take(M2_T / 10 * HD);
         m.ebt = take(Ne * bit_words(Ne)); m.cls = take(Ne); m.cval = take(M2_MCLS); m.csize = take(M2_MCLS);
         m.cmask = take(M2_MCLS * bit_words(Ne)); m.cmeta = take(8);
+        m.blkE = m.wEe = m.gamE = m.DgE = m.RA = m.CA = m.cpart = 0;
+        if (edge) { m.blkE = take(M2_BLKE); m.wEe = take(4 * HD); m.gamE = take(HD); m.DgE = take(HD); m.RA = take(Ne); m.CA = take(Ne); m.cpart = take(M2_NW * 32); }
     }
     m.dx2 = take(Ne); m.nb = take(4 * Nc); m.dnb = take(4 * Nc);
     m.ebits = take(Ne * bit_words(Ne)); m.ybits = take(Nc * bit_words(Nc));
@@ -84,8 +89,8 @@ __host__ __device__ inline Mid2Smem mid2_layout(int Ne, int Nc, bool train, bool
     m.total = o;
     return m;
 }
-__host__ __device__ inline size_t mid2_smem_bytes(int Ne, int Nc, bool train, bool dlt_smem = true, bool scache = false, bool inl = false) {
-    return (size_t)mid2_layout(Ne, Nc, train, dlt_smem, scache, inl).total * 4 + 16;
+__host__ __device__ inline size_t mid2_smem_bytes(int Ne, int Nc, bool train, bool dlt_smem = true, bool scache = false, bool inl = false, bool edge = false) {
+    return (size_t)mid2_layout(Ne, Nc, train, dlt_smem, scache, inl, edge).total * 4 + 16;
 }
 
 struct Mid2Args {
@@ -104,6 +109,9 @@ struct Mid2Args {
     long long* clk;                          // per-phase clock64 stamps (B,24) or null
     float* dlt_g;                            // (B, Nc, CW*32) dL/dlogit table in HBM when it does not fit smem, else null
     int scache;                              // keep the entity effect sums S (Ne x 20) in shared memory from the forward to the backward
+    int edge;                                // variant 4: the entity-edge branch (model_4.py:92-98, 206-304) inside this kernel
+    float* RSEg; float* CSEg; float* REg; float* CEg;      // (B,Ne,20) each: edge-branch pair sums and second-layer outputs, kept for the backward
+    float* A1F;                              // (B, Ne (Ne-1)) soft edges a1 in flat pair order, written and read for commits with L < Ne only
     unsigned long long* hits_acc;            // running count of arg-max hits (EvaluationFuncs.py:27-37) over all commits, or null
     const int* wait_flag; int wait_tag;      // host-fed step: the staging copies of this step are complete once *wait_flag == wait_tag
                                              // (written by the copy stream's DMA after the data); null = inputs already ordered
@@ -335,6 +343,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
     // previous step's optimizer kernel, so the weights are read after pdl_wait (below); otherwise its predecessor is
     // ent_fwd2, which does not write them, and the loads overlap that kernel's tail.
     float* wE = sm + L_.entw;                   // inline entity stage: U[20] V[20] c[20] D[20] (model_2.py:167-170)
+    float* blkE = sm + L_.blkE; float* wEe = sm + L_.wEe; float* gamE = sm + L_.gamE; float* DgE = sm + L_.DgE;     // variant 4
     const float nb5 = 2.f * (float)(Ne - 1);
     auto load_weights = [&]() {
         {   // both weight blocks with all global loads in flight before the first store
@@ -348,6 +357,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
                 const int idx = tid + u * M2_T;
                 v[u] = idx < n1 ? p1[idx] : (idx < n1 + M2_BLK2 ? p2[idx - n1] : 0.f);
             }
+            if (a.edge) for (int i = tid; i < M2_BLKE; i += M2_T) blkE[i] = par[po.edg_w11 + i];
             float e0 = 0.f, e1 = 0.f, e2 = 0.f;
             if (a.inl && tid < HD) {
                 e0 = par[po.ent_w1 + 2 * HD + tid]; e1 = par[po.ent_w1 + 3 * HD + tid]; e2 = par[po.ent_b1 + tid];
@@ -366,6 +376,13 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             gam[tid] = G2[2 * tid + 1] - G2[2 * tid];
             Dh[tid] = V1[9 * HD + tid] - V1[8 * HD + tid];
             Dg[tid] = G1[HD + tid] - G1[tid];
+        }
+        if (a.edge && tid < HD) {
+            // edge-branch first layer, tied weights (model_4.py:219-222): pre = w11 (x_i + x_j) + b1 + W12[l]
+            wEe[tid] = blkE[tid]; wEe[HD + tid] = blkE[tid];
+            wEe[2 * HD + tid] = blkE[60 + tid] + blkE[20 + tid]; wEe[3 * HD + tid] = blkE[40 + tid] - blkE[20 + tid];
+            gamE[tid] = blkE[960 + 2 * tid + 1] - blkE[960 + 2 * tid];
+            DgE[tid] = blkE[500 + HD + tid] - blkE[500 + tid];
         }
         if (TRAIN) for (int e = tid; e < 400; e += M2_T) G1g[e] = G1[2 * HD + e] * (G2[2 * (e % HD) + 1] - G2[2 * (e % HD)]);
         if (a.ent) {
@@ -490,7 +507,9 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
     // 16 partial sums per thread
     const int uni_floats = L_.sc - L_.uni;
     int m_max = M2_MCLS;
-    while (m_max > 0 && (2 * m_max * m_max * HD + 4 * Ne * m_max > uni_floats || 2 * m_max * m_max * HD + Ne * m_max + 16 * M2_T > uni_floats)) --m_max;
+    const int uni_edge = a.edge ? 2 * Ne * HD : 0;          // variant 4: the edge branch's RS / CS sit at the end of the union region
+    while (m_max > 0 && (2 * m_max * m_max * HD + 4 * Ne * m_max + uni_edge > uni_floats ||
+                         2 * m_max * m_max * HD + Ne * m_max + 16 * M2_T + uni_edge > uni_floats)) --m_max;
     if (a.inl) {
         const int WU = (Ne + 31) >> 5;
         {   // stable rank sort: three threads per node count over a third of the nodes each (integer atomics: exact)
@@ -579,6 +598,10 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         M2_PHASE(16);
         // ---------------- entity pair layer forward: S_n = sum_{j != n} relu(pre_nj) + sum_{i != n} relu(pre_in) -------------
         const bool use_cls = cmeta[1] != 0;
+        // w: U V c D of the layer (80 floats); outR / outC: [Ne][20] row-sum and column-sum targets (the same array: their sum);
+        // counts: build the neighbour counts (first call)
+        auto ent_fwd = [&](const float* w, float* outR, float* outC, bool counts) {
+        const bool sum_mode = outR == outC;
         if (use_cls) {
             // CLASS TABLES (at most m_max distinct attribute values).  relu(pre_ij[k]) depends on (class of i, class of j,
             // l_ij, k) only: H_l[a][b][k] = relu(U_k val_a + V_k val_b + c_k + l D_k).  With c1o(n,b) / c1i(n,b) = number of
@@ -590,11 +613,11 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             float4* cntf = reinterpret_cast<float4*>(uni + 2 * m * m * HD);      // [Ne][m]  {c0o, c1o, c0i, c1i} as floats
             for (int e = tid; e < m * m * HD; e += M2_T) {
                 const int k = e % HD, ab = e / HD, bq = ab % m, aq = ab / m;
-                const float t0 = fmaf(cval[bq], wE[HD + k], fmaf(cval[aq], wE[k], wE[2 * HD + k]));
-                H0[e] = fmaxf(t0, 0.f); H1[e] = fmaxf(t0 + wE[3 * HD + k], 0.f);
+                const float t0 = fmaf(cval[bq], w[HD + k], fmaf(cval[aq], w[k], w[2 * HD + k]));
+                H0[e] = fmaxf(t0, 0.f); H1[e] = fmaxf(t0 + w[3 * HD + k], 0.f);
             }
             const int WU = (Ne + 31) >> 5;
-            for (int e = tid; e < Ne * m; e += M2_T) {
+            if (counts) for (int e = tid; e < Ne * m; e += M2_T) {
                 const int n = e / m, bq = e - n * m;
                 int co = 0, ci = 0;
                 for (int w = 0; w < WU; ++w) {
@@ -608,11 +631,10 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             // One owner per (node, 4 channels); the lanes of a warp take CONSECUTIVE RANKS of the sorted order, i.e. mostly one
             // class: the four table loads of an iteration are (near-)uniform across the warp and the count loads are contiguous,
             // so the loop is not bound by shared-memory bandwidth.  Every sum runs in class order.
-            float* Sall = sm + L_.sc;
             const int k4 = 4 * (tid / (M2_T / KG));
             for (int r = tid % (M2_T / KG); r < Ne; r += M2_T / KG) {
                 const int n = ordv[r], aq = clsv[n] & 0xffff;
-                float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), t4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 const float* hab0 = H0 + aq * m * HD + k4; const float* hab1 = H1 + aq * m * HD + k4;
                 const float* hba0 = H0 + aq * HD + k4;     const float* hba1 = H1 + aq * HD + k4;
                 const float4* cf = cntf + r;
@@ -620,25 +642,32 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
                     const float4 c = cf[bq * Ne];
                     const float4 a0 = *reinterpret_cast<const float4*>(hab0 + bq * HD), a1 = *reinterpret_cast<const float4*>(hab1 + bq * HD);
                     const float4 b0 = *reinterpret_cast<const float4*>(hba0 + bq * m * HD), b1 = *reinterpret_cast<const float4*>(hba1 + bq * m * HD);
-                    s4.x = fmaf(c.x, a0.x, s4.x); s4.x = fmaf(c.y, a1.x, s4.x); s4.x = fmaf(c.z, b0.x, s4.x); s4.x = fmaf(c.w, b1.x, s4.x);
-                    s4.y = fmaf(c.x, a0.y, s4.y); s4.y = fmaf(c.y, a1.y, s4.y); s4.y = fmaf(c.z, b0.y, s4.y); s4.y = fmaf(c.w, b1.y, s4.y);
-                    s4.z = fmaf(c.x, a0.z, s4.z); s4.z = fmaf(c.y, a1.z, s4.z); s4.z = fmaf(c.z, b0.z, s4.z); s4.z = fmaf(c.w, b1.z, s4.z);
-                    s4.w = fmaf(c.x, a0.w, s4.w); s4.w = fmaf(c.y, a1.w, s4.w); s4.w = fmaf(c.z, b0.w, s4.w); s4.w = fmaf(c.w, b1.w, s4.w);
+                    if (sum_mode) {
+                        s4.x = fmaf(c.x, a0.x, s4.x); s4.x = fmaf(c.y, a1.x, s4.x); s4.x = fmaf(c.z, b0.x, s4.x); s4.x = fmaf(c.w, b1.x, s4.x);
+                        s4.y = fmaf(c.x, a0.y, s4.y); s4.y = fmaf(c.y, a1.y, s4.y); s4.y = fmaf(c.z, b0.y, s4.y); s4.y = fmaf(c.w, b1.y, s4.y);
+                        s4.z = fmaf(c.x, a0.z, s4.z); s4.z = fmaf(c.y, a1.z, s4.z); s4.z = fmaf(c.z, b0.z, s4.z); s4.z = fmaf(c.w, b1.z, s4.z);
+                        s4.w = fmaf(c.x, a0.w, s4.w); s4.w = fmaf(c.y, a1.w, s4.w); s4.w = fmaf(c.z, b0.w, s4.w); s4.w = fmaf(c.w, b1.w, s4.w);
+                    } else {        // row sums (out-neighbours) and column sums (in-neighbours) kept apart
+                        s4.x = fmaf(c.x, a0.x, s4.x); s4.x = fmaf(c.y, a1.x, s4.x); t4.x = fmaf(c.z, b0.x, t4.x); t4.x = fmaf(c.w, b1.x, t4.x);
+                        s4.y = fmaf(c.x, a0.y, s4.y); s4.y = fmaf(c.y, a1.y, s4.y); t4.y = fmaf(c.z, b0.y, t4.y); t4.y = fmaf(c.w, b1.y, t4.y);
+                        s4.z = fmaf(c.x, a0.z, s4.z); s4.z = fmaf(c.y, a1.z, s4.z); t4.z = fmaf(c.z, b0.z, t4.z); t4.z = fmaf(c.w, b1.z, t4.z);
+                        s4.w = fmaf(c.x, a0.w, s4.w); s4.w = fmaf(c.y, a1.w, s4.w); t4.w = fmaf(c.z, b0.w, t4.w); t4.w = fmaf(c.w, b1.w, t4.w);
+                    }
                 }
-                *reinterpret_cast<float4*>(Sall + (size_t)n * HD + k4) = s4;
+                *reinterpret_cast<float4*>(outR + (size_t)n * HD + k4) = s4;
+                if (!sum_mode) *reinterpret_cast<float4*>(outC + (size_t)n * HD + k4) = t4;
             }
             __syncthreads();
         } else {
             // GENERAL attributes: sorted prefix sums for the l = 0 part, edge walk for the l = 1 pairs (entsp.cuh)
             // dense (l = 0) part: one owner thread per (node, channel pair), two binary searches per channel
-            float* Sall = sm + L_.sc;
             int* headrow = reinterpret_cast<int*>(sm + L_.headrow); float* headp = sm + L_.headp;
             int P2 = 1;
             while (P2 <= Ne) P2 <<= 1;
             constexpr int NSLOT = M2_T / 10;
             const int slot = tid / 10, c0 = 2 * (tid % 10);
-            const float Uc[2] = {wE[c0], wE[c0 + 1]}, Vc[2] = {wE[HD + c0], wE[HD + c0 + 1]};
-            const float Cc[2] = {wE[2 * HD + c0], wE[2 * HD + c0 + 1]}, Dc[2] = {wE[3 * HD + c0], wE[3 * HD + c0 + 1]};
+            const float Uc[2] = {w[c0], w[c0 + 1]}, Vc[2] = {w[HD + c0], w[HD + c0 + 1]};
+            const float Cc[2] = {w[2 * HD + c0], w[2 * HD + c0 + 1]}, Dc[2] = {w[3 * HD + c0], w[3 * HD + c0 + 1]};
             const int WU = (Ne + 31) >> 5;
             for (int n = slot; n < Ne; n += NSLOT) {
                 const float xn = xs[n];
@@ -656,16 +685,21 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
                         if (probe < Ne && act != (sw[u] >= 0.f)) r[u] += step;
                     }
                 }
-                float acc[2];
+                float acc[2], acd[2];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     float cnt, sx;
                     entsp_active(r[h], Ne, Vc[h] >= 0.f, SXs, cnt, sx);
                     acc[h] = fmaf(cnt, pb[h], Vc[h] * sx) - fmaxf(fmaf(xn, Vc[h], pb[h]), 0.f);
                     entsp_active(r[2 + h], Ne, Uc[h] >= 0.f, SXs, cnt, sx);
-                    acc[h] += fmaf(cnt, qb[h], Uc[h] * sx) - fmaxf(fmaf(xn, Uc[h], qb[h]), 0.f);
+                    acd[h] = fmaf(cnt, qb[h], Uc[h] * sx) - fmaxf(fmaf(xn, Uc[h], qb[h]), 0.f);
                 }
-                *reinterpret_cast<float2*>(Sall + (size_t)n * HD + c0) = make_float2(acc[0], acc[1]);
+                if (sum_mode) {
+                    *reinterpret_cast<float2*>(outR + (size_t)n * HD + c0) = make_float2(acc[0] + acd[0], acc[1] + acd[1]);
+                } else {
+                    *reinterpret_cast<float2*>(outR + (size_t)n * HD + c0) = make_float2(acc[0], acc[1]);
+                    *reinterpret_cast<float2*>(outC + (size_t)n * HD + c0) = make_float2(acd[0], acd[1]);
+                }
             }
             __syncthreads();
             M2_PHASE(20);
@@ -676,6 +710,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             for (int pass = 0; pass < 2; ++pass) {
                 const uint32_t* bm = pass ? ebT : ebits;
                 const int* ptr = pass ? cptr : rptr;
+                float* Sall = pass ? outC : outR;
                 const float Wo[2] = {pass ? Vc[0] : Uc[0], pass ? Vc[1] : Uc[1]}, Wn[2] = {pass ? Uc[0] : Vc[0], pass ? Uc[1] : Vc[1]};
                 const int nnz = ptr[Ne], per = (nnz + NSLOT - 1) / NSLOT, e0 = min(slot * per, nnz), e1 = min(e0 + per, nnz);
                 int hrow = -1;
@@ -720,6 +755,102 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
                 }
                 __syncthreads();
                 M2_PHASE(21 + pass);
+            }
+        }
+        };
+        ent_fwd(wE, sm + L_.sc, sm + L_.sc, true);
+        if (a.edge) {
+            // ---------------- variant 4: entity-edge branch forward (model_4.py:92-94, 206-304) -----------------------------
+            // pair sums of relu(w11 (x_i + x_j) + b1 + W12[l_ij]) by the same machinery, rows and columns kept apart
+            float* RSs = uni + uni_floats - 2 * Ne * HD; float* CSs = RSs + Ne * HD;
+            ent_fwd(wEe, RSs, CSs, false);
+            float* rse_g = a.RSEg + (size_t)b * Ne * HD; float* cse_g = a.CSEg + (size_t)b * Ne * HD;
+            float* re_g = a.REg + (size_t)b * Ne * HD;   float* ce_g = a.CEg + (size_t)b * Ne * HD;
+            if (TRAIN) for (int i = tid; i < Ne * 5; i += M2_T) {      // kept for the backward
+                reinterpret_cast<float4*>(rse_g)[i] = reinterpret_cast<const float4*>(RSs)[i];
+                reinterpret_cast<float4*>(cse_g)[i] = reinterpret_cast<const float4*>(CSs)[i];
+            }
+            // second (linear) layer on the sums and the tables of the soft-edge head (model_4.py:225-240, 292-297):
+            //   r_n = (Ne-1) b2 + RSe_n W2,  PRe_n = b1h + G1[0] + r_n G1e;   c_n = (Ne-1) b2 + CSe_n W2,  PCe_n = c_n G1e
+            const float* W2e = blkE + 80; const float* b2e = blkE + 480; const float* G1E = blkE + 500; const float* g1be = blkE + 940;
+            float* PRe01 = uni; float* PCe = uni + Ne * PROW; float* rtmp = PCe + Ne * HD;       // rtmp [M2_T / KG][20]
+            for (int it0 = 0; it0 < 2 * Ne; it0 += M2_T / KG) {
+                const int t = it0 + tid / KG, k4 = 4 * (tid % KG);
+                const bool live = t < 2 * Ne, cside = t >= Ne;
+                const int n = cside ? t - Ne : t;
+                if (live) {
+                    const float fn1 = (float)(Ne - 1);
+                    const float4 bb = *reinterpret_cast<const float4*>(b2e + k4);
+                    const float4 r4 = gemv20_k4((cside ? CSs : RSs) + n * HD, W2e, k4, make_float4(fn1 * bb.x, fn1 * bb.y, fn1 * bb.z, fn1 * bb.w));
+                    *reinterpret_cast<float4*>(rtmp + (tid / KG) * HD + k4) = r4;
+                    if (TRAIN) *reinterpret_cast<float4*>((cside ? ce_g : re_g) + n * HD + k4) = r4;
+                }
+                __syncthreads();
+                if (live) {
+                    float4 init = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (!cside) {
+                        const float4 g = *reinterpret_cast<const float4*>(g1be + k4), g0 = *reinterpret_cast<const float4*>(G1E + k4);
+                        init = make_float4(g.x + g0.x, g.y + g0.y, g.z + g0.z, g.w + g0.w);
+                    }
+                    const float4 pq = gemv20_k4(rtmp + (tid / KG) * HD, G1E + 2 * HD, k4, init);
+                    if (cside) {
+                        *reinterpret_cast<float4*>(PCe + n * HD + k4) = pq;
+                    } else {
+                        const float4 d = *reinterpret_cast<const float4*>(DgE + k4);
+                        float* dst = PRe01 + (size_t)n * PROW + 2 * k4;
+                        *reinterpret_cast<float4*>(dst) = pq;
+                        *reinterpret_cast<float4*>(dst + 4) = make_float4(pq.x + d.x, pq.y + d.y, pq.z + d.z, pq.w + d.w);
+                    }
+                }
+                __syncthreads();
+            }
+            // soft edges a_ij = softmax(G2^T relu(PRe_i + PCe_j + l_ij DgE) + b2h) (model_4.py:286-304).  Pooling consumes their row
+            // and column sums; with every index line present (L = Ne) these are the sums over the grid rows / columns (RA, CA), with
+            // L < Ne the local L x L grid is a reshape of the FLAT pair order, so those commits keep a1 in that order (A1F).
+            float* RA = sm + L_.RA; float* CA = sm + L_.CA;
+            float* a1f = (!ident && Lb >= 2) ? a.A1F + (size_t)b * Ne * nm1 : nullptr;
+            float* cpart = sm + L_.cpart;                       // [M2_NW][32] column partials of one column block
+            const float bdE = blkE[1001] - blkE[1000];
+            for (int i = tid; i < Ne; i += M2_T) RA[i] = 0.f;
+            __syncthreads();
+            const int WUe = (Ne + 31) >> 5;
+            for (int cb = 0; cb < WUe; ++cb) {
+                const int j = cb * 32 + lane;
+                const bool ok = j < Ne;
+                float Q[HD];
+#pragma unroll
+                for (int q4 = 0; q4 < 5; ++q4) {
+                    float4 v = make_float4(NEG_BIG, NEG_BIG, NEG_BIG, NEG_BIG);
+                    if (ok) v = *reinterpret_cast<const float4*>(PCe + j * HD + 4 * q4);
+                    Q[4 * q4] = v.x; Q[4 * q4 + 1] = v.y; Q[4 * q4 + 2] = v.z; Q[4 * q4 + 3] = v.w;
+                }
+                float cacc = 0.f;
+                for (int r = warp; r < Ne; r += M2_NW) {
+                    const uint32_t bit = (ebits[r * WPe + cb] >> lane) & 1u;
+                    const float* prow = PRe01 + (size_t)r * PROW + bit * 4;
+                    float d = bdE;
+#pragma unroll
+                    for (int q4 = 0; q4 < 5; ++q4) {
+                        const float4 pv = *reinterpret_cast<const float4*>(prow + q4 * 8);
+                        d = fmaf(fmaxf(pv.x + Q[4 * q4], 0.f), gamE[4 * q4], d); d = fmaf(fmaxf(pv.y + Q[4 * q4 + 1], 0.f), gamE[4 * q4 + 1], d);
+                        d = fmaf(fmaxf(pv.z + Q[4 * q4 + 2], 0.f), gamE[4 * q4 + 2], d); d = fmaf(fmaxf(pv.w + Q[4 * q4 + 3], 0.f), gamE[4 * q4 + 3], d);
+                    }
+                    const float e = expf(-fabsf(d)), inv = 1.f / (1.f + e);
+                    const float a1 = (ok && j != r) ? (d >= 0.f ? inv : e * inv) : 0.f;
+                    cacc += a1;
+                    const float rs = warp_sum(a1);
+                    if (lane == 0) RA[r] += rs;                 // one owner warp per row, column blocks in order
+                    if (a1f && ok && j != r) a1f[(size_t)r * nm1 + j - (j > r)] = a1;
+                }
+                cpart[warp * 32 + lane] = cacc;
+                __syncthreads();
+                if (tid < 32 && cb * 32 + tid < Ne) {
+                    float t = 0.f;
+#pragma unroll
+                    for (int w = 0; w < M2_NW; ++w) t += cpart[w * 32 + tid];
+                    CA[cb * 32 + tid] = t;
+                }
+                __syncthreads();
             }
         }
         M2_PHASE(17);
@@ -807,7 +938,8 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         M2_PHASE(14);
         for (int i = tid; i < Ne; i += M2_T) {              // degrees: SP[.][3] / TP[.][3] (computed before the wait), or the edge
             const float xi = x2[i], fn = (float)nm1;        // prefix counts of the inline entity stage
-            if (a.inl) { SP[4 * i + 3] = (float)(rptr[i + 1] - rptr[i]); TP[4 * i + 3] = (float)(cptr[i + 1] - cptr[i]); }
+            if (a.edge) { SP[4 * i + 3] = (sm + L_.RA)[i]; TP[4 * i + 3] = (sm + L_.CA)[i]; }       // variant 4: soft edges instead of degrees
+            else if (a.inl) { SP[4 * i + 3] = (float)(rptr[i + 1] - rptr[i]); TP[4 * i + 3] = (float)(cptr[i + 1] - cptr[i]); }
             SP[4 * i] = fn * xi; SP[4 * i + 1] = X - xi; SP[4 * i + 2] = fn - SP[4 * i + 3];
             TP[4 * i] = X - xi; TP[4 * i + 1] = fn * xi; TP[4 * i + 2] = fn - TP[4 * i + 3];
         }
@@ -869,6 +1001,23 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             float t = 0.f;
             for (int c = 0; c < nchunk; ++c) t += partC[(size_t)c * Lb * 4 + idx];
             TP[idx] = t;
+        }
+        if (a.edge) {
+            // variant 4: channels 2, 3 are the soft edges.  In the flat pair order the local grid is the row-major [L][m] reshape of
+            // the first L m entries: SP = its row sums, TP[lj] = sum_li a1[li m + lj - (lj > li)]
+            __syncthreads();
+            const float* a1f = a.A1F + (size_t)b * Ne * nm1;
+            for (int li = warp; li < Lb; li += M2_NW) {
+                float acc = 0.f;
+                for (int sidx = lane; sidx < m; sidx += 32) acc += __ldcg(a1f + (size_t)li * m + sidx);
+                acc = warp_sum(acc);
+                if (lane == 0) { SP[4 * li + 3] = acc; SP[4 * li + 2] = (float)m - acc; }
+            }
+            for (int lj = tid; lj < Lb; lj += M2_T) {
+                float acc = 0.f;
+                for (int li = 0; li < Lb; ++li) if (li != lj) acc += __ldcg(a1f + (size_t)li * m + lj - (lj > li ? 1 : 0));
+                TP[4 * lj + 3] = acc; TP[4 * lj + 2] = (float)m - acc;
+            }
         }
     }
     __syncthreads();

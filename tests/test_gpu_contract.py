@@ -117,3 +117,29 @@ def test_inference_sweep_shapes(Nc):
             "ce": relerr(loss.cpu().numpy()[0], plan["ce"])}
     assert all(e < (TOL if k == "probs" else TIGHT) for k, e in errs.items()), errs
     eng.close()
+
+
+@pytest.mark.parametrize("attr", ["classes", "continuous"])
+@pytest.mark.parametrize("B,Ne,Nc", [(3, 64, 32), (2, 200, 74), (2, 97, 74)])
+def test_variant4_forward(B, Ne, Nc, attr):
+    """model_4 (entity-edge branch, soft edges) forward through hdgnn_forward: commits with L = Ne and L < Ne, categorical and
+    continuous node attributes."""
+    from hdgnn_b200.engine import Engine, DeviceBatch
+    cb = make_commits(B, Ne, Nc, seed=700 + Ne, p_short=0.5)
+    cb.L[0] = Ne
+    if B > 1:
+        cb.L[1] = max(2, Ne - 7)
+    if attr == "continuous":
+        cb.x[:] = np.random.default_rng(Ne).normal(scale=2.0, size=cb.x.shape)
+    flat = _params(4)
+    plan = PN.train_step_plan(4, flat, cb.adj, cb.x, cb.hmap, cb.L, cb.Y)
+    eng = Engine(Ne, Nc, variant=4, max_batch=B)
+    db = DeviceBatch.from_numpy(cb.adj, cb.x, cb.hmap, cb.L, cb.Y, eng.tdev)
+    probs, logits, loss = eng.forward(db, flat.float().cuda())
+    torch.cuda.synchronize()
+    errs = {"probs": relerr(probs.cpu().numpy(), plan["probs"]), "logits": relerr(logits.cpu().numpy(), plan["logits"]),
+            "ce": relerr(loss.cpu().numpy()[0], plan["ce"])}
+    for bb in range(B):
+        errs[f"logits[{bb}]"] = relerr(logits[bb].cpu().numpy(), plan["logits"][bb])
+    assert all(e < (TOL if k == "probs" else TIGHT) for k, e in errs.items()), (errs, eng.last_launch_count())
+    eng.close()
