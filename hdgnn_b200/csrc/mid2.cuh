@@ -1661,46 +1661,46 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         // v_ij[k] = [pre_ij[k] > 0] (GE_i[k] + GE_j[k]);  db = sum v, dU = sum x_i v, dV = sum x_j v, LS = sum over l_ij = 1
         __syncthreads();
         M2_PHASE(18);
-        const float* GEs = sm + L_.sc;
         const bool use_cls = cmeta[1] != 0;
         const int mcl = cmeta[0];
-        float* SGs = uni;                                   // general path: [20][Ne + 1] suffix sums of GE over the sorted order, per channel
-        // [M2_T][8] per-thread partial sums behind the path's tables
-        float* part = uni + (use_cls ? ((2 * mcl * mcl * HD + Ne * mcl + 3) & ~3) : 20 * (Ne + 1));      // per-thread partial sums
-        float db[2] = {0.f, 0.f}, dU[2] = {0.f, 0.f}, dV[2] = {0.f, 0.f}, LS[2] = {0.f, 0.f};
+        // w: U V c D of the layer; GRs / GCs: [Ne][20] d/d(row sums), d/d(column sums) (the node branch passes GE twice).
+        // Leaves db, dU, dV, LS (20 each) in red[0..80).  Uses the union region from its start.
+        auto ent_bwd = [&](const float* w, const float* GRs, const float* GCs) {
+        const bool same = GRs == GCs;
         if (use_cls) {
-            // CLASS TABLES: v_ij[k] = g_l[a][b][k] (GE_i[k] + GE_j[k]) with the 0/1 gates g_l[a][b][k] = [H_l[a][b][k] > 0].  All four
+            // CLASS TABLES: v_ij[k] = g_l[a][b][k] (GR_i[k] + GC_j[k]) with the 0/1 gates g_l[a][b][k] = [H_l[a][b][k] > 0].  All four
             // results are sums over pairs, so with the number of active pairs per node,
             //   Wrow_i = sum_j g_ij,  XWrow_i = sum_j x_j g_ij,  W1row_i = sum_{l_ij = 1} g_ij   (and the column forms over i),
-            //   db = sum_n GE_n (Wrow_n + Wcol_n),      dU = sum_n GE_n (x_n Wrow_n + XWcol_n),
-            //   dV = sum_n GE_n (XWrow_n + x_n Wcol_n), LS = sum_n GE_n (W1row_n + W1col_n),
+            //   db = sum_n GR_n Wrow_n + GC_n Wcol_n,          dU = sum_n GR_n x_n Wrow_n + GC_n XWcol_n,
+            //   dV = sum_n GR_n XWrow_n + GC_n x_n Wcol_n,     LS = sum_n GR_n W1row_n + GC_n W1col_n,
             // and the W's come from the same neighbour counts as the forward.
             const int m = mcl;
             float* G0 = uni; float* G1t = uni + m * m * HD;
-            uint32_t* cnt = reinterpret_cast<uint32_t*>(uni + 2 * m * m * HD);      // [Ne][m]  c1o | c1i << 16
+            uint32_t* cnt = reinterpret_cast<uint32_t*>(uni + 2 * m * m * HD);      // [m][Ne]  c1o | c1i << 16
+            float* part = uni + ((2 * m * m * HD + Ne * m + 3) & ~3);                // [M2_T][16] per-thread partial sums
             for (int e = tid; e < m * m * HD; e += M2_T) {
                 const int k = e % HD, ab = e / HD, bq = ab % m, aq = ab / m;
-                const float t0 = fmaf(cval[bq], wE[HD + k], fmaf(cval[aq], wE[k], wE[2 * HD + k]));      // as in the forward: same gates
-                G0[e] = t0 > 0.f ? 1.f : 0.f; G1t[e] = (t0 + wE[3 * HD + k]) > 0.f ? 1.f : 0.f;
+                const float t0 = fmaf(cval[bq], w[HD + k], fmaf(cval[aq], w[k], w[2 * HD + k]));      // as in the forward: same gates
+                G0[e] = t0 > 0.f ? 1.f : 0.f; G1t[e] = (t0 + w[3 * HD + k]) > 0.f ? 1.f : 0.f;
             }
             const int WU = (Ne + 31) >> 5;
             for (int e = tid; e < Ne * m; e += M2_T) {
                 const int n = e / m, bq = e - n * m;
                 int co = 0, ci = 0;
-                for (int w = 0; w < WU; ++w) {
-                    const uint32_t mk = cmask[bq * WPe + w];
-                    co += __popc(ebits[n * WPe + w] & mk); ci += __popc(ebT[n * WPe + w] & mk);
+                for (int wq = 0; wq < WU; ++wq) {
+                    const uint32_t mk = cmask[bq * WPe + wq];
+                    co += __popc(ebits[n * WPe + wq] & mk); ci += __popc(ebT[n * WPe + wq] & mk);
                 }
                 cnt[bq * Ne + (clsv[n] >> 16)] = (uint32_t)co | ((uint32_t)ci << 16);      // [class][rank]
             }
             __syncthreads();
-            M2_PHASE(19);
             const int k4 = 4 * (tid / (M2_T / KG));
             float a_db[4] = {0.f, 0.f, 0.f, 0.f}, a_dU[4] = {0.f, 0.f, 0.f, 0.f}, a_dV[4] = {0.f, 0.f, 0.f, 0.f}, a_LS[4] = {0.f, 0.f, 0.f, 0.f};
             for (int r = tid % (M2_T / KG); r < Ne; r += M2_T / KG) {      // lanes = consecutive ranks (see the forward)
                 const int n = ordv[r], aq = clsv[n] & 0xffff;
                 const float xn = xs[n];
-                const float4 gn4 = *reinterpret_cast<const float4*>(GEs + (size_t)n * HD + k4);
+                const float4 gr4 = *reinterpret_cast<const float4*>(GRs + (size_t)n * HD + k4);
+                const float4 gc4 = *reinterpret_cast<const float4*>(GCs + (size_t)n * HD + k4);
                 float wr[4] = {0.f, 0.f, 0.f, 0.f}, xwr[4] = {0.f, 0.f, 0.f, 0.f}, w1r[4] = {0.f, 0.f, 0.f, 0.f};
                 float wc[4] = {0.f, 0.f, 0.f, 0.f}, xwc[4] = {0.f, 0.f, 0.f, 0.f}, w1c[4] = {0.f, 0.f, 0.f, 0.f};
                 const float* gab0 = G0 + aq * m * HD + k4; const float* gab1 = G1t + aq * m * HD + k4;
@@ -1720,13 +1720,13 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
                         wc[c] += ci2; xwc[c] = fmaf(vb, ci2, xwc[c]); w1c[c] += l1i;
                     }
                 }
-                const float gv[4] = {gn4.x, gn4.y, gn4.z, gn4.w};
+                const float gr[4] = {gr4.x, gr4.y, gr4.z, gr4.w}, gc[4] = {gc4.x, gc4.y, gc4.z, gc4.w};
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    a_db[c] = fmaf(gv[c], wr[c] + wc[c], a_db[c]);
-                    a_dU[c] = fmaf(gv[c], fmaf(xn, wr[c], xwc[c]), a_dU[c]);
-                    a_dV[c] = fmaf(gv[c], fmaf(xn, wc[c], xwr[c]), a_dV[c]);
-                    a_LS[c] = fmaf(gv[c], w1r[c] + w1c[c], a_LS[c]);
+                    a_db[c] = fmaf(gr[c], wr[c], fmaf(gc[c], wc[c], a_db[c]));
+                    a_dU[c] = fmaf(gr[c], xn * wr[c], fmaf(gc[c], xwc[c], a_dU[c]));
+                    a_dV[c] = fmaf(gr[c], xwr[c], fmaf(gc[c], xn * wc[c], a_dV[c]));
+                    a_LS[c] = fmaf(gr[c], w1r[c], fmaf(gc[c], w1c[c], a_LS[c]));
                 }
             }
             float4* p4 = reinterpret_cast<float4*>(part + (size_t)tid * 16);
@@ -1740,32 +1740,38 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
                 red[tid] = t;
             }
         } else {
-            {
-                const int k = warp;                             // M2_NW == HD: one warp per channel
+            // GENERAL attributes: suffix sums of GC (for the row sums) and of GR (for the column sums) over the sorted order,
+            // one warp per channel (M2_NW == HD), then searches + the edge walk
+            float* SGC = uni; float* SGR = same ? uni : uni + 20 * (Ne + 1);
+            float* part = uni + (same ? 20 : 40) * (Ne + 1);                         // [M2_T][8]
+            for (int pass = 0; pass < (same ? 1 : 2); ++pass) {
+                const float* G = pass ? GRs : GCs;
+                const int k = warp;
                 const int per = (Ne + 31) >> 5, lo = min(lane * per, Ne), hi = min(lo + per, Ne);
                 float sum = 0.f;
-                for (int r = hi - 1; r >= lo; --r) sum += GEs[(size_t)ordv[r] * HD + k];
+                for (int r = hi - 1; r >= lo; --r) sum += G[(size_t)ordv[r] * HD + k];
                 float incl = sum;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_down_sync(0xffffffffu, incl, o); if (lane + o < 32) incl += t; }
                 float run = incl - sum;
-                float* dst = SGs + (size_t)k * (Ne + 1);
-                for (int r = hi - 1; r >= lo; --r) { run += GEs[(size_t)ordv[r] * HD + k]; dst[r] = run; }
+                float* dst = (pass ? SGR : SGC) + (size_t)k * (Ne + 1);
+                for (int r = hi - 1; r >= lo; --r) { run += G[(size_t)ordv[r] * HD + k]; dst[r] = run; }
                 if (lane == 0) dst[Ne] = 0.f;
             }
             __syncthreads();
-            M2_PHASE(19);
             int P2 = 1;
             while (P2 <= Ne) P2 <<= 1;
             constexpr int NSLOT = M2_T / 10;
             const int slot = tid / 10, c0 = 2 * (tid % 10);
-            const float Uc[2] = {wE[c0], wE[c0 + 1]}, Vc[2] = {wE[HD + c0], wE[HD + c0 + 1]};
-            const float Cc[2] = {wE[2 * HD + c0], wE[2 * HD + c0 + 1]}, Dc[2] = {wE[3 * HD + c0], wE[3 * HD + c0 + 1]};
+            const float Uc[2] = {w[c0], w[c0 + 1]}, Vc[2] = {w[HD + c0], w[HD + c0 + 1]};
+            const float Cc[2] = {w[2 * HD + c0], w[2 * HD + c0 + 1]}, Dc[2] = {w[3 * HD + c0], w[3 * HD + c0 + 1]};
             const int WU = (Ne + 31) >> 5;
+            float db[2] = {0.f, 0.f}, dU[2] = {0.f, 0.f}, dV[2] = {0.f, 0.f}, LS[2] = {0.f, 0.f};
             for (int n = slot; n < Ne; n += NSLOT) {             // dense (l = 0) part
                 const float xn = xs[n];
-                const float2 gn2 = *reinterpret_cast<const float2*>(GEs + (size_t)n * HD + c0);
-                const float gn[2] = {gn2.x, gn2.y};
+                const float2 gr2 = *reinterpret_cast<const float2*>(GRs + (size_t)n * HD + c0);
+                const float2 gc2 = *reinterpret_cast<const float2*>(GCs + (size_t)n * HD + c0);
+                const float gr[2] = {gr2.x, gr2.y}, gc[2] = {gc2.x, gc2.y};
                 float pb[2], qb[2];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) { pb[h] = fmaf(xn, Uc[h], Cc[h]); qb[h] = fmaf(xn, Vc[h], Cc[h]); }
@@ -1783,10 +1789,10 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     float cnt, sg;
-                    entsp_active(r[h], Ne, Vc[h] >= 0.f, SGs + (size_t)(c0 + h) * (Ne + 1), cnt, sg);
-                    const float rsd = fmaf(cnt, gn[h], sg) - (fmaf(xn, Vc[h], pb[h]) > 0.f ? 2.f * gn[h] : 0.f);
-                    entsp_active(r[2 + h], Ne, Uc[h] >= 0.f, SGs + (size_t)(c0 + h) * (Ne + 1), cnt, sg);
-                    const float csd = fmaf(cnt, gn[h], sg) - (fmaf(xn, Uc[h], qb[h]) > 0.f ? 2.f * gn[h] : 0.f);
+                    entsp_active(r[h], Ne, Vc[h] >= 0.f, SGC + (size_t)(c0 + h) * (Ne + 1), cnt, sg);
+                    const float rsd = fmaf(cnt, gr[h], sg) - (fmaf(xn, Vc[h], pb[h]) > 0.f ? gr[h] + gc[h] : 0.f);
+                    entsp_active(r[2 + h], Ne, Uc[h] >= 0.f, SGR + (size_t)(c0 + h) * (Ne + 1), cnt, sg);
+                    const float csd = fmaf(cnt, gc[h], sg) - (fmaf(xn, Uc[h], qb[h]) > 0.f ? gr[h] + gc[h] : 0.f);
                     db[h] += rsd; dU[h] = fmaf(xn, rsd, dU[h]); dV[h] = fmaf(xn, csd, dV[h]);
                 }
             }
@@ -1794,23 +1800,23 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
                 const int nnz = rptr[Ne], per = (nnz + NSLOT - 1) / NSLOT, e0 = min(slot * per, nnz), e1 = min(e0 + per, nnz);
                 if (e1 > e0) {
                     const EdgeCursor cur = edge_seek(ebits, WPe, rptr, Ne, P2, e0);
-                    int row = cur.row, w = cur.w;
+                    int row = cur.row, wq = cur.w;
                     uint32_t bits = cur.bits;
                     float xo = xs[row], b0 = fmaf(xo, Uc[0], Cc[0]), b1 = fmaf(xo, Uc[1], Cc[1]);
-                    float2 go = *reinterpret_cast<const float2*>(GEs + (size_t)row * HD + c0);
+                    float2 go = *reinterpret_cast<const float2*>(GRs + (size_t)row * HD + c0);
                     for (int e = e0; e < e1; ++e) {
                         while (!bits) {
-                            if (++w == WU) {
-                                w = 0; ++row;
+                            if (++wq == WU) {
+                                wq = 0; ++row;
                                 xo = xs[row]; b0 = fmaf(xo, Uc[0], Cc[0]); b1 = fmaf(xo, Uc[1], Cc[1]);
-                                go = *reinterpret_cast<const float2*>(GEs + (size_t)row * HD + c0);
+                                go = *reinterpret_cast<const float2*>(GRs + (size_t)row * HD + c0);
                             }
-                            bits = ebits[row * WPe + w];
+                            bits = ebits[row * WPe + wq];
                         }
-                        const int j = (w << 5) + __ffs(bits) - 1;
+                        const int j = (wq << 5) + __ffs(bits) - 1;
                         bits &= bits - 1;
                         const float xj = xs[j];
-                        const float2 gj = *reinterpret_cast<const float2*>(GEs + (size_t)j * HD + c0);
+                        const float2 gj = *reinterpret_cast<const float2*>(GCs + (size_t)j * HD + c0);
                         const float t0 = fmaf(xj, Vc[0], b0), t1 = fmaf(xj, Vc[1], b1), g0 = go.x + gj.x, g1 = go.y + gj.y;
                         const float v10 = (t0 + Dc[0]) > 0.f ? g0 : 0.f, v11 = (t1 + Dc[1]) > 0.f ? g1 : 0.f;
                         const float d0 = v10 - (t0 > 0.f ? g0 : 0.f), d1 = v11 - (t1 > 0.f ? g1 : 0.f);
@@ -1821,7 +1827,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
                     }
                 }
             }
-                    *reinterpret_cast<float4*>(part + (size_t)tid * 8) = make_float4(db[0], db[1], dU[0], dU[1]);
+            *reinterpret_cast<float4*>(part + (size_t)tid * 8) = make_float4(db[0], db[1], dU[0], dU[1]);
             *reinterpret_cast<float4*>(part + (size_t)tid * 8 + 4) = make_float4(dV[0], dV[1], LS[0], LS[1]);
             __syncthreads();
             if (tid < 4 * HD) {                                 // fixed-order sum over the 64 threads that own a channel pair
@@ -1832,6 +1838,9 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             }
         }
         __syncthreads();
+        };
+        ent_bwd(wE, sm + L_.sc, sm + L_.sc);
+        M2_PHASE(19);
         if (tid < HD) {
             const float dbk = red[tid], lsk = red[3 * HD + tid];
             gp[po.ent_b1 + tid] = dbk;
