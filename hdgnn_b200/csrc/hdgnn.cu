@@ -599,7 +599,7 @@ int fused_forward(hdgnn_handle_t h, int B, int B_global, const Inputs& in, float
     m.wait_flag = in.wait_flag; m.wait_tag = in.wait_tag;
     m.hits_acc = h->hits_acc;
     m.edge = h->edge_fused ? 1 : 0;
-    if (m.edge) { m.RSEg = F(h, "RSEG"); m.CSEg = F(h, "CSEG"); m.REg = F(h, "REG"); m.CEg = F(h, "CEG"); m.A1F = F(h, "A1F"); }
+    if (m.edge) { m.RSEg = F(h, "RSEG"); m.CSEg = F(h, "CSEG"); m.REg = F(h, "REG"); m.CEg = F(h, "CEG"); m.A1F = F(h, "A1F"); m.PREg = F(h, "PREG"); }
     m.lay = mid2_layout(h->Ne, h->Nc, train, !dlt_g, m.scache != 0, h->inl, h->edge_fused);
     const size_t smem = mid2_smem_bytes(h->Ne, h->Nc, train, !dlt_g, m.scache != 0, h->inl, h->edge_fused);
     const int cwc = (h->Nc + 31) / 32;
@@ -781,7 +781,14 @@ int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out) {
             ok = (size_t)L.total * 4 + 16 <= lim && h->Ne * 60 + (M2_T / KG) * HD <= (L.sc - L.uni) - 2 * h->Ne * HD;
         }
         h->edge_fused = ok;
-        h->edge_fused_train = ok && env_int("HDGNN_V4_FUSED_TRAIN", 0) != 0;
+        bool okt = ok && env_int("HDGNN_V4_FUSED_TRAIN", 1) != 0;
+        if (okt) {      // backward: head tables + column delta sums + a 32-row de tile; later five Ne x 20 arrays + GCe at the end;
+                        // the general-attribute form of ent_bwd needs two sets of suffix tables beside GCe
+            const Mid2Smem L = mid2_layout(h->Ne, h->Nc, true, !h->dlt_global, true, true, true);
+            const int uf = L.sc - L.uni, wue = (h->Ne + 31) / 32;
+            okt = h->Ne * 80 + 32 * wue * 32 <= uf && h->Ne * 120 <= uf && 40 * (h->Ne + 1) + 8 * M2_T + h->Ne * HD <= uf;
+        }
+        h->edge_fused_train = okt;
         if (!ok) { h->fused = false; h->inl = false; }
     }
     h->host_bits = (cfg->flags & HDGNN_F_LABEL_BITS) != 0;
@@ -829,7 +836,7 @@ int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out) {
         {"CLK", B * 24 * sizeof(long long), h->fused && h->debug},
         {"DLT", B * Nc * (size_t)((h->Nc + 31) / 32 * 32) * f, h->fused && h->dlt_global},
         {"RSEG", B * Ne * HD * f, h->edge_fused}, {"CSEG", B * Ne * HD * f, h->edge_fused}, {"REG", B * Ne * HD * f, h->edge_fused},
-        {"CEG", B * Ne * HD * f, h->edge_fused}, {"A1F", B * Ne * (Ne - 1) * f, h->edge_fused},
+        {"CEG", B * Ne * HD * f, h->edge_fused}, {"A1F", B * Ne * (Ne - 1) * f, h->edge_fused}, {"PREG", B * Ne * 60 * f, h->edge_fused},
         {"RSE", B * Ne * HD * f, h->edge}, {"CSEP", B * Se * Ne * HD * f, h->edge}, {"CSEF", B * Ne * HD * f, h->edge},
         {"PRE", B * Ne * HD * f, h->edge}, {"PCE", B * Ne * HD * f, h->edge},
         {"SOFT", B * Ne * Ne * 2 * f, h->edge}, {"DSOFT", B * Ne * Ne * 2 * f, h->edge},

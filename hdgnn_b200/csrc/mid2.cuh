@@ -72,7 +72,8 @@ __host__ __device__ inline Mid2Smem mid2_layout(int Ne, int Nc, bool train, bool
     m.ebits = take(Ne * bit_words(Ne)); m.ybits = take(Nc * bit_words(Nc));
     const int cwc = (Nc + 31) / 32;
     const int comb = (M2_NRG / 2) * cwc * 32 * HD, pool = 2 * 4 * 4 * Ne;     // column combine | pooling partials
-    m.scratch = take(comb > pool ? comb : pool);
+    const int comb_e = edge ? (M2_NRG / 2) * 4 * 32 * HD : 0;      // variant 4: combine_cols<4> of the soft-edge delta sweep
+    m.scratch = take(comb > pool ? (comb > comb_e ? comb : comb_e) : (pool > comb_e ? pool : comb_e));
     m.red = take(64 + M2_NW * HD + 64);
     m.uni = o;
     // union region: [hunk tables 12 Nc 20][dlt (training) | SP TP dl (pooling: dead while dlt is live)]; the
@@ -111,6 +112,7 @@ struct Mid2Args {
     int scache;                              // keep the entity effect sums S (Ne x 20) in shared memory from the forward to the backward
     int edge;                                // variant 4: the entity-edge branch (model_4.py:92-98, 206-304) inside this kernel
     float* RSEg; float* CSEg; float* REg; float* CEg;      // (B,Ne,20) each: edge-branch pair sums and second-layer outputs, kept for the backward
+    float* PREg;                             // (B,Ne,60): soft-edge head tables PRe01 (Ne x 40) then PCe (Ne x 20), kept for the backward
     float* A1F;                              // (B, Ne (Ne-1)) soft edges a1 in flat pair order, written and read for commits with L < Ne only
     unsigned long long* hits_acc;            // running count of arg-max hits (EvaluationFuncs.py:27-37) over all commits, or null
     const int* wait_flag; int wait_tag;      // host-fed step: the staging copies of this step are complete once *wait_flag == wait_tag
@@ -807,6 +809,10 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             // soft edges a_ij = softmax(G2^T relu(PRe_i + PCe_j + l_ij DgE) + b2h) (model_4.py:286-304).  Pooling consumes their row
             // and column sums; with every index line present (L = Ne) these are the sums over the grid rows / columns (RA, CA), with
             // L < Ne the local L x L grid is a reshape of the FLAT pair order, so those commits keep a1 in that order (A1F).
+            if (TRAIN) {
+                float4* dst = reinterpret_cast<float4*>(a.PREg + (size_t)b * Ne * 60);
+                for (int i = tid; i < Ne * 15; i += M2_T) dst[i] = reinterpret_cast<const float4*>(uni)[i];      // PRe01 | PCe are contiguous
+            }
             float* RA = sm + L_.RA; float* CA = sm + L_.CA;
             float* a1f = (!ident && Lb >= 2) ? a.A1F + (size_t)b * Ne * nm1 : nullptr;
             float* cpart = sm + L_.cpart;                       // [M2_NW][32] column partials of one column block
@@ -1443,6 +1449,10 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         dl[idx] = (i < Lb && hm[i] >= 0) ? dnb[4 * hm[i] + chn] : 0.f;
     }
     __syncthreads();
+    if (a.edge) {       // variant 4: d/d(a1 - a0) per index line, u_l = dl[l][3] - dl[l][2]; a pair (li, lj) receives u_li + u_lj
+        float* uE = sm + L_.RA;                             // the row sums of a1 are dead since the pooling forward
+        for (int i = tid; i < Ne; i += M2_T) uE[i] = dl[4 * i + 3] - dl[4 * i + 2];
+    }
     M2_PHASE(12);
     if (ident) {
         float p0 = 0.f, p1 = 0.f;
@@ -1848,6 +1858,248 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             gp[po.ent_w1 + HD + tid] = red[2 * HD + tid];
             gp[po.ent_w1 + 2 * HD + tid] = dbk - lsk;
             gp[po.ent_w1 + 3 * HD + tid] = lsk;
+        }
+        if (a.edge) {
+            // ---------------- variant 4: entity-edge branch backward (model_4.py:92-98, 206-304) ----------------------------------
+            // de_ij = a1 a0 (u_li + u_lj) is d/d(logit difference) of the soft edge of pair (i,j); from there the chain is the relation
+            // head's: delta sums over the Ne x Ne grid (rows in chunks of E_RCH: pass A recomputes the soft edge and tabulates de,
+            // pass B accumulates the gated row / column / label sums four channels per warp), the head's node-level backward, and
+            // the first (tied, rank-1) layer through ent_bwd.
+            constexpr int E_RCH = 32;
+            __syncthreads();
+            const int WUe = (Ne + 31) >> 5, DWe = WUe * 32;
+            const float* uE = sm + L_.RA;
+            float* PRe01 = uni; float* PCe = uni + Ne * PROW;
+            float* CSmE = uni + Ne * 60;                        // [Ne][20]
+            float* det = CSmE + Ne * HD;                        // [E_RCH][DWe] de of the current row chunk
+            float* RSmE = sm + L_.sc;                           // [Ne][20] (GE is dead)
+            {
+                const float4* src = reinterpret_cast<const float4*>(a.PREg + (size_t)b * Ne * 60);
+                for (int i = tid; i < Ne * 15; i += M2_T) reinterpret_cast<float4*>(uni)[i] = __ldcg(src + i);
+            }
+            const float bdE = blkE[1001] - blkE[1000];
+            const bool gen = !ident;
+            const int mloc = Lb - 1, qmaxE = Lb >= 2 ? Lb * mloc : 0;
+            const float inv_m = mloc > 0 ? 1.f / (float)mloc : 0.f;
+            float dsum_acc = 0.f;
+            u64 lsmE[2] = {0ull, 0ull};
+            __syncthreads();
+            for (int r0 = 0; r0 < Ne; r0 += E_RCH) {
+                const int nr = min(E_RCH, Ne - r0);
+                // pass A: lanes = columns, all 20 channels: the soft edge again, then de
+                for (int cb = 0; cb < WUe; ++cb) {
+                    const int j = cb * 32 + lane;
+                    const bool ok = j < Ne;
+                    float Q[HD];
+#pragma unroll
+                    for (int q4 = 0; q4 < 5; ++q4) {
+                        float4 v = make_float4(NEG_BIG, NEG_BIG, NEG_BIG, NEG_BIG);
+                        if (ok) v = *reinterpret_cast<const float4*>(PCe + j * HD + 4 * q4);
+                        Q[4 * q4] = v.x; Q[4 * q4 + 1] = v.y; Q[4 * q4 + 2] = v.z; Q[4 * q4 + 3] = v.w;
+                    }
+                    const float uj = ok ? uE[j] : 0.f;
+                    for (int rl = warp; rl < nr; rl += M2_NW) {
+                        const int r = r0 + rl;
+                        const uint32_t bit = (ebits[r * WPe + cb] >> lane) & 1u;
+                        const float* prow = PRe01 + (size_t)r * PROW + bit * 4;
+                        float d = bdE;
+#pragma unroll
+                        for (int q4 = 0; q4 < 5; ++q4) {
+                            const float4 pv = *reinterpret_cast<const float4*>(prow + q4 * 8);
+                            d = fmaf(fmaxf(pv.x + Q[4 * q4], 0.f), gamE[4 * q4], d); d = fmaf(fmaxf(pv.y + Q[4 * q4 + 1], 0.f), gamE[4 * q4 + 1], d);
+                            d = fmaf(fmaxf(pv.z + Q[4 * q4 + 2], 0.f), gamE[4 * q4 + 2], d); d = fmaf(fmaxf(pv.w + Q[4 * q4 + 3], 0.f), gamE[4 * q4 + 3], d);
+                        }
+                        const float e = expf(-fabsf(d)), inv = 1.f / (1.f + e);
+                        const float a1 = d >= 0.f ? inv : e * inv, a0 = d >= 0.f ? e * inv : inv;
+                        float up = 0.f;
+                        if (ok && j != r) {
+                            if (!gen) {
+                                up = uE[r] + uj;
+                            } else {
+                                const int q = r * nm1 + j - (j > r ? 1 : 0);
+                                if (q < qmaxE) {                    // local coordinates of the pair (utils2.py:123-137)
+                                    int li = (int)(((float)q + 0.5f) * inv_m);
+                                    int sl = q - li * mloc;
+                                    if (sl < 0) { --li; sl += mloc; } else if (sl >= mloc) { ++li; sl -= mloc; }
+                                    up = uE[li] + uE[sl + (sl >= li ? 1 : 0)];
+                                }
+                            }
+                        }
+                        const float de = a1 * a0 * up;
+                        det[rl * DWe + cb * 32 + lane] = de;
+                        dsum_acc += de;
+                    }
+                }
+                __syncthreads();
+                // pass B: a warp owns four channels and a quarter of the chunk's rows; columns in passes of four segments
+                for (int cp = 0; cp * 4 < WUe; ++cp) {
+                    u64 Q[4][2], col[4][2];
+#pragma unroll
+                    for (int sg = 0; sg < 4; ++sg) {
+                        const int j = (cp * 4 + sg) * 32 + lane;
+                        ulonglong2 q = make_ulonglong2(pk2(NEG_BIG, NEG_BIG), pk2(NEG_BIG, NEG_BIG));
+                        if (j < Ne) q = *reinterpret_cast<const ulonglong2*>(PCe + j * HD + k0);
+                        Q[sg][0] = q.x; Q[sg][1] = q.y; col[sg][0] = 0ull; col[sg][1] = 0ull;
+                    }
+                    const uint32_t lmask = 1u << lane;
+                    for (int rl = rg; rl < nr; rl += M2_NRG) {
+                        const int r = r0 + rl;
+                        const float* prow0 = PRe01 + (size_t)r * PROW + kg * 8;
+                        const float* prow1 = prow0 + 4;
+                        u64 rp0 = 0ull, rp1 = 0ull;
+#pragma unroll
+                        for (int sg = 0; sg < 4; ++sg) {
+                            const int wi = cp * 4 + sg;
+                            if (wi < WUe) {
+                                const bool bit = (ebits[r * WPe + wi] & lmask) != 0u;
+                                const ulonglong2 pq = *reinterpret_cast<const ulonglong2*>(bit ? prow1 : prow0);
+                                const float dv = det[rl * DWe + wi * 32 + lane];
+                                const u64 d2 = pk2(dv, dv);
+                                const u64 v0 = gate2(add2(pq.x, Q[sg][0]), d2), v1 = gate2(add2(pq.y, Q[sg][1]), d2);
+                                col[sg][0] = add2(col[sg][0], v0); col[sg][1] = add2(col[sg][1], v1);
+                                rp0 = add2(rp0, v0); rp1 = add2(rp1, v1);
+                                const float lf = bit ? 1.f : 0.f;
+                                const u64 l2 = pk2(lf, lf);
+                                lsmE[0] = fma2(l2, v0, lsmE[0]); lsmE[1] = fma2(l2, v1, lsmE[1]);
+                            }
+                        }
+                        const float tot = reduce4(rp0, rp1, lane);
+                        if ((lane & 7) == 0) {
+                            float* dst = RSmE + (size_t)r * HD + k0 + ch;
+                            if (cp == 0) *dst = tot; else *dst += tot;
+                        }
+                    }
+                    combine_cols<4>(col, scratch, rg, M2_NRG, kg, lane);
+                    if (rg == 0) {
+#pragma unroll
+                        for (int sg = 0; sg < 4; ++sg) {
+                            const int j = (cp * 4 + sg) * 32 + lane;
+                            if (j < Ne) {
+                                float c0v, c1v, c2v, c3v;
+                                upk2(col[sg][0], c0v, c1v); upk2(col[sg][1], c2v, c3v);
+                                float4* dst = reinterpret_cast<float4*>(CSmE + (size_t)j * HD + k0);
+                                if (r0 == 0) *dst = make_float4(c0v, c1v, c2v, c3v);
+                                else { const float4 o = *dst; *dst = make_float4(o.x + c0v, o.y + c1v, o.z + c2v, o.w + c3v); }
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+            {
+                const float t = reduce4(lsmE[0], lsmE[1], lane);
+                if ((lane & 7) == 0) lsw[rg * HD + k0 + ch] = t;
+            }
+            const float dsumE = mid2_block_sum(dsum_acc, red);
+            if (tid < HD) {
+                float ls = 0.f;
+                for (int w = 0; w < M2_NRG; ++w) ls += lsw[w * HD + tid];
+                misc[tid] = ls;
+            }
+            if (tid == 0) { gp[po.eup_b2 + 1] = dsumE; gp[po.eup_b2] = -dsumE; }
+            __syncthreads();
+            // node level (the hunk head's phase H with the edge branch's weights): HS, bias and label rows
+            const int slice = tid & 15, grp = tid >> 4;
+            if (grp < 5) {
+                const int kb = 4 * grp;
+                float hs[4] = {0.f, 0.f, 0.f, 0.f}, cs[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int n = slice; n < Ne; n += 16) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float rs = RSmE[n * HD + kb + j];
+                        hs[j] = fmaf(PRe01[p01_idx(n, kb + j)], rs, hs[j]);
+                        hs[j] = fmaf(PCe[n * HD + kb + j], CSmE[n * HD + kb + j], hs[j]);
+                        cs[j] += rs;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { hs[j] = half_sum(hs[j]); cs[j] = half_sum(cs[j]); }
+                if (slice < 4) {
+                    const int k = kb + slice;
+                    const float hh = fmaf(DgE[k], misc[k], slice == 0 ? hs[0] : slice == 1 ? hs[1] : slice == 2 ? hs[2] : hs[3]);
+                    const float c = (slice == 0 ? cs[0] : slice == 1 ? cs[1] : slice == 2 ? cs[2] : cs[3]) * gamE[k];
+                    const float ls4 = misc[k] * gamE[k];
+                    gp[po.eup_w2 + 2 * k + 1] = hh; gp[po.eup_w2 + 2 * k] = -hh;
+                    gp[po.eup_b1 + k] = c; gp[po.eup_w1 + HD + k] = ls4; gp[po.eup_w1 + k] = c - ls4;
+                }
+            }
+            // G1g of the edge head (the hunk head's table is dead): G1gE[q][m] = G1E[2 + q][m] gamE[m]
+            for (int e = tid; e < 400; e += M2_T) G1g[e] = blkE[500 + 2 * HD + e] * gamE[e % HD];
+            __syncthreads();
+            // r, c -> shared memory over the (dead) head tables; eup_w1 rows 2.. = r^T RS4 + c^T CS4
+            float* reS = uni; float* ceS = uni + Ne * HD; float* drE = uni + 2 * Ne * HD; float* dcE = det;     // det is dead
+            for (int i = tid; i < Ne * 5; i += M2_T) {
+                reinterpret_cast<float4*>(reS)[i] = __ldcg(reinterpret_cast<const float4*>(a.REg + (size_t)b * Ne * HD) + i);
+                reinterpret_cast<float4*>(ceS)[i] = __ldcg(reinterpret_cast<const float4*>(a.CEg + (size_t)b * Ne * HD) + i);
+            }
+            __syncthreads();
+            if (grp < 25) {
+                float acc[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+                const int a0 = 4 * (grp / 5), b0 = 4 * (grp % 5);
+                tile_acc(acc, reS, HD, RSmE, HD, a0, b0, slice, Ne);
+                tile_acc(acc, ceS, HD, CSmE, HD, a0, b0, slice, Ne);
+                const float v = reduce16(acc, lane);
+                const int mm = a0 + (slice >> 2), k = b0 + (slice & 3);
+                gp[po.eup_w1 + 2 * HD + mm * HD + k] = v * gamE[k];
+            }
+            // dr = RSm G1gE^T, dc = CSm G1gE^T (one thread per (node, side))
+            for (int t = tid; t < 2 * Ne; t += M2_T) {
+                const bool cside = t >= Ne;
+                const int n = cside ? t - Ne : t;
+                float in[HD], out[HD];
+                load20s(in, (cside ? CSmE : RSmE) + n * HD);
+                gemv20t(out, in, G1g);
+                store20s((cside ? dcE : drE) + n * HD, out);
+            }
+            __syncthreads();
+            // edg_w2 = RSe^T dr + CSe^T dc, edg_b2 = (Ne-1) sum (dr + dc); RSe / CSe over r / c (dead)
+            for (int i = tid; i < Ne * 5; i += M2_T) {
+                reinterpret_cast<float4*>(reS)[i] = __ldcg(reinterpret_cast<const float4*>(a.RSEg + (size_t)b * Ne * HD) + i);
+                reinterpret_cast<float4*>(ceS)[i] = __ldcg(reinterpret_cast<const float4*>(a.CSEg + (size_t)b * Ne * HD) + i);
+            }
+            __syncthreads();
+            if (grp < 25) {
+                float acc[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+                const int a0 = 4 * (grp / 5), b0 = 4 * (grp % 5);
+                tile_acc(acc, reS, HD, drE, HD, a0, b0, slice, Ne);
+                tile_acc(acc, ceS, HD, dcE, HD, a0, b0, slice, Ne);
+                const float v = reduce16(acc, lane);
+                gp[po.edg_w2 + (a0 + (slice >> 2)) * HD + b0 + (slice & 3)] = v;
+            } else if (grp < 30) {
+                const int kb = 4 * (grp - 25);
+                float cs[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int n = slice; n < Ne; n += 16)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) cs[j] += drE[n * HD + kb + j] + dcE[n * HD + kb + j];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) cs[j] = half_sum(cs[j]);
+                if (slice < 4)
+                    gp[po.edg_b2 + kb + slice] = (float)(Ne - 1) * (slice == 0 ? cs[0] : slice == 1 ? cs[1] : slice == 2 ? cs[2] : cs[3]);
+            }
+            __syncthreads();
+            // GRe = dr W2e^T -> the S / GE region, GCe = dc W2e^T -> the end of the union region; then the tied first layer
+            float* GRe = sm + L_.sc; float* GCe = uni + uni_floats - Ne * HD;
+            for (int t = tid; t < 2 * Ne; t += M2_T) {
+                const bool cside = t >= Ne;
+                const int n = cside ? t - Ne : t;
+                float in[HD], out[HD];
+                load20s(in, (cside ? dcE : drE) + n * HD);
+                gemv20t(out, in, blkE + 80);
+                store20s((cside ? GCe : GRe) + n * HD, out);
+            }
+            __syncthreads();
+            ent_bwd(wEe, GRe, GCe);
+            if (tid < HD) {
+                const float dbk = red[tid], lsk = red[3 * HD + tid];
+                gp[po.edg_b1 + tid] = dbk;
+                gp[po.edg_w11 + tid] = red[HD + tid] + red[2 * HD + tid];      // tied: the same row multiplies x_i and x_j
+                gp[po.edg_w12 + tid] = dbk - lsk;
+                gp[po.edg_w12 + HD + tid] = lsk;
+            }
         }
     }
     M2_PHASE(11);

@@ -56,17 +56,17 @@ def test_forward_backward_matches_oracle(B, Ne, Nc, variant, path):
     params = flat.float().cuda()
     probs, logits, loss, grads = eng.forward_backward(db, params, want_logits=True)
     torch.cuda.synchronize()
-    if path != "legacy" and variant != 4 and Nc <= 150:
+    if path != "legacy" and Nc <= 150 and (variant != 4 or eng.last_launch_count() <= 5):
         # the fused path ran: pack_bits, mid (entity pair layer inline), reduce -- or, with the dense entity sweeps (flag, or the
         # inline state not fitting one SM next to mid's: Ne=250 with Nc=150), pack_bits, ent_fwd, mid, ent_bwd, reduce
-        want = (3,) if variant != 2 else ((5,) if path == "dense" else (3, 5))
+        want = (3,) if variant not in (2, 4) else ((5,) if path == "dense" else (3, 5))
         assert eng.last_launch_count() in want, eng.last_launch_count()
     errs = {}
     I = plan["I"]
     def ws(name, shape):
         return eng.workspace(name, shape).cpu().numpy()
     if variant in (2, 4):
-        if variant == 4 or path == "legacy" or eng.last_launch_count() == 5:      # inline entity stage: only RS + CS exists
+        if path == "legacy" or eng.last_launch_count() >= 5:      # inline entity stage (variants 2 and 4): only RS + CS exists
             errs["RS1"] = relerr(ws("RS1", (B, Ne, 20)), I["RS1"])
         errs["S1"] = relerr(ws("S1", (B, Ne, 20)), I["RS1"] + I["CS1"])
         errs["X2"] = relerr(ws("X2", (B, Ne)), I["x2"])

@@ -95,8 +95,12 @@ def test_host_bits_refused_on_the_multi_kernel_path():
     from hdgnn_b200 import _lib
     from hdgnn_b200.engine import Engine, F_LABEL_BITS
     with pytest.raises(_lib.HdgnnError) as e:
-        Engine(48, 20, variant=4, max_batch=4, flags=F_LABEL_BITS)
+        Engine(48, 300, variant=2, max_batch=4, flags=F_LABEL_BITS)         # Nc > 256: per-commit state beyond one SM
     assert e.value.code == _lib.E_UNSUPPORTED
+    with pytest.raises(_lib.HdgnnError) as e:
+        Engine(48, 20, variant=4, max_batch=4, flags=F_LABEL_BITS | 4)      # HDGNN_F_LEGACY forces the multi-kernel path
+    assert e.value.code == _lib.E_UNSUPPORTED
+    Engine(48, 20, variant=4, max_batch=4, flags=F_LABEL_BITS).close()      # variant 4 runs on the fused path now
 
 
 @pytest.mark.gpu
