@@ -766,6 +766,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             // pair sums of relu(w11 (x_i + x_j) + b1 + W12[l_ij]) by the same machinery, rows and columns kept apart
             float* RSs = uni + uni_floats - 2 * Ne * HD; float* CSs = RSs + Ne * HD;
             ent_fwd(wEe, RSs, CSs, false);
+            M2_PHASE(20);
             float* rse_g = a.RSEg + (size_t)b * Ne * HD; float* cse_g = a.CSEg + (size_t)b * Ne * HD;
             float* re_g = a.REg + (size_t)b * Ne * HD;   float* ce_g = a.CEg + (size_t)b * Ne * HD;
             if (TRAIN) for (int i = tid; i < Ne * 5; i += M2_T) {      // kept for the backward
@@ -809,6 +810,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             // soft edges a_ij = softmax(G2^T relu(PRe_i + PCe_j + l_ij DgE) + b2h) (model_4.py:286-304).  Pooling consumes their row
             // and column sums; with every index line present (L = Ne) these are the sums over the grid rows / columns (RA, CA), with
             // L < Ne the local L x L grid is a reshape of the FLAT pair order, so those commits keep a1 in that order (A1F).
+            M2_PHASE(21);
             if (TRAIN) {
                 float4* dst = reinterpret_cast<float4*>(a.PREg + (size_t)b * Ne * 60);
                 for (int i = tid; i < Ne * 15; i += M2_T) dst[i] = reinterpret_cast<const float4*>(uni)[i];      // PRe01 | PCe are contiguous
@@ -817,30 +819,36 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             float* a1f = (!ident && Lb >= 2) ? a.A1F + (size_t)b * Ne * nm1 : nullptr;
             float* cpart = sm + L_.cpart;                       // [M2_NW][32] column partials of one column block
             const float bdE = blkE[1001] - blkE[1000];
+            u64 gam2[HD / 2];
+#pragma unroll
+            for (int k = 0; k < HD / 2; ++k) gam2[k] = pk2(gamE[2 * k], gamE[2 * k + 1]);
             for (int i = tid; i < Ne; i += M2_T) RA[i] = 0.f;
             __syncthreads();
             const int WUe = (Ne + 31) >> 5;
             for (int cb = 0; cb < WUe; ++cb) {
                 const int j = cb * 32 + lane;
                 const bool ok = j < Ne;
-                float Q[HD];
+                u64 Q2[HD / 2];          // packed pairs: one add2 / fma2 per two channels
 #pragma unroll
                 for (int q4 = 0; q4 < 5; ++q4) {
-                    float4 v = make_float4(NEG_BIG, NEG_BIG, NEG_BIG, NEG_BIG);
-                    if (ok) v = *reinterpret_cast<const float4*>(PCe + j * HD + 4 * q4);
-                    Q[4 * q4] = v.x; Q[4 * q4 + 1] = v.y; Q[4 * q4 + 2] = v.z; Q[4 * q4 + 3] = v.w;
+                    ulonglong2 v = make_ulonglong2(pk2(NEG_BIG, NEG_BIG), pk2(NEG_BIG, NEG_BIG));
+                    if (ok) v = *reinterpret_cast<const ulonglong2*>(PCe + j * HD + 4 * q4);
+                    Q2[2 * q4] = v.x; Q2[2 * q4 + 1] = v.y;
                 }
                 float cacc = 0.f;
                 for (int r = warp; r < Ne; r += M2_NW) {
                     const uint32_t bit = (ebits[r * WPe + cb] >> lane) & 1u;
                     const float* prow = PRe01 + (size_t)r * PROW + bit * 4;
-                    float d = bdE;
+                    u64 da = pk2(bdE, 0.f), db2 = 0ull;
 #pragma unroll
                     for (int q4 = 0; q4 < 5; ++q4) {
-                        const float4 pv = *reinterpret_cast<const float4*>(prow + q4 * 8);
-                        d = fmaf(fmaxf(pv.x + Q[4 * q4], 0.f), gamE[4 * q4], d); d = fmaf(fmaxf(pv.y + Q[4 * q4 + 1], 0.f), gamE[4 * q4 + 1], d);
-                        d = fmaf(fmaxf(pv.z + Q[4 * q4 + 2], 0.f), gamE[4 * q4 + 2], d); d = fmaf(fmaxf(pv.w + Q[4 * q4 + 3], 0.f), gamE[4 * q4 + 3], d);
+                        const ulonglong2 pv = *reinterpret_cast<const ulonglong2*>(prow + q4 * 8);
+                        da = fma2(relu2(add2(pv.x, Q2[2 * q4])), gam2[2 * q4], da);
+                        db2 = fma2(relu2(add2(pv.y, Q2[2 * q4 + 1])), gam2[2 * q4 + 1], db2);
                     }
+                    float dlo, dhi;
+                    upk2(add2(da, db2), dlo, dhi);
+                    const float d = dlo + dhi;
                     const float e = expf(-fabsf(d)), inv = 1.f / (1.f + e);
                     const float a1 = (ok && j != r) ? (d >= 0.f ? inv : e * inv) : 0.f;
                     cacc += a1;
@@ -858,6 +866,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
                 }
                 __syncthreads();
             }
+            M2_PHASE(22);
         }
         M2_PHASE(17);
     }
@@ -1019,10 +1028,21 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
                 acc = warp_sum(acc);
                 if (lane == 0) { SP[4 * li + 3] = acc; SP[4 * li + 2] = (float)m - acc; }
             }
-            for (int lj = tid; lj < Lb; lj += M2_T) {
-                float acc = 0.f;
-                for (int li = 0; li < Lb; ++li) if (li != lj) acc += __ldcg(a1f + (size_t)li * m + lj - (lj > li ? 1 : 0));
-                TP[4 * lj + 3] = acc; TP[4 * lj + 2] = (float)m - acc;
+            for (int t0 = 0; t0 < 4 * Lb; t0 += M2_T) {           // four threads per column (interleaved rows), eight loads in flight each
+                const int t = t0 + tid, lj = t >> 2, part = t & 3;
+                const bool live = t < 4 * Lb;
+                float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                for (int li0 = part; live && li0 < Lb; li0 += 32) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int li = li0 + 4 * u;
+                        if (li < Lb && li != lj) acc[u] += __ldcg(a1f + (size_t)li * m + lj - (lj > li ? 1 : 0));
+                    }
+                }
+                float tot = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+                tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+                tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+                if (live && part == 0) { TP[4 * lj + 3] = tot; TP[4 * lj + 2] = (float)m - tot; }
             }
         }
     }
@@ -1137,34 +1157,41 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
     {
         const size_t npair = (size_t)Nc * (Nc - 1);
         const float bd = gb2[1] - gb2[0], b20 = gb2[0];
+        u64 gam2[HD / 2];        // packed pairs in registers: one add2 / fma2 per two channels
+#pragma unroll
+        for (int k = 0; k < HD / 2; ++k) gam2[k] = pk2(gam[2 * k], gam[2 * k + 1]);
         for (int cb = 0; cb < CWT; ++cb) {
             const int j = cb * 32 + lane;
             const bool ok = j < Nc;
-            float Q[HD];
+            u64 Q2[HD / 2];
 #pragma unroll
             for (int q4 = 0; q4 < 5; ++q4) {
-                float4 v = make_float4(NEG_BIG, NEG_BIG, NEG_BIG, NEG_BIG);
-                if (ok) v = *reinterpret_cast<const float4*>(PC + j * HD + 4 * q4);
-                Q[4 * q4] = v.x; Q[4 * q4 + 1] = v.y; Q[4 * q4 + 2] = v.z; Q[4 * q4 + 3] = v.w;
+                ulonglong2 v = make_ulonglong2(pk2(NEG_BIG, NEG_BIG), pk2(NEG_BIG, NEG_BIG));
+                if (ok) v = *reinterpret_cast<const ulonglong2*>(PC + j * HD + 4 * q4);
+                Q2[2 * q4] = v.x; Q2[2 * q4 + 1] = v.y;
             }
             for (int r = warp; r < Nc; r += M2_NW) {
                 const bool valid = ok && j != r;
                 const uint32_t bit = (ybits[r * WPc + cb] >> lane) & 1u;
                 const bool lab = bit != 0u;
                 const float* prow = PR01 + (size_t)r * PROW + bit * 4;
-                float d = bd, l0 = b20;
+                u64 da = pk2(bd, 0.f), db2 = 0ull;
+                float l0 = b20;
 #pragma unroll
                 for (int q4 = 0; q4 < 5; ++q4) {
-                    const float4 p = *reinterpret_cast<const float4*>(prow + q4 * 8);
-                    const float h0 = fmaxf(p.x + Q[4 * q4], 0.f), h1 = fmaxf(p.y + Q[4 * q4 + 1], 0.f);
-                    const float h2 = fmaxf(p.z + Q[4 * q4 + 2], 0.f), h3 = fmaxf(p.w + Q[4 * q4 + 3], 0.f);
-                    d = fmaf(h0, gam[4 * q4], d); d = fmaf(h1, gam[4 * q4 + 1], d);
-                    d = fmaf(h2, gam[4 * q4 + 2], d); d = fmaf(h3, gam[4 * q4 + 3], d);
+                    const ulonglong2 p = *reinterpret_cast<const ulonglong2*>(prow + q4 * 8);
+                    const u64 ha = relu2(add2(p.x, Q2[2 * q4])), hb = relu2(add2(p.y, Q2[2 * q4 + 1]));
+                    da = fma2(ha, gam2[2 * q4], da); db2 = fma2(hb, gam2[2 * q4 + 1], db2);
                     if (LOGITS) {
+                        float h0, h1, h2, h3;
+                        upk2(ha, h0, h1); upk2(hb, h2, h3);
                         l0 = fmaf(h0, G2[2 * (4 * q4)], l0); l0 = fmaf(h1, G2[2 * (4 * q4 + 1)], l0);
                         l0 = fmaf(h2, G2[2 * (4 * q4 + 2)], l0); l0 = fmaf(h3, G2[2 * (4 * q4 + 3)], l0);
                     }
                 }
+                float dlo, dhi;
+                upk2(add2(da, db2), dlo, dhi);
+                const float d = dlo + dhi;
                 const float e = expf(-fabsf(d));
                 const float inv = 1.f / (1.f + e);
                 const float p1 = d >= 0.f ? inv : e * inv, p0 = d >= 0.f ? e * inv : inv;
@@ -1878,6 +1905,9 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
                 for (int i = tid; i < Ne * 15; i += M2_T) reinterpret_cast<float4*>(uni)[i] = __ldcg(src + i);
             }
             const float bdE = blkE[1001] - blkE[1000];
+            u64 gam2[HD / 2];
+#pragma unroll
+            for (int k = 0; k < HD / 2; ++k) gam2[k] = pk2(gamE[2 * k], gamE[2 * k + 1]);
             const bool gen = !ident;
             const int mloc = Lb - 1, qmaxE = Lb >= 2 ? Lb * mloc : 0;
             const float inv_m = mloc > 0 ? 1.f / (float)mloc : 0.f;
@@ -1890,25 +1920,28 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
                 for (int cb = 0; cb < WUe; ++cb) {
                     const int j = cb * 32 + lane;
                     const bool ok = j < Ne;
-                    float Q[HD];
+                    u64 Q2[HD / 2];
 #pragma unroll
                     for (int q4 = 0; q4 < 5; ++q4) {
-                        float4 v = make_float4(NEG_BIG, NEG_BIG, NEG_BIG, NEG_BIG);
-                        if (ok) v = *reinterpret_cast<const float4*>(PCe + j * HD + 4 * q4);
-                        Q[4 * q4] = v.x; Q[4 * q4 + 1] = v.y; Q[4 * q4 + 2] = v.z; Q[4 * q4 + 3] = v.w;
+                        ulonglong2 v = make_ulonglong2(pk2(NEG_BIG, NEG_BIG), pk2(NEG_BIG, NEG_BIG));
+                        if (ok) v = *reinterpret_cast<const ulonglong2*>(PCe + j * HD + 4 * q4);
+                        Q2[2 * q4] = v.x; Q2[2 * q4 + 1] = v.y;
                     }
                     const float uj = ok ? uE[j] : 0.f;
                     for (int rl = warp; rl < nr; rl += M2_NW) {
                         const int r = r0 + rl;
                         const uint32_t bit = (ebits[r * WPe + cb] >> lane) & 1u;
                         const float* prow = PRe01 + (size_t)r * PROW + bit * 4;
-                        float d = bdE;
+                        u64 da = pk2(bdE, 0.f), db2 = 0ull;         // the forward's arithmetic, operation for operation
 #pragma unroll
                         for (int q4 = 0; q4 < 5; ++q4) {
-                            const float4 pv = *reinterpret_cast<const float4*>(prow + q4 * 8);
-                            d = fmaf(fmaxf(pv.x + Q[4 * q4], 0.f), gamE[4 * q4], d); d = fmaf(fmaxf(pv.y + Q[4 * q4 + 1], 0.f), gamE[4 * q4 + 1], d);
-                            d = fmaf(fmaxf(pv.z + Q[4 * q4 + 2], 0.f), gamE[4 * q4 + 2], d); d = fmaf(fmaxf(pv.w + Q[4 * q4 + 3], 0.f), gamE[4 * q4 + 3], d);
+                            const ulonglong2 pv = *reinterpret_cast<const ulonglong2*>(prow + q4 * 8);
+                            da = fma2(relu2(add2(pv.x, Q2[2 * q4])), gam2[2 * q4], da);
+                            db2 = fma2(relu2(add2(pv.y, Q2[2 * q4 + 1])), gam2[2 * q4 + 1], db2);
                         }
+                        float dlo, dhi;
+                        upk2(add2(da, db2), dlo, dhi);
+                        const float d = dlo + dhi;
                         const float e = expf(-fabsf(d)), inv = 1.f / (1.f + e);
                         const float a1 = d >= 0.f ? inv : e * inv, a0 = d >= 0.f ? e * inv : inv;
                         float up = 0.f;
@@ -1990,6 +2023,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
                 const float t = reduce4(lsmE[0], lsmE[1], lane);
                 if ((lane & 7) == 0) lsw[rg * HD + k0 + ch] = t;
             }
+            M2_PHASE(23);
             const float dsumE = mid2_block_sum(dsum_acc, red);
             if (tid < HD) {
                 float ls = 0.f;

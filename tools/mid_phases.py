@@ -6,8 +6,9 @@ from hdgnn_b200.engine import Engine, DeviceBatch
 from hdgnn_b200.synthetic import make_commits
 
 Ne, Nc, B = (int(v) for v in (sys.argv[1:4] if len(sys.argv) > 3 else (200, 74, 100)))
+variant = int(sys.argv[4]) if len(sys.argv) > 4 else 2
 cb = make_commits(B, Ne, Nc, seed=20260)
-eng = Engine(Ne, Nc, variant=2, max_batch=B, flags=2)
+eng = Engine(Ne, Nc, variant=variant, max_batch=B, flags=2)
 db = DeviceBatch.from_numpy(cb.adj, cb.x, cb.hmap, cb.L, cb.Y, eng.tdev)
 params = (0.1 * torch.randn(eng.n_params)).cuda()
 for _ in range(3):
@@ -36,7 +37,10 @@ if clk[:, 16].any():
     print("inline entity stage: prologue incl. sort (0->1) %.0f | weights (1->16) %.0f | fwd items (16->17) %.0f | node fwd (17->2) %.0f | L (10->18) %.0f | SG scan (18->19) %.0f | bwd items+reduce (19->11) %.0f" % (
         (clk[:, 1] - clk[:, 0]).mean(), (clk[:, 16] - clk[:, 1]).mean(), (clk[:, 17] - clk[:, 16]).mean(), (clk[:, 2] - clk[:, 17]).mean(),
         (clk[:, 18] - clk[:, 10]).mean(), (clk[:, 19] - clk[:, 18]).mean(), (clk[:, 11] - clk[:, 19]).mean()))
-if clk[:, 16].any():
+if variant == 4:
+    print("variant 4: node-branch entity fwd (16->20 incl. edge pair sums) %.0f | edge head tables (20->21) %.0f | soft-edge fwd sweep (21->22) %.0f | edge bwd sweeps (node ent bwd end ->23) ... total after L: (18->23) %.0f | edge node-level + tied layer (23->11) %.0f" % (
+        (clk[:, 20] - clk[:, 16]).mean(), (clk[:, 21] - clk[:, 20]).mean(), (clk[:, 22] - clk[:, 21]).mean(), (clk[:, 23] - clk[:, 18]).mean(), (clk[:, 11] - clk[:, 23]).mean()))
+elif clk[:, 16].any():
     print("  fwd items: dense part (16->20) %.0f | row walk (20->21) %.0f | column walk (21->22) %.0f" % (
         (clk[:, 20] - clk[:, 16]).mean(), (clk[:, 21] - clk[:, 20]).mean(), (clk[:, 22] - clk[:, 21]).mean()))
 tot = clk[:, 11] - clk[:, 0]
