@@ -1,14 +1,20 @@
-// libhdgnn.so -- C ABI (include/hdgnn.h) over the sm_100a kernels of pairsum.cuh, score.cuh and
-// node.cuh.  Host side only: argument validation, scratch ownership, the launch sequence of one
-// forward / forward+backward / optimizer step, optional CUDA-graph replay.  No torch types.
+// libhdgnn.so -- C ABI (include/hdgnn.h) over the sm_100a kernels.  Host side only: argument validation, scratch
+// ownership, the launch sequence of one forward / forward+backward / optimizer step, staging of host buffers, the
+// peer-memory set-up.  No torch types.
 //
-// Launch sequence (variant 2 = model_2.py:86-118; [E] = entity-edge branch of model_4.py:92-98):
-//   fwd : pairsum(ent) -> [E: pairsum(edge) -> head_fwd(edge) -> score(edge, soft out)] -> pool_fwd
-//         -> pairsum(hunk) -> head_fwd(hunk) -> score(hunk: logits/probs/CE [+ delta sums]) -> loss
-//   bwd : head_bwd(hunk) -> pairsum_bwd(hunk) -> pool_bwd -> pairsum_bwd(ent) -> rank1_grad(ent)
-//         -> [E: score(edge, train: recompute + delta sums) -> head_bwd(edge) -> pairsum_bwd(edge)
-//             -> rank1_grad(edge, tied)] -> grad_reduce
-//   opt : adam (regularisers fused)
+// Launch sequences of a training step:
+//   fused path (all four variants when the per-commit state fits one SM; mid2.cuh, entsp.cuh, final.cuh):
+//       [pack_bits, byte-grid inputs only] -> mid2 (the whole per-commit forward + backward) -> reduce_adam
+//       (gradient reduction [+ peer all-reduce] + regularisers + TF-Adam).  With HDGNN_F_DENSE_SWEEP, or when the inline
+//       entity state does not fit: [pack_bits] -> ent_fwd2 -> mid2 -> ent_bwd2 -> reduce_adam (ent2.cuh).
+//   multi-kernel path (HDGNN_F_LEGACY, Nc > 256, Ne = 512; pairsum.cuh, score.cuh, node.cuh;
+//   [E] = entity-edge branch of model_4.py:92-98):
+//       fwd : pairsum(ent) -> [E: pairsum(edge) -> head_fwd(edge) -> score(edge, soft out)] -> pool_fwd
+//             -> pairsum(hunk) -> head_fwd(hunk) -> score(hunk: logits/probs/CE [+ delta sums]) -> loss
+//       bwd : head_bwd(hunk) -> pairsum_bwd(hunk) -> pool_bwd -> pairsum_bwd(ent) -> rank1_grad(ent)
+//             -> [E: score(edge, train: recompute + delta sums) -> head_bwd(edge) -> pairsum_bwd(edge)
+//                 -> rank1_grad(edge, tied)] -> grad_reduce
+//       opt : adam (regularisers fused)
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
