@@ -150,7 +150,8 @@ def run_reference(args, wl, config):
 
 def make_config(wl, variant, world):
     """The `config` object of the JSON line: identical for the GPU arm and the reference arm."""
-    return {"workload": wl["desc"], "variant": variant, "commits_per_gpu_per_step": wl["B"], "global_batch": wl["B"] * world}
+    return {"workload": wl["desc"], "variant": variant, "commits_per_gpu_per_step": wl["B"], "global_batch": wl["B"] * world,
+            "parallelism": f"dp{world} (commit-sharded)"}
 
 
 def measured_peaks():
@@ -315,8 +316,9 @@ def main():
         model.epoch, model.mini_batch_num = keep
         if world == 1:
             loop = {"value": epochs * nbat * B / dt, "unit": "commits/s", "ms_per_step": dt * 1e3 / (epochs * nbat), "epochs": epochs,
-                    "batches_per_epoch": nbat, "api": "graph2graph.train(): per step H2D of the batch, the fused step, arg-max hit counters "
-                    "(hdgnn_eval_counts) on the device; per epoch one synchronize, the log line and the theta read-back; no checkpoint writes"}
+                    "batches_per_epoch": nbat, "api": "graph2graph.train(): per step H2D of the batch and the fused step with the arg-max hit counter inside it; per epoch "
+                    "an asynchronous snapshot of the parameters + hit count to pinned memory and the reference's log line, written "
+                    "while the next epoch runs (no checkpoint files in this measurement)"}
         model.initialize(model.params.clone())
 
     # per-kernel timing pass (events around every launch; perturbs the step, so never the headline)
@@ -336,7 +338,7 @@ def main():
     top = max(agg, key=lambda n: agg[n][0])
     top_us = kernels[top]["avg_us"]
     ner, ncr = Ne * (Ne - 1), Nc * (Nc - 1)
-    ent_inline = variant == 2 and "ent_fwd" not in kernels and "pairsum_fwd(ent)" not in kernels
+    ent_inline = variant in (2, 4) and "ent_fwd" not in kernels and "pairsum_fwd(ent)" not in kernels
     alg = {   # canonical (un-collapsed) algorithmic FLOPs per launch of the reference ops each kernel covers (SURVEY 8(d) x pairs x B)
         "pairsum_fwd(ent)": B * ner * 1000, "pairsum_bwd(ent)": B * ner * 2000,
         "pairsum_fwd(edge)": B * ner * 1020, "pairsum_bwd(edge)": B * ner * 2040,
@@ -436,18 +438,18 @@ def main():
         except Exception as e:
             cpu["dense_leg"] = {"error": repr(e)}
     if rank == 0:
-        config = make_config(wl, variant, world)
-        config.update({"parallelism": f"commit-sharded dp{world}, " + (
-                           "no collective" if world == 1 else
-                           "gradient all-reduce fused into the reduce+Adam kernel over NVLink peer memory (no NCCL call in the step)"
-                           if model.peer else "one NCCL gradient all-reduce/step between backward and Adam"),
-                       "l2": f"inputs rotate through {pool_n} batch buffers ({n_distinct} distinct batches) = {pool_n * batch_bytes / 2**20:.0f} MiB > 126 MiB L2",
-                       "entity_stage": "inline (class tables / sorted prefix + edge walk)" if ent_inline else "dense sweeps" if variant in (2, 4) else "none"})
+        config = make_config(wl, variant, world)         # identical to the reference arm's
+        setup = {"collective": ("none" if world == 1 else
+                                "gradient all-reduce fused into the reduce+Adam kernel over NVLink peer memory (no NCCL call in the step)"
+                                if model.peer else "one NCCL gradient all-reduce/step between backward and Adam"),
+                 "l2": f"inputs rotate through {pool_n} batch buffers ({n_distinct} distinct batches) = {pool_n * batch_bytes / 2**20:.0f} MiB > 126 MiB L2",
+                 "entity_stage": ("inline (class tables / sorted prefix + edge walk)" if "ent_fwd" not in kernels and "pairsum_fwd(ent)" not in kernels
+                                  else "dense sweeps") if variant in (2, 4) else "none"}
         line = {
             "metric": METRIC, "value": value, "unit": "commits/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config,
+            "config": config, "setup": setup,
             "timing": {"device": spread(blocks_dev), "e2e": spread(blocks_e2e),
                        "note": f"{args.repeats} blocks of exactly {args.steps} steps, each bracketed by barrier + synchronize and timed with CUDA events "
                                "(max over ranks); value / e2e are the MEDIAN block"},

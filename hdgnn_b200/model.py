@@ -187,9 +187,9 @@ class graph2graph(object):
         """Pinned host batch in the wire format this model's engine takes."""
         return HostBatch(cb, bits=self.host_bits)
 
-    def named_params(self):
+    def named_params(self, flat=None):
         out = {}
-        flat = self.params.detach().cpu()
+        flat = self.params.detach().cpu() if flat is None else torch.as_tensor(flat)
         for name in PARAM_NAMES[self.variant]:
             o = self.offsets[name]
             out[name] = flat[o:o + int(np.prod(_SHAPES[name]))].reshape(_SHAPES[name]).clone()
@@ -271,7 +271,9 @@ class graph2graph(object):
         """model_2.py:335-424.  `args` needs .Repo and .checkpoint_dir (main.py's namespace).
         The loop body is one asynchronous library call per batch: the batches are pinned (and bit-packed) once, the losses of
         an epoch land in a pinned ring, top_ACC (EvaluationFuncs.py:27-37) is counted inside the relation-head phase of the
-        step (hdgnn_set_hits_accumulator), and the host synchronises once per epoch to print the reference's log line."""
+        step (hdgnn_set_hits_accumulator).  The host never waits for the epoch it has just enqueued: at the end of epoch i
+        the parameters / Adam state / hit count are copied to pinned memory asynchronously and an event is recorded; the log
+        line, the result file and the checkpoint of epoch i are written while epoch i+1 runs (same order, same content)."""
         from .engine import eval_counts
         repo = getattr(args, "Repo", self.Repo)
         ckpt = getattr(args, "checkpoint_dir", self.checkpoint_dir)
@@ -284,62 +286,93 @@ class graph2graph(object):
         nb = int(train.B / mb)                                      # remainder batch dropped (model_2.py:364)
         per = mb // self.world
         dev = self.engine.tdev
-        hits = torch.zeros(1, dtype=torch.int64, device=dev)
-        in_kernel_hits = self.engine.set_hits_accumulator(hits)     # False on the multi-kernel path (variant 4, very large grids)
+        E, P = self.epoch, self.n_params
+        hits_dev = torch.zeros(max(E, 1), dtype=torch.int64, device=dev)          # one counter per epoch: no memset in the loop
+        in_kernel_hits = self.engine.set_hits_accumulator(hits_dev[0:1])          # False on the multi-kernel path (very large grids)
         probs_d = None if in_kernel_hits else torch.zeros(per, 2, self.Ncr, dtype=torch.float32, device=dev)
-        ring = torch.zeros(max(nb, 1), 3, dtype=torch.float32).pin_memory()
+        ring = torch.zeros(2, max(nb, 1), 3, dtype=torch.float32).pin_memory()    # losses, by epoch parity
+        snap = torch.zeros(2, 3 * P + 1, dtype=torch.float32).pin_memory()        # params | m | v | step count at the end of an epoch
+        hits_h = torch.zeros(2, dtype=torch.int64).pin_memory()
+        done = [torch.cuda.Event(), torch.cuda.Event()]
+        side = torch.cuda.Stream(device=dev) if self.world > 1 else None
         keep3 = self.loss3
-        counter = 1
         history = []
         # the data set is static across epochs: pin (and bit-pack) every batch once
         batches = [self.host_batch(self._batch(train, train, j, quirk_q2)) for j in range(nb)]
         y_dev = None if in_kernel_hits else [hb.Y.to(dev) for hb in batches]
+        o2 = self.offsets["theta2"]
         if self.world > 1:
             torch.distributed.barrier()          # data preparation can skew the ranks by seconds: line up before the first exchange
+
+        def finish(i):
+            """Log line, result file and checkpoint of epoch i (its event has been recorded)."""
+            s = i & 1
+            done[s].synchronize()
+            ce_steps = ring[s, :nb, 0].double()
+            nhits = int(hits_h[s].item())
+            if self.world > 1:                                      # on a side stream: the training stream keeps running
+                with torch.cuda.stream(side):
+                    t = torch.cat([ce_steps if not self.peer else torch.zeros(0, dtype=torch.float64),
+                                   torch.tensor([float(nhits)], dtype=torch.float64)]).to(dev)
+                    torch.distributed.all_reduce(t)
+                    t = t.cpu()
+                if not self.peer:                                   # CE partials add up to the global mean
+                    ce_steps = t[:nb]
+                nhits = int(round(float(t[-1])))
+            tr_loss_Hedge = float(ce_steps.sum())
+            tr_loss_map = float(ring[s, :nb, 1].double().sum())
+            acc_top = float(nhits / (nb * mb * self.Ncr)) if nb else float("nan")
+            flat = snap[s, :P]
+            theta = flat[o2:o2 + 2].numpy().copy()
+            resultString = "Epoch " + str(i + 1) + \
+                           " acc: " + str(acc_top)[0:6] + \
+                           " Hedge loss: " + str(tr_loss_Hedge / nb)[0:6] + \
+                           " map MSE: " + str(tr_loss_map / nb)[0:6] + \
+                           " theta: " + str(theta[0]) + ' ' + str(theta[1]) + '\n'
+            history.append(dict(epoch=i + 1, acc=acc_top, hedge_loss=tr_loss_Hedge / nb, map_loss=tr_loss_map / nb))
+            if self.rank == 0 and save_checkpoints:
+                filepath = r'outputSelf/{}/model_{}/{}/result_{}.npy'.format(repo, self.variant, self.Step, self.Step)
+                filepath = os.path.join(root, filepath)
+                os.makedirs(os.path.dirname(filepath), exist_ok=True)
+                with open(filepath, "a", encoding='utf-8') as f:
+                    f.write(resultString)
+            if self.rank == 0:
+                log(resultString)
+            if self.rank == 0 and save_checkpoints:                 # counter = i + 2: the reference increments before saving
+                self.save(os.path.join(root, ckpt) if not os.path.isabs(ckpt) else ckpt, i + 2,
+                          snapshot=dict(params=flat.clone(), m=snap[s, P:2 * P].clone(), v=snap[s, 2 * P:3 * P].clone(),
+                                        t=np.array([int(round(float(snap[s, 3 * P])))], dtype=np.int32)))
+
         start_time1 = time.time()
         try:
-            for i in range(self.epoch):
-                hits.zero_()
+            for i in range(E):
+                s = i & 1
+                if in_kernel_hits:
+                    self.engine.set_hits_accumulator(hits_dev[i:i + 1])
                 for j in range(nb):
                     hb = batches[j]
-                    self.loss3 = ring[j]
+                    self.loss3 = ring[s, j]
                     if in_kernel_hits:
                         self.train_step(hb)
                     else:
                         self.train_step(hb, want_probs=True, probs_out=probs_d)
                         counts, _ = eval_counts(probs_d[:hb.B], y_dev[j])
-                        hits += counts[:, 0].sum()
-                torch.cuda.current_stream().synchronize()           # once per epoch
-                if self.peer:
-                    self.engine.peer_status()        # a timed-out exchange raises here instead of training on with diverged replicas
-                ce_steps = ring[:nb, 0].double()
-                if self.world > 1 and not self.peer:                # CE partials add up to the global mean
-                    t = ce_steps.to(dev)
-                    torch.distributed.all_reduce(t)
-                    ce_steps = t.cpu()
-                tr_loss_Hedge = float(ce_steps.sum())
-                tr_loss_map = float(ring[:nb, 1].double().sum())
-                if self.world > 1:
-                    torch.distributed.all_reduce(hits)
-                acc_top = float(int(hits.item()) / (nb * mb * self.Ncr)) if nb else float("nan")
-                theta = self.named_params()["theta2"].numpy().reshape([2])
-                resultString = "Epoch " + str(i + 1) + \
-                               " acc: " + str(acc_top)[0:6] + \
-                               " Hedge loss: " + str(tr_loss_Hedge / nb)[0:6] + \
-                               " map MSE: " + str(tr_loss_map / nb)[0:6] + \
-                               " theta: " + str(theta[0]) + ' ' + str(theta[1]) + '\n'
-                history.append(dict(epoch=i + 1, acc=acc_top, hedge_loss=tr_loss_Hedge / nb, map_loss=tr_loss_map / nb))
-                if self.rank == 0 and save_checkpoints:
-                    filepath = r'outputSelf/{}/model_{}/{}/result_{}.npy'.format(repo, self.variant, self.Step, self.Step)
-                    filepath = os.path.join(root, filepath)
-                    os.makedirs(os.path.dirname(filepath), exist_ok=True)
-                    with open(filepath, "a", encoding='utf-8') as f:
-                        f.write(resultString)
-                if self.rank == 0:
-                    log(resultString)
-                counter += 1
-                if self.rank == 0 and save_checkpoints:
-                    self.save(os.path.join(root, ckpt) if not os.path.isabs(ckpt) else ckpt, counter)
+                        hits_dev[i:i + 1] += counts[:, 0].sum()
+                snap[s, :P].copy_(self.params, non_blocking=True)
+                if save_checkpoints:
+                    snap[s, P:2 * P].copy_(self.m, non_blocking=True)
+                    snap[s, 2 * P:3 * P].copy_(self.v, non_blocking=True)
+                    snap[s, 3 * P:].copy_(self.step_counter.float(), non_blocking=True)
+                hits_h[s:s + 1].copy_(hits_dev[i:i + 1], non_blocking=True)
+                done[s].record()
+                if i >= 1:
+                    finish(i - 1)                                   # while epoch i runs
+                if self.peer and (i & 31) == 31:
+                    self.engine.peer_status()    # a timed-out exchange raises here instead of training on with diverged replicas
+            if E:
+                finish(E - 1)
+            if self.peer:
+                self.engine.peer_status()
         finally:
             self.loss3 = keep3
             self.engine.set_hits_accumulator(None)
@@ -418,15 +451,19 @@ class graph2graph(object):
 
     # ------------------------------------------------------------------------------------------
     # checkpoints: same directory layout and naming as tf.train.Saver (model_2.py:427-451), as .npz
-    def save(self, checkpoint_dir, step):
+    def save(self, checkpoint_dir, step, snapshot=None):
+        """snapshot: host copies dict(params, m, v, t) taken at the end of the epoch (train() passes them so that the file
+        is written while the next epoch runs); None reads the device state now."""
         model_name = "g2g.model"
         checkpoint_dir = os.path.join(checkpoint_dir, self._model_dir())
         os.makedirs(checkpoint_dir, exist_ok=True)
-        named = {TF_NAMES[k].replace("/", "__"): v.numpy() for k, v in self.named_params().items()}
+        if snapshot is None:
+            snapshot = dict(params=self.params.detach().cpu(), m=self.m.cpu(), v=self.v.cpu(), t=self.step_counter.cpu().numpy())
+        named = {TF_NAMES[k].replace("/", "__"): v.numpy() for k, v in self.named_params(snapshot["params"]).items()}
         path = os.path.join(checkpoint_dir, f"{model_name}-{step}.npz")
-        np.savez(path, __flat__=self.params.detach().cpu().numpy(), __variant__=np.int32(self.variant),
-                 __adam_m__=self.m.cpu().numpy(), __adam_v__=self.v.cpu().numpy(),
-                 __adam_t__=self.step_counter.cpu().numpy(), **named)
+        np.savez(path, __flat__=np.asarray(snapshot["params"]), __variant__=np.int32(self.variant),
+                 __adam_m__=np.asarray(snapshot["m"]), __adam_v__=np.asarray(snapshot["v"]),
+                 __adam_t__=np.asarray(snapshot["t"]), **named)
         index = os.path.join(checkpoint_dir, "checkpoint")
         # max_to_keep = 5 is tracked IN MEMORY per model object, as tf.train.Saver does: files of an earlier run are
         # never deleted, and a name that is still among the last five is never removed (a rerun writes the same names)
