@@ -58,20 +58,45 @@ __global__ void __launch_bounds__(CB_T) prop_bwd_commit_kernel(int N, int d_in, 
         for (int n = 0; n < N; ++n) acc = fmaf(Hs[n * d_in + i], Zs[n * d_out + o], acc);
         pb[e] = acc;
     }
+    // bias partial: column sums of dPre, coalesced (thread -> column t % d_out, row slot t / d_out), slots combined in order
+    __syncthreads();
     const float* Pb = dPre + (size_t)b * N * d_out;
+    const int nslot = CB_T / d_out;
+    float* red = Hs;                                        // Hs is dead
+    if (tid < nslot * d_out) {
+        const int o = tid % d_out, sl = tid / d_out;
+        float acc = 0.f;
+        for (int n = sl; n < N; n += nslot) acc += Pb[(size_t)n * d_out + o];
+        red[sl * d_out + o] = acc;
+    }
+    __syncthreads();
     for (int o = tid; o < d_out; o += CB_T) {
         float acc = 0.f;
-        for (int n = 0; n < N; ++n) acc += Pb[(size_t)n * d_out + o];
+        for (int sl = 0; sl < nslot; ++sl) acc += red[sl * d_out + o];
         pb[d_in * d_out + o] = acc;
     }
 }
 
-// out[e] = sum_b partial[b][e] in batch order
-__global__ void batch_sum_kernel(const float* __restrict__ partial, int B, int stride, int lo, int n, float* __restrict__ out) {
+// stage 1: part2[c][e] = sum over the c-th of BS_CH batch chunks of partial[b][e] (batch order); stage 2 adds the chunks in order
+constexpr int BS_CH = 32;
+__global__ void batch_sum1_kernel(const float* __restrict__ partial, int B, int stride, float* __restrict__ part2) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+    if (e >= stride) return;
+    const int per = (B + BS_CH - 1) / BS_CH, b0 = c * per, b1 = min(b0 + per, B);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int b = b0;
+    for (; b + 3 < b1; b += 4) {                            // four loads in flight, fixed combination order
+        a0 += partial[(size_t)b * stride + e]; a1 += partial[(size_t)(b + 1) * stride + e];
+        a2 += partial[(size_t)(b + 2) * stride + e]; a3 += partial[(size_t)(b + 3) * stride + e];
+    }
+    for (; b < b1; ++b) a0 += partial[(size_t)b * stride + e];
+    part2[(size_t)c * stride + e] = (a0 + a1) + (a2 + a3);
+}
+__global__ void batch_sum2_kernel(const float* __restrict__ part2, int stride, int lo, int n, float* __restrict__ out) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     float acc = 0.f;
-    for (int b = 0; b < B; ++b) acc += partial[(size_t)b * stride + lo + e];
+    for (int c = 0; c < BS_CH; ++c) acc += part2[(size_t)c * stride + lo + e];
     out[e] = acc;
 }
 
@@ -170,7 +195,7 @@ using namespace hdgnn;
 
 extern "C" size_t hdgnn_propagate_backward_work(int B, int N, int d_in, int d_out) {
     if (B < 1 || N < 1 || d_in < 1 || d_out < 1) return 0;
-    return (size_t)2 * B * N * d_out + (size_t)B * (d_in * d_out + d_out);
+    return (size_t)2 * B * N * d_out + (size_t)(B + BS_CH) * (d_in * d_out + d_out);
 }
 
 extern "C" int hdgnn_normalize_propagate_backward(int B, int N, const uint8_t* adj, int adj_pitch, const float* H, int d_in,
@@ -192,7 +217,8 @@ extern "C" int hdgnn_normalize_propagate_backward(int B, int N, const uint8_t* a
     const int flipped = keep | ((flags & HDGNN_P_NO_TRANSPOSE) ? 0 : HDGNN_P_NO_TRANSPOSE);
     int rc = hdgnn_normalize_propagate(B, N, adj, adj_pitch, dpre_src, d_out, nullptr, nullptr, d_out, eps, flipped, dZ, nullptr, stream);
     if (rc) return rc;
-    const size_t smem = ((size_t)N * (d_in + d_out) + (size_t)d_in * d_out) * sizeof(float);
+    size_t smem = ((size_t)N * (d_in + d_out) + (size_t)d_in * d_out) * sizeof(float);
+    if (smem < CB_T * sizeof(float)) smem = CB_T * sizeof(float);      // the bias slots reuse the head of the tile
     int dev = 0, optin = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
         return HDGNN_E_CUDA;
@@ -200,8 +226,10 @@ extern "C" int hdgnn_normalize_propagate_backward(int B, int N, const uint8_t* a
     if (cudaFuncSetAttribute(prop_bwd_commit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return HDGNN_E_CUDA;
     prop_bwd_commit_kernel<<<B, CB_T, smem, st>>>(N, d_in, d_out, H, W, dZ, dpre_src, dH, partial);
     const int stride = d_in * d_out + d_out;
-    if (dW && W) batch_sum_kernel<<<(d_in * d_out + 127) / 128, 128, 0, st>>>(partial, B, stride, 0, d_in * d_out, dW);
-    if (dbias) batch_sum_kernel<<<1, 128, 0, st>>>(partial, B, stride, d_in * d_out, d_out, dbias);
+    float* part2 = partial + (size_t)B * stride;
+    if ((dW && W) || dbias) batch_sum1_kernel<<<dim3((stride + 127) / 128, BS_CH), 128, 0, st>>>(partial, B, stride, part2);
+    if (dW && W) batch_sum2_kernel<<<(d_in * d_out + 127) / 128, 128, 0, st>>>(part2, stride, 0, d_in * d_out, dW);
+    if (dbias) batch_sum2_kernel<<<1, 128, 0, st>>>(part2, stride, d_in * d_out, d_out, dbias);
     return cudaGetLastError() == cudaSuccess ? HDGNN_OK : HDGNN_E_CUDA;
 }
 

@@ -2,7 +2,7 @@
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from hdgnn_b200.engine import normalize_propagate, map_conv, label_pitch
+from hdgnn_b200.engine import normalize_propagate, map_conv, normalize_propagate_backward, map_conv_backward, label_pitch
 
 peak = 6543.4
 try:
@@ -18,11 +18,14 @@ for (B, N, d, p) in [(4096, 200, 1, 0.05), (4096, 200, 20, 0.05), (4096, 200, 20
     x = torch.rand(B, N, device="cuda", generator=g)
     H = torch.rand(B, N, d, device="cuda", generator=g)
     theta = torch.tensor([0.1, -0.2], device="cuda")
+    dOut = torch.rand(B, N, d, device="cuda", generator=g)
     for name, fn, nbytes in [("map_conv", lambda: map_conv(adj, x, theta), B * (N * pitch + 4 * N + 4)),
-                             (f"normalize_propagate d={d}", lambda: normalize_propagate(adj, H), B * (N * pitch + 8 * N * d + 4 * N))]:
-        if name == "map_conv" and d != 1:
+                             ("map_conv_backward", lambda: map_conv_backward(adj, x, theta), B * (N * pitch + 8 * N + 8)),
+                             (f"normalize_propagate d={d}", lambda: normalize_propagate(adj, H), B * (N * pitch + 8 * N * d + 4 * N)),
+                             (f"normalize_propagate_backward d={d}", lambda: normalize_propagate_backward(adj, H, dOut), B * (N * pitch + 12 * N * d))]:
+        if name.startswith("map_conv") and d != 1:
             continue
-        if name != "map_conv" and d == 1:
+        if not name.startswith("map_conv") and d == 1:
             continue
         for _ in range(3):
             fn()
