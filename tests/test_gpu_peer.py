@@ -14,11 +14,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
-@pytest.mark.parametrize("variant,Ne,Nc,per", [(2, 48, 20, 6), (1, 30, 12, 3), (2, 200, 74, 10)])
+@pytest.mark.parametrize("variant,Ne,Nc,per", [(2, 48, 20, 6), (1, 30, 12, 3), (2, 200, 74, 10), (4, 64, 24, 4)])
 def test_peer_exchange_matches_nccl_and_single_gpu(tmp_path, variant, Ne, Nc, per, world):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
-    if world > 2 and Ne == 30:
+    if world > 2 and Ne in (30, 64):
         pytest.skip("covered at world 2")
     steps = 4
     port = 29600 + (os.getpid() % 300) + world
