@@ -9,11 +9,13 @@ namespace hdgnn {
 
 // kernel handle for cudaFuncSetAttribute / occupancy queries (nullptr if not instantiated)
 const void* ent2_fn_rt(int cwt, int nrg, bool bwd);
-const void* mid2_fn_rt(int cwt, bool train);
+const void* mid2_fn_rt(int cwt, bool train, bool gt);
+// which table placements are compiled for a hunk-grid width: shared memory for cwt <= 5, global memory for cwt >= 5
+bool mid2_gt_supported(int cwt, bool gt);
 // pdl: launch with programmatic stream serialization (the kernel calls pdl_wait() before it reads its
 // predecessor's outputs, so its prologue overlaps the predecessor's tail)
 void launch_ent2(int cwt, int nrg, bool bwd, int grid, size_t smem, cudaStream_t st, const Ent2Args& a, bool pdl);
-void launch_mid2(int cwt, bool train, int grid, size_t smem, cudaStream_t st, const Mid2Args& a, bool pdl);
+void launch_mid2(int cwt, bool train, bool gt, int grid, size_t smem, cudaStream_t st, const Mid2Args& a, bool pdl);
 
 template <typename Kern, typename Args>
 inline cudaError_t launch_ex(Kern kern, int grid, int block, size_t smem, cudaStream_t st, bool pdl, const Args& a) {

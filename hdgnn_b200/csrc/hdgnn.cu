@@ -109,6 +109,8 @@ struct hdgnn_handle_s {
     bool pdl = true;                                           // programmatic dependent launch between the fused kernels
     int bslot = 0;                                             // bitmap buffer of the current step (two alternate)
     bool dlt_global = false;                                   // mid2's dL/dlogit table in HBM instead of shared memory
+    bool gt = false;                                           // mid2's hunk-stage tables in global memory (Nc > 128), workspace TABS
+    bool scg = false;                                          // ... and its S / GE rows in the GE workspace instead of shared memory
     bool mid_scache = false;                                   // mid2 keeps the entity effect sums in shared memory for its backward
     bool inl = false;                                          // entity pair layer inside mid2 (entsp.cuh): no ent_fwd2 / ent_bwd2 launch
     bool edge_fused = false;                                   // variant 4: the entity-edge branch inside mid2 as well
@@ -606,13 +608,14 @@ int fused_forward(hdgnn_handle_t h, int B, int B_global, const Inputs& in, float
     m.hits_acc = h->hits_acc;
     m.edge = h->edge_fused ? 1 : 0;
     if (m.edge) { m.RSEg = F(h, "RSEG"); m.CSEg = F(h, "CSEG"); m.REg = F(h, "REG"); m.CEg = F(h, "CEG"); m.A1F = F(h, "A1F"); m.PREg = F(h, "PREG"); }
-    m.lay = mid2_layout(h->Ne, h->Nc, train, !dlt_g, m.scache != 0, h->inl, h->edge_fused);
-    const size_t smem = mid2_smem_bytes(h->Ne, h->Nc, train, !dlt_g, m.scache != 0, h->inl, h->edge_fused);
+    m.lay = mid2_layout(h->Ne, h->Nc, train, !dlt_g, m.scache != 0, h->inl, h->edge_fused, h->gt, h->scg);
+    m.tabs_g = h->gt ? F(h, "TABS") : nullptr;
+    const size_t smem = mid2_smem_bytes(h->Ne, h->Nc, train, !dlt_g, m.scache != 0, h->inl, h->edge_fused, h->gt, h->scg);
     const int cwc = (h->Nc + 31) / 32;
     PROF_BEGIN(h, st);
     // inline entity stage: this kernel reads the weights after its pdl_wait, so it may follow the previous step's optimizer
     // kernel (or pack_bits) under programmatic dependent launch; otherwise PDL only behind ent_fwd2
-    launch_mid2(cwc, train, B, smem, st, m, h->pdl && (h->ent || h->inl));
+    launch_mid2(cwc, train, h->gt, B, smem, st, m, h->pdl && (h->ent || h->inl));
     LAUNCH_CHECK(h, train ? "mid(train)" : "mid(infer)", st);
     if (h->debug) return debug_scatter(h, B, st);
     return HDGNN_OK;
@@ -653,8 +656,8 @@ cudaError_t setup_fused(hdgnn_handle_t h, int optin) {
     cudaError_t e = cudaSuccess;
     auto acc = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
     const int cwc = (h->Nc + 31) / 32;
-    acc(cudaFuncSetAttribute(mid2_fn_rt(cwc, true), A, optin));
-    acc(cudaFuncSetAttribute(mid2_fn_rt(cwc, false), A, optin));
+    acc(cudaFuncSetAttribute(mid2_fn_rt(cwc, true, h->gt), A, optin));
+    acc(cudaFuncSetAttribute(mid2_fn_rt(cwc, false, h->gt), A, optin));
     if (h->ent) {
         acc(cudaFuncSetAttribute(ent2_fn_rt(h->fwd_cwt, h->fwd_nrg, false), A, optin));
         acc(cudaFuncSetAttribute(ent2_fn_rt(h->bwd_cwt, h->bwd_nrg, true), A, optin));
@@ -762,19 +765,36 @@ int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out) {
     h->bwd_nrg = env_int("HDGNN_BWD_NRG", 1);
     if (h->fwd_nrg != 1 && h->fwd_nrg != 2 && h->fwd_nrg != 4) h->fwd_nrg = 1;
     if (h->bwd_nrg != 1 && h->bwd_nrg != 2 && h->bwd_nrg != 4) h->bwd_nrg = 1;
-    // the fused path needs the per-commit state of mid2 in one SM's shared memory and a hunk grid of <= 8 segments
-    h->fused = !(cfg->flags & HDGNN_F_LEGACY) && h->Nc <= 256;
-    if (h->fused) {     // per-commit state of mid2 in one SM; the per-pair dL/dlogit table may spill to HBM (L2-resident)
-        h->dlt_global = mid2_smem_bytes(h->Ne, h->Nc, true, true) > (size_t)prop.sharedMemPerBlockOptin;
-        h->fused = mid2_smem_bytes(h->Ne, h->Nc, true, !h->dlt_global) <= (size_t)prop.sharedMemPerBlockOptin;
-        h->mid_scache = h->fused && mid2_smem_bytes(h->Ne, h->Nc, true, !h->dlt_global, true) <= (size_t)prop.sharedMemPerBlockOptin;
-    }
-    if (h->fused && h->ent && !(cfg->flags & HDGNN_F_DENSE_SWEEP) && env_int("HDGNN_DENSE_SWEEP", 0) == 0) {
-        // entity pair layer inside mid2 (sorted prefix sums + edge walk) when its extra state fits beside mid2's
+    // the fused path needs the per-commit state of mid2 in one SM's shared memory and a hunk grid of <= 8 segments.  The twelve
+    // hunk-stage tables (12 Nc 20 floats) either sit in shared memory (compiled for Nc <= 160) or in a per-commit slice of global
+    // memory (compiled for Nc > 128: mid2_kernel<.., GT>); the placement that admits the inline entity stage wins, shared memory
+    // on a tie
+    {
         const size_t lim = (size_t)prop.sharedMemPerBlockOptin;
-        if (mid2_smem_bytes(h->Ne, h->Nc, true, true, true, true) <= lim) { h->inl = true; h->dlt_global = false; }
-        else if (mid2_smem_bytes(h->Ne, h->Nc, true, false, true, true) <= lim) { h->inl = true; h->dlt_global = true; }
-        if (h->inl) h->mid_scache = true;
+        const int cwc = (h->Nc + 31) / 32;
+        const bool want_inl = h->ent && !(cfg->flags & HDGNN_F_DENSE_SWEEP) && env_int("HDGNN_DENSE_SWEEP", 0) == 0;
+        struct Plan { bool fused = false, dlt_global = false, scache = false, inl = false, scg = false; };
+        auto plan = [&](bool gt) {
+            Plan p;
+            if ((cfg->flags & HDGNN_F_LEGACY) || h->Nc > 256 || !mid2_gt_supported(cwc, gt)) return p;
+            // per-commit state of mid2 in one SM; the per-pair dL/dlogit table may spill to HBM (L2-resident)
+            p.dlt_global = mid2_smem_bytes(h->Ne, h->Nc, true, true, false, false, false, gt) > lim;
+            p.fused = mid2_smem_bytes(h->Ne, h->Nc, true, !p.dlt_global, false, false, false, gt) <= lim;
+            p.scache = p.fused && mid2_smem_bytes(h->Ne, h->Nc, true, !p.dlt_global, true, false, false, gt) <= lim;
+            if (p.fused && want_inl) {
+                // entity pair layer inside mid2 (sorted prefix sums + edge walk) when its extra state fits beside mid2's
+                if (mid2_smem_bytes(h->Ne, h->Nc, true, true, true, true, false, gt) <= lim) { p.inl = true; p.dlt_global = false; }
+                else if (mid2_smem_bytes(h->Ne, h->Nc, true, false, true, true, false, gt) <= lim) { p.inl = true; p.dlt_global = true; }
+                // ... or (global tables only) with the S / GE rows in global memory as well: Ne = 512 beside Nc = 256
+                else if (gt && mid2_smem_bytes(h->Ne, h->Nc, true, false, true, true, false, gt, true) <= lim) { p.inl = true; p.dlt_global = true; p.scg = true; }
+                if (p.inl) p.scache = true;
+            }
+            return p;
+        };
+        const Plan ps = plan(false), pg = plan(env_int("HDGNN_GT", 1) != 0);
+        const bool use_gt = env_int("HDGNN_GT", 1) == 2 ? pg.fused : (pg.fused && (!ps.fused || (pg.inl && !ps.inl)));
+        const Plan& pp = use_gt ? pg : ps;
+        h->gt = use_gt; h->fused = pp.fused; h->dlt_global = pp.dlt_global; h->mid_scache = pp.scache; h->inl = pp.inl; h->scg = pp.scg;
     }
     if (h->edge) {
         // variant 4 on the fused path: needs the inline entity stage, the soft-edge head tables (Ne x 60 floats + a 128-row
@@ -782,15 +802,15 @@ int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out) {
         bool ok = h->fused && h->inl && env_int("HDGNN_V4_FUSED", 1) != 0;
         if (ok) {
             const size_t lim = (size_t)prop.sharedMemPerBlockOptin;
-            h->dlt_global = mid2_smem_bytes(h->Ne, h->Nc, true, true, true, true, true) > lim;
-            const Mid2Smem L = mid2_layout(h->Ne, h->Nc, true, !h->dlt_global, true, true, true);
+            h->dlt_global = mid2_smem_bytes(h->Ne, h->Nc, true, true, true, true, true, h->gt, h->scg) > lim;
+            const Mid2Smem L = mid2_layout(h->Ne, h->Nc, true, !h->dlt_global, true, true, true, h->gt, h->scg);
             ok = (size_t)L.total * 4 + 16 <= lim && h->Ne * 60 + (M2_T / KG) * HD <= (L.sc - L.uni) - 2 * h->Ne * HD;
         }
         h->edge_fused = ok;
         bool okt = ok && env_int("HDGNN_V4_FUSED_TRAIN", 1) != 0;
         if (okt) {      // backward: head tables + column delta sums + a 32-row de tile; later five Ne x 20 arrays + GCe at the end;
                         // the general-attribute form of ent_bwd needs two sets of suffix tables beside GCe
-            const Mid2Smem L = mid2_layout(h->Ne, h->Nc, true, !h->dlt_global, true, true, true);
+            const Mid2Smem L = mid2_layout(h->Ne, h->Nc, true, !h->dlt_global, true, true, true, h->gt, h->scg);
             const int uf = L.sc - L.uni, wue = (h->Ne + 31) / 32;
             okt = h->Ne * 80 + 32 * wue * 32 <= uf && h->Ne * 120 <= uf && 40 * (h->Ne + 1) + 8 * M2_T + h->Ne * HD <= uf;
         }
@@ -841,6 +861,7 @@ int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out) {
         {"DBG", B * mid2_dbg_floats(h->Ne, h->Nc) * f, h->fused && h->debug},
         {"CLK", B * 24 * sizeof(long long), h->fused && h->debug},
         {"DLT", B * Nc * (size_t)((h->Nc + 31) / 32 * 32) * f, h->fused && h->dlt_global},
+        {"TABS", B * (size_t)mid2_tab_floats(h->Nc) * f, h->fused && h->gt},
         {"RSEG", B * Ne * HD * f, h->edge_fused}, {"CSEG", B * Ne * HD * f, h->edge_fused}, {"REG", B * Ne * HD * f, h->edge_fused},
         {"CEG", B * Ne * HD * f, h->edge_fused}, {"A1F", B * Ne * (Ne - 1) * f, h->edge_fused}, {"PREG", B * Ne * 60 * f, h->edge_fused},
         {"RSE", B * Ne * HD * f, h->edge}, {"CSEP", B * Se * Ne * HD * f, h->edge}, {"CSEF", B * Ne * HD * f, h->edge},

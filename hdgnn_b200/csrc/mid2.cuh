@@ -39,6 +39,12 @@ constexpr int M2_BLKE = 20 + 40 + 20 + 400 + 20 + 440 + 20 + 40 + 2;    // 1002
 // DNB[Nc*4] DX2[Ne]
 __host__ __device__ inline size_t mid2_dbg_floats(int Ne, int Nc) { return (size_t)Ne * 22 + (size_t)Nc * 88; }
 
+// floats of the twelve hunk-stage tables of one commit (PH01 x2, QH, RS3, CS3, r, c, PR01 x2, PC, RSm, CSm), 32-byte granule
+__host__ __device__ inline int mid2_tab_floats(int Nc) { return (12 * Nc * HD + 7) & ~7; }
+
+// float offset of the pooling row table inside the scratch region: behind the column partials [nchunk][L][4], nchunk L <= min(4 Ne, M2_T)
+__host__ __device__ inline int mid2_rowtab_off(int Ne) { return 4 * (4 * Ne < M2_T ? 4 * Ne : M2_T); }
+
 struct Mid2Smem {
     // offsets in floats
     int blk1, blk2, gam, Dh, Dg, G1g, W5U, c1p;   // weight blocks (contiguous copies of the parameter blob), derived tables
@@ -47,11 +53,18 @@ struct Mid2Smem {
     int rptr, cptr, headrow, headp;          // edge prefix counts by row / by column, head partials of the edge-walk slots
     int ebt, cls, cval, csize, cmask, cmeta;  // transposed bitmap; attribute classes: class of a node, value / size / node mask of a class
     int blkE, wEe, gamE, DgE, RA, CA, cpart; // variant 4: edge-branch weight block, its first layer (U V c D), head tables, row / column sums of a1
+    int gt;                                  // hunk-stage tables (12 Nc 20 floats) in global memory (Mid2Args::tabs_g) instead of the union region
+    int scg;                                 // (GT kernels) the S / GE rows (Ne x 20) in global memory (Mid2Args::GE) instead of the sc region
+    int stg;                                 // (GT kernels) staging region of the hunk sweeps' row tables (3 Nc 20 floats), behind the dlt table
 };
 
 // dlt_smem: keep the per-pair dL/dlogit table of the training path in shared memory (else it lives in HBM / L2)
-__host__ __device__ inline Mid2Smem mid2_layout(int Ne, int Nc, bool train, bool dlt_smem = true, bool scache = false, bool inl = false, bool edge = false) {
+// gt: the twelve hunk-stage tables live in global memory (per-commit scratch, L1/L2-resident) -- the form for hunk grids whose
+//     tables do not fit one SM beside the rest of the commit's state (Nc > 128)
+__host__ __device__ inline Mid2Smem mid2_layout(int Ne, int Nc, bool train, bool dlt_smem = true, bool scache = false, bool inl = false, bool edge = false,
+                                                bool gt = false, bool scg = false) {
     Mid2Smem m;
+    m.gt = gt ? 1 : 0; m.scg = (gt && scg) ? 1 : 0;
     if (inl) scache = true;
     int o = 0;
     auto take = [&](int n) { int r = o; o += (n + 7) & ~7; return r; };      // 32-byte granules
@@ -70,10 +83,15 @@ __host__ __device__ inline Mid2Smem mid2_layout(int Ne, int Nc, bool train, bool
     }
     m.dx2 = take(Ne); m.nb = take(4 * Nc); m.dnb = take(4 * Nc);
     m.ebits = take(Ne * bit_words(Ne)); m.ybits = take(Nc * bit_words(Nc));
-    const int cwc = (Nc + 31) / 32;
-    const int comb = (M2_NRG / 2) * cwc * 32 * HD, pool = 2 * 4 * 4 * Ne;     // column combine | pooling partials
+    const int cwc = (Nc + 31) / 32, wue = (Ne + 31) / 32;
+    // scratch users: column combine of the hunk sweeps (two passes of half the segments from 5 segments on) | pooling partials
+    // [<= 4 chunks][L][4] + the row table [L] int2 | prologue counters [8][wue][8] + [wue][Nc] | backward partials [<= M2_T]
+    const int comb = (M2_NRG / 2) * (cwc >= 5 ? (cwc + 1) / 2 : cwc) * 32 * HD;
+    const int pool = mid2_rowtab_off(Ne) + 2 * Ne, prol = 64 * wue + wue * Nc;
     const int comb_e = edge ? (M2_NRG / 2) * 4 * 32 * HD : 0;      // variant 4: combine_cols<4> of the soft-edge delta sweep
-    m.scratch = take(comb > pool ? (comb > comb_e ? comb : comb_e) : (pool > comb_e ? pool : comb_e));
+    int scr = comb > pool ? comb : pool;
+    scr = scr > comb_e ? scr : comb_e; scr = scr > prol ? scr : prol; scr = scr > M2_T ? scr : M2_T;
+    m.scratch = take(scr);
     m.red = take(64 + M2_NW * HD + 64);
     m.uni = o;
     // union region: [hunk tables 12 Nc 20][dlt (training) | SP TP dl (pooling: dead while dlt is live)]; the
@@ -82,16 +100,22 @@ __host__ __device__ inline Mid2Smem mid2_layout(int Ne, int Nc, bool train, bool
     // plus 8 partial sums per thread here: both below M2_CH * M2_NODE_F for Ne <= 512)
     const int ent_phase = M2_CH * M2_NODE_F;
     const int dlt = (train && dlt_smem) ? Nc * cwc * 32 : 0, pool3 = 3 * ((4 * Ne + 7) & ~7);
-    const int hunk_phase = ((12 * Nc * HD + 7) & ~7) + (dlt > pool3 ? dlt : pool3);
-    m.SP = m.uni + ((12 * Nc * HD + 7) & ~7); m.TP = m.SP + ((4 * Ne + 7) & ~7); m.dl = m.TP + ((4 * Ne + 7) & ~7);
+    const int tabs = gt ? 0 : mid2_tab_floats(Nc);
+    // global tables: the row tables of a sweep (P01 rows, and the row gradients of the backward sweep) are staged in shared memory
+    // for the duration of the sweep, behind the dlt table (SP / TP / dl are dead while the sweeps run)
+    const int stage = gt ? ((3 * Nc * HD + 7) & ~7) : 0;
+    m.stg = m.uni + dlt;
+    const int hunk_phase = gt ? (dlt + stage > pool3 ? dlt + stage : pool3) : tabs + (dlt > pool3 ? dlt : pool3);
+    m.SP = m.uni + tabs; m.TP = m.SP + ((4 * Ne + 7) & ~7); m.dl = m.TP + ((4 * Ne + 7) & ~7);
     o += ent_phase > hunk_phase ? ent_phase : hunk_phase;
     m.sc = o;
-    if (scache) o += (Ne * HD + 7) & ~7;
+    if (scache && !m.scg) o += (Ne * HD + 7) & ~7;
     m.total = o;
     return m;
 }
-__host__ __device__ inline size_t mid2_smem_bytes(int Ne, int Nc, bool train, bool dlt_smem = true, bool scache = false, bool inl = false, bool edge = false) {
-    return (size_t)mid2_layout(Ne, Nc, train, dlt_smem, scache, inl, edge).total * 4 + 16;
+__host__ __device__ inline size_t mid2_smem_bytes(int Ne, int Nc, bool train, bool dlt_smem = true, bool scache = false, bool inl = false, bool edge = false,
+                                                  bool gt = false, bool scg = false) {
+    return (size_t)mid2_layout(Ne, Nc, train, dlt_smem, scache, inl, edge, gt, scg).total * 4 + 16;
 }
 
 struct Mid2Args {
@@ -119,6 +143,7 @@ struct Mid2Args {
                                              // (written by the copy stream's DMA after the data); null = inputs already ordered
     Mid2Smem lay;                            // shared-memory layout (mid2_layout), computed once on the host: the offsets are kernel
                                              // arguments (constant bank) instead of per-thread arithmetic
+    float* tabs_g;                           // (B, mid2_tab_floats(Nc)) hunk-stage tables when lay.gt (kernel template GT), else unused
     int inl;                                 // entity pair layer and its backward INSIDE this kernel (entsp.cuh: sorted prefix sums +
                                              // edge walk): RS1 / CS1p / GE are not used, the step has no ent_fwd2 / ent_bwd2 launch and
                                              // this kernel follows the previous step's optimizer kernel (weights are read after pdl_wait)
@@ -283,7 +308,9 @@ __device__ __forceinline__ int p01_idx(int n, int k) { return n * PROW + (k >> 2
 
 #define M2_PHASE(i) do { if (a.clk && tid == 0) a.clk[(size_t)b * 24 + (i)] = clock64(); } while (0)
 
-template <int CWT, bool TRAIN>
+// GT: the hunk-stage tables are addressed in global memory (a.tabs_g, this commit's private slice: written and read by this CTA
+// only, ordered by the block barriers) -- same code, generic loads / stores instead of shared ones
+template <int CWT, bool TRAIN, bool GT>
 __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
     extern __shared__ __align__(128) unsigned char sm_raw[];
     float* sm = reinterpret_cast<float*>(sm_raw);
@@ -305,6 +332,15 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
     uint32_t* ybits = reinterpret_cast<uint32_t*>(sm + L_.ybits);
     float* scratch = sm + L_.scratch; float* red = sm + L_.red;
     float* uni = sm + L_.uni;
+    // S (entity effect sums, forward -> backward), later GE: its own region, or (wide GT shapes) this commit's rows of a.GE
+    float* SC = (GT && L_.scg) ? a.GE + (size_t)b * Ne * HD : sm + L_.sc;
+    // hunk-stage tables: union region, or (GT) this commit's slice of global memory -- there the slice also holds the neighbour
+    // counts of the class-table entity stage while the hunk tables are not live
+    float* tabs = GT ? a.tabs_g + (size_t)b * mid2_tab_floats(Nc) : uni;
+    float* stg = sm + L_.stg;
+    auto stage_rows = [&](float* dst, const float* src, int nfl) {       // nfl: multiple of 4, both 16-byte aligned
+        for (int e = tid; e < (nfl >> 2); e += M2_T) reinterpret_cast<float4*>(dst)[e] = reinterpret_cast<const float4*>(src)[e];
+    };
     uint64_t* bar = reinterpret_cast<uint64_t*>(sm + L_.total);
     const float* par = a.params;
     const ParamOff& po = a.po;
@@ -510,8 +546,12 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
     const int uni_floats = L_.sc - L_.uni;
     int m_max = M2_MCLS;
     const int uni_edge = a.edge ? 2 * Ne * HD : 0;          // variant 4: the edge branch's RS / CS sit at the end of the union region
-    while (m_max > 0 && (2 * m_max * m_max * HD + 4 * Ne * m_max + uni_edge > uni_floats ||
-                         2 * m_max * m_max * HD + Ne * m_max + 16 * M2_T + uni_edge > uni_floats)) --m_max;
+    if (GT) {       // the count tables ([Ne][m] float4 forward, [m][Ne] packed backward) sit in the global slice
+        while (m_max > 0 && (2 * m_max * m_max * HD + 16 * M2_T + 4 + uni_edge > uni_floats || 4 * Ne * m_max > mid2_tab_floats(Nc))) --m_max;
+    } else {
+        while (m_max > 0 && (2 * m_max * m_max * HD + 4 * Ne * m_max + uni_edge > uni_floats ||
+                             2 * m_max * m_max * HD + Ne * m_max + 16 * M2_T + uni_edge > uni_floats)) --m_max;
+    }
     if (a.inl) {
         const int WU = (Ne + 31) >> 5;
         {   // stable rank sort: three threads per node count over a third of the nodes each (integer atomics: exact)
@@ -612,7 +652,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             // no search, no edge walk, every sum in class order.
             const int m = cmeta[0];
             float* H0 = uni; float* H1 = uni + m * m * HD;
-            float4* cntf = reinterpret_cast<float4*>(uni + 2 * m * m * HD);      // [Ne][m]  {c0o, c1o, c0i, c1i} as floats
+            float4* cntf = reinterpret_cast<float4*>(GT ? tabs : uni + 2 * m * m * HD);      // [Ne][m]  {c0o, c1o, c0i, c1i} as floats
             for (int e = tid; e < m * m * HD; e += M2_T) {
                 const int k = e % HD, ab = e / HD, bq = ab % m, aq = ab / m;
                 const float t0 = fmaf(cval[bq], w[HD + k], fmaf(cval[aq], w[k], w[2 * HD + k]));
@@ -760,7 +800,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             }
         }
         };
-        ent_fwd(wE, sm + L_.sc, sm + L_.sc, true);
+        ent_fwd(wE, SC, SC, true);
         if (a.edge) {
             // ---------------- variant 4: entity-edge branch forward (model_4.py:92-94, 206-304) -----------------------------
             // pair sums of relu(w11 (x_i + x_j) + b1 + W12[l_ij]) by the same machinery, rows and columns kept apart
@@ -919,8 +959,8 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
     if (a.ent) {
         // S for all nodes -> its own region (kept for the backward) or the still unused head of the union region (unless
         // that would run into SP / TP)
-        const bool coopS = a.scache || Ne <= 12 * Nc;
-        float* Sall = a.scache ? sm + L_.sc : uni;
+        const bool coopS = a.scache || (!GT && Ne <= 12 * Nc);
+        float* Sall = a.scache ? SC : uni;
         if (coopS && !a.inl) { coop_load_S(Sall, HD, 0, Ne); __syncthreads(); }
         for (int base = 0; base < 2 * Ne; base += M2_T) {
             const int t = base + tid, node = t >> 1, h = t & 1;
@@ -971,7 +1011,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         int nchunk = M2_T / Lb;
         nchunk = nchunk < 1 ? 1 : (nchunk > 4 ? 4 : nchunk);
         float* partC = scratch;                         // [nchunk][Lb][4]
-        int2* rowtab = reinterpret_cast<int2*>(scratch + 16 * Ne);      // [Lb] grid coordinates (row, offset) of flat index li m
+        int2* rowtab = reinterpret_cast<int2*>(scratch + mid2_rowtab_off(Ne));      // [Lb] grid coordinates (row, offset) of flat index li m
         for (int li = tid; li < Lb; li += M2_T) { const int q = li * m, g = q / n; rowtab[li] = make_int2(g, q - g * n); }
         __syncthreads();
         for (int t = tid; t < nchunk * Lb; t += M2_T) {
@@ -1061,19 +1101,19 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
 
     // ---------------- hunk-stage tables (union region) ---------------------------------------------
     const int T = Nc * HD;
-    float* PH01 = uni;              // [Nc][KG][2][4]
-    float* QH = uni + 2 * T;
-    float* RS3 = uni + 3 * T;
-    float* CS3 = uni + 4 * T;
-    float* rr = uni + 5 * T;        // r, later GC
-    float* cc = uni + 6 * T;
-    float* PR01 = uni + 7 * T;      // [Nc][KG][2][4]; later dr (first T) and GR (second T)
-    float* PC = uni + 9 * T;        // later dc
-    float* RSm = uni + 10 * T;      // later RS3d
-    float* CSm = uni + 11 * T;      // later CS3d
+    float* PH01 = tabs;             // [Nc][KG][2][4]
+    float* QH = tabs + 2 * T;
+    float* RS3 = tabs + 3 * T;
+    float* CS3 = tabs + 4 * T;
+    float* rr = tabs + 5 * T;       // r, later GC
+    float* cc = tabs + 6 * T;
+    float* PR01 = tabs + 7 * T;     // [Nc][KG][2][4]; later dr (first T) and GR (second T)
+    float* PC = tabs + 9 * T;       // later dc
+    float* RSm = tabs + 10 * T;     // later RS3d
+    float* CSm = tabs + 11 * T;     // later CS3d
     constexpr int DW = CWT * 32;
     // [Nc][CWT*32] dL/dlogit-difference per pair (training); in smem it aliases SP/TP/dl, else HBM (L2-resident)
-    float* dlt = a.dlt_g ? a.dlt_g + (size_t)b * Nc * DW : uni + ((12 * T + 7) & ~7);
+    float* dlt = a.dlt_g ? a.dlt_g + (size_t)b * Nc * DW : uni + (GT ? 0 : mid2_tab_floats(Nc));
     for (int idx = tid; idx < T; idx += M2_T) {
         const int c = idx / HD, k = idx - c * HD;
         float p = d1[k] + V1[8 * HD + k], q = 0.f;
@@ -1097,8 +1137,11 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             if (j < Nc) q = *reinterpret_cast<const ulonglong2*>(QH + j * HD + k0);
             Q[sg][0] = q.x; Q[sg][1] = q.y; col[sg][0] = 0ull; col[sg][1] = 0ull;
         }
-        sweep2_fwd<CWT, false>(PH01, ybits, WPc, Nc, rg, M2_NRG, kg, Q, col, RS3, lane);
-        combine_cols<CWT>(col, scratch, rg, M2_NRG, kg, lane);
+        const float* PH01s = PH01;
+        if (GT) { stage_rows(stg, PH01, 2 * T); __syncthreads(); PH01s = stg; }
+        sweep2_fwd<CWT, false>(PH01s, ybits, WPc, Nc, rg, M2_NRG, kg, Q, col, RS3, lane);
+        if constexpr (CWT >= 5) combine_cols_2pass<CWT>(col, scratch, rg, M2_NRG, kg, lane);
+        else combine_cols<CWT>(col, scratch, rg, M2_NRG, kg, lane);
         if (rg == 0) {
 #pragma unroll
             for (int sg = 0; sg < CWT; ++sg) {
@@ -1154,6 +1197,8 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
 
     // ---------------- G1. relation head: logits, softmax, CE (lanes = columns, all 20 channels) ---------
     float ce_acc = 0.f, d_acc = 0.f, hit_acc = 0.f;
+    const float* PR01s = PR01;          // row tables of the two head sweeps (G1, G2)
+    if (GT) { stage_rows(stg, PR01, 2 * T); __syncthreads(); PR01s = stg; }
     {
         const size_t npair = (size_t)Nc * (Nc - 1);
         const float bd = gb2[1] - gb2[0], b20 = gb2[0];
@@ -1174,7 +1219,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
                 const bool valid = ok && j != r;
                 const uint32_t bit = (ybits[r * WPc + cb] >> lane) & 1u;
                 const bool lab = bit != 0u;
-                const float* prow = PR01 + (size_t)r * PROW + bit * 4;
+                const float* prow = PR01s + (size_t)r * PROW + bit * 4;
                 u64 da = pk2(bd, 0.f), db2 = 0ull;
                 float l0 = b20;
 #pragma unroll
@@ -1246,7 +1291,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         auto delta_row = [&](int r, u64& rp0, u64& rp1) {
             uint32_t w[CWT];
             load_words<CWT>(w, ybits + (size_t)r * WPc);
-            const float* prow0 = PR01 + (size_t)r * PROW + kg * 8;
+            const float* prow0 = PR01s + (size_t)r * PROW + kg * 8;
             const float* prow1 = prow0 + 4;
             const float* drow = dlt + (size_t)r * DW + lane;
             float dvs[CWT];
@@ -1293,7 +1338,8 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             const float tot = reduce4(a0, a1, lane);
             if ((lane & 7) == 0) RSm[r * HD + k0 + ch] = tot;
         }
-        combine_cols<CWT>(col, scratch, rg, M2_NRG, kg, lane);
+        if constexpr (CWT >= 5) combine_cols_2pass<CWT>(col, scratch, rg, M2_NRG, kg, lane);
+        else combine_cols<CWT>(col, scratch, rg, M2_NRG, kg, lane);
         if (rg == 0) {
 #pragma unroll
             for (int sg = 0; sg < CWT; ++sg) {
@@ -1357,6 +1403,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         __syncthreads();
         // round 2: dr = RS4 G1e^T = RSm G1g^T, dc = CSm G1g^T (one thread per (hunk, side))
         for (int t = tid; t < 2 * Nc; t += M2_T) {
+            if (GT) asm volatile("" ::: "memory");      // global tables: keeps the (loop-invariant) weight loads inside the loop; hoisted, they spill
             const bool cside = t >= Nc;
             const int n = cside ? t - Nc : t;
             float in[HD], out[HD];
@@ -1389,6 +1436,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         } else {
             // threads 480..639: GR / GC rows (rr is dead: its last readers ran in round 1)
             for (int t = tid - 480; t < 2 * Nc; t += M2_T - 480) {
+                if (GT) asm volatile("" ::: "memory");
                 const bool cside = t >= Nc;
                 const int n = cside ? t - Nc : t;
                 float in[HD], out[HD];
@@ -1416,8 +1464,11 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             }
             Q[sg][0] = q.x; Q[sg][1] = q.y; GCr[sg][0] = g.x; GCr[sg][1] = g.y; col[sg][0] = 0ull; col[sg][1] = 0ull;
         }
-        sweep2_bwd<CWT, false>(PH01, GR, ybits, WPc, Nc, rg, M2_NRG, kg, Q, GCr, col, ls3, RS3d, lane);
-        combine_cols<CWT>(col, scratch, rg, M2_NRG, kg, lane);
+        const float* PH01s = PH01; const float* GRs = GR;
+        if (GT) { stage_rows(stg, PH01, 2 * T); stage_rows(stg + 2 * T, GR, T); __syncthreads(); PH01s = stg; GRs = stg + 2 * T; }
+        sweep2_bwd<CWT, false>(PH01s, GRs, ybits, WPc, Nc, rg, M2_NRG, kg, Q, GCr, col, ls3, RS3d, lane);
+        if constexpr (CWT >= 5) combine_cols_2pass<CWT>(col, scratch, rg, M2_NRG, kg, lane);
+        else combine_cols<CWT>(col, scratch, rg, M2_NRG, kg, lane);
         if (rg == 0) {
 #pragma unroll
             for (int sg = 0; sg < CWT; ++sg) {
@@ -1572,7 +1623,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         for (int c0 = 0; c0 < Ne; c0 += M2_CH) {
             const int nn = min(M2_CH, Ne - c0);
             if (a.scache) {                              // S rows of the chunk: from the forward's copy, else from HBM / L2 again
-                const float* Sall = sm + L_.sc;
+                const float* Sall = SC;
                 for (int e = tid; e < nn * 5; e += M2_T) {
                     const int n = e / 5, j = e - n * 5;
                     *reinterpret_cast<float4*>(Sa + n * 24 + 4 * j) = *reinterpret_cast<const float4*>(Sall + (size_t)(c0 + n) * HD + 4 * j);
@@ -1616,7 +1667,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
                 }
                 if (valid) {                           // GE_n[q] = sum_k W5U[q][k] dz[k], q = 10 h .. 10 h + 9
                     // inline entity stage: GE takes the place of S in shared memory (this chunk's S rows were copied to Sa)
-                    float* ge = (a.inl ? sm + L_.sc + (size_t)node * HD : a.GE + ((size_t)b * Ne + node) * HD) + 10 * h;
+                    float* ge = (a.inl ? SC + (size_t)node * HD : a.GE + ((size_t)b * Ne + node) * HD) + 10 * h;
                     float* ge_dbg = (a.inl && dbg) ? a.GE + ((size_t)b * Ne + node) * HD + 10 * h : nullptr;
 #pragma unroll
                     for (int j2 = 0; j2 < 5; ++j2) {
@@ -1713,8 +1764,8 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             // and the W's come from the same neighbour counts as the forward.
             const int m = mcl;
             float* G0 = uni; float* G1t = uni + m * m * HD;
-            uint32_t* cnt = reinterpret_cast<uint32_t*>(uni + 2 * m * m * HD);      // [m][Ne]  c1o | c1i << 16
-            float* part = uni + ((2 * m * m * HD + Ne * m + 3) & ~3);                // [M2_T][16] per-thread partial sums
+            uint32_t* cnt = reinterpret_cast<uint32_t*>(GT ? tabs : uni + 2 * m * m * HD);      // [m][Ne]  c1o | c1i << 16
+            float* part = uni + ((2 * m * m * HD + (GT ? 0 : Ne * m) + 3) & ~3);     // [M2_T][16] per-thread partial sums
             for (int e = tid; e < m * m * HD; e += M2_T) {
                 const int k = e % HD, ab = e / HD, bq = ab % m, aq = ab / m;
                 const float t0 = fmaf(cval[bq], w[HD + k], fmaf(cval[aq], w[k], w[2 * HD + k]));      // as in the forward: same gates
@@ -1876,7 +1927,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         }
         __syncthreads();
         };
-        ent_bwd(wE, sm + L_.sc, sm + L_.sc);
+        ent_bwd(wE, SC, SC);
         M2_PHASE(19);
         if (tid < HD) {
             const float dbk = red[tid], lsk = red[3 * HD + tid];
@@ -1899,7 +1950,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             float* PRe01 = uni; float* PCe = uni + Ne * PROW;
             float* CSmE = uni + Ne * 60;                        // [Ne][20]
             float* det = CSmE + Ne * HD;                        // [E_RCH][DWe] de of the current row chunk
-            float* RSmE = sm + L_.sc;                           // [Ne][20] (GE is dead)
+            float* RSmE = SC;                           // [Ne][20] (GE is dead)
             {
                 const float4* src = reinterpret_cast<const float4*>(a.PREg + (size_t)b * Ne * 60);
                 for (int i = tid; i < Ne * 15; i += M2_T) reinterpret_cast<float4*>(uni)[i] = __ldcg(src + i);
@@ -2116,7 +2167,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             }
             __syncthreads();
             // GRe = dr W2e^T -> the S / GE region, GCe = dc W2e^T -> the end of the union region; then the tied first layer
-            float* GRe = sm + L_.sc; float* GCe = uni + uni_floats - Ne * HD;
+            float* GRe = SC; float* GCe = uni + uni_floats - Ne * HD;
             for (int t = tid; t < 2 * Ne; t += M2_T) {
                 const bool cside = t >= Ne;
                 const int n = cside ? t - Ne : t;

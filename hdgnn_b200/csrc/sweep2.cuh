@@ -273,4 +273,33 @@ __device__ __forceinline__ void combine_cols(u64 (&col)[CW][2], float* scratch, 
     }
 }
 
+// The same tree with the column segments taken in two halves, for wide grids: `scratch` holds (NRG / 2 rounded up) *
+// ceil(CW / 2)*32*20 floats.  Same additions in the same order as combine_cols.
+template <int CW>
+__device__ __forceinline__ void combine_cols_2pass(u64 (&col)[CW][2], float* scratch, int rg, int nrg, int kg, int lane) {
+    constexpr int H = (CW + 1) / 2;
+    const int slot_floats = H * 32 * HD;
+#pragma unroll
+    for (int s0 = 0; s0 < CW; s0 += H) {
+        for (int half = (nrg + 1) >> 1, n = nrg; n > 1; n = half, half = (half + 1) >> 1) {
+            if (rg >= half && rg < n) {
+                float* dst = scratch + (size_t)(rg - half) * slot_floats + kg * 4;
+#pragma unroll
+                for (int sg = s0; sg < s0 + H && sg < CW; ++sg)
+                    *reinterpret_cast<ulonglong2*>(dst + (size_t)((sg - s0) * 32 + lane) * HD) = make_ulonglong2(col[sg][0], col[sg][1]);
+            }
+            __syncthreads();
+            if (rg < n - half) {
+                const float* src = scratch + (size_t)rg * slot_floats + kg * 4;
+#pragma unroll
+                for (int sg = s0; sg < s0 + H && sg < CW; ++sg) {
+                    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(src + (size_t)((sg - s0) * 32 + lane) * HD);
+                    col[sg][0] = add2(col[sg][0], v.x); col[sg][1] = add2(col[sg][1], v.y);
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
 }  // namespace hdgnn

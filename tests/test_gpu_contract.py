@@ -46,11 +46,10 @@ def _ce_grad(plan, flat, variant):
     return plan["grad"] - reg, offs
 
 
-def test_glide_bench_launch_shape_three_adam_steps():
-    """B=100, Ne=200, Nc=74, variant 2, label bitmaps, hdgnn_train_step: what bench.py times."""
+def _adam_steps_vs_oracle(B, Ne, Nc, variant, steps, seed=20260, **gen):
+    """hdgnn_train_step with label bitmaps for `steps` Adam steps against the fp64 plan + TF-form Adam of the oracle."""
     from hdgnn_b200.engine import Engine, DeviceBatch
-    B, Ne, Nc, variant = 100, 200, 74, 2
-    cb = make_commits(B, Ne, Nc, seed=20260)                       # the bench's generator settings (20 % short index files)
+    cb = make_commits(B, Ne, Nc, seed=seed, **gen)
     flat = _params(variant)
     eng = Engine(Ne, Nc, variant=variant, max_batch=B, flags=F_LABEL_BITS)
     db = DeviceBatch.from_numpy(cb.adj, cb.x, cb.hmap, cb.L, cb.Y, eng.tdev, bits=True)
@@ -58,7 +57,7 @@ def test_glide_bench_launch_shape_three_adam_steps():
     step = torch.zeros(1, dtype=torch.int32, device="cuda"); loss3 = torch.zeros(3, device="cuda")
     probs = torch.zeros(B, 2, eng.Ncr, device="cuda")
     p_ref = flat.numpy().copy(); m_ref = np.zeros_like(p_ref); v_ref = np.zeros_like(p_ref)
-    for t in range(1, 4):
+    for t in range(1, steps + 1):
         eng.train_step(db, p, m, v, step, loss3, probs=probs)
         torch.cuda.synchronize()
         assert eng.last_launch_count() <= 4
@@ -73,6 +72,18 @@ def test_glide_bench_launch_shape_three_adam_steps():
         sure = np.abs(pp[:, 1] - pp[:, 0]) > 1e-4
         assert np.array_equal((pc[:, 1] > pc[:, 0])[sure], (pp[:, 1] > pp[:, 0])[sure])      # identical predicted classes
     eng.close()
+
+
+def test_glide_bench_launch_shape_three_adam_steps():
+    """B=100, Ne=200, Nc=74, variant 2, label bitmaps, hdgnn_train_step: what bench.py times."""
+    _adam_steps_vs_oracle(100, 200, 74, 2, 3)                      # the bench's generator settings (20 % short index files)
+
+
+@pytest.mark.parametrize("B,Ne,Nc", [(3, 250, 150), (2, 512, 256), (3, 200, 256), (3, 200, 160)])
+def test_wide_hunk_grids_fused_train_step(B, Ne, Nc):
+    """Nc > 128: the hunk-stage tables of the per-commit kernel live in global memory (mid2_kernel<.., GT>); cfg3, cfg4 and the
+    widest fused inference shape run the 2-launch step with label bitmaps like glide does."""
+    _adam_steps_vs_oracle(B, Ne, Nc, 2, 2, seed=500 + Nc, p_short=0.5)
 
 
 @pytest.mark.parametrize("B,Ne,Nc,variant", [(2, 250, 114, 2), (2, 250, 150, 2), (1, 512, 256, 2), (2, 200, 74, 4),

@@ -331,11 +331,12 @@ def test_smallest_grids(Ne, Nc):
 
 
 @pytest.mark.parametrize("attr", ["many_integers", "continuous", "two_values", "constant"])
-@pytest.mark.parametrize("B,Ne,Nc,p_edge", [(3, 70, 33, 0.1), (2, 200, 74, 0.05), (2, 130, 40, 0.6)])
+@pytest.mark.parametrize("B,Ne,Nc,p_edge", [(3, 70, 33, 0.1), (2, 200, 74, 0.05), (2, 130, 40, 0.6), (2, 120, 170, 0.1), (1, 512, 256, 0.05)])
 def test_entity_stage_attribute_alphabets(B, Ne, Nc, p_edge, attr):
     """The inline entity pair layer picks its form per commit from the node attributes (utils2.py:35: x_i = A_ii): class
     tables for at most 16 distinct values, sorted prefix sums + edge walk otherwise.  Both against the oracle, including
-    dense graphs (the edge walk's worst case) and degenerate alphabets."""
+    dense graphs (the edge walk's worst case) and degenerate alphabets; the last two shapes keep the hunk tables (and the
+    class tables' neighbour counts) in global memory."""
     from hdgnn_b200.engine import Engine, DeviceBatch
     cb = make_commits(B, Ne, Nc, seed=500 + Ne, p_edge=p_edge, p_short=0.5)
     rng = np.random.default_rng(Ne)
