@@ -1274,77 +1274,87 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
     if (!TRAIN) return;
 
     // ---------------- G2. delta sums: RSm_i = sum_j m_ij dlt_ij, CSm_j, LSm (label-1 pairs) ----------------
+    // Grids of 7-8 column segments take the columns in two passes of four segments (the accumulators of eight do not fit the
+    // register file: measured spills); the second pass adds to the row sums of the first.
+    constexpr int PWC = CWT >= 7 ? 4 : CWT;             // segments per column pass
+    constexpr int NPASS = (CWT + PWC - 1) / PWC;
     float* lsw = red + 64;                   // [M2_NRG][20]
     float* misc = red + 64 + M2_NW * HD;     // [0..19] LSm then LS4, [40] dsum
     {
         const float d_tot = mid2_block_sum(d_acc, red);      // leading __syncthreads orders the dlt stores
         if (tid == 0) misc[40] = d_tot;
-        u64 Q[CWT][2], col[CWT][2], lsm[2] = {0ull, 0ull};
-#pragma unroll
-        for (int sg = 0; sg < CWT; ++sg) {
-            const int j = sg * 32 + lane;
-            ulonglong2 q = make_ulonglong2(pk2(NEG_BIG, NEG_BIG), pk2(NEG_BIG, NEG_BIG));
-            if (j < Nc) q = *reinterpret_cast<const ulonglong2*>(PC + j * HD + k0);
-            Q[sg][0] = q.x; Q[sg][1] = q.y; col[sg][0] = 0ull; col[sg][1] = 0ull;
-        }
+        u64 lsm[2] = {0ull, 0ull};
         const uint32_t lmask = 1u << lane;
-        auto delta_row = [&](int r, u64& rp0, u64& rp1) {
-            uint32_t w[CWT];
-            load_words<CWT>(w, ybits + (size_t)r * WPc);
-            const float* prow0 = PR01s + (size_t)r * PROW + kg * 8;
-            const float* prow1 = prow0 + 4;
-            const float* drow = dlt + (size_t)r * DW + lane;
-            float dvs[CWT];
 #pragma unroll
-            for (int sg = 0; sg < CWT; ++sg) dvs[sg] = drow[sg * 32];      // all loads of the row in flight (HBM/L2 when spilled)
-            rp0 = 0ull; rp1 = 0ull;
+        for (int pass = 0; pass < NPASS; ++pass) {
+            const int sg0 = pass * PWC;
+            u64 Q[PWC][2], col[PWC][2];
 #pragma unroll
-            for (int sg = 0; sg < CWT; ++sg) {
-                const bool bit = (w[sg] & lmask) != 0u;
-                const ulonglong2 p = *reinterpret_cast<const ulonglong2*>(bit ? prow1 : prow0);
-                const float dv = dvs[sg];
-                const u64 d2 = pk2(dv, dv);
-                const u64 v0 = gate2(add2(p.x, Q[sg][0]), d2), v1 = gate2(add2(p.y, Q[sg][1]), d2);
-                col[sg][0] = add2(col[sg][0], v0); col[sg][1] = add2(col[sg][1], v1);
-                rp0 = add2(rp0, v0); rp1 = add2(rp1, v1);
-                const float lf = bit ? 1.f : 0.f;
-                const u64 l2 = pk2(lf, lf);
-                lsm[0] = fma2(l2, v0, lsm[0]); lsm[1] = fma2(l2, v1, lsm[1]);
+            for (int sg = 0; sg < PWC; ++sg) {
+                const int j = (sg0 + sg) * 32 + lane;
+                ulonglong2 q = make_ulonglong2(pk2(NEG_BIG, NEG_BIG), pk2(NEG_BIG, NEG_BIG));
+                if (j < Nc) q = *reinterpret_cast<const ulonglong2*>(PC + j * HD + k0);
+                Q[sg][0] = q.x; Q[sg][1] = q.y; col[sg][0] = 0ull; col[sg][1] = 0ull;
             }
-        };
-        int r = rg;
-        for (; r + 3 * M2_NRG < Nc; r += 4 * M2_NRG) {       // four rows per trip: two independent transpose-reduces in flight
-            u64 a0, a1, c0, c1, e0, e1, g0, g1;
-            delta_row(r, a0, a1);
-            delta_row(r + M2_NRG, c0, c1);
-            delta_row(r + 2 * M2_NRG, e0, e1);
-            delta_row(r + 3 * M2_NRG, g0, g1);
-            const float tot = reduce8(a0, a1, c0, c1, lane), tot2 = reduce8(e0, e1, g0, g1, lane);
-            if ((lane & 3) == 0) {
-                RSm[((lane & 16) ? r + M2_NRG : r) * HD + k0 + reduce8_channel(lane)] = tot;
-                RSm[((lane & 16) ? r + 3 * M2_NRG : r + 2 * M2_NRG) * HD + k0 + reduce8_channel(lane)] = tot2;
-            }
-        }
-        for (; r + M2_NRG < Nc; r += 2 * M2_NRG) {
-            u64 a0, a1, c0, c1;
-            delta_row(r, a0, a1);
-            delta_row(r + M2_NRG, c0, c1);
-            const float tot = reduce8(a0, a1, c0, c1, lane);
-            if ((lane & 3) == 0) RSm[((lane & 16) ? r + M2_NRG : r) * HD + k0 + reduce8_channel(lane)] = tot;
-        }
-        if (r < Nc) {
-            u64 a0, a1;
-            delta_row(r, a0, a1);
-            const float tot = reduce4(a0, a1, lane);
-            if ((lane & 7) == 0) RSm[r * HD + k0 + ch] = tot;
-        }
-        if constexpr (CWT >= 5) combine_cols_2pass<CWT>(col, scratch, rg, M2_NRG, kg, lane);
-        else combine_cols<CWT>(col, scratch, rg, M2_NRG, kg, lane);
-        if (rg == 0) {
+            auto delta_row = [&](int r, u64& rp0, u64& rp1) {
+                uint32_t w[PWC];
+                load_words<PWC>(w, ybits + (size_t)r * WPc + sg0);
+                const float* prow0 = PR01s + (size_t)r * PROW + kg * 8;
+                const float* prow1 = prow0 + 4;
+                const float* drow = dlt + (size_t)r * DW + sg0 * 32 + lane;
+                float dvs[PWC];
 #pragma unroll
-            for (int sg = 0; sg < CWT; ++sg) {
-                const int j = sg * 32 + lane;
-                if (j < Nc) *reinterpret_cast<ulonglong2*>(CSm + j * HD + k0) = make_ulonglong2(col[sg][0], col[sg][1]);
+                for (int sg = 0; sg < PWC; ++sg) dvs[sg] = sg0 + sg < CWT ? drow[sg * 32] : 0.f;      // all loads of the row in flight (HBM/L2 when spilled)
+                rp0 = 0ull; rp1 = 0ull;
+#pragma unroll
+                for (int sg = 0; sg < PWC; ++sg) {
+                    const bool bit = (w[sg] & lmask) != 0u;
+                    const ulonglong2 p = *reinterpret_cast<const ulonglong2*>(bit ? prow1 : prow0);
+                    const float dv = dvs[sg];
+                    const u64 d2 = pk2(dv, dv);
+                    const u64 v0 = gate2(add2(p.x, Q[sg][0]), d2), v1 = gate2(add2(p.y, Q[sg][1]), d2);
+                    col[sg][0] = add2(col[sg][0], v0); col[sg][1] = add2(col[sg][1], v1);
+                    rp0 = add2(rp0, v0); rp1 = add2(rp1, v1);
+                    const float lf = bit ? 1.f : 0.f;
+                    const u64 l2 = pk2(lf, lf);
+                    lsm[0] = fma2(l2, v0, lsm[0]); lsm[1] = fma2(l2, v1, lsm[1]);
+                }
+            };
+            auto put = [&](int row, int k, float tot) { float* d = RSm + row * HD + k; if (pass == 0) *d = tot; else *d += tot; };
+            int r = rg;
+            for (; r + 3 * M2_NRG < Nc; r += 4 * M2_NRG) {       // four rows per trip: two independent transpose-reduces in flight
+                u64 a0, a1, c0, c1, e0, e1, g0, g1;
+                delta_row(r, a0, a1);
+                delta_row(r + M2_NRG, c0, c1);
+                delta_row(r + 2 * M2_NRG, e0, e1);
+                delta_row(r + 3 * M2_NRG, g0, g1);
+                const float tot = reduce8(a0, a1, c0, c1, lane), tot2 = reduce8(e0, e1, g0, g1, lane);
+                if ((lane & 3) == 0) {
+                    put((lane & 16) ? r + M2_NRG : r, k0 + reduce8_channel(lane), tot);
+                    put((lane & 16) ? r + 3 * M2_NRG : r + 2 * M2_NRG, k0 + reduce8_channel(lane), tot2);
+                }
+            }
+            for (; r + M2_NRG < Nc; r += 2 * M2_NRG) {
+                u64 a0, a1, c0, c1;
+                delta_row(r, a0, a1);
+                delta_row(r + M2_NRG, c0, c1);
+                const float tot = reduce8(a0, a1, c0, c1, lane);
+                if ((lane & 3) == 0) put((lane & 16) ? r + M2_NRG : r, k0 + reduce8_channel(lane), tot);
+            }
+            if (r < Nc) {
+                u64 a0, a1;
+                delta_row(r, a0, a1);
+                const float tot = reduce4(a0, a1, lane);
+                if ((lane & 7) == 0) put(r, k0 + ch, tot);
+            }
+            if constexpr (PWC >= 5) combine_cols_2pass<PWC>(col, scratch, rg, M2_NRG, kg, lane);
+            else combine_cols<PWC>(col, scratch, rg, M2_NRG, kg, lane);
+            if (rg == 0) {
+#pragma unroll
+                for (int sg = 0; sg < PWC; ++sg) {
+                    const int j = (sg0 + sg) * 32 + lane;
+                    if (j < Nc) *reinterpret_cast<ulonglong2*>(CSm + j * HD + k0) = make_ulonglong2(col[sg][0], col[sg][1]);
+                }
             }
         }
         const float t = reduce4(lsm[0], lsm[1], lane);
@@ -1453,27 +1463,33 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
 
     // ---------------- I. hunk pair layer backward sweep ------------------------------------------------------
     {
-        u64 Q[CWT][2], GCr[CWT][2], col[CWT][2], ls3[2] = {0ull, 0ull};
-#pragma unroll
-        for (int sg = 0; sg < CWT; ++sg) {
-            const int j = sg * 32 + lane;
-            ulonglong2 q = make_ulonglong2(pk2(NEG_BIG, NEG_BIG), pk2(NEG_BIG, NEG_BIG)), g = make_ulonglong2(0ull, 0ull);
-            if (j < Nc) {
-                q = *reinterpret_cast<const ulonglong2*>(QH + j * HD + k0);
-                g = *reinterpret_cast<const ulonglong2*>(GC + j * HD + k0);
-            }
-            Q[sg][0] = q.x; Q[sg][1] = q.y; GCr[sg][0] = g.x; GCr[sg][1] = g.y; col[sg][0] = 0ull; col[sg][1] = 0ull;
-        }
+        u64 ls3[2] = {0ull, 0ull};
         const float* PH01s = PH01; const float* GRs = GR;
         if (GT) { stage_rows(stg, PH01, 2 * T); stage_rows(stg + 2 * T, GR, T); __syncthreads(); PH01s = stg; GRs = stg + 2 * T; }
-        sweep2_bwd<CWT, false>(PH01s, GRs, ybits, WPc, Nc, rg, M2_NRG, kg, Q, GCr, col, ls3, RS3d, lane);
-        if constexpr (CWT >= 5) combine_cols_2pass<CWT>(col, scratch, rg, M2_NRG, kg, lane);
-        else combine_cols<CWT>(col, scratch, rg, M2_NRG, kg, lane);
-        if (rg == 0) {
 #pragma unroll
-            for (int sg = 0; sg < CWT; ++sg) {
-                const int j = sg * 32 + lane;
-                if (j < Nc) *reinterpret_cast<ulonglong2*>(CS3d + j * HD + k0) = make_ulonglong2(col[sg][0], col[sg][1]);
+        for (int pass = 0; pass < NPASS; ++pass) {          // column passes as in G2
+            const int sg0 = pass * PWC;
+            u64 Q[PWC][2], GCr[PWC][2], col[PWC][2];
+#pragma unroll
+            for (int sg = 0; sg < PWC; ++sg) {
+                const int j = (sg0 + sg) * 32 + lane;
+                ulonglong2 q = make_ulonglong2(pk2(NEG_BIG, NEG_BIG), pk2(NEG_BIG, NEG_BIG)), g = make_ulonglong2(0ull, 0ull);
+                if (j < Nc) {
+                    q = *reinterpret_cast<const ulonglong2*>(QH + j * HD + k0);
+                    g = *reinterpret_cast<const ulonglong2*>(GC + j * HD + k0);
+                }
+                Q[sg][0] = q.x; Q[sg][1] = q.y; GCr[sg][0] = g.x; GCr[sg][1] = g.y; col[sg][0] = 0ull; col[sg][1] = 0ull;
+            }
+            if (pass == 0) sweep2_bwd<PWC, false>(PH01s, GRs, ybits + sg0, WPc, Nc, rg, M2_NRG, kg, Q, GCr, col, ls3, RS3d, lane);
+            else sweep2_bwd<PWC, true>(PH01s, GRs, ybits + sg0, WPc, Nc, rg, M2_NRG, kg, Q, GCr, col, ls3, RS3d, lane);
+            if constexpr (PWC >= 5) combine_cols_2pass<PWC>(col, scratch, rg, M2_NRG, kg, lane);
+            else combine_cols<PWC>(col, scratch, rg, M2_NRG, kg, lane);
+            if (rg == 0) {
+#pragma unroll
+                for (int sg = 0; sg < PWC; ++sg) {
+                    const int j = (sg0 + sg) * 32 + lane;
+                    if (j < Nc) *reinterpret_cast<ulonglong2*>(CS3d + j * HD + k0) = make_ulonglong2(col[sg][0], col[sg][1]);
+                }
             }
         }
         const float t = reduce4(ls3[0], ls3[1], lane);
