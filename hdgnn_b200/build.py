@@ -39,8 +39,13 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     nvcc = _nvcc()
 
+    hdr_t = max(os.path.getmtime(os.path.join(CSRC, x)) for x in HEADERS)
+
     def compile_one(src):
         obj = os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
+        # an object newer than its source and every header is reused (a .cu-only edit recompiles one translation unit)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(hdr_t, os.path.getmtime(os.path.join(CSRC, src))):
+            return obj, ""
         cmd = [nvcc, *NVCC_FLAGS, "-c", "-o", obj, os.path.join(CSRC, src)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")

@@ -3,11 +3,12 @@
 // peer-memory set-up.  No torch types.
 //
 // Launch sequences of a training step:
-//   fused path (all four variants when the per-commit state fits one SM; mid2.cuh, entsp.cuh, final.cuh):
-//       [pack_bits, byte-grid inputs only] -> mid2 (the whole per-commit forward + backward) -> reduce_adam
-//       (gradient reduction [+ peer all-reduce] + regularisers + TF-Adam).  With HDGNN_F_DENSE_SWEEP, or when the inline
-//       entity state does not fit: [pack_bits] -> ent_fwd2 -> mid2 -> ent_bwd2 -> reduce_adam (ent2.cuh).
-//   multi-kernel path (HDGNN_F_LEGACY, Nc > 256, Ne = 512; pairsum.cuh, score.cuh, node.cuh;
+//   fused path (all four variants, Nc <= 256, forward only up to Nc = 512; mid2.cuh, entsp.cuh, final.cuh):
+//       [pack_bits, byte-grid inputs only] -> mid2 (the whole per-commit forward + backward; above 128 hunks with its hunk-stage
+//       tables in the per-commit global slice TABS) -> reduce_adam (gradient reduction [+ peer all-reduce] + regularisers +
+//       TF-Adam).  With HDGNN_F_DENSE_SWEEP, or when the inline entity state does not fit (Ne = 512 beside Nc <= 128):
+//       [pack_bits] -> ent_fwd2 -> mid2 -> ent_bwd2 -> reduce_adam (ent2.cuh).
+//   multi-kernel path (HDGNN_F_LEGACY, training with Nc > 256; pairsum.cuh, score.cuh, node.cuh;
 //   [E] = entity-edge branch of model_4.py:92-98):
 //       fwd : pairsum(ent) -> [E: pairsum(edge) -> head_fwd(edge) -> score(edge, soft out)] -> pool_fwd
 //             -> pairsum(hunk) -> head_fwd(hunk) -> score(hunk: logits/probs/CE [+ delta sums]) -> loss
@@ -111,6 +112,7 @@ struct hdgnn_handle_s {
     bool dlt_global = false;                                   // mid2's dL/dlogit table in HBM instead of shared memory
     bool gt = false;                                           // mid2's hunk-stage tables in global memory (Nc > 128), workspace TABS
     bool scg = false;                                          // ... and its S / GE rows in the GE workspace instead of shared memory
+    bool infer_only = false;                                   // 256 < Nc <= 512: the fused kernel exists forward-only; training takes the multi-kernel path
     bool mid_scache = false;                                   // mid2 keeps the entity effect sums in shared memory for its backward
     bool inl = false;                                          // entity pair layer inside mid2 (entsp.cuh): no ent_fwd2 / ent_bwd2 launch
     bool edge_fused = false;                                   // variant 4: the entity-edge branch inside mid2 as well
@@ -184,7 +186,9 @@ namespace {
 
 // which path a call takes: variant 4 runs its forward on the fused path as soon as the edge branch fits (edge_fused), its
 // training step only with edge_fused_train; everything else follows h->fused
-bool fused_for(hdgnn_handle_t h, bool train) { return h->fused && (!h->edge || (train ? h->edge_fused_train : h->edge_fused)); }
+bool fused_for(hdgnn_handle_t h, bool train) {
+    return h->fused && !(train && h->infer_only) && (!h->edge || (train ? h->edge_fused_train : h->edge_fused));
+}
 
 int fail(hdgnn_handle_t h, int code, const std::string& msg) {
     if (h) h->err = msg; else g_create_error = msg;
@@ -656,7 +660,7 @@ cudaError_t setup_fused(hdgnn_handle_t h, int optin) {
     cudaError_t e = cudaSuccess;
     auto acc = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
     const int cwc = (h->Nc + 31) / 32;
-    acc(cudaFuncSetAttribute(mid2_fn_rt(cwc, true, h->gt), A, optin));
+    if (!h->infer_only) acc(cudaFuncSetAttribute(mid2_fn_rt(cwc, true, h->gt), A, optin));
     acc(cudaFuncSetAttribute(mid2_fn_rt(cwc, false, h->gt), A, optin));
     if (h->ent) {
         acc(cudaFuncSetAttribute(ent2_fn_rt(h->fwd_cwt, h->fwd_nrg, false), A, optin));
@@ -774,23 +778,27 @@ int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out) {
         const int cwc = (h->Nc + 31) / 32;
         const bool want_inl = h->ent && !(cfg->flags & HDGNN_F_DENSE_SWEEP) && env_int("HDGNN_DENSE_SWEEP", 0) == 0;
         struct Plan { bool fused = false, dlt_global = false, scache = false, inl = false, scg = false; };
+        // above 256 hunks only the forward kernel exists (BASELINE config 5: the inference sweep to Nc = 512); variants 1-3
+        const bool fwd_only = h->Nc > 256;
+        const bool tr = !fwd_only;                  // the layout the plan must fit: training, or forward only
         auto plan = [&](bool gt) {
             Plan p;
-            if ((cfg->flags & HDGNN_F_LEGACY) || h->Nc > 256 || !mid2_gt_supported(cwc, gt)) return p;
+            if ((cfg->flags & HDGNN_F_LEGACY) || (fwd_only && cfg->variant == 4) || !mid2_gt_supported(cwc, gt)) return p;
             // per-commit state of mid2 in one SM; the per-pair dL/dlogit table may spill to HBM (L2-resident)
-            p.dlt_global = mid2_smem_bytes(h->Ne, h->Nc, true, true, false, false, false, gt) > lim;
-            p.fused = mid2_smem_bytes(h->Ne, h->Nc, true, !p.dlt_global, false, false, false, gt) <= lim;
-            p.scache = p.fused && mid2_smem_bytes(h->Ne, h->Nc, true, !p.dlt_global, true, false, false, gt) <= lim;
+            p.dlt_global = tr && mid2_smem_bytes(h->Ne, h->Nc, tr, true, false, false, false, gt) > lim;
+            p.fused = mid2_smem_bytes(h->Ne, h->Nc, tr, !p.dlt_global, false, false, false, gt) <= lim;
+            p.scache = p.fused && mid2_smem_bytes(h->Ne, h->Nc, tr, !p.dlt_global, true, false, false, gt) <= lim;
             if (p.fused && want_inl) {
                 // entity pair layer inside mid2 (sorted prefix sums + edge walk) when its extra state fits beside mid2's
-                if (mid2_smem_bytes(h->Ne, h->Nc, true, true, true, true, false, gt) <= lim) { p.inl = true; p.dlt_global = false; }
-                else if (mid2_smem_bytes(h->Ne, h->Nc, true, false, true, true, false, gt) <= lim) { p.inl = true; p.dlt_global = true; }
+                if (mid2_smem_bytes(h->Ne, h->Nc, tr, true, true, true, false, gt) <= lim) { p.inl = true; p.dlt_global = false; }
+                else if (tr && mid2_smem_bytes(h->Ne, h->Nc, tr, false, true, true, false, gt) <= lim) { p.inl = true; p.dlt_global = true; }
                 // ... or (global tables only) with the S / GE rows in global memory as well: Ne = 512 beside Nc = 256
-                else if (gt && mid2_smem_bytes(h->Ne, h->Nc, true, false, true, true, false, gt, true) <= lim) { p.inl = true; p.dlt_global = true; p.scg = true; }
+                else if (gt && mid2_smem_bytes(h->Ne, h->Nc, tr, false, true, true, false, gt, true) <= lim) { p.inl = true; p.dlt_global = tr; p.scg = true; }
                 if (p.inl) p.scache = true;
             }
             return p;
         };
+        h->infer_only = fwd_only;
         const Plan ps = plan(false), pg = plan(env_int("HDGNN_GT", 1) != 0);
         const bool use_gt = env_int("HDGNN_GT", 1) == 2 ? pg.fused : (pg.fused && (!ps.fused || (pg.inl && !ps.inl)));
         const Plan& pp = use_gt ? pg : ps;
@@ -820,7 +828,7 @@ int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out) {
     h->host_bits = (cfg->flags & HDGNN_F_LABEL_BITS) != 0;
     if (h->host_bits && !fused_for(h, true)) {
         delete h;
-        return fail(nullptr, HDGNN_E_UNSUPPORTED, "HDGNN_F_LABEL_BITS needs the fused path (variants 1-3, per-commit state within one SM)");
+        return fail(nullptr, HDGNN_E_UNSUPPORTED, "HDGNN_F_LABEL_BITS needs the fused training path (Nc <= 256, per-commit state within one SM)");
     }
     cudaError_t e = set_attrs(h, (int)prop.sharedMemPerBlockOptin);
     if (e == cudaSuccess && h->fused) e = setup_fused(h, (int)prop.sharedMemPerBlockOptin);
@@ -932,7 +940,7 @@ static void peer_layout(int world, int total, int* stride, int* ncta, size_t* of
 int hdgnn_peer_export(hdgnn_handle_t h, int world, unsigned char* ipc_handle_out) {
     if (!h) return HDGNN_E_INVALID;
     if (world < 2 || world > PEER_MAX || !ipc_handle_out) return fail(h, HDGNN_E_INVALID, "world must be 2..8");
-    if (!fused_for(h, true)) return fail(h, HDGNN_E_UNSUPPORTED, "the peer exchange is fused into the reduce+Adam kernel of the fused path (variants 1-3, per-commit state within one SM)");
+    if (!fused_for(h, true)) return fail(h, HDGNN_E_UNSUPPORTED, "the peer exchange is fused into the reduce+Adam kernel of the fused path (Nc <= 256, per-commit state within one SM)");
     static_assert(sizeof(cudaIpcMemHandle_t) == HDGNN_IPC_HANDLE_BYTES, "IPC handle size");
     CK(h, cudaSetDevice(h->cfg.device));
     if (h->peer_box) return fail(h, HDGNN_E_INVALID, "hdgnn_peer_export was already called on this handle");
@@ -990,7 +998,7 @@ int hdgnn_peer_attach(hdgnn_handle_t h, int rank, int world, const unsigned char
 
 int hdgnn_set_hits_accumulator(hdgnn_handle_t h, uint64_t* acc) {
     if (!h) return HDGNN_E_INVALID;
-    if (acc && !fused_for(h, true)) return fail(h, HDGNN_E_UNSUPPORTED, "the hit counter lives in the fused per-commit kernel (variants 1-3, per-commit state within one SM); use hdgnn_eval_counts");
+    if (acc && !fused_for(h, true)) return fail(h, HDGNN_E_UNSUPPORTED, "the hit counter lives in the fused per-commit kernel (Nc <= 256, per-commit state within one SM); use hdgnn_eval_counts");
     h->hits_acc = (unsigned long long*)acc;
     return HDGNN_OK;
 }

@@ -84,9 +84,10 @@ __host__ __device__ inline Mid2Smem mid2_layout(int Ne, int Nc, bool train, bool
     m.dx2 = take(Ne); m.nb = take(4 * Nc); m.dnb = take(4 * Nc);
     m.ebits = take(Ne * bit_words(Ne)); m.ybits = take(Nc * bit_words(Nc));
     const int cwc = (Nc + 31) / 32, wue = (Ne + 31) / 32;
-    // scratch users: column combine of the hunk sweeps (two passes of half the segments from 5 segments on) | pooling partials
+    // scratch users: column combine of the hunk sweeps (two passes of half the segments for 5-6 segments, column passes of four
+    // segments from 7 on) | pooling partials
     // [<= 4 chunks][L][4] + the row table [L] int2 | prologue counters [8][wue][8] + [wue][Nc] | backward partials [<= M2_T]
-    const int comb = (M2_NRG / 2) * (cwc >= 5 ? (cwc + 1) / 2 : cwc) * 32 * HD;
+    const int comb = (M2_NRG / 2) * (cwc >= 7 ? 4 : cwc >= 5 ? (cwc + 1) / 2 : cwc) * 32 * HD;
     const int pool = mid2_rowtab_off(Ne) + 2 * Ne, prol = 64 * wue + wue * Nc;
     const int comb_e = edge ? (M2_NRG / 2) * 4 * 32 * HD : 0;      // variant 4: combine_cols<4> of the soft-edge delta sweep
     int scr = comb > pool ? comb : pool;
@@ -103,7 +104,7 @@ __host__ __device__ inline Mid2Smem mid2_layout(int Ne, int Nc, bool train, bool
     const int tabs = gt ? 0 : mid2_tab_floats(Nc);
     // global tables: the row tables of a sweep (P01 rows, and the row gradients of the backward sweep) are staged in shared memory
     // for the duration of the sweep, behind the dlt table (SP / TP / dl are dead while the sweeps run)
-    const int stage = gt ? ((3 * Nc * HD + 7) & ~7) : 0;
+    const int stage = gt ? (((train ? 3 : 2) * Nc * HD + 7) & ~7) : 0;
     m.stg = m.uni + dlt;
     const int hunk_phase = gt ? (dlt + stage > pool3 ? dlt + stage : pool3) : tabs + (dlt > pool3 ? dlt : pool3);
     m.SP = m.uni + tabs; m.TP = m.SP + ((4 * Ne + 7) & ~7); m.dl = m.TP + ((4 * Ne + 7) & ~7);
@@ -1128,25 +1129,36 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
     __syncthreads();
 
     // ---------------- E. hunk pair layer forward: row / column sums ---------------------------------
+    // Grids of 7 and more column segments take the columns in passes of four segments (the accumulators of eight do not fit the
+    // register file: measured spills); later passes add to the row sums of the first.  The widest instantiation (CWT = 16) also
+    // serves every narrower grid above 256 hunks: passes / segments beyond Nc are skipped.
+    constexpr int PWC = CWT >= 7 ? 4 : CWT;             // segments per column pass
+    constexpr int NPASS = (CWT + PWC - 1) / PWC;
     {
-        u64 Q[CWT][2], col[CWT][2];
-#pragma unroll
-        for (int sg = 0; sg < CWT; ++sg) {
-            const int j = sg * 32 + lane;
-            ulonglong2 q = make_ulonglong2(pk2(NEG_BIG, NEG_BIG), pk2(NEG_BIG, NEG_BIG));
-            if (j < Nc) q = *reinterpret_cast<const ulonglong2*>(QH + j * HD + k0);
-            Q[sg][0] = q.x; Q[sg][1] = q.y; col[sg][0] = 0ull; col[sg][1] = 0ull;
-        }
         const float* PH01s = PH01;
         if (GT) { stage_rows(stg, PH01, 2 * T); __syncthreads(); PH01s = stg; }
-        sweep2_fwd<CWT, false>(PH01s, ybits, WPc, Nc, rg, M2_NRG, kg, Q, col, RS3, lane);
-        if constexpr (CWT >= 5) combine_cols_2pass<CWT>(col, scratch, rg, M2_NRG, kg, lane);
-        else combine_cols<CWT>(col, scratch, rg, M2_NRG, kg, lane);
-        if (rg == 0) {
 #pragma unroll
-            for (int sg = 0; sg < CWT; ++sg) {
-                const int j = sg * 32 + lane;
-                if (j < Nc) *reinterpret_cast<ulonglong2*>(CS3 + j * HD + k0) = make_ulonglong2(col[sg][0], col[sg][1]);
+        for (int pass = 0; pass < NPASS; ++pass) {
+            const int sg0 = pass * PWC;
+            if (sg0 * 32 >= Nc) break;
+            u64 Q[PWC][2], col[PWC][2];
+#pragma unroll
+            for (int sg = 0; sg < PWC; ++sg) {
+                const int j = (sg0 + sg) * 32 + lane;
+                ulonglong2 q = make_ulonglong2(pk2(NEG_BIG, NEG_BIG), pk2(NEG_BIG, NEG_BIG));
+                if (j < Nc) q = *reinterpret_cast<const ulonglong2*>(QH + j * HD + k0);
+                Q[sg][0] = q.x; Q[sg][1] = q.y; col[sg][0] = 0ull; col[sg][1] = 0ull;
+            }
+            if (pass == 0) sweep2_fwd<PWC, false>(PH01s, ybits + sg0, WPc, Nc, rg, M2_NRG, kg, Q, col, RS3, lane);
+            else sweep2_fwd<PWC, true>(PH01s, ybits + sg0, WPc, Nc, rg, M2_NRG, kg, Q, col, RS3, lane);
+            if constexpr (PWC >= 5) combine_cols_2pass<PWC>(col, scratch, rg, M2_NRG, kg, lane);
+            else combine_cols<PWC>(col, scratch, rg, M2_NRG, kg, lane);
+            if (rg == 0) {
+#pragma unroll
+                for (int sg = 0; sg < PWC; ++sg) {
+                    const int j = (sg0 + sg) * 32 + lane;
+                    if (j < Nc) *reinterpret_cast<ulonglong2*>(CS3 + j * HD + k0) = make_ulonglong2(col[sg][0], col[sg][1]);
+                }
             }
         }
     }
@@ -1206,6 +1218,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
 #pragma unroll
         for (int k = 0; k < HD / 2; ++k) gam2[k] = pk2(gam[2 * k], gam[2 * k + 1]);
         for (int cb = 0; cb < CWT; ++cb) {
+            if (cb * 32 >= Nc) break;
             const int j = cb * 32 + lane;
             const bool ok = j < Nc;
             u64 Q2[HD / 2];
@@ -1274,10 +1287,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
     if (!TRAIN) return;
 
     // ---------------- G2. delta sums: RSm_i = sum_j m_ij dlt_ij, CSm_j, LSm (label-1 pairs) ----------------
-    // Grids of 7-8 column segments take the columns in two passes of four segments (the accumulators of eight do not fit the
-    // register file: measured spills); the second pass adds to the row sums of the first.
-    constexpr int PWC = CWT >= 7 ? 4 : CWT;             // segments per column pass
-    constexpr int NPASS = (CWT + PWC - 1) / PWC;
+    // column passes as in E
     float* lsw = red + 64;                   // [M2_NRG][20]
     float* misc = red + 64 + M2_NW * HD;     // [0..19] LSm then LS4, [40] dsum
     {

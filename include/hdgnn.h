@@ -68,12 +68,13 @@ typedef struct {
 
 /* flag value 1 is reserved */
 #define HDGNN_F_DEBUG   2   /* keep named copies of intermediates for hdgnn_workspace (tests) */
-#define HDGNN_F_LEGACY  4   /* force the multi-kernel path (the only path for variant 4 and for Nc above ~160) */
+#define HDGNN_F_LEGACY  4   /* force the multi-kernel path (otherwise taken only by TRAINING above 256 hunks; the per-commit kernel
+                               serves every variant up to Nc = 256 and the forward pass up to Nc = 512) */
 #define HDGNN_F_LABEL_BITS 8 /* every entry point receives LABEL BITMAPS instead of byte grids: adj (device) / adj_host is
                                (B, Ne, hdgnn_bit_words(Ne)) uint32 and Y / Y_host (B, Nc, hdgnn_bit_words(Nc)) uint32, word w of a
                                row holding column 32 w + k at bit k (little-endian np.packbits order), diagonal and padding
                                bits ZERO; adj_pitch / y_pitch = 4 * hdgnn_bit_words(n).  1/8 of the bytes on the wire and
-                               in HBM and no packing kernel; fused path only (hdgnn_create fails with
+                               in HBM and no packing kernel; fused path only (Nc <= 256; hdgnn_create fails with
                                HDGNN_E_UNSUPPORTED otherwise).  hdgnn_pack_label_bits builds the format on the device. */
 
 #define HDGNN_F_DENSE_SWEEP 16 /* variants 2 / 3: run the entity pair layer (model_2.py:161-188) as the dense Ne x Ne sweep kernels
@@ -169,8 +170,8 @@ int hdgnn_forward_backward_host(hdgnn_handle_t h, int B, int B_global,
  * on all ranks) and applies the regularisers + TF1 Adam -- the step has the same 5 launches as on one GPU and no NCCL call.
  * Set-up: (1) every rank calls hdgnn_peer_export and receives a 64-byte CUDA IPC handle; (2) the handles are gathered by
  * the caller (torch.distributed / MPI / files) into world*64 bytes ordered by rank; (3) every rank calls
- * hdgnn_peer_attach, then the ranks synchronise once (barrier) before the first step.  Fused path only (variants 1-3
- * with the per-commit state within one SM), world <= 8, equal shards. */
+ * hdgnn_peer_attach, then the ranks synchronise once (barrier) before the first step.  Fused path only (Nc <= 256),
+ * world <= 8, equal shards. */
 #define HDGNN_IPC_HANDLE_BYTES 64
 int hdgnn_peer_export(hdgnn_handle_t h, int world, unsigned char* ipc_handle_out);
 int hdgnn_peer_attach(hdgnn_handle_t h, int rank, int world, const unsigned char* ipc_handles);

@@ -124,6 +124,7 @@ def test_inference_sweep_shapes(Nc):
     db = DeviceBatch.from_numpy(cb.adj, cb.x, cb.hmap, cb.L, cb.Y, eng.tdev)
     probs, logits, loss = eng.forward(db, flat.float().cuda())
     torch.cuda.synchronize()
+    assert eng.last_launch_count() <= 3            # pack_bits, the per-commit kernel (16-segment forward instantiation above 256 hunks), loss
     errs = {"probs": relerr(probs.cpu().numpy(), plan["probs"]), "logits": relerr(logits.cpu().numpy(), plan["logits"]),
             "ce": relerr(loss.cpu().numpy()[0], plan["ce"])}
     assert all(e < (TOL if k == "probs" else TIGHT) for k, e in errs.items()), errs
@@ -148,6 +149,7 @@ def test_variant4_forward(B, Ne, Nc, attr):
     db = DeviceBatch.from_numpy(cb.adj, cb.x, cb.hmap, cb.L, cb.Y, eng.tdev)
     probs, logits, loss = eng.forward(db, flat.float().cuda())
     torch.cuda.synchronize()
+    assert eng.last_launch_count() <= 3            # pack_bits, the per-commit kernel (16-segment forward instantiation above 256 hunks), loss
     errs = {"probs": relerr(probs.cpu().numpy(), plan["probs"]), "logits": relerr(logits.cpu().numpy(), plan["logits"]),
             "ce": relerr(loss.cpu().numpy()[0], plan["ce"])}
     for bb in range(B):
