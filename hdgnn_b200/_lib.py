@@ -48,6 +48,7 @@ def _load():
         "hdgnn_peer_attach": ([vp, i32, i32, vp], i32),
         "hdgnn_peer_status": ([vp], i32),
         "hdgnn_set_hits_accumulator": ([vp, vp], i32),
+        "hdgnn_set_eval_counters": ([vp, vp], i32),
         "hdgnn_train_step_peer": ([vp, i32, i32, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, f32, f32, f32, f32, vp, vp, vp, vp], i32),
         "hdgnn_train_step_peer_host": ([vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, f32, f32, f32, vp, vp, vp], i32),
         "hdgnn_infer_host": ([vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp], i32),

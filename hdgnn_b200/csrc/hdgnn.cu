@@ -141,6 +141,7 @@ struct hdgnn_handle_s {
     // host-fed steps whose first kernel is mid2: that kernel polls a tag the copy stream's last DMA writes (no event wait on
     // the caller's stream, which would break the programmatic launch chain optimizer -> mid2)
     unsigned long long* hits_acc = nullptr;   // hdgnn_set_hits_accumulator
+    unsigned long long* evc = nullptr;        // hdgnn_set_eval_counters
     uint32_t* tag_table = nullptr;         // pinned, tag_table[i] = i: immutable DMA source
     unsigned int slot_uses[2] = {0, 0};
     int cur_tag = -1;                      // tag of the staging slot filled by the last stage_inputs call, -1 = ordered by event
@@ -610,6 +611,7 @@ int fused_forward(hdgnn_handle_t h, int B, int B_global, const Inputs& in, float
     m.inl = h->inl ? 1 : 0;
     m.wait_flag = in.wait_flag; m.wait_tag = in.wait_tag;
     m.hits_acc = h->hits_acc;
+    m.evc = h->evc;
     m.edge = h->edge_fused ? 1 : 0;
     if (m.edge) { m.RSEg = F(h, "RSEG"); m.CSEg = F(h, "CSEG"); m.REg = F(h, "REG"); m.CEg = F(h, "CEG"); m.A1F = F(h, "A1F"); m.PREg = F(h, "PREG"); }
     m.lay = mid2_layout(h->Ne, h->Nc, train, !dlt_g, m.scache != 0, h->inl, h->edge_fused, h->gt, h->scg);
@@ -1000,6 +1002,14 @@ int hdgnn_set_hits_accumulator(hdgnn_handle_t h, uint64_t* acc) {
     if (!h) return HDGNN_E_INVALID;
     if (acc && !fused_for(h, true)) return fail(h, HDGNN_E_UNSUPPORTED, "the hit counter lives in the fused per-commit kernel (Nc <= 256, per-commit state within one SM); use hdgnn_eval_counts");
     h->hits_acc = (unsigned long long*)acc;
+    return HDGNN_OK;
+}
+
+int hdgnn_set_eval_counters(hdgnn_handle_t h, int64_t* counts) {
+    if (!h) return HDGNN_E_INVALID;
+    if (counts && !fused_for(h, false)) return fail(h, HDGNN_E_UNSUPPORTED, "the evaluation counters live in the fused per-commit kernel; use hdgnn_eval_counts");
+    if ((uintptr_t)counts & 7) return fail(h, HDGNN_E_INVALID, "counts must be 8-byte aligned");
+    h->evc = (unsigned long long*)counts;
     return HDGNN_OK;
 }
 

@@ -140,6 +140,8 @@ struct Mid2Args {
     float* PREg;                             // (B,Ne,60): soft-edge head tables PRe01 (Ne x 40) then PCe (Ne x 20), kept for the backward
     float* A1F;                              // (B, Ne (Ne-1)) soft edges a1 in flat pair order, written and read for commits with L < Ne only
     unsigned long long* hits_acc;            // running count of arg-max hits (EvaluationFuncs.py:27-37) over all commits, or null
+    unsigned long long* evc;                 // (B,8) per-commit evaluation counters in the layout of hdgnn_eval_counts (EvaluationFuncs.py:27-37,
+                                             // 92-117), ADDED to by the relation head, or null
     const int* wait_flag; int wait_tag;      // host-fed step: the staging copies of this step are complete once *wait_flag == wait_tag
                                              // (written by the copy stream's DMA after the data); null = inputs already ordered
     Mid2Smem lay;                            // shared-memory layout (mid2_layout), computed once on the host: the offsets are kernel
@@ -1209,6 +1211,8 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
 
     // ---------------- G1. relation head: logits, softmax, CE (lanes = columns, all 20 channels) ---------
     float ce_acc = 0.f, d_acc = 0.f, hit_acc = 0.f;
+    const bool EVC = a.evc != nullptr;
+    uint32_t ev_tpc = 0u, ev_fpc = 0u, ev_tpq = 0u, ev_fpq = 0u, ev_pos = 0u;      // warp-uniform partial counts
     const float* PR01s = PR01;          // row tables of the two head sweeps (G1, G2)
     if (GT) { stage_rows(stg, PR01, 2 * T); __syncthreads(); PR01s = stg; }
     {
@@ -1221,6 +1225,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             if (cb * 32 >= Nc) break;
             const int j = cb * 32 + lane;
             const bool ok = j < Nc;
+            const uint32_t colmask = Nc - cb * 32 >= 32 ? 0xffffffffu : (1u << (Nc - cb * 32)) - 1u;      // columns of this segment below Nc
             u64 Q2[HD / 2];
 #pragma unroll
             for (int q4 = 0; q4 < 5; ++q4) {
@@ -1230,7 +1235,8 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             }
             for (int r = warp; r < Nc; r += M2_NW) {
                 const bool valid = ok && j != r;
-                const uint32_t bit = (ybits[r * WPc + cb] >> lane) & 1u;
+                const uint32_t yw = ybits[r * WPc + cb];
+                const uint32_t bit = (yw >> lane) & 1u;
                 const bool lab = bit != 0u;
                 const float* prow = PR01s + (size_t)r * PROW + bit * 4;
                 u64 da = pk2(bd, 0.f), db2 = 0ull;
@@ -1267,6 +1273,15 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
                     ce_acc += fmaxf(z, 0.f) + __logf(1.f + e);     // e in (0, 1]: absolute error ~1e-7
                     hit_acc += ((p1 > p0) == lab) ? 1.f : 0.f;      // np.argmax over the two channels: a tie is class 0
                 }
+                if (EVC) {
+                    // evaluation counters: two ballots per 32 pairs, then warp-uniform popcounts against the label word (its
+                    // diagonal and padding bits are zero).  am: arg-max is class 1 (a tie is class 0); qp: the reference's
+                    // ceil-on-channel-0 prediction (EvaluationFuncs.py:95-99)
+                    const uint32_t vm = (r >> 5) == cb ? colmask & ~(1u << (r & 31)) : colmask;
+                    const uint32_t am = __ballot_sync(0xffffffffu, p1 > p0) & vm, qp = __ballot_sync(0xffffffffu, p0 > 0.f) & vm;
+                    ev_tpc += __popc(am & yw); ev_fpc += __popc(am & ~yw); ev_tpq += __popc(qp & ~yw); ev_fpq += __popc(qp & yw);
+                    ev_pos += __popc(yw & vm);
+                }
                 if (TRAIN) {
                     const float dv = valid ? a.scale * (p1 - (lab ? 1.f : 0.f)) : 0.f;
                     d_acc += dv;
@@ -1282,6 +1297,24 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             const float hit_tot = mid2_block_sum(hit_acc, red);
             if (tid == 0) atomicAdd(a.hits_acc, (unsigned long long)(hit_tot + 0.5f));
         }
+    }
+    if (EVC) {
+        uint32_t* evs = reinterpret_cast<uint32_t*>(red + 64);        // [M2_NW][8] (the label-sum slots of G2: not live yet)
+        __syncthreads();
+        if (lane == 0) { uint32_t* e = evs + warp * 8; e[0] = ev_tpc; e[1] = ev_fpc; e[2] = ev_tpq; e[3] = ev_fpq; e[4] = ev_pos; }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long t[5] = {0ull, 0ull, 0ull, 0ull, 0ull};
+            for (int w = 0; w < M2_NW; ++w)
+                for (int q = 0; q < 5; ++q) t[q] += evs[w * 8 + q];
+            const unsigned long long npair = (unsigned long long)Nc * (Nc - 1), pos = t[4], neg = npair - pos;
+            unsigned long long* o = a.evc + (size_t)b * 8;       // this commit's slots: one writer
+            o[0] += t[0] + (neg - t[1]);                          // arg-max hits = tp + tn
+            o[1] += t[2]; o[2] += t[3]; o[3] += neg - t[2];       // reference form: y_true = 1 - Y, y_pred = [p0 > 0]
+            o[4] += t[0]; o[5] += t[1]; o[6] += pos - t[0];       // conventional form: y_true = Y, y_pred = [p1 > p0]
+            o[7] += pos;
+        }
+        __syncthreads();
     }
     M2_PHASE(6);
     if (!TRAIN) return;

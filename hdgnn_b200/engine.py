@@ -244,6 +244,18 @@ class Engine:
         self._hits_ref = acc            # keep the tensor alive while the handle points at it
         return True
 
+    def set_eval_counters(self, counts: Optional[torch.Tensor]) -> bool:
+        """counts: (B, 8) int64 CUDA tensor (layout of eval_counts) that the relation head of every later forward / training call
+        adds the commits' evaluation counters to (None: off).  Returns False on the multi-kernel path (use eval_counts)."""
+        if counts is not None:
+            assert counts.dtype == torch.int64 and counts.is_cuda and counts.is_contiguous() and counts.shape[-1] == 8
+        rc = lib.hdgnn_set_eval_counters(self._h, _p(counts))
+        if rc == _lib.E_UNSUPPORTED:
+            return False
+        check(rc, self._h)
+        self._evc_ref = counts          # keep the tensor alive while the handle points at it
+        return True
+
     def peer_status(self):
         """Raises HdgnnError(E_PEER) if a gradient exchange timed out since peer_attach (synchronises with the device)."""
         check(lib.hdgnn_peer_status(self._h), self._h)

@@ -268,6 +268,14 @@ int hdgnn_eval_counts(int B, int Nc, const float* probs, const uint8_t* Y, int y
  * path only (HDGNN_E_UNSUPPORTED otherwise: use hdgnn_eval_counts). */
 int hdgnn_set_hits_accumulator(hdgnn_handle_t h, uint64_t* acc);
 
+/* The evaluation counters of hdgnn_eval_counts without a second kernel and without the label bytes: while `counts` (device,
+ * (B,8) int64 in that function's layout, caller-owned, row b = commit b of a call) is set, the relation head of every forward
+ * / training call ADDS the commit's counters (EvaluationFuncs.py:27-37 top_ACC, :92-117 prec / recall / f1 in the reference's
+ * and in the conventional form) -- two warp votes per 32 hunk pairs against the label bitmap the kernel already holds.  The
+ * caller zeroes the rows and re-points `counts` per batch.  NULL switches it off.  AUC (EvaluationFuncs.py:119-153) needs the
+ * sorted scores: hdgnn_eval_counts.  Fused path only (HDGNN_E_UNSUPPORTED otherwise). */
+int hdgnn_set_eval_counters(hdgnn_handle_t h, int64_t* counts);
+
 /* Debug / test introspection: device pointer and size in bytes of a named scratch buffer
  * (RS1 CS1 S1 X2 NB PH QH RS3 CS3 PR PC GRH GCH RS3D CS3D DNB GE RS1D CS1D GPART ...). */
 int hdgnn_workspace(hdgnn_handle_t h, const char* name, void** ptr, size_t* bytes);

@@ -129,3 +129,38 @@ def test_eval_counts_bit_exact_vs_array_metrics(N, Nc, dens):
     assert np.array_equal(c2, counts) and np.array_equal(a2[N - 1], auc[N - 1]) and not a2[:N - 1].any()
     with pytest.raises(ZeroDivisionError):
         EV.auc_from_counts(counts[:N - 1], auc[:N - 1], Ncr, quirks=True)      # last commit has one class (Q7)
+
+
+@pytest.mark.parametrize("Ne,Nc,variant", [(60, 33, 2), (200, 74, 2), (120, 170, 2), (90, 300, 1)])
+def test_in_kernel_eval_counters_equal_eval_counts(Ne, Nc, variant):
+    """hdgnn_set_eval_counters: the relation head's own counters (two warp votes per 32 pairs) are, integer for integer, what
+    hdgnn_eval_counts computes from the probabilities the same call wrote (EvaluationFuncs.py:27-37, 92-117) -- on the
+    shared-memory, the global-slice and the forward-only 16-segment forms of the per-commit kernel, added up over two calls."""
+    from hdgnn_b200.engine import Engine, DeviceBatch, eval_counts
+    from hdgnn_b200.synthetic import make_commits
+    B = 5
+    cb = make_commits(B, Ne, Nc, seed=77 + Nc, p_short=0.4, p_noise=0.3)
+    eng = Engine(Ne, Nc, variant=variant, max_batch=B)
+    db = DeviceBatch.from_numpy(cb.adj, cb.x, cb.hmap, cb.L, cb.Y, eng.tdev)
+    from hdgnn_b200 import _lib
+    g = torch.Generator().manual_seed(5)
+    params = (0.3 * torch.randn(eng.n_params, generator=g)).cuda()
+    _, logits, _ = eng.forward(db, params, want_logits=True)
+    off = _lib.lib.hdgnn_param_offset(variant, b"scr_b2")                 # centre the logit difference: both classes get predicted
+    assert off >= 0
+    params[off + 1] -= (logits[:, 1] - logits[:, 0]).median()
+    counts = torch.zeros(B, 8, dtype=torch.int64, device="cuda")
+    assert eng.set_eval_counters(counts)
+    probs, _, _ = eng.forward(db, params, want_logits=False)
+    torch.cuda.synchronize()
+    ref, _ = eval_counts(probs, torch.as_tensor(cb.Y).cuda())
+    assert torch.equal(counts, ref), (counts, ref)
+    assert 0 < int(ref[:, 4].sum() + ref[:, 5].sum()) < B * Nc * (Nc - 1)      # the case exercises both predictions
+    eng.forward(db, params, want_logits=False)                           # the counters ADD
+    torch.cuda.synchronize()
+    assert torch.equal(counts, 2 * ref)
+    eng.set_eval_counters(None)
+    eng.forward(db, params, want_logits=False)
+    torch.cuda.synchronize()
+    assert torch.equal(counts, 2 * ref)
+    eng.close()

@@ -37,7 +37,18 @@ for Nc in (74, 114, 150, 256, 384, 512):
         eval_counts(probs, ybytes[k % 8])
     e1.record(); torch.cuda.synchronize()
     ms_eval = e0.elapsed_time(e1) / steps
-    rec = {"label_bits": eng.host_bits, "ms_per_batch_with_eval": ms_eval,"Ne": Ne, "Nc": Nc, "B": B, "ms_per_batch": ms, "commits_per_s": B / ms * 1e3,
+    # ... and with the counters taken inside the relation head (hdgnn_set_eval_counters): what graph2graph.test() does
+    counts = torch.zeros(B, 8, dtype=torch.int64, device="cuda")
+    ms_evk = None
+    if eng.set_eval_counters(counts):
+        eng.forward(pool[0], params, want_logits=False)
+        e0.record()
+        for k in range(steps):
+            eng.forward(pool[k % 8], params, want_logits=False)
+        e1.record(); torch.cuda.synchronize()
+        ms_evk = e0.elapsed_time(e1) / steps
+        eng.set_eval_counters(None)
+    rec = {"label_bits": eng.host_bits, "ms_per_batch_with_eval": ms_eval, "ms_per_batch_with_in_kernel_counters": ms_evk,"Ne": Ne, "Nc": Nc, "B": B, "ms_per_batch": ms, "commits_per_s": B / ms * 1e3,
            "hunk_pairs_per_s": B * Nc * (Nc - 1) / ms * 1e3, "launches": eng.last_launch_count(),
            "probs_GBps": B * 8 * Nc * (Nc - 1) / ms / 1e6}
     print(rec)
