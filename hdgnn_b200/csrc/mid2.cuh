@@ -43,7 +43,7 @@ __host__ __device__ inline size_t mid2_dbg_floats(int Ne, int Nc) { return (size
 __host__ __device__ inline int mid2_tab_floats(int Nc) { return (12 * Nc * HD + 7) & ~7; }
 
 // float offset of the pooling row table inside the scratch region: behind the column partials [nchunk][L][4], nchunk L <= min(4 Ne, M2_T)
-__host__ __device__ inline int mid2_rowtab_off(int Ne) { return 4 * (4 * Ne < M2_T ? 4 * Ne : M2_T); }
+__host__ __device__ inline int mid2_rowtab_off(int Ne) { return 4 * (4 * Ne < M2_T ? 4 * Ne : M2_T); }      // a multiple of 4: 16-byte aligned
 
 struct Mid2Smem {
     // offsets in floats
@@ -86,9 +86,9 @@ __host__ __device__ inline Mid2Smem mid2_layout(int Ne, int Nc, bool train, bool
     const int cwc = (Nc + 31) / 32, wue = (Ne + 31) / 32;
     // scratch users: column combine of the hunk sweeps (two passes of half the segments for 5-6 segments, column passes of four
     // segments from 7 on) | pooling partials
-    // [<= 4 chunks][L][4] + the row table [L] int2 | prologue counters [8][wue][8] + [wue][Nc] | backward partials [<= M2_T]
+    // [<= 4 chunks][L][4] + the row table [L] int4 | prologue counters [8][wue][8] + [wue][Nc] | backward partials [<= M2_T]
     const int comb = (M2_NRG / 2) * (cwc >= 7 ? 4 : cwc >= 5 ? (cwc + 1) / 2 : cwc) * 32 * HD;
-    const int pool = mid2_rowtab_off(Ne) + 2 * Ne, prol = 64 * wue + wue * Nc;
+    const int pool = mid2_rowtab_off(Ne) + 4 * Ne, prol = 64 * wue + wue * Nc;
     const int comb_e = edge ? (M2_NRG / 2) * 4 * 32 * HD : 0;      // variant 4: combine_cols<4> of the soft-edge delta sweep
     int scr = comb > pool ? comb : pool;
     scr = scr > comb_e ? scr : comb_e; scr = scr > prol ? scr : prol; scr = scr > M2_T ? scr : M2_T;
@@ -1014,28 +1014,44 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         int nchunk = M2_T / Lb;
         nchunk = nchunk < 1 ? 1 : (nchunk > 4 ? 4 : nchunk);
         float* partC = scratch;                         // [nchunk][Lb][4]
-        int2* rowtab = reinterpret_cast<int2*>(scratch + mid2_rowtab_off(Ne));      // [Lb] grid coordinates (row, offset) of flat index li m
-        for (int li = tid; li < Lb; li += M2_T) { const int q = li * m, g = q / n; rowtab[li] = make_int2(g, q - g * n); }
+        // per index line li: grid coordinates (row g0, offset p0) of flat index li m as {p0 - n, g0} and the two node values a local
+        // row can see in channel 0 (m < n: at most one row wrap), one 16-byte broadcast load per visit
+        int4* rowtab = reinterpret_cast<int4*>(scratch + mid2_rowtab_off(Ne));      // [Lb]
+        for (int li = tid; li < Lb; li += M2_T) {
+            const int q = li * m, g = q / n;
+            rowtab[li] = make_int4(q - g * n - n, g, __float_as_int(x2[g]), __float_as_int(x2[min(g + 1, Ne - 1)]));
+        }
         __syncthreads();
         for (int t = tid; t < nchunk * Lb; t += M2_T) {
             const int c = t / Lb, me = t - c * Lb;
             const int lo = (c * Lb) / nchunk, hi = ((c + 1) * Lb) / nchunk;
             float q0 = 0.f, q1 = 0.f;
             int q3 = 0;
-            const int cnt = (hi - lo) - ((me >= lo && me < hi) ? 1 : 0);
-            // no loop-carried index state: iteration li starts from the tabulated coordinates of li m (m < n: at most
-            // one row wrap), so the loads of several iterations overlap
+            const bool own = me >= lo && me < hi;       // the chunk holds the diagonal visit li == me
+            const int cnt = (hi - lo) - (own ? 1 : 0);
+            // one visit: local pair (li, me) -> flat index li m + me - (me > li) -> grid pair (gi, gj).  No loop-carried index
+            // state, so the loads of several iterations overlap.  The diagonal visit is swept like the others (its indices stay
+            // inside the commit's tile) and taken out again below: no per-visit select
+            auto visit = [&](int li, float& xa, float& xb, int& bit) {
+                const int4 e = rowtab[li];
+                const int tt = e.x + me - (li < me ? 1 : 0);       // p - n
+                const bool w = tt >= 0;                            // the local row has wrapped into grid row g0 + 1
+                const int pp = w ? tt : tt + n;
+                const int gi = e.y + (w ? 1 : 0), gj = pp + (pp >= gi ? 1 : 0);
+                xa = __int_as_float(w ? e.w : e.z);
+                xb = x2[gj];
+                bit = (int)((ebits[gi * WPe + (gj >> 5)] >> (gj & 31)) & 1u);
+            };
 #pragma unroll 4
             for (int li = lo; li < hi; ++li) {
-                const int2 e = rowtab[li];
-                int pp = e.y + me - (li < me ? 1 : 0);
-                const int w = pp >= n;
-                pp -= w ? n : 0;
-                const int gi = e.x + w, gj = pp + (pp >= gi);
-                const bool valid = li != me;
-                const float xa = x2[gi], xb = x2[gj];
-                const uint32_t bit = (ebits[gi * WPe + (gj >> 5)] >> (gj & 31)) & 1u;
-                q0 += valid ? xa : 0.f; q1 += valid ? xb : 0.f; q3 += valid ? bit : 0u;
+                float xa, xb; int bit;
+                visit(li, xa, xb, bit);
+                q0 += xa; q1 += xb; q3 += bit;
+            }
+            if (own) {
+                float xa, xb; int bit;
+                visit(me, xa, xb, bit);
+                q0 -= xa; q1 -= xb; q3 -= bit;
             }
             float* pc = partC + ((size_t)c * Lb + me) * 4;
             pc[0] = q0; pc[1] = q1; pc[2] = (float)(cnt - q3); pc[3] = (float)q3;
