@@ -87,7 +87,8 @@ def test_wide_hunk_grids_fused_train_step(B, Ne, Nc):
 
 
 @pytest.mark.parametrize("B,Ne,Nc,variant", [(2, 250, 114, 2), (2, 250, 150, 2), (1, 512, 256, 2), (2, 200, 74, 4),
-                                             (3, 200, 74, 1), (2, 200, 74, 3), (2, 250, 150, 4)])
+                                             (3, 200, 74, 1), (2, 200, 74, 3), (2, 250, 150, 4),
+                                             (1, 60, 300, 2)])       # above 256 hunks: fused forward kernel, multi-kernel training
 def test_contract_shapes_forward_backward(B, Ne, Nc, variant):
     from hdgnn_b200.engine import Engine, DeviceBatch
     cb = make_commits(B, Ne, Nc, seed=300 + Nc, p_short=0.5)
