@@ -9,22 +9,33 @@ namespace hdgnn {
 
 // kernel handle for cudaFuncSetAttribute / occupancy queries (nullptr if not instantiated)
 const void* ent2_fn_rt(int cwt, int nrg, bool bwd);
-const void* mid2_fn_rt(int cwt, bool train, bool gt);
+const void* mid2_fn_rt(int cwt, bool train, bool gt, bool cl = false);
+int mid2_max_clusters(int cwt, bool train, size_t smem);
 // which table placements are compiled for a hunk-grid width: shared memory for cwt <= 5, global memory for cwt >= 5
 bool mid2_gt_supported(int cwt, bool gt);
 // pdl: launch with programmatic stream serialization (the kernel calls pdl_wait() before it reads its
 // predecessor's outputs, so its prologue overlaps the predecessor's tail)
 void launch_ent2(int cwt, int nrg, bool bwd, int grid, size_t smem, cudaStream_t st, const Ent2Args& a, bool pdl);
-void launch_mid2(int cwt, bool train, bool gt, int grid, size_t smem, cudaStream_t st, const Mid2Args& a, bool pdl);
+void launch_mid2(int cwt, bool train, bool gt, bool cl, int grid, size_t smem, cudaStream_t st, const Mid2Args& a, bool pdl);
 
+// cluster: CTAs per thread-block cluster (1 = none; the grid must be a multiple)
 template <typename Kern, typename Args>
-inline cudaError_t launch_ex(Kern kern, int grid, int block, size_t smem, cudaStream_t st, bool pdl, const Args& a) {
+inline cudaError_t launch_ex(Kern kern, int grid, int block, size_t smem, cudaStream_t st, bool pdl, const Args& a, int cluster = 1) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    if (pdl) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (cluster > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = cluster; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    cfg.attrs = attr; cfg.numAttrs = n;
     return cudaLaunchKernelEx(&cfg, kern, a);
 }
 

@@ -112,6 +112,8 @@ struct hdgnn_handle_s {
     bool dlt_global = false;                                   // mid2's dL/dlogit table in HBM instead of shared memory
     bool gt = false;                                           // mid2's hunk-stage tables in global memory (Nc > 128), workspace TABS
     bool scg = false;                                          // ... and its S / GE rows in the GE workspace instead of shared memory
+    bool cl_ok = false;                                        // the cluster form of mid2 (two CTAs share a commit) exists for this handle
+    int cl_max[2] = {0, 0};                                    // co-resident clusters of two: [inference, training] shared-memory size
     bool infer_only = false;                                   // 256 < Nc <= 512: the fused kernel exists forward-only; training takes the multi-kernel path
     bool mid_scache = false;                                   // mid2 keeps the entity effect sums in shared memory for its backward
     bool inl = false;                                          // entity pair layer inside mid2 (entsp.cuh): no ent_fwd2 / ent_bwd2 launch
@@ -618,10 +620,20 @@ int fused_forward(hdgnn_handle_t h, int B, int B_global, const Inputs& in, float
     m.tabs_g = h->gt ? F(h, "TABS") : nullptr;
     const size_t smem = mid2_smem_bytes(h->Ne, h->Nc, train, !dlt_g, m.scache != 0, h->inl, h->edge_fused, h->gt, h->scg);
     const int cwc = (h->Nc + 31) / 32;
+    // Batches below one wave of SMs: clusters of two CTAs, the `S` costliest commits shared by both CTAs of a cluster (mid2.cuh),
+    // as many as there are spare SMs and co-resident clusters
+    bool cl = false;
+    int grid = B;
+    if (h->cl_ok && B < h->nsm) {
+        const int maxc = h->cl_max[train ? 1 : 0];
+        int S = B < h->nsm - B ? B : h->nsm - B;
+        if (S > 2 * maxc - B) S = 2 * maxc - B;
+        if (S > 0) { cl = true; m.B = B; m.nsplit = S; grid = 2 * (S + (B - S + 1) / 2); }
+    }
     PROF_BEGIN(h, st);
     // inline entity stage: this kernel reads the weights after its pdl_wait, so it may follow the previous step's optimizer
     // kernel (or pack_bits) under programmatic dependent launch; otherwise PDL only behind ent_fwd2
-    launch_mid2(cwc, train, h->gt, B, smem, st, m, h->pdl && (h->ent || h->inl));
+    launch_mid2(cwc, train, h->gt, cl, grid, smem, st, m, h->pdl && (h->ent || h->inl));
     LAUNCH_CHECK(h, train ? "mid(train)" : "mid(infer)", st);
     if (h->debug) return debug_scatter(h, B, st);
     return HDGNN_OK;
@@ -656,6 +668,8 @@ int fused_backward(hdgnn_handle_t h, int B, int B_global, const Inputs& in, floa
     return HDGNN_OK;
 }
 
+int env_int(const char* name, int dflt);
+
 // opt-in shared memory + occupancy of the fused kernels for this handle's shapes
 cudaError_t setup_fused(hdgnn_handle_t h, int optin) {
     const cudaFuncAttribute A = cudaFuncAttributeMaxDynamicSharedMemorySize;
@@ -664,6 +678,20 @@ cudaError_t setup_fused(hdgnn_handle_t h, int optin) {
     const int cwc = (h->Nc + 31) / 32;
     if (!h->infer_only) acc(cudaFuncSetAttribute(mid2_fn_rt(cwc, true, h->gt), A, optin));
     acc(cudaFuncSetAttribute(mid2_fn_rt(cwc, false, h->gt), A, optin));
+    // cluster form: shared-memory tables, at most 128 hunks, no global side outputs of the entity stage (inline stage or no entity
+    // branch), not variant 4, not the debug dumps
+    h->cl_ok = !h->gt && cwc <= 4 && (h->inl || !h->ent) && !h->edge && !h->debug && env_int("HDGNN_CLUSTER", 1) != 0;
+    if (h->cl_ok) {
+        acc(cudaFuncSetAttribute(mid2_fn_rt(cwc, true, false, true), A, optin));
+        acc(cudaFuncSetAttribute(mid2_fn_rt(cwc, false, false, true), A, optin));
+        if (e == cudaSuccess) {
+            const bool dlt_g = h->dlt_global;
+            const bool sc_t = (h->ent && h->mid_scache) || h->inl, sc_i = h->inl;
+            h->cl_max[1] = mid2_max_clusters(cwc, true, mid2_smem_bytes(h->Ne, h->Nc, true, !dlt_g, sc_t, h->inl, false, false, false));
+            h->cl_max[0] = mid2_max_clusters(cwc, false, mid2_smem_bytes(h->Ne, h->Nc, false, true, sc_i, h->inl, false, false, false));
+            if (h->cl_max[0] <= 0 || h->cl_max[1] <= 0) h->cl_ok = false;
+        }
+    }
     if (h->ent) {
         acc(cudaFuncSetAttribute(ent2_fn_rt(h->fwd_cwt, h->fwd_nrg, false), A, optin));
         acc(cudaFuncSetAttribute(ent2_fn_rt(h->bwd_cwt, h->bwd_nrg, true), A, optin));
@@ -864,7 +892,7 @@ int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out) {
         {"RS3D", B * Nc * HD * f, lg}, {"CS3DP", B * Sc * Nc * HD * f, lg}, {"LS3P", B * Sc * HD * f, lg},
         {"DNB", B * Nc * 4 * f, dbgbuf}, {"GE", B * Ne * HD * f, true}, {"DX2", B * Ne * f, dbgbuf},
         {"RS1D", B * Ne * HD * f, h->ent && lg}, {"CS1DP", B * Se * Ne * HD * f, h->ent && lg}, {"LS1P", B * Se * HD * f, h->ent && lg},
-        {"GPART", B * (size_t)h->po.total * f, true},
+        {"GPART", 2 * B * (size_t)h->po.total * f, true},       // second half: spare rows of the cluster form (mid2.cuh)
         {"GPE", ((size_t)Gb_max + 1) * 4 * HD * f, h->fused && h->ent}, {"FIN_L2", 256 * f, h->fused}, {"FIN_CNT", 16, h->fused},
         {"EBITS0", B * Ne * (size_t)h->WPe * 4, h->fused}, {"YBITS0", B * Nc * (size_t)h->WPc * 4, h->fused},
         {"EBITS1", B * Ne * (size_t)h->WPe * 4, h->fused}, {"YBITS1", B * Nc * (size_t)h->WPc * 4, h->fused},

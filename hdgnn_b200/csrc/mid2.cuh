@@ -147,6 +147,9 @@ struct Mid2Args {
     Mid2Smem lay;                            // shared-memory layout (mid2_layout), computed once on the host: the offsets are kernel
                                              // arguments (constant bank) instead of per-thread arithmetic
     float* tabs_g;                           // (B, mid2_tab_floats(Nc)) hunk-stage tables when lay.gt (kernel template GT), else unused
+    int B, nsplit;                           // (kernel template CL: launched as clusters of two CTAs) commits of the launch; the first
+                                             // `nsplit` commits of the cost order (short index files first) are shared by the two CTAs
+                                             // of a cluster -- row halves of the four hunk sweeps --, the rest take one CTA each
     int inl;                                 // entity pair layer and its backward INSIDE this kernel (entsp.cuh: sorted prefix sums +
                                              // edge walk): RS1 / CS1p / GE are not used, the step has no ent_fwd2 / ent_bwd2 launch and
                                              // this kernel follows the previous step's optimizer kernel (weights are read after pdl_wait)
@@ -313,11 +316,69 @@ __device__ __forceinline__ int p01_idx(int n, int k) { return n * PROW + (k >> 2
 
 // GT: the hunk-stage tables are addressed in global memory (a.tabs_g, this commit's private slice: written and read by this CTA
 // only, ordered by the block barriers) -- same code, generic loads / stores instead of shared ones
-template <int CWT, bool TRAIN, bool GT>
+// CL: the grid is launched as clusters of two CTAs so that a batch below one wave still occupies the SMs.  A cluster either
+// SHARES one commit (both CTAs run every phase redundantly on identical state, except the four hunk sweeps, of which each takes
+// half the rows; row sums, column partials and the scalar sums cross through distributed shared memory and are added in rank
+// order, so both CTAs -- and any other launch geometry -- hold bitwise the same values; rank 0 writes the outputs) or holds two
+// independent commits (no cluster barrier is ever executed in such a cluster).
+template <int CWT, bool TRAIN, bool GT, bool CL>
 __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
     extern __shared__ __align__(128) unsigned char sm_raw[];
     float* sm = reinterpret_cast<float*>(sm_raw);
-    const int Ne = a.Ne, Nc = a.Nc, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int Ne = a.Ne, Nc = a.Nc, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int b = blockIdx.x;
+    bool split = false, wr = true;          // wr: this CTA writes the commit's global outputs
+    uint32_t crank = 0;
+    if constexpr (CL) {
+        if (a.wait_flag) {                  // the commit assignment reads L: wait for the staged inputs first (see phase A)
+            if (tid == 0) {
+                unsigned int spin = 0;
+                while (*reinterpret_cast<const volatile int*>(a.wait_flag) != a.wait_tag) {
+                    __nanosleep(spin < 16 ? 64 : 2000);
+                    if (++spin > (1u << 22)) __trap();
+                }
+                __threadfence_system();
+            }
+            __syncthreads();
+        }
+        // cost order: commits with a short index file (2 <= L < Ne: the O(L^2) pooling gathers) first, otherwise by index
+        uint32_t* gen_w = reinterpret_cast<uint32_t*>(sm + a.lay.red);       // [8] (no static shared memory: the dynamic size is the opt-in maximum)
+        int* role = reinterpret_cast<int*>(gen_w + 8);                       // [2]
+        crank = cluster_ctarank();
+        const int nw = (a.B + 31) >> 5;
+        if (warp < nw) {
+            const int i = warp * 32 + lane;
+            const int Li = i < a.B ? a.L[i] : Ne;
+            const uint32_t bal = __ballot_sync(0xffffffffu, i < a.B && Li < Ne && Li >= 2);
+            if (lane == 0) gen_w[warp] = bal;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const int c = blockIdx.x >> 1, S = a.nsplit;
+            const int idx = c < S ? c : S + 2 * (c - S) + (int)crank;
+            int commit = -1;
+            if (idx < a.B) {
+                int G = 0;
+                for (int w = 0; w < nw; ++w) G += __popc(gen_w[w]);
+                const bool gen = idx < G;
+                int k = gen ? idx : idx - G;                 // k-th commit of its class, in index order
+                for (int w = 0; w < nw && commit < 0; ++w) {
+                    const uint32_t valid = (w + 1) * 32 <= a.B ? 0xffffffffu : (1u << (a.B - w * 32)) - 1u;
+                    uint32_t m = gen ? gen_w[w] : ~gen_w[w] & valid;
+                    const int pc = __popc(m);
+                    if (k < pc) { for (int t = 0; t < k; ++t) m &= m - 1u; commit = w * 32 + __ffs(m) - 1; }
+                    k -= pc;
+                }
+            }
+            role[0] = commit; role[1] = c < S ? 1 : 0;
+        }
+        __syncthreads();
+        b = role[0]; split = role[1] != 0;
+        if (b < 0) return;                  // odd number of unshared commits: the last cluster's second CTA has nothing to do
+        wr = !split || crank == 0;
+    }
+    const int Nh = (Nc + 1) >> 1;           // hunk-grid rows of rank 0 of a sharing cluster
+    const int hr0 = split && crank ? Nh : 0, hr1 = split && !crank ? Nh : Nc;      // this CTA's rows in the four hunk sweeps
     const int kg = warp % KG, rg = warp / KG, k0 = kg * 4;
     const int WPe = a.WPe, WPc = a.WPc;
     const Mid2Smem& L_ = a.lay;
@@ -350,7 +411,33 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
     const int ch = reduce4_channel(lane);
     const bool LOGITS = a.logits != nullptr;
     float* dbg = a.dbg ? a.dbg + (size_t)b * mid2_dbg_floats(Ne, Nc) : nullptr;
-    float* gp = a.gpart ? a.gpart + (size_t)b * a.total : nullptr;
+    // gradient partials of the commit; the second CTA of a sharing cluster computes the same values and parks them in a spare row
+    float* gp = a.gpart ? a.gpart + (size_t)(wr ? b : a.B + (int)(blockIdx.x >> 1)) * a.total : nullptr;
+    // exchange after a split sweep: the peer's rows of RS are copied in, the column partials CS (Nc x 20 <= M2_T float4) and a
+    // small vector `sv` (n <= 64 floats, may be null) become rank 0's + rank 1's on both CTAs
+    auto xchg = [&](float* RS, float* CS, float* sv, int n) {
+        cluster_sync_all();                                     // both partials are complete
+        const uint32_t peer = crank ^ 1u;
+        const int pr0 = crank ? 0 : Nh, pr1 = crank ? Nh : Nc;  // the peer's rows
+        if (RS) {
+            const uint32_t prs = peer_smem(RS + (size_t)pr0 * HD, peer);
+            for (int e = tid; e < (pr1 - pr0) * (HD / 4); e += M2_T) reinterpret_cast<float4*>(RS + (size_t)pr0 * HD)[e] = ld_peer4(prs + 16u * e);
+        }
+        float4 pc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool have = CS && tid < Nc * (HD / 4);
+        if (have) pc = ld_peer4(peer_smem(CS, peer) + 16u * tid);
+        float ps = 0.f;
+        const bool hs = sv && tid >= M2_T - 64 && tid - (M2_T - 64) < n;
+        if (hs) ps = ld_peer(peer_smem(sv, peer) + 4u * (tid - (M2_T - 64)));
+        cluster_sync_all();                                     // both have read the other's partials
+        if (have) {
+            const float4 own = reinterpret_cast<float4*>(CS)[tid];
+            const float4 lo = crank ? pc : own, hi = crank ? own : pc;
+            reinterpret_cast<float4*>(CS)[tid] = make_float4(lo.x + hi.x, lo.y + hi.y, lo.z + hi.z, lo.w + hi.w);
+        }
+        if (hs) { const float own = sv[tid - (M2_T - 64)]; sv[tid - (M2_T - 64)] = crank ? ps + own : own + ps; }
+        __syncthreads();
+    };
     M2_PHASE(0);
 
     // ---------------- A. label bitmaps (TMA), weights and per-commit vectors -> shared memory ------
@@ -1167,8 +1254,10 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
                 if (j < Nc) q = *reinterpret_cast<const ulonglong2*>(QH + j * HD + k0);
                 Q[sg][0] = q.x; Q[sg][1] = q.y; col[sg][0] = 0ull; col[sg][1] = 0ull;
             }
-            if (pass == 0) sweep2_fwd<PWC, false>(PH01s, ybits + sg0, WPc, Nc, rg, M2_NRG, kg, Q, col, RS3, lane);
-            else sweep2_fwd<PWC, true>(PH01s, ybits + sg0, WPc, Nc, rg, M2_NRG, kg, Q, col, RS3, lane);
+            // rows hr0 .. hr1 (all of them unless a cluster shares the commit)
+            const float* Prow = PH01s + (size_t)hr0 * PROW; const uint32_t* brow = ybits + sg0 + (size_t)hr0 * WPc; float* rsrow = RS3 + (size_t)hr0 * HD;
+            if (pass == 0) sweep2_fwd<PWC, false>(Prow, brow, WPc, hr1 - hr0, rg, M2_NRG, kg, Q, col, rsrow, lane);
+            else sweep2_fwd<PWC, true>(Prow, brow, WPc, hr1 - hr0, rg, M2_NRG, kg, Q, col, rsrow, lane);
             if constexpr (PWC >= 5) combine_cols_2pass<PWC>(col, scratch, rg, M2_NRG, kg, lane);
             else combine_cols<PWC>(col, scratch, rg, M2_NRG, kg, lane);
             if (rg == 0) {
@@ -1181,6 +1270,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         }
     }
     __syncthreads();
+    if (CL && split) xchg(RS3, CS3, nullptr, 0);
     for (int idx = tid; idx < T; idx += M2_T) {       // remove the diagonal pair (l = 0)
         const int c = idx / HD, k = idx - c * HD;
         const float d = fmaxf(PH01[p01_idx(c, k)] + QH[idx], 0.f);
@@ -1249,7 +1339,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
                 if (ok) v = *reinterpret_cast<const ulonglong2*>(PC + j * HD + 4 * q4);
                 Q2[2 * q4] = v.x; Q2[2 * q4 + 1] = v.y;
             }
-            for (int r = warp; r < Nc; r += M2_NW) {
+            for (int r = hr0 + warp; r < hr1; r += M2_NW) {
                 const bool valid = ok && j != r;
                 const uint32_t yw = ybits[r * WPc + cb];
                 const uint32_t bit = (yw >> lane) & 1u;
@@ -1307,30 +1397,47 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         }
     }
     {
-        const float ce_tot = mid2_block_sum(ce_acc, red);
-        if (tid == 0 && a.cep) a.cep[b] = ce_tot;
-        if (a.hits_acc) {                                    // per-commit counts are below 2^24: exact in float; integer atomic: order independent
-            const float hit_tot = mid2_block_sum(hit_acc, red);
-            if (tid == 0) atomicAdd(a.hits_acc, (unsigned long long)(hit_tot + 0.5f));
-        }
-    }
-    if (EVC) {
+        float ce_tot = mid2_block_sum(ce_acc, red);
+        float hit_tot = a.hits_acc ? mid2_block_sum(hit_acc, red) : 0.f;     // per-commit counts are below 2^24: exact in float
         uint32_t* evs = reinterpret_cast<uint32_t*>(red + 64);        // [M2_NW][8] (the label-sum slots of G2: not live yet)
-        __syncthreads();
-        if (lane == 0) { uint32_t* e = evs + warp * 8; e[0] = ev_tpc; e[1] = ev_fpc; e[2] = ev_tpq; e[3] = ev_fpq; e[4] = ev_pos; }
-        __syncthreads();
-        if (tid == 0) {
-            unsigned long long t[5] = {0ull, 0ull, 0ull, 0ull, 0ull};
-            for (int w = 0; w < M2_NW; ++w)
-                for (int q = 0; q < 5; ++q) t[q] += evs[w * 8 + q];
-            const unsigned long long npair = (unsigned long long)Nc * (Nc - 1), pos = t[4], neg = npair - pos;
-            unsigned long long* o = a.evc + (size_t)b * 8;       // this commit's slots: one writer
-            o[0] += t[0] + (neg - t[1]);                          // arg-max hits = tp + tn
-            o[1] += t[2]; o[2] += t[3]; o[3] += neg - t[2];       // reference form: y_true = 1 - Y, y_pred = [p0 > 0]
-            o[4] += t[0]; o[5] += t[1]; o[6] += pos - t[0];       // conventional form: y_true = Y, y_pred = [p1 > p0]
-            o[7] += pos;
+        unsigned long long t[5] = {0ull, 0ull, 0ull, 0ull, 0ull};
+        if (EVC) {
+            __syncthreads();
+            if (lane == 0) { uint32_t* e = evs + warp * 8; e[0] = ev_tpc; e[1] = ev_fpc; e[2] = ev_tpq; e[3] = ev_fpq; e[4] = ev_pos; }
+            __syncthreads();
+            if (tid == 0)
+                for (int w = 0; w < M2_NW; ++w)
+                    for (int q = 0; q < 5; ++q) t[q] += evs[w * 8 + q];
         }
-        __syncthreads();
+        if (CL && split) {
+            // the two halves' scalars: rank 0 adds the peer's (integers and a two-term float sum: order-free)
+            float* xs = red + 64 + M2_NW * 8;                         // [8]
+            __syncthreads();
+            if (tid == 0) {
+                xs[0] = ce_tot; xs[1] = hit_tot;
+                for (int q = 0; q < 5; ++q) xs[2 + q] = __uint_as_float((uint32_t)t[q]);
+            }
+            cluster_sync_all();
+            if (tid == 0 && wr) {
+                const uint32_t px = peer_smem(xs, crank ^ 1u);
+                ce_tot += ld_peer(px); hit_tot += ld_peer(px + 4u);
+                for (int q = 0; q < 5; ++q) t[q] += __float_as_uint(ld_peer(px + 4u * (2 + q)));
+            }
+            cluster_sync_all();
+        }
+        if (wr && tid == 0) {
+            if (a.cep) a.cep[b] = ce_tot;
+            if (a.hits_acc) atomicAdd(a.hits_acc, (unsigned long long)(hit_tot + 0.5f));      // integer atomic: order independent
+            if (EVC) {
+                const unsigned long long npair = (unsigned long long)Nc * (Nc - 1), pos = t[4], neg = npair - pos;
+                unsigned long long* o = a.evc + (size_t)b * 8;       // this commit's slots: one writer
+                o[0] += t[0] + (neg - t[1]);                          // arg-max hits = tp + tn
+                o[1] += t[2]; o[2] += t[3]; o[3] += neg - t[2];       // reference form: y_true = 1 - Y, y_pred = [p0 > 0]
+                o[4] += t[0]; o[5] += t[1]; o[6] += pos - t[0];       // conventional form: y_true = Y, y_pred = [p1 > p0]
+                o[7] += pos;
+            }
+        }
+        if (EVC || (CL && split)) __syncthreads();
     }
     M2_PHASE(6);
     if (!TRAIN) return;
@@ -1380,8 +1487,8 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
                 }
             };
             auto put = [&](int row, int k, float tot) { float* d = RSm + row * HD + k; if (pass == 0) *d = tot; else *d += tot; };
-            int r = rg;
-            for (; r + 3 * M2_NRG < Nc; r += 4 * M2_NRG) {       // four rows per trip: two independent transpose-reduces in flight
+            int r = hr0 + rg;
+            for (; r + 3 * M2_NRG < hr1; r += 4 * M2_NRG) {      // four rows per trip: two independent transpose-reduces in flight
                 u64 a0, a1, c0, c1, e0, e1, g0, g1;
                 delta_row(r, a0, a1);
                 delta_row(r + M2_NRG, c0, c1);
@@ -1393,14 +1500,14 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
                     put((lane & 16) ? r + 3 * M2_NRG : r + 2 * M2_NRG, k0 + reduce8_channel(lane), tot2);
                 }
             }
-            for (; r + M2_NRG < Nc; r += 2 * M2_NRG) {
+            for (; r + M2_NRG < hr1; r += 2 * M2_NRG) {
                 u64 a0, a1, c0, c1;
                 delta_row(r, a0, a1);
                 delta_row(r + M2_NRG, c0, c1);
                 const float tot = reduce8(a0, a1, c0, c1, lane);
                 if ((lane & 3) == 0) put((lane & 16) ? r + M2_NRG : r, k0 + reduce8_channel(lane), tot);
             }
-            if (r < Nc) {
+            if (r < hr1) {
                 u64 a0, a1;
                 delta_row(r, a0, a1);
                 const float tot = reduce4(a0, a1, lane);
@@ -1425,6 +1532,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             misc[tid] = ls;
         }
         __syncthreads();
+        if (CL && split) xchg(RSm, CSm, misc, 41);        // label sums [0, 20) and the sum of the deltas [40]
     }
     M2_PHASE(7);
 
@@ -1539,8 +1647,10 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
                 }
                 Q[sg][0] = q.x; Q[sg][1] = q.y; GCr[sg][0] = g.x; GCr[sg][1] = g.y; col[sg][0] = 0ull; col[sg][1] = 0ull;
             }
-            if (pass == 0) sweep2_bwd<PWC, false>(PH01s, GRs, ybits + sg0, WPc, Nc, rg, M2_NRG, kg, Q, GCr, col, ls3, RS3d, lane);
-            else sweep2_bwd<PWC, true>(PH01s, GRs, ybits + sg0, WPc, Nc, rg, M2_NRG, kg, Q, GCr, col, ls3, RS3d, lane);
+            const float* Prow = PH01s + (size_t)hr0 * PROW; const float* Grow = GRs + (size_t)hr0 * HD;
+            const uint32_t* brow = ybits + sg0 + (size_t)hr0 * WPc; float* rsrow = RS3d + (size_t)hr0 * HD;
+            if (pass == 0) sweep2_bwd<PWC, false>(Prow, Grow, brow, WPc, hr1 - hr0, rg, M2_NRG, kg, Q, GCr, col, ls3, rsrow, lane);
+            else sweep2_bwd<PWC, true>(Prow, Grow, brow, WPc, hr1 - hr0, rg, M2_NRG, kg, Q, GCr, col, ls3, rsrow, lane);
             if constexpr (PWC >= 5) combine_cols_2pass<PWC>(col, scratch, rg, M2_NRG, kg, lane);
             else combine_cols<PWC>(col, scratch, rg, M2_NRG, kg, lane);
             if (rg == 0) {
@@ -1555,6 +1665,16 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         if ((lane & 7) == 0) lsw[rg * HD + k0 + ch] = t;
     }
     __syncthreads();
+    if (CL && split) {
+        // label sums of this half in row-group order -> lsw[0][.], the other row groups zero, so that phase J's sum over the row
+        // groups yields rank 0's + rank 1's
+        float ls = 0.f;
+        if (tid < HD) for (int w = 0; w < M2_NRG; ++w) ls += lsw[w * HD + tid];
+        __syncthreads();
+        if (tid < M2_NRG * HD) lsw[tid] = tid < HD ? ls : 0.f;
+        __syncthreads();
+        xchg(RS3d, CS3d, lsw, HD);
+    }
     for (int idx = tid; idx < T; idx += M2_T) {       // diagonal pair: l = 0
         const int c = idx / HD, k = idx - c * HD;
         const float d = (PH01[p01_idx(c, k)] + QH[idx]) > 0.f ? GR[idx] + GC[idx] : 0.f;

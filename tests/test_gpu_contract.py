@@ -157,3 +157,32 @@ def test_variant4_forward(B, Ne, Nc, attr):
         errs[f"logits[{bb}]"] = relerr(logits[bb].cpu().numpy(), plan["logits"][bb])
     assert all(e < (TOL if k == "probs" else TIGHT) for k, e in errs.items()), (errs, eng.last_launch_count())
     eng.close()
+
+
+@pytest.mark.parametrize("B,variant", [(7, 2), (50, 2), (100, 2), (50, 1)])
+def test_cluster_form_equals_one_cta_per_commit(B, variant, monkeypatch):
+    """Batches below one wave of SMs launch the per-commit kernel as clusters of two CTAs; the costliest commits (short index
+    files first) are shared by the two CTAs of a cluster, which split the rows of the four hunk sweeps and exchange row sums /
+    column partials through distributed shared memory.  Same results as one CTA per commit up to the association of two-term
+    float sums (1e-5 on logits / CE / gradients), and bitwise repeatable."""
+    from hdgnn_b200.engine import Engine, DeviceBatch
+    Ne, Nc = 200, 74
+    cb = make_commits(B, Ne, Nc, seed=900 + B, p_short=0.4)
+    flat = _params(variant).float().cuda()
+    outs = []
+    for cluster in ("1", "0", "1"):
+        monkeypatch.setenv("HDGNN_CLUSTER", cluster)
+        eng = Engine(Ne, Nc, variant=variant, max_batch=B, flags=F_LABEL_BITS)
+        db = DeviceBatch.from_numpy(cb.adj, cb.x, cb.hmap, cb.L, cb.Y, eng.tdev, bits=True)
+        counts = torch.zeros(B, 8, dtype=torch.int64, device="cuda")
+        eng.set_eval_counters(counts)
+        probs, logits, loss, grads = eng.forward_backward(db, flat, want_logits=True)
+        torch.cuda.synchronize()
+        outs.append((probs.cpu().numpy().copy(), logits.cpu().numpy().copy(), loss.cpu().numpy().copy(), grads.cpu().numpy().copy(),
+                     counts.cpu().numpy().copy()))
+        eng.close()
+    (p1, l1, c1, g1, n1), (p0, l0, c0, g0, n0), (p2, l2, c2, g2, n2) = outs
+    assert np.array_equal(p1, p2) and np.array_equal(l1, l2) and np.array_equal(c1, c2) and np.array_equal(g1, g2)      # repeatable
+    assert np.array_equal(n1, n0) and np.array_equal(n1, n2)                                                              # integers
+    for name, x, y in (("probs", p1, p0), ("logits", l1, l0), ("ce", c1[:1], c0[:1]), ("grads", g1, g0)):
+        assert relerr(x, y) < (TOL if name == "probs" else 1e-5), (name, relerr(x, y))      # probs: see the module docstring
