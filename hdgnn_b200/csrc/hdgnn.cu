@@ -16,6 +16,7 @@
 //             -> [E: score(edge, train: recompute + delta sums) -> head_bwd(edge) -> pairsum_bwd(edge)
 //                 -> rank1_grad(edge, tied)] -> grad_reduce
 //       opt : adam (regularisers fused)
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -92,6 +93,8 @@ struct Buf { void* p = nullptr; size_t bytes = 0; };
 
 }  // namespace
 
+constexpr int NSLOT = 3;         // staging slots of the *_host entry points
+
 struct hdgnn_handle_s {
     hdgnn_config_t cfg;
     ParamOff po;
@@ -130,9 +133,17 @@ struct hdgnn_handle_s {
     // host-entry staging: two slots filled on a private copy stream so the H2D copies of call k+1 overlap
     // the kernels of call k (both calls only enqueue work; ordering is by events)
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
-    bool done_valid[2] = {false, false};
-    int slot = 0, cur = 0;
+    cudaEvent_t ev_copy[NSLOT] = {}, ev_done[NSLOT] = {};
+    bool done_valid[NSLOT] = {};
+    // OPT-IN (HDGNN_WAIT_VALUE=1): host-fed training steps on the tag path release their slot by a VALUE the optimizer kernel
+    // writes (final.cuh: done_flag) and the copy stream waits on (cuStreamWaitValue32) instead of an event record / wait pair.
+    // Measured slower than the event (the stream memory operation reacts late): off by default
+    void* wait32 = nullptr;                // cuStreamWaitValue32 (driver entry point), null: events
+    bool flag_release = false;             // the step being enqueued releases its slot by value
+    bool want_flag_release = false;        // the entry point being served ends in reduce_adam (training)
+    unsigned int done_seq[NSLOT] = {};     // last value promised for a slot
+    bool done_by_flag[NSLOT] = {};
+    int slot = 0, cur = 0, cur_B = 0;      // next slot, the slot (and its batch size) filled by the last stage_inputs call
     // peer exchange (commit sharding over NVLink, final.cuh): own mailbox + the peers' mailboxes mapped through CUDA IPC
     PeerArgs peer{};
     void* peer_box = nullptr;              // own mailbox (cudaMalloc)
@@ -145,7 +156,7 @@ struct hdgnn_handle_s {
     unsigned long long* hits_acc = nullptr;   // hdgnn_set_hits_accumulator
     unsigned long long* evc = nullptr;        // hdgnn_set_eval_counters
     uint32_t* tag_table = nullptr;         // pinned, tag_table[i] = i: immutable DMA source
-    unsigned int slot_uses[2] = {0, 0};
+    unsigned int slot_uses[NSLOT] = {};
     int cur_tag = -1;                      // tag of the staging slot filled by the last stage_inputs call, -1 = ordered by event
     // HDGNN_F_LABEL_BITS: the *_host entry points receive label bitmaps (bits.cuh layout) instead of byte grids
     bool host_bits = false;
@@ -662,6 +673,11 @@ int fused_backward(hdgnn_handle_t h, int B, int B_global, const Inputs& in, floa
         f.reg_losses = adam->reg;
         if (adam->peer) f.peer = h->peer;
     }
+    if (h->flag_release) {
+        const int s = h->cur;
+        f.done_flag = (int*)h->ws["H_DONE"].p + s; f.done_seq = (int)++h->done_seq[s];
+        h->done_by_flag[s] = true; h->done_valid[s] = true;
+    }
     PROF_BEGIN(h, st);
     launch_ex(reduce_adam_kernel, (h->po.total + FIN_P - 1) / FIN_P, FIN_P * FIN_SL, 0, st, h->pdl, f);
     LAUNCH_CHECK(h, adam ? (adam->peer ? "reduce_allreduce_adam(peer)" : "reduce_adam") : "grad_reduce", st);
@@ -669,6 +685,19 @@ int fused_backward(hdgnn_handle_t h, int B, int B_global, const Inputs& in, floa
 }
 
 int env_int(const char* name, int dflt);
+
+// HDGNN_F_LABEL_BITS: byte offsets of the five inputs of a batch of B commits inside one staging block (every section starts at
+// the next multiple of 16 bytes).  Host buffers laid out the same way travel in ONE DMA (stage_inputs).
+struct WireOff { size_t eb, yb, x, hm, L, total; };
+WireOff wire_layout(hdgnn_handle_t h, int B) {
+    WireOff w{};
+    size_t o = 0;
+    auto take = [&](size_t n) { const size_t r = o; o += (n + 15) & ~(size_t)15; return r; };
+    w.eb = take((size_t)B * h->Ne * h->WPe * 4); w.yb = take((size_t)B * h->Nc * h->WPc * 4);
+    w.x = take((size_t)B * h->Ne * 4); w.hm = take((size_t)B * h->Ne * 4); w.L = take((size_t)B * 4);
+    w.total = o;
+    return w;
+}
 
 // opt-in shared memory + occupancy of the fused kernels for this handle's shapes
 cudaError_t setup_fused(hdgnn_handle_t h, int optin) {
@@ -910,15 +939,16 @@ int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out) {
         {"GRE", B * Ne * HD * f, h->edge}, {"GCE", B * Ne * HD * f, h->edge},
         {"RSED", B * Ne * HD * f, h->edge}, {"CSEDP", B * Se * Ne * HD * f, h->edge}, {"LSEP", B * Se * HD * f, h->edge},
         // staging for the *_host entry points
-        {"H_ADJ0", B * Ne * (size_t)h->pe, true}, {"H_Y0", B * Nc * (size_t)h->pc, true}, {"H_X0", B * Ne * f, true},
-        {"H_ADJ_RAW0", B * Ne * Ne, h->pe != h->Ne}, {"H_Y_RAW0", B * Nc * Nc, h->pc != h->Nc},
-        {"H_HMAP0", B * Ne * sizeof(int32_t), true}, {"H_L0", B * sizeof(int32_t), true},
-        {"H_ADJ1", B * Ne * (size_t)h->pe, true}, {"H_Y1", B * Nc * (size_t)h->pc, true}, {"H_X1", B * Ne * f, true},
-        {"H_ADJ_RAW1", B * Ne * Ne, h->pe != h->Ne}, {"H_Y_RAW1", B * Nc * Nc, h->pc != h->Nc},
-        {"H_HMAP1", B * Ne * sizeof(int32_t), true}, {"H_L1", B * sizeof(int32_t), true},
-        {"H_EBITS0", B * Ne * (size_t)h->WPe * 4, h->host_bits}, {"H_YBITS0", B * Nc * (size_t)h->WPc * 4, h->host_bits},
-        {"H_EBITS1", B * Ne * (size_t)h->WPe * 4, h->host_bits}, {"H_YBITS1", B * Nc * (size_t)h->WPc * 4, h->host_bits},
-        {"H_FLAG", 16, true}, {"H_PROBS", B * 2 * Nc * (Nc - 1) * f, true}, {"H_LOSS", 4 * f, true}, {"H_GRADS", (size_t)h->po.total * f, true},
+        {"H_ADJ0", B * Ne * (size_t)h->pe, !h->host_bits}, {"H_Y0", B * Nc * (size_t)h->pc, !h->host_bits}, {"H_X0", B * Ne * f, !h->host_bits},
+        {"H_ADJ_RAW0", B * Ne * Ne, !h->host_bits && h->pe != h->Ne}, {"H_Y_RAW0", B * Nc * Nc, !h->host_bits && h->pc != h->Nc},
+        {"H_HMAP0", B * Ne * sizeof(int32_t), !h->host_bits}, {"H_L0", B * sizeof(int32_t), !h->host_bits},
+        {"H_ADJ1", B * Ne * (size_t)h->pe, !h->host_bits}, {"H_Y1", B * Nc * (size_t)h->pc, !h->host_bits}, {"H_X1", B * Ne * f, !h->host_bits},
+        {"H_ADJ_RAW1", B * Ne * Ne, !h->host_bits && h->pe != h->Ne}, {"H_Y_RAW1", B * Nc * Nc, !h->host_bits && h->pc != h->Nc},
+        {"H_HMAP1", B * Ne * sizeof(int32_t), !h->host_bits}, {"H_L1", B * sizeof(int32_t), !h->host_bits},
+        // label-bitmap wire block of a staging slot: [entity bitmaps][hunk bitmaps][x][hmap][L], 16-byte aligned sections
+        {"H_WIRE0", wire_layout(h, cfg->max_batch).total, h->host_bits}, {"H_WIRE1", wire_layout(h, cfg->max_batch).total, h->host_bits},
+        {"H_WIRE2", wire_layout(h, cfg->max_batch).total, h->host_bits},
+        {"H_FLAG", 16, true}, {"H_DONE", 16, true}, {"H_PROBS", B * 2 * Nc * (Nc - 1) * f, true}, {"H_LOSS", 4 * f, true}, {"H_GRADS", (size_t)h->po.total * f, true},
     };
     for (auto& p : plan) {
         if (!p.need) continue;
@@ -933,7 +963,13 @@ int hdgnn_create(const hdgnn_config_t* cfg, hdgnn_handle_t* out) {
     if (ok && env_int("HDGNN_TAG_WAIT", 1) != 0 && cudaHostAlloc((void**)&h->tag_table, 256 * sizeof(uint32_t), cudaHostAllocDefault) == cudaSuccess) {
         for (int i = 0; i < 256; ++i) h->tag_table[i] = (uint32_t)i;
     } else { cudaGetLastError(); h->tag_table = nullptr; }
-    for (int i = 0; i < 2 && ok; ++i)
+    if (ok && env_int("HDGNN_WAIT_VALUE", 0) != 0) {      // opt-in (measured slower than the event: 113 vs 101 us per step); driver entry point, no link-time dependency on libcuda
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess) h->wait32 = fn;
+        else cudaGetLastError();
+    }
+    for (int i = 0; i < NSLOT && ok; ++i)
         ok = cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) {
@@ -949,7 +985,7 @@ int hdgnn_destroy(hdgnn_handle_t h) {
     if (!h) return HDGNN_OK;
     cudaSetDevice(h->cfg.device);
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
-    for (int i = 0; i < 2; ++i) { if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]); if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]); }
+    for (int i = 0; i < NSLOT; ++i) { if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]); if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]); }
     for (auto& kv : h->ws) cudaFree(kv.second.p);
     if (h->tag_table) cudaFreeHost(h->tag_table);
     for (int r = 0; r < PEER_MAX; ++r) if (h->peer_map[r]) cudaIpcCloseMemHandle(h->peer_map[r]);
@@ -1052,6 +1088,8 @@ int hdgnn_peer_status(hdgnn_handle_t h) {
 
 // forward [+ backward [+ adam]] on device-resident inputs; dispatches to the fused or the
 // multi-kernel path.
+static int release_slot(hdgnn_handle_t h, cudaStream_t st);
+
 static int run_step(hdgnn_handle_t h, int B, int B_global, const Inputs& in, float* logits, float* probs, float* loss,
                     float* grads, const AdamArgs* adam, cudaStream_t st) {
     const bool train = grads != nullptr;
@@ -1059,6 +1097,7 @@ static int run_step(hdgnn_handle_t h, int B, int B_global, const Inputs& in, flo
     if (fused_for(h, train)) {
         rc = fused_forward(h, B, B_global, in, logits, probs, train, st);
         if (rc) return rc;
+
         if (!train) {
             if (loss) {
                 PROF_BEGIN(h, st);
@@ -1126,7 +1165,7 @@ int hdgnn_train_step(hdgnn_handle_t h, int B, const uint8_t* adj, int adj_pitch,
 // Host buffers -> staging slot `h->cur` (un-pitched rows are re-pitched on the device).  Outside stream capture the
 // copies run on the handle's copy stream: slot s is reused only after the kernels that read it (two calls ago)
 // have finished, and the caller's stream waits for the copies, so consecutive calls overlap copy and compute.
-static std::string slot_name(const char* base, int slot) { return std::string(base) + (slot ? "1" : "0"); }
+static std::string slot_name(const char* base, int slot) { return std::string(base) + (char)('0' + slot); }
 
 static int stage_inputs(hdgnn_handle_t h, int B, const uint8_t* adj_host, const float* x_host, const int32_t* hmap_host,
                         const int32_t* L_host, const uint8_t* Y_host, cudaStream_t st) {
@@ -1136,12 +1175,36 @@ static int stage_inputs(hdgnn_handle_t h, int B, const uint8_t* adj_host, const 
     const bool side = cap == cudaStreamCaptureStatusNone;
     const int slot = h->slot;
     h->cur = slot;
-    h->slot ^= 1;
+    h->slot = (slot + 1) % (h->host_bits && env_int("HDGNN_SLOTS", 2) == 3 ? 3 : 2);     // a third slot (label bitmaps) is there to try: no gain measured
     cudaStream_t cs = side ? h->copy_stream : st;
-    if (side && h->done_valid[slot]) CK(h, cudaStreamWaitEvent(cs, h->ev_done[slot], 0));
+    if (side && h->done_valid[slot]) {
+        if (h->done_by_flag[slot]) {
+            typedef CUresult (*wait32_t)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+            const CUresult r = ((wait32_t)h->wait32)((CUstream)cs, (CUdeviceptr)((int*)h->ws["H_DONE"].p + slot), (cuuint32_t)h->done_seq[slot],
+                                                     CU_STREAM_WAIT_VALUE_GEQ);
+            if (r != CUDA_SUCCESS) return fail(h, HDGNN_E_CUDA, "cuStreamWaitValue32 failed");
+        } else {
+            CK(h, cudaStreamWaitEvent(cs, h->ev_done[slot], 0));
+        }
+    }
+    h->cur_B = B;
     if (h->host_bits) {
-        CK(h, cudaMemcpyAsync(h->ws[slot_name("H_EBITS", slot)].p, adj_host, (size_t)B * Ne * h->WPe * 4, cudaMemcpyHostToDevice, cs));
-        CK(h, cudaMemcpyAsync(h->ws[slot_name("H_YBITS", slot)].p, Y_host, (size_t)B * Nc * h->WPc * 4, cudaMemcpyHostToDevice, cs));
+        // one staging block per slot; host arrays that already sit back to back in that layout (one pinned block, what
+        // HostBatch builds) are copied with a single DMA, anything else section by section
+        const WireOff W = wire_layout(h, B);
+        char* base = (char*)h->ws[slot_name("H_WIRE", slot)].p;
+        const char* hb = (const char*)adj_host;
+        const bool packed = (const char*)Y_host == hb + W.yb && (const char*)x_host == hb + W.x &&
+                            (const char*)hmap_host == hb + W.hm && (const char*)L_host == hb + W.L;
+        if (packed) {
+            CK(h, cudaMemcpyAsync(base, hb, W.L + (size_t)B * 4, cudaMemcpyHostToDevice, cs));
+        } else {
+            CK(h, cudaMemcpyAsync(base + W.eb, adj_host, (size_t)B * Ne * h->WPe * 4, cudaMemcpyHostToDevice, cs));
+            CK(h, cudaMemcpyAsync(base + W.yb, Y_host, (size_t)B * Nc * h->WPc * 4, cudaMemcpyHostToDevice, cs));
+            CK(h, cudaMemcpyAsync(base + W.x, x_host, (size_t)B * Ne * sizeof(float), cudaMemcpyHostToDevice, cs));
+            CK(h, cudaMemcpyAsync(base + W.hm, hmap_host, (size_t)B * Ne * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
+            CK(h, cudaMemcpyAsync(base + W.L, L_host, (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
+        }
     }
     const uint8_t* srcs[2] = {adj_host, Y_host};
     const char* raw[2] = {"H_ADJ_RAW", "H_Y_RAW"};
@@ -1164,9 +1227,11 @@ static int stage_inputs(hdgnn_handle_t h, int B, const uint8_t* adj_host, const 
             LAUNCH_CHECK(h, "repitch_kernel", cs);
         }
     }
-    CK(h, cudaMemcpyAsync(h->ws[slot_name("H_X", slot)].p, x_host, (size_t)B * Ne * sizeof(float), cudaMemcpyHostToDevice, cs));
-    CK(h, cudaMemcpyAsync(h->ws[slot_name("H_HMAP", slot)].p, hmap_host, (size_t)B * Ne * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
-    CK(h, cudaMemcpyAsync(h->ws[slot_name("H_L", slot)].p, L_host, (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
+    if (!h->host_bits) {
+        CK(h, cudaMemcpyAsync(h->ws[slot_name("H_X", slot)].p, x_host, (size_t)B * Ne * sizeof(float), cudaMemcpyHostToDevice, cs));
+        CK(h, cudaMemcpyAsync(h->ws[slot_name("H_HMAP", slot)].p, hmap_host, (size_t)B * Ne * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
+        CK(h, cudaMemcpyAsync(h->ws[slot_name("H_L", slot)].p, L_host, (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
+    }
     h->cur_tag = -1;
     if (side) {
         if (h->tag_table && h->host_bits && h->fused && (h->inl || !h->ent)) {
@@ -1174,6 +1239,7 @@ static int stage_inputs(hdgnn_handle_t h, int B, const uint8_t* adj_host, const 
             const int tag = (int)(++h->slot_uses[slot] & 0xffu);
             CK(h, cudaMemcpyAsync((int*)h->ws["H_FLAG"].p + slot, h->tag_table + tag, sizeof(int), cudaMemcpyHostToDevice, cs));
             h->cur_tag = tag;
+            h->flag_release = h->wait32 != nullptr && h->want_flag_release;      // set by the training entry points (reduce_adam follows)
         } else {
             CK(h, cudaEventRecord(h->ev_copy[slot], cs));
             CK(h, cudaStreamWaitEvent(st, h->ev_copy[slot], 0));
@@ -1189,8 +1255,10 @@ static Inputs staged_inputs(hdgnn_handle_t h, const float* params) {
               (const int32_t*)h->ws[slot_name("H_HMAP", s)].p, (const int32_t*)h->ws[slot_name("H_L", s)].p,
               (const uint8_t*)h->ws[slot_name("H_Y", s)].p, params};
     if (h->host_bits) {
-        in.ebits = (const uint32_t*)h->ws[slot_name("H_EBITS", s)].p;
-        in.ybits = (const uint32_t*)h->ws[slot_name("H_YBITS", s)].p;
+        const WireOff W = wire_layout(h, h->cur_B);
+        const char* base = (const char*)h->ws[slot_name("H_WIRE", s)].p;
+        in.ebits = (const uint32_t*)(base + W.eb); in.ybits = (const uint32_t*)(base + W.yb);
+        in.x = (const float*)(base + W.x); in.hmap = (const int32_t*)(base + W.hm); in.L = (const int32_t*)(base + W.L);
     }
     if (h->cur_tag >= 0) { in.wait_flag = (const int*)h->ws["H_FLAG"].p + s; in.wait_tag = h->cur_tag; }
     return in;
@@ -1198,11 +1266,12 @@ static Inputs staged_inputs(hdgnn_handle_t h, const float* params) {
 
 // the kernels reading slot h->cur have been enqueued on `st`: the slot may be refilled once they are done
 static int release_slot(hdgnn_handle_t h, cudaStream_t st) {
+    if (h->flag_release) { h->flag_release = false; return HDGNN_OK; }      // released by value (fused_backward)
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(st, &cap);
     if (cap != cudaStreamCaptureStatusNone) return HDGNN_OK;
     CK(h, cudaEventRecord(h->ev_done[h->cur], st));
-    h->done_valid[h->cur] = true;
+    h->done_valid[h->cur] = true; h->done_by_flag[h->cur] = false;
     return HDGNN_OK;
 }
 
@@ -1226,7 +1295,9 @@ int hdgnn_train_step_host(hdgnn_handle_t h, int B, const uint8_t* adj_host, cons
         return fail(h, HDGNN_E_INVALID, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     h->launches = 0;
+    h->want_flag_release = fused_for(h, true);
     int rc = stage_inputs(h, B, adj_host, x_host, hmap_host, L_host, Y_host, st);
+    h->want_flag_release = false;
     if (rc) return rc;
     Inputs in = staged_inputs(h, params);
     float* probs_d = probs_host ? F(h, "H_PROBS") : nullptr;
@@ -1270,7 +1341,9 @@ int hdgnn_train_step_peer_host(hdgnn_handle_t h, int B, int B_global, const uint
     if (B_global != B * h->peer.world) return fail(h, HDGNN_E_INVALID, "B_global must be B * world (equal shards)");
     cudaStream_t st = (cudaStream_t)stream;
     h->launches = 0;
+    h->want_flag_release = true;            // the peer step always ends in reduce_adam (fused path only)
     int rc = stage_inputs(h, B, adj_host, x_host, hmap_host, L_host, Y_host, st);
+    h->want_flag_release = false;
     if (rc) return rc;
     Inputs in = staged_inputs(h, params);
     float* probs_d = probs_out ? F(h, "H_PROBS") : nullptr;

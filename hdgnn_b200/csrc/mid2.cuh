@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
                     __nanosleep(spin < 16 ? 64 : 2000);
                     if (++spin > (1u << 22)) __trap();
                 }
-                __threadfence_system();
+                asm volatile("fence.acq_rel.sys;" ::: "memory");       // the data were written before the tag
             }
             __syncthreads();
         }
@@ -414,8 +414,8 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
     // gradient partials of the commit; the second CTA of a sharing cluster computes the same values and parks them in a spare row
     float* gp = a.gpart ? a.gpart + (size_t)(wr ? b : a.B + (int)(blockIdx.x >> 1)) * a.total : nullptr;
     // exchange after a split sweep: the peer's rows of RS are copied in, the column partials CS (Nc x 20 <= M2_T float4) and a
-    // small vector `sv` (n <= 64 floats, may be null) become rank 0's + rank 1's on both CTAs
-    auto xchg = [&](float* RS, float* CS, float* sv, int n) {
+    // small vector `sv` (n <= 64 floats, may be null) become rank 0's + rank 1's on both CTAs (`CS` is any array of ncs4 float4)
+    auto xchg = [&](float* RS, float* CS, int ncs4, float* sv, int n) {
         cluster_sync_all();                                     // both partials are complete
         const uint32_t peer = crank ^ 1u;
         const int pr0 = crank ? 0 : Nh, pr1 = crank ? Nh : Nc;  // the peer's rows
@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             for (int e = tid; e < (pr1 - pr0) * (HD / 4); e += M2_T) reinterpret_cast<float4*>(RS + (size_t)pr0 * HD)[e] = ld_peer4(prs + 16u * e);
         }
         float4 pc = make_float4(0.f, 0.f, 0.f, 0.f);
-        const bool have = CS && tid < Nc * (HD / 4);
+        const bool have = CS && tid < ncs4;                      // ncs4 <= M2_T float4 of column partials
         if (have) pc = ld_peer4(peer_smem(CS, peer) + 16u * tid);
         float ps = 0.f;
         const bool hs = sv && tid >= M2_T - 64 && tid - (M2_T - 64) < n;
@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
     M2_PHASE(0);
 
     // ---------------- A. label bitmaps (TMA), weights and per-commit vectors -> shared memory ------
-    if (a.wait_flag) {
+    if (!CL && a.wait_flag) {               // (the cluster form has waited before it assigned the commits)
         // Host-fed step: the inputs are copied on the library's copy stream.  A cross-stream event wait in front of this
         // kernel would undo its programmatic launch behind the optimizer kernel, so the copy stream's LAST DMA writes a tag
         // and the kernel polls it here (the copies were enqueued a whole step earlier: the first poll normally succeeds).
@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
                 __nanosleep(spin < 16 ? 64 : 2000);
                 if (++spin > (1u << 22)) __trap();          // ~8 s without the copy: a lost DMA traps instead of hanging the GPU
             }
-            __threadfence_system();
+            asm volatile("fence.acq_rel.sys;" ::: "memory");
         }
         __syncthreads();
     }
@@ -1109,9 +1109,11 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             rowtab[li] = make_int4(q - g * n - n, g, __float_as_int(x2[g]), __float_as_int(x2[min(g + 1, Ne - 1)]));
         }
         __syncthreads();
+        // index lines of this CTA: all of them, or (a cluster shares the commit) one half -- the column sums are added below
+        const int lr0 = CL && split && crank ? (Lb + 1) >> 1 : 0, lr1 = CL && split && !crank ? (Lb + 1) >> 1 : Lb;
         for (int t = tid; t < nchunk * Lb; t += M2_T) {
             const int c = t / Lb, me = t - c * Lb;
-            const int lo = (c * Lb) / nchunk, hi = ((c + 1) * Lb) / nchunk;
+            const int lo = lr0 + (c * (lr1 - lr0)) / nchunk, hi = lr0 + ((c + 1) * (lr1 - lr0)) / nchunk;
             float q0 = 0.f, q1 = 0.f;
             int q3 = 0;
             const bool own = me >= lo && me < hi;       // the chunk holds the diagonal visit li == me
@@ -1163,6 +1165,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             for (int c = 0; c < nchunk; ++c) t += partC[(size_t)c * Lb * 4 + idx];
             TP[idx] = t;
         }
+        if (CL && split) { __syncthreads(); xchg(nullptr, TP, Lb, nullptr, 0); }
         if (a.edge) {
             // variant 4: channels 2, 3 are the soft edges.  In the flat pair order the local grid is the row-major [L][m] reshape of
             // the first L m entries: SP = its row sums, TP[lj] = sum_li a1[li m + lj - (lj > li)]
@@ -1270,7 +1273,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         }
     }
     __syncthreads();
-    if (CL && split) xchg(RS3, CS3, nullptr, 0);
+    if (CL && split) xchg(RS3, CS3, Nc * (HD / 4), nullptr, 0);
     for (int idx = tid; idx < T; idx += M2_T) {       // remove the diagonal pair (l = 0)
         const int c = idx / HD, k = idx - c * HD;
         const float d = fmaxf(PH01[p01_idx(c, k)] + QH[idx], 0.f);
@@ -1532,7 +1535,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             misc[tid] = ls;
         }
         __syncthreads();
-        if (CL && split) xchg(RSm, CSm, misc, 41);        // label sums [0, 20) and the sum of the deltas [40]
+        if (CL && split) xchg(RSm, CSm, Nc * (HD / 4), misc, 41);        // label sums [0, 20) and the sum of the deltas [40]
     }
     M2_PHASE(7);
 
@@ -1673,7 +1676,7 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         __syncthreads();
         if (tid < M2_NRG * HD) lsw[tid] = tid < HD ? ls : 0.f;
         __syncthreads();
-        xchg(RS3d, CS3d, lsw, HD);
+        xchg(RS3d, CS3d, Nc * (HD / 4), lsw, HD);
     }
     for (int idx = tid; idx < T; idx += M2_T) {       // diagonal pair: l = 0
         const int c = idx / HD, k = idx - c * HD;
@@ -1752,9 +1755,12 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
         float* dl1 = TP;                                // channel 1 of dl, planar (TP is dead after the forward)
         for (int i = tid; i < Ne; i += M2_T) dl1[i] = dl[4 * i + 1];
         __syncthreads();
+        // grid rows of this CTA: all of them, or (a cluster shares the commit) one half of the rows below qmax
+        const int gtot = min(Ne, (qmax + n - 1) / n);
+        const int gr0 = CL && split && crank ? (gtot + 1) >> 1 : 0, gr1 = CL && split ? (crank ? gtot : (gtot + 1) >> 1) : Ne;
         for (int t = tid; t < nchunk * Ne; t += M2_T) {
             const int c = t / Ne, me = t - c * Ne;
-            const int lo = (c * Ne) / nchunk, hi = ((c + 1) * Ne) / nchunk;
+            const int lo = gr0 + (c * (gr1 - gr0)) / nchunk, hi = gr0 + ((c + 1) * (gr1 - gr0)) / nchunk;
             float acc = 0.f;
 #pragma unroll
             for (int part = 0; part < 2; ++part) {      // gi < gj (flat column gj - 1), then gi > gj (flat column gj)
@@ -1801,7 +1807,13 @@ __global__ void __launch_bounds__(M2_T, 1) mid2_kernel(const Mid2Args a) {
             }
             float t = 0.f;
             for (int c = 0; c < nchunk; ++c) t += partC[(size_t)c * Ne + gi];
-            dx2[gi] = acc + t;
+            if (CL && split) { dx2[gi] = acc; partC[gi] = t; }     // the column part is this half's: completed below
+            else dx2[gi] = acc + t;
+        }
+        if (CL && split) {
+            __syncthreads();
+            xchg(nullptr, partC, (Ne + 3) >> 2, nullptr, 0);
+            for (int gi = tid; gi < Ne; gi += M2_T) dx2[gi] += partC[gi];
         }
     }
     __syncthreads();

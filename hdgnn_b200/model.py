@@ -66,31 +66,56 @@ def truncated_normal_init(variant: int, seed: Optional[int] = None) -> torch.Ten
 
 class HostBatch:
     """Pinned host copy of a compact commit batch (the wire format into the hot path).  bits=True: the two label
-    grids travel as bitmaps (HDGNN_F_LABEL_BITS, 1/8 of the bytes); Y is kept as bytes too for the evaluation kernel."""
+    grids travel as bitmaps (HDGNN_F_LABEL_BITS, 1/8 of the bytes); Y is kept as bytes too for the evaluation kernel.
+    With bitmaps the five arrays sit back to back in ONE pinned block, every array starting at the next multiple of 16 bytes in
+    the order adj, Y, x, hmap, L -- the layout the library's staging slot has, so a step's inputs travel in a single DMA
+    (include/hdgnn.h, the *_host entry points)."""
 
     def __init__(self, cb: CommitBatch, bits: bool = False):
-        pin = torch.cuda.is_available()
-        mk = lambda a, dt: (torch.as_tensor(np.ascontiguousarray(a, dtype=dt)).pin_memory() if pin
-                            else torch.as_tensor(np.ascontiguousarray(a, dtype=dt)))
         self.bits = bits
-        self.Y = mk(cb.Y, np.uint8)
+        self.Y = self._pin(torch.as_tensor(np.ascontiguousarray(cb.Y, dtype=np.uint8)))
         if bits:
-            self.adj = mk(pack_label_bits(cb.adj).view(np.int32), np.int32)
-            self.Yw = mk(pack_label_bits(cb.Y).view(np.int32), np.int32)
+            self._fill(pack_label_bits(cb.adj).view(np.int32), pack_label_bits(cb.Y).view(np.int32), cb.x, cb.hmap, cb.L)
         else:
+            mk = lambda a, dt: self._pin(torch.as_tensor(np.ascontiguousarray(a, dtype=dt)))
             self.adj, self.Yw = mk(cb.adj, np.uint8), self.Y
-        self.x = mk(cb.x, np.float32)
-        self.hmap, self.L = mk(cb.hmap, np.int32), mk(cb.L, np.int32)
+            self.x = mk(cb.x, np.float32)
+            self.hmap, self.L = mk(cb.hmap, np.int32), mk(cb.L, np.int32)
         self.B = self.adj.shape[0]
+
+    @staticmethod
+    def _pin(t):
+        return t.pin_memory() if torch.cuda.is_available() else t
+
+    def _fill(self, adj, Yw, x, hmap, L):
+        """adj, Yw int32 bitmaps; x float32; hmap, L int32 (numpy or torch): copies them into one pinned block."""
+        parts = [torch.as_tensor(np.ascontiguousarray(a)) if not torch.is_tensor(a) else a.contiguous() for a in (adj, Yw, x, hmap, L)]
+        parts = [p.to(dt) for p, dt in zip(parts, (torch.int32, torch.int32, torch.float32, torch.int32, torch.int32))]
+        offs, o = [], 0
+        for p in parts:
+            offs.append(o)
+            o += (p.numel() * p.element_size() + 15) & ~15
+        block = self._pin(torch.zeros(max(o, 16), dtype=torch.uint8))
+        views = []
+        for p, off in zip(parts, offs):
+            n = p.numel() * p.element_size()
+            v = block[off:off + n].view(p.dtype).view(p.shape)
+            v.copy_(p)
+            views.append(v)
+        self._block = block
+        self.adj, self.Yw, self.x, self.hmap, self.L = views
 
     def clone(self) -> "HostBatch":
         """Same batch in freshly pinned buffers."""
         c = object.__new__(HostBatch)
         c.bits, c.B = self.bits, self.B
-        pin = torch.cuda.is_available()
-        for k in ("adj", "x", "hmap", "L", "Y", "Yw"):
-            t = getattr(self, k).clone()
-            setattr(c, k, t.pin_memory() if pin else t)
+        c.Y = self._pin(self.Y.clone())
+        if self.bits:
+            c._fill(self.adj, self.Yw, self.x, self.hmap, self.L)
+        else:
+            for k in ("adj", "x", "hmap", "L"):
+                setattr(c, k, self._pin(getattr(self, k).clone()))
+            c.Yw = c.Y
         return c
 
     def nbytes(self):
