@@ -134,3 +134,31 @@ def test_commit_sharded_data_parallel_arithmetic_gloo(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "ok" in o
+
+
+def test_host_batch_wire_block_layout():
+    """HostBatch(bits=True) keeps the five inputs of a step in ONE block, every array starting at the next multiple of 16 bytes in
+    the order adj, Y, x, hmap, L -- the layout the *_host entry points copy with a single DMA (include/hdgnn.h, HDGNN_F_LABEL_BITS)
+    -- with the same contents as the separately allocated form."""
+    from hdgnn_b200 import _lib
+    from hdgnn_b200.model import HostBatch
+    from hdgnn_b200.synthetic import make_commits
+    from hdgnn_b200.engine import pack_label_bits
+    for B, Ne, Nc in ((5, 200, 74), (3, 33, 12), (1, 250, 150)):
+        cb = make_commits(B, Ne, Nc, seed=B)
+        hb = HostBatch(cb, bits=True)
+        WPe, WPc = _lib.lib.hdgnn_bit_words(Ne), _lib.lib.hdgnn_bit_words(Nc)
+        sizes = [B * Ne * WPe * 4, B * Nc * WPc * 4, B * Ne * 4, B * Ne * 4, B * 4]
+        offs, o = [], 0
+        for n in sizes:
+            offs.append(o)
+            o += (n + 15) & ~15
+        base = hb.adj.data_ptr()
+        assert [t.data_ptr() - base for t in (hb.adj, hb.Yw, hb.x, hb.hmap, hb.L)] == offs
+        assert hb.adj.shape == (B, Ne, WPe) and hb.Yw.shape == (B, Nc, WPc) and hb.nbytes() == sum(sizes)
+        assert np.array_equal(hb.adj.numpy().view(np.uint32), pack_label_bits(cb.adj)) and np.array_equal(hb.Yw.numpy().view(np.uint32), pack_label_bits(cb.Y))
+        assert np.array_equal(hb.x.numpy(), cb.x) and np.array_equal(hb.hmap.numpy(), cb.hmap) and np.array_equal(hb.L.numpy(), cb.L)
+        c = hb.clone()
+        assert c.adj.data_ptr() != base and all(torch.equal(a, b) for a, b in zip(hb.tensors(), c.tensors()))
+        plain = HostBatch(cb, bits=False)
+        assert plain.adj.shape == (B, Ne, Ne) and plain.Yw is plain.Y
