@@ -444,7 +444,11 @@ def main():
                                 if model.peer else "one NCCL gradient all-reduce/step between backward and Adam"),
                  "l2": f"inputs rotate through {pool_n} batch buffers ({n_distinct} distinct batches) = {pool_n * batch_bytes / 2**20:.0f} MiB > 126 MiB L2",
                  "entity_stage": ("inline (class tables / sorted prefix + edge walk)" if "ent_fwd" not in kernels and "pairsum_fwd(ent)" not in kernels
-                                  else "dense sweeps") if variant in (2, 4) else "none"}
+                                  else "dense sweeps") if variant in (2, 4) else "none",
+                 # informational: what hdgnn.cu's fused_forward does for this shape
+                 "per_commit_kernel": ("clusters of two CTAs, the costliest commits shared by both CTAs of a cluster"
+                                       if (B < 148 and Nc <= 128 and variant != 4 and os.environ.get("HDGNN_CLUSTER", "1") != "0")
+                                       else "one CTA per commit")}
         line = {
             "metric": METRIC, "value": value, "unit": "commits/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
